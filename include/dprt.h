@@ -1,0 +1,122 @@
+/*
+ * dprt.h -- C ABI of libdprt.so: the B200-native per-sample / per-bounce inner loop of the PG2024
+ * data-parallel ray tracer, one opaque context per rank (= per GPU = per scene-chunk owner).
+ *
+ * The reference has no plugin/FFI layer; its boundary is the set of call sites inside
+ * src/render/renderer.cpp:runSample. Each entry point below names the reference call
+ * site it replaces (paths relative to the reference tree). Plain pointers and sizes only; every function
+ * returns 0 on success or a negative dprt_error, never aborts, never throws across the boundary.
+ * All "host" pointers are caller-owned host memory; the context owns every device buffer.
+ * A context is driven by one host thread; all work is enqueued on one CUDA stream per context.
+ */
+#ifndef DPRT_H
+#define DPRT_H
+
+#include "dprt_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dprt_ctx dprt_ctx;
+typedef struct dprt_bvh8 dprt_bvh8;
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+/* MPI_Init + cudaSetDevice + buffer allocation (renderer.cpp:547-741 mallocBuffers/deferredMallocBuffers).
+ * nccl_unique_id: 128 bytes from dprt_get_unique_id() on rank 0 (broadcast by the caller), or NULL for a
+ * context that is only driven single-rank or through dprt_*_group(). */
+int  dprt_get_unique_id(void* out128);
+int  dprt_create(const dprt_config* cfg, int rank, int world, int device, const void* nccl_unique_id, dprt_ctx** out);
+void dprt_destroy(dprt_ctx* ctx);
+const char* dprt_last_error(const dprt_ctx* ctx);   /* ctx may be NULL: last create-time error */
+int  dprt_synchronize(dprt_ctx* ctx);
+int  dprt_get_stats(const dprt_ctx* ctx, dprt_stats* out);
+int  dprt_reset_stats(dprt_ctx* ctx);
+
+/* ---- scene (renderer.cpp:1725-1849: lights, AccelerationStructure table; GAS build is OptiX's) -- */
+/* Host-side BVH8 build, exposed so that harnesses can inspect the structure the kernels walk. */
+int  dprt_bvh8_build(const float* verts9, const int32_t* mat_ids, int64_t ntris, float pad, dprt_bvh8** out);
+int  dprt_bvh8_info(const dprt_bvh8* b, int64_t* nnodes, int64_t* ntris, int32_t* max_depth);
+int  dprt_bvh8_copy(const dprt_bvh8* b, dprt_bvh8_node* nodes_out, dprt_bvh8_tri* tris_out);
+void dprt_bvh8_free(dprt_bvh8* b);
+
+/* Scene object `scene_index` is real geometry on this rank: verts9 = ntris*9 floats, normals9 = ntris*9
+ * floats (per-corner shading normals, HitGroupData.normals/normalIndices of pipeline_helper.cpp:182-193),
+ * mat_ids = ntris ints into the material table. */
+int  dprt_upload_chunk(dprt_ctx* ctx, int scene_index, const dprt_object_desc* desc, const float* verts9,
+                       const float* normals9, const int32_t* mat_ids, int64_t ntris);
+/* Scene object `scene_index` is a proxy on this rank: AABB + world->object transform + the two proxy MLPs
+ * (torch::jit::load of vis/depth modules, renderer.cpp:1884-1905). Weight blobs use the packed fp32 layout
+ * documented in DESIGN.md ("proxy weight blob"); either may be NULL ("padding" entries of the reference). */
+int  dprt_upload_proxy(dprt_ctx* ctx, int scene_index, const dprt_object_desc* desc, const void* vis_blob,
+                       size_t vis_bytes, const void* depth_blob, size_t depth_bytes);
+int  dprt_set_materials(dprt_ctx* ctx, const dprt_material* mats, int n);
+int  dprt_set_lights(dprt_ctx* ctx, const dprt_light_tri* lights, int n);   /* renderer.cpp:1798-1808 */
+int  dprt_set_camera(dprt_ctx* ctx, const dprt_camera* cam);                /* params.camera, :1990 */
+
+/* ---- stage entry points: one per reference call site ----------------------------------------- */
+int  dprt_reset_frame(dprt_ctx* ctx);                 /* resetFrameBuffers            renderer.cpp:416-451 */
+int  dprt_begin_sample(dprt_ctx* ctx, int sample);    /* resetSampleBuffers + params  renderer.cpp:1497-1512 */
+int  dprt_path_gen(dprt_ctx* ctx);                    /* optixLaunch(PathGen)         renderer.cpp:1514-1527 */
+int  dprt_traverse(dprt_ctx* ctx);                    /* optixLaunch(TraRay)          renderer.cpp:1232-1243 */
+int  dprt_partition(dprt_ctx* ctx);                   /* Work_Efficient_Scan          cuda_compaction.cu:352 */
+int  dprt_exchange(dprt_ctx* ctx, int* done);         /* Alltoall+Alltoallv+Allreduce renderer.cpp:1254-1314 */
+int  dprt_shade(dprt_ctx* ctx);                       /* optixLaunch(MainRay)         renderer.cpp:1320-1347 */
+int  dprt_reset_nn(dprt_ctx* ctx);                    /* resetNNBuffers               renderer.cpp:367-414 */
+int  dprt_shadow_trace(dprt_ctx* ctx);                /* optixLaunch(ShadowRay)       renderer.cpp:1366-1379 */
+int  dprt_secondary_trace(dprt_ctx* ctx);             /* optixLaunch(SecondaryRay)    renderer.cpp:1426-1437 */
+/* which: 0 = shadow queries (mc*shadowPathSize slots), 1 = secondary queries (mc*pathSize slots).
+ * inside_only != 0 is Work_Efficient_Scan_For_NN_HIT_INSIDE (cuda_compaction.cu:532), else ..._For_NN (:441). */
+int  dprt_bucket_queries(dprt_ctx* ctx, int which, int inside_only, int* total);
+/* kind: 0 = vis model -> pred[0..total), 1 = depth model -> pred[pred_offset..): the batched
+ * torch::jit forward loops of renderer.cpp:768-839 (depth, offset 0), :841-1011, :1014-1159. */
+int  dprt_proxy_infer(dprt_ctx* ctx, int kind, int pred_offset);
+int  dprt_frame_buffer_update(dprt_ctx* ctx);         /* Frame_Buffer_Update   frame_buffer_update.cu:129 */
+int  dprt_depth_buffer_update(dprt_ctx* ctx);         /* Depth_Buffer_Update   frame_buffer_update.cu:194 */
+int  dprt_target_node_update(dprt_ctx* ctx);          /* Target_Node_Update    frame_buffer_update.cu:326 */
+/* composite modules, same order as the reference helpers */
+int  dprt_primary_ray_module(dprt_ctx* ctx);          /* primaryRayModule          renderer.cpp:1212-1318 */
+int  dprt_shadow_ray_module(dprt_ctx* ctx);           /* shadowRayModuleBasedNN    renderer.cpp:1349-1405 */
+int  dprt_secondary_ray_module(dprt_ctx* ctx);        /* secondaryRayModuleBasedNN renderer.cpp:1407-1452 */
+int  dprt_render_sample(dprt_ctx* ctx, int sample);   /* runSample                 renderer.cpp:1457-1574 */
+/* (direct+env)/spp on device, ncclReduce(sum) to root, copy to out_host (3*N floats, root only; may be NULL
+ * elsewhere): renderer.cpp:2031-2052. */
+int  dprt_reduce_image(dprt_ctx* ctx, int root, float* out_host);
+
+/* ---- in-process rank group: W contexts driven by one thread (tests on fewer GPUs than ranks) --- */
+int  dprt_exchange_group(dprt_ctx** ctxs, int world, int* done);
+int  dprt_render_sample_group(dprt_ctx** ctxs, int world, int sample);
+int  dprt_reduce_image_group(dprt_ctx** ctxs, int world, int root, float* out_host);
+
+/* ---- state access for harnesses -------------------------------------------------------------- */
+int  dprt_get_path_size(const dprt_ctx* ctx, int* path_size, int* shadow_path_size);
+int  dprt_set_path_size(dprt_ctx* ctx, int path_size);
+int  dprt_buffer_bytes(const dprt_ctx* ctx, int buffer_id, size_t* bytes);
+int  dprt_download(dprt_ctx* ctx, int buffer_id, size_t offset_bytes, void* host, size_t bytes);
+int  dprt_upload(dprt_ctx* ctx, int buffer_id, size_t offset_bytes, const void* host, size_t bytes);
+int  dprt_enable_hit_prim(dprt_ctx* ctx, int enable);
+
+/* ---- standalone operators --------------------------------------------------------------------- */
+/* Closest hit of n host rays against this rank's local geometry: H2D, trace, D2H (the optixTrace closest-hit
+ * launch of BASELINE config 2 through host buffers). */
+int  dprt_trace_closest(dprt_ctx* ctx, const dprt_ray* rays_host, int64_t n, dprt_hit* hits_host);
+/* Same on device-resident buffers obtained from dprt_device_alloc. */
+int  dprt_trace_closest_device(dprt_ctx* ctx, const void* rays_dev, int64_t n, void* hits_dev);
+/* Proxy MLP forward of scene object `scene_index`: x_host [n,5] fp16 -> y_host [n] fp16 (module.forward,
+ * renderer.cpp:809-816). kind 0 = vis, 1 = depth. */
+int  dprt_mlp_infer(dprt_ctx* ctx, int scene_index, int kind, const dprt_half* x_host, int64_t n, dprt_half* y_host);
+int  dprt_mlp_infer_device(dprt_ctx* ctx, int scene_index, int kind, const void* x_dev, int64_t n, void* y_dev);
+
+int  dprt_device_alloc(dprt_ctx* ctx, size_t bytes, void** dev_ptr);
+int  dprt_device_free(dprt_ctx* ctx, void* dev_ptr);
+int  dprt_memcpy_h2d(dprt_ctx* ctx, void* dev, const void* host, size_t bytes);
+int  dprt_memcpy_d2h(dprt_ctx* ctx, void* host, const void* dev, size_t bytes);
+/* CUDA-event timing on the context's stream (the harness times stages the way the kernels are launched). */
+int  dprt_timer_start(dprt_ctx* ctx);
+int  dprt_timer_stop(dprt_ctx* ctx, float* ms);
+int  dprt_flush_l2(dprt_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPRT_H */

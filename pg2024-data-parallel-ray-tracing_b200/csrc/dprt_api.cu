@@ -1,0 +1,991 @@
+// dprt_api.cu -- context, buffer ownership, stage sequencing and the C ABI of libdprt.so.
+//
+// Host-side restatement of src/render/renderer.cpp: mallocBuffers/deferredMallocBuffers (:547-741), the reset
+// helpers (:336-514), primaryRayModule (:1212-1318), generateSecondaryAndShadowRay (:1320-1347),
+// shadowRayModuleBasedNN (:1349-1405), secondaryRayModuleBasedNN (:1407-1452), runSample (:1457-1574) and the
+// image average + reduce of launch() (:2031-2052). OptiX launches become the kernels of kernels.cu, the
+// Work_Efficient_Scan* loops the single-pass partition of partition.cu, torch::jit forward the fused MLP of
+// mlp.cu, and host-staged MPI becomes NCCL on device buffers. There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is bound at run time (see NcclApi)
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dprt.h"
+#include "dprt_internal.cuh"
+#include "bvh_build.h"
+#include "mlp.cuh"
+
+using namespace dprt;
+
+struct dprt_bvh8 { Bvh8 b; };
+
+namespace {
+
+std::string g_create_error;
+
+// NCCL is resolved with dlopen("libnccl.so.2") on first use instead of a link-time dependency: when the
+// process already holds a copy (torch bundles its own, newer one) glibc hands back that very library, and a
+// single-rank user of libdprt never needs NCCL at all.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool load() {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!handle) { error = std::string("dlopen(libnccl.so.2): ") + dlerror(); return false; }
+        auto sym = [&](const char* n) { void* p = dlsym(handle, n); if (!p) error = std::string("dlsym ") + n; return p; };
+        GetUniqueId = (decltype(GetUniqueId))sym("ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+        AllGather = (decltype(AllGather))sym("ncclAllGather");
+        Send = (decltype(Send))sym("ncclSend");
+        Recv = (decltype(Recv))sym("ncclRecv");
+        Reduce = (decltype(Reduce))sym("ncclReduce");
+        GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd");
+        GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+        if (!error.empty()) { dlclose(handle); handle = nullptr; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+struct ObjectHost {
+    bool present = false;
+    dprt_object_desc desc{};
+    void* d_nodes = nullptr; void* d_tris = nullptr; void* d_normals = nullptr;
+    int64_t nnodes = 0, ntris = 0;
+    MlpModel* vis = nullptr; MlpModel* depth = nullptr;
+};
+
+}  // namespace
+
+struct dprt_ctx {
+    dprt_config cfg{};
+    int rank = 0, world = 1, device = 0;
+    int N = 0;
+    cudaStream_t stream = nullptr;
+    ncclComm_t comm = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevParams hp{};
+    std::vector<ObjectHost> objects;
+    DevObject* d_objects = nullptr;
+    dprt_material* d_materials = nullptr;
+    dprt_light_tri* d_lights = nullptr;
+    size_t buf_bytes[DPRT_BUF_COUNT] = {0};
+    void* buf_ptr[DPRT_BUF_COUNT] = {nullptr};
+    int32_t* d_hist = nullptr;          // 32 path + 64 query counters
+    PartitionScratch scratch{};
+    float* d_image = nullptr;           // averaged image, 3N
+    float* d_image_sum = nullptr;       // reduce target, 3N
+    int32_t* d_gather = nullptr;        // W*(W+1) offsets of all ranks
+    int32_t* h_pinned = nullptr;        // pinned staging for counts/offsets
+    void* d_flush = nullptr; size_t flush_bytes = 0;
+    void* d_io = nullptr; size_t io_bytes = 0;   // staging for the standalone host-buffer operators
+    int pathSize = 0, shadowPathSize = 0;
+    int sample = 0;
+    int queryTotal = 0;                 // rows of the last bucketing
+    int queryWhich = 0;
+    std::vector<int> h_sceneOffset;
+    bool histFresh = false;             // pathHist holds the histogram of the current paths
+    bool qhistFresh = false;            // queryHist holds the histograms of the current queries
+    std::vector<int> h_offsets;         // last transferOffset (W+1)
+    dprt_stats stats{};
+    std::string err;
+    std::vector<void*> user_allocs;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+            return DPRT_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t e_ = (call);                                                                  \
+        if (e_ != ncclSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + g_nccl.GetErrorString(e_);                         \
+            return DPRT_ERR_NCCL;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+int fail(dprt_ctx* ctx, int code, const std::string& msg) { ctx->err = msg; return code; }
+
+int alloc_buf(dprt_ctx* ctx, int id, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 256);
+    CK(cudaMalloc(&ctx->buf_ptr[id], bytes));
+    CK(cudaMemsetAsync(ctx->buf_ptr[id], 0, bytes, ctx->stream));
+    ctx->buf_bytes[id] = bytes;
+    return 0;
+}
+
+void sync_params(dprt_ctx* ctx) {
+    DevParams& p = ctx->hp;
+    p.pathSize = ctx->pathSize; p.shadowPathSize = ctx->shadowPathSize;
+    p.spc = ctx->cfg.shadowPathCount; p.mc = ctx->cfg.maxCount; p.sceneSize = ctx->cfg.sceneSize;
+    p.worldID = ctx->rank; p.worldSize = ctx->world; p.sampleCount = ctx->sample;
+    p.frameBufferSize = ctx->N; p.proxyMode = ctx->cfg.proxyMode; p.pathGenMode = ctx->cfg.pathGenMode;
+    for (int k = 0; k < 3; k++) p.envColor[k] = ctx->cfg.envColor[k];
+}
+
+int upload_objects(dprt_ctx* ctx) {
+    std::vector<DevObject> h(ctx->cfg.sceneSize);
+    for (int i = 0; i < ctx->cfg.sceneSize; i++) {
+        const ObjectHost& o = ctx->objects[i];
+        DevObject d{};
+        d.nodeID = o.present ? o.desc.nodeID : 0; d.isProxy = o.present ? (o.desc.isProxy ? 1 : 0) : 2;   // 2 = slot not uploaded: skipped everywhere
+        if (!o.present) {   // never hit: inverted box
+            for (int a = 0; a < 3; a++) { d.aabbMin[a] = 1.f; d.aabbMax[a] = -1.f; }
+            d.w2o[0] = d.w2o[5] = d.w2o[10] = 1.f;
+        } else {
+            std::memcpy(d.aabbMin, o.desc.aabbMin, 12); std::memcpy(d.aabbMax, o.desc.aabbMax, 12);
+            d.maxLength = o.desc.maxLength; std::memcpy(d.w2o, o.desc.worldToObject, 48);
+        }
+        d.nodes = (const uint4*)o.d_nodes; d.tris = (const float4*)o.d_tris; d.normals = (const float*)o.d_normals;
+        h[i] = d;
+    }
+    CK(cudaMemcpyAsync(ctx->d_objects, h.data(), h.size() * sizeof(DevObject), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int ensure_io(dprt_ctx* ctx, size_t bytes) {
+    if (ctx->io_bytes >= bytes) return 0;
+    if (ctx->d_io) cudaFree(ctx->d_io);
+    ctx->d_io = nullptr; ctx->io_bytes = 0;
+    CK(cudaMalloc(&ctx->d_io, bytes));
+    ctx->io_bytes = bytes;
+    return 0;
+}
+
+// reads transferOffset (W+1 ints) to the host
+int read_offsets(dprt_ctx* ctx) {
+    const int W = ctx->world;
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->hp.transferOffset, (W + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->h_offsets.assign(ctx->h_pinned, ctx->h_pinned + W + 1);
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int dprt_get_unique_id(void* out128) {
+    if (!out128) return DPRT_ERR_INVALID;
+    ncclUniqueId id;
+    if (!g_nccl.load()) { g_create_error = g_nccl.error; return DPRT_ERR_NCCL; }
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return DPRT_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    std::memcpy(out128, &id, 128);
+    return 0;
+}
+
+const char* dprt_last_error(const dprt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int dprt_create(const dprt_config* cfg, int rank, int world, int device, const void* nccl_unique_id, dprt_ctx** out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return DPRT_ERR_INVALID; }
+    *out = nullptr;
+    if (world < 1 || world > DPRT_MAX_WORLD || rank < 0 || rank >= world || cfg->width <= 0 || cfg->height <= 0 ||
+        cfg->sceneSize < 1 || cfg->sceneSize > 32 || cfg->shadowPathCount < 1 || cfg->maxCount < 1 || cfg->maxCount > 8 ||
+        cfg->shadowPathCount > 16) {
+        g_create_error = "invalid configuration"; return DPRT_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(ce) + " (libdprt has no CPU fallback)";
+        return DPRT_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return DPRT_ERR_INVALID; }
+    dprt_ctx* ctx = new dprt_ctx();
+    ctx->cfg = *cfg; ctx->rank = rank; ctx->world = world; ctx->device = device;
+    ctx->N = cfg->width * cfg->height;
+    auto bail = [&](int code) { g_create_error = ctx->err; dprt_destroy(ctx); return code; };
+    auto body = [&]() -> int {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
+        const size_t N = ctx->N, spc = cfg->shadowPathCount, mc = cfg->maxCount;
+        ctx->objects.resize(cfg->sceneSize);
+        CK(cudaMalloc(&ctx->d_objects, sizeof(DevObject) * cfg->sceneSize));
+        CK(cudaMalloc(&ctx->d_materials, sizeof(dprt_material) * DPRT_MAX_MATERIALS));
+        CK(cudaMemsetAsync(ctx->d_materials, 0, sizeof(dprt_material) * DPRT_MAX_MATERIALS, ctx->stream));
+        CK(cudaMalloc(&ctx->d_lights, sizeof(dprt_light_tri) * DPRT_MAX_LIGHTS));
+        int r;
+        if ((r = alloc_buf(ctx, DPRT_BUF_PATHS, (1 + spc) * N * sizeof(dprt_path_record)))) return r;
+        if ((r = alloc_buf(ctx, DPRT_BUF_TRANSFER, N * sizeof(dprt_path_record)))) return r;
+        if ((r = alloc_buf(ctx, DPRT_BUF_TRANSFER_OFFSET, 64 * sizeof(int32_t)))) return r;
+        if ((r = alloc_buf(ctx, DPRT_BUF_DIRECT, spc * 3 * N * sizeof(float)))) return r;
+        if ((r = alloc_buf(ctx, DPRT_BUF_ENV, 3 * N * sizeof(float)))) return r;
+        if ((r = alloc_buf(ctx, DPRT_BUF_SCENE_OFFSET, 64 * sizeof(int32_t)))) return r;
+        if ((r = alloc_buf(ctx, DPRT_BUF_OCCLUSION, N * mc * spc * sizeof(float)))) return r;
+        if ((r = alloc_buf(ctx, DPRT_BUF_CONTRIBUTION, 3 * N * spc * sizeof(float)))) return r;
+        const size_t Q = cfg->proxyMode ? N * mc * spc : 1;
+        if ((r = alloc_buf(ctx, DPRT_BUF_NN_INPUT, Q * 5 * sizeof(dprt_half)))) return r;
+        if ((r = alloc_buf(ctx, DPRT_BUF_NN_PACKED_INPUT, Q * 5 * sizeof(dprt_half) + 64))) return r;
+        if ((r = alloc_buf(ctx, DPRT_BUF_NN_QUERY, Q * sizeof(dprt_nn_query)))) return r;
+        if ((r = alloc_buf(ctx, DPRT_BUF_NN_PACKED_QUERY, Q * sizeof(dprt_nn_query)))) return r;
+        if ((r = alloc_buf(ctx, DPRT_BUF_PRED, Q * 4 * sizeof(dprt_half)))) return r;
+        CK(cudaMalloc(&ctx->d_hist, 128 * sizeof(int32_t)));
+        CK(cudaMemsetAsync(ctx->d_hist, 0, 128 * sizeof(int32_t), ctx->stream));
+        ctx->scratch.maxTiles = (int)((std::max(Q, N) + 1023) / 1024) + 1;
+        CK(cudaMalloc(&ctx->scratch.tileState, (size_t)ctx->scratch.maxTiles * 32 * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->scratch.tileCounter, sizeof(int32_t)));
+        CK(cudaMalloc(&ctx->d_image, 3 * N * sizeof(float)));
+        CK(cudaMalloc(&ctx->d_image_sum, 3 * N * sizeof(float)));
+        CK(cudaMalloc(&ctx->d_gather, sizeof(int32_t) * (size_t)world * (world + 1)));
+        CK(cudaMallocHost(&ctx->h_pinned, sizeof(int32_t) * std::max<size_t>(256, (size_t)world * (world + 1))));
+
+        DevParams& p = ctx->hp;
+        p.objects = ctx->d_objects; p.materials = ctx->d_materials; p.lights = ctx->d_lights;
+        p.paths = (dprt_path_record*)ctx->buf_ptr[DPRT_BUF_PATHS];
+        p.transfer = (dprt_path_record*)ctx->buf_ptr[DPRT_BUF_TRANSFER];
+        p.transferOffset = (int32_t*)ctx->buf_ptr[DPRT_BUF_TRANSFER_OFFSET];
+        p.pathHist = ctx->d_hist; p.queryHist = ctx->d_hist + 32;
+        p.direct = (float*)ctx->buf_ptr[DPRT_BUF_DIRECT]; p.env = (float*)ctx->buf_ptr[DPRT_BUF_ENV];
+        p.contribution = (float*)ctx->buf_ptr[DPRT_BUF_CONTRIBUTION]; p.occlusion = (float*)ctx->buf_ptr[DPRT_BUF_OCCLUSION];
+        p.nnInput = (dprt_half*)ctx->buf_ptr[DPRT_BUF_NN_INPUT]; p.nnPackedInput = (dprt_half*)ctx->buf_ptr[DPRT_BUF_NN_PACKED_INPUT];
+        p.nnQuery = (dprt_nn_query*)ctx->buf_ptr[DPRT_BUF_NN_QUERY]; p.nnPackedQuery = (dprt_nn_query*)ctx->buf_ptr[DPRT_BUF_NN_PACKED_QUERY];
+        p.sceneOffset = (int32_t*)ctx->buf_ptr[DPRT_BUF_SCENE_OFFSET];
+        p.pred = (dprt_half*)ctx->buf_ptr[DPRT_BUF_PRED];
+        p.hitPrim = nullptr;
+        p.camera.width = cfg->width; p.camera.height = cfg->height;
+        p.lightCount = 0;
+        sync_params(ctx);
+        ctx->h_sceneOffset.assign(cfg->sceneSize + 1, 0);
+        ctx->h_offsets.assign(world + 1, 0);
+        for (int i = 0; i < cfg->sceneSize; i++) { ctx->objects[i].desc.nodeID = 0; ctx->objects[i].desc.isProxy = 1; }
+        if ((r = upload_objects(ctx))) return r;
+        if (nccl_unique_id && world > 1) {
+            ncclUniqueId id; std::memcpy(&id, nccl_unique_id, 128);
+            if (!g_nccl.load()) { ctx->err = g_nccl.error; return DPRT_ERR_NCCL; }
+            NK(g_nccl.CommInitRank(&ctx->comm, world, id, rank));
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    };
+    int r = body();
+    if (r) return bail(r);
+    *out = ctx;
+    return 0;
+}
+
+void dprt_destroy(dprt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
+    for (auto& o : ctx->objects) {
+        if (o.d_nodes) cudaFree(o.d_nodes);
+        if (o.d_tris) cudaFree(o.d_tris);
+        if (o.d_normals) cudaFree(o.d_normals);
+        if (o.vis) mlp_destroy(o.vis);
+        if (o.depth) mlp_destroy(o.depth);
+    }
+    for (int i = 0; i < DPRT_BUF_COUNT; i++) if (ctx->buf_ptr[i]) cudaFree(ctx->buf_ptr[i]);
+    for (void* p : ctx->user_allocs) cudaFree(p);
+    if (ctx->d_objects) cudaFree(ctx->d_objects);
+    if (ctx->d_materials) cudaFree(ctx->d_materials);
+    if (ctx->d_lights) cudaFree(ctx->d_lights);
+    if (ctx->d_hist) cudaFree(ctx->d_hist);
+    if (ctx->scratch.tileState) cudaFree(ctx->scratch.tileState);
+    if (ctx->scratch.tileCounter) cudaFree(ctx->scratch.tileCounter);
+    if (ctx->d_image) cudaFree(ctx->d_image);
+    if (ctx->d_image_sum) cudaFree(ctx->d_image_sum);
+    if (ctx->d_gather) cudaFree(ctx->d_gather);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->d_flush) cudaFree(ctx->d_flush);
+    if (ctx->d_io) cudaFree(ctx->d_io);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int dprt_synchronize(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+int dprt_get_stats(const dprt_ctx* ctx, dprt_stats* out) { if (!ctx || !out) return DPRT_ERR_INVALID; *out = ctx->stats; return 0; }
+int dprt_reset_stats(dprt_ctx* ctx) { if (!ctx) return DPRT_ERR_INVALID; ctx->stats = dprt_stats{}; return 0; }
+
+// ---- scene -------------------------------------------------------------------------------------
+int dprt_bvh8_build(const float* verts9, const int32_t* mat_ids, int64_t ntris, float pad, dprt_bvh8** out) {
+    if (!out) return DPRT_ERR_INVALID;
+    dprt_bvh8* b = new dprt_bvh8();
+    if (bvh8_build(verts9, mat_ids, ntris, pad, b->b)) { delete b; *out = nullptr; return DPRT_ERR_INVALID; }
+    *out = b; return 0;
+}
+int dprt_bvh8_info(const dprt_bvh8* b, int64_t* nnodes, int64_t* ntris, int32_t* max_depth) {
+    if (!b) return DPRT_ERR_INVALID;
+    if (nnodes) *nnodes = (int64_t)b->b.nodes.size();
+    if (ntris) *ntris = (int64_t)b->b.tris.size();
+    if (max_depth) *max_depth = b->b.max_depth;
+    return 0;
+}
+int dprt_bvh8_copy(const dprt_bvh8* b, dprt_bvh8_node* nodes_out, dprt_bvh8_tri* tris_out) {
+    if (!b) return DPRT_ERR_INVALID;
+    if (nodes_out) std::memcpy(nodes_out, b->b.nodes.data(), b->b.nodes.size() * sizeof(dprt_bvh8_node));
+    if (tris_out) std::memcpy(tris_out, b->b.tris.data(), b->b.tris.size() * sizeof(dprt_bvh8_tri));
+    return 0;
+}
+void dprt_bvh8_free(dprt_bvh8* b) { delete b; }
+
+int dprt_upload_chunk(dprt_ctx* ctx, int si, const dprt_object_desc* desc, const float* verts9, const float* normals9,
+                      const int32_t* mat_ids, int64_t ntris) {
+    if (!ctx || !desc || !verts9 || si < 0 || si >= ctx->cfg.sceneSize || ntris <= 0) return DPRT_ERR_INVALID;
+    if (desc->nodeID < 0 || desc->nodeID >= ctx->world) return fail(ctx, DPRT_ERR_INVALID, "nodeID out of range");
+    CK(cudaSetDevice(ctx->device));
+    Bvh8 b;
+    if (bvh8_build(verts9, mat_ids, ntris, -1.f, b)) return fail(ctx, DPRT_ERR_INVALID, "bvh8_build failed");
+    if (b.max_depth > 36) return fail(ctx, DPRT_ERR_CAPACITY, "BVH8 deeper than the traversal stack");
+    ObjectHost& o = ctx->objects[si];
+    if (o.d_nodes) cudaFree(o.d_nodes);
+    if (o.d_tris) cudaFree(o.d_tris);
+    if (o.d_normals) cudaFree(o.d_normals);
+    o.d_nodes = o.d_tris = o.d_normals = nullptr;
+    o.desc = *desc; o.desc.isProxy = 0; o.present = true;
+    o.nnodes = (int64_t)b.nodes.size(); o.ntris = (int64_t)b.tris.size();
+    CK(cudaMalloc(&o.d_nodes, b.nodes.size() * sizeof(dprt_bvh8_node)));
+    CK(cudaMalloc(&o.d_tris, b.tris.size() * sizeof(dprt_bvh8_tri)));
+    CK(cudaMemcpy(o.d_nodes, b.nodes.data(), b.nodes.size() * sizeof(dprt_bvh8_node), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(o.d_tris, b.tris.data(), b.tris.size() * sizeof(dprt_bvh8_tri), cudaMemcpyHostToDevice));
+    if (normals9) {
+        CK(cudaMalloc(&o.d_normals, (size_t)ntris * 9 * sizeof(float)));
+        CK(cudaMemcpy(o.d_normals, normals9, (size_t)ntris * 9 * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return upload_objects(ctx);
+}
+
+int dprt_upload_proxy(dprt_ctx* ctx, int si, const dprt_object_desc* desc, const void* vis_blob, size_t vis_bytes,
+                      const void* depth_blob, size_t depth_bytes) {
+    if (!ctx || !desc || si < 0 || si >= ctx->cfg.sceneSize) return DPRT_ERR_INVALID;
+    if (desc->nodeID < 0 || desc->nodeID >= ctx->world) return fail(ctx, DPRT_ERR_INVALID, "nodeID out of range");
+    CK(cudaSetDevice(ctx->device));
+    ObjectHost& o = ctx->objects[si];
+    o.desc = *desc; o.desc.isProxy = 1; o.present = true;
+    if (o.vis) { mlp_destroy(o.vis); o.vis = nullptr; }
+    if (o.depth) { mlp_destroy(o.depth); o.depth = nullptr; }
+    if (vis_blob && mlp_create(vis_blob, vis_bytes, ctx->cfg.mlpDtype, &o.vis, ctx->err)) return DPRT_ERR_INVALID;
+    if (depth_blob && mlp_create(depth_blob, depth_bytes, ctx->cfg.mlpDtype, &o.depth, ctx->err)) return DPRT_ERR_INVALID;
+    return upload_objects(ctx);
+}
+
+int dprt_set_materials(dprt_ctx* ctx, const dprt_material* mats, int n) {
+    if (!ctx || !mats || n < 1 || n > DPRT_MAX_MATERIALS) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(ctx->d_materials, mats, sizeof(dprt_material) * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+int dprt_set_lights(dprt_ctx* ctx, const dprt_light_tri* lights, int n) {
+    if (!ctx || !lights || n < 1 || n > DPRT_MAX_LIGHTS) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(ctx->d_lights, lights, sizeof(dprt_light_tri) * n, cudaMemcpyHostToDevice));
+    ctx->hp.lightCount = n;
+    return 0;
+}
+int dprt_set_camera(dprt_ctx* ctx, const dprt_camera* cam) {
+    if (!ctx || !cam) return DPRT_ERR_INVALID;
+    if (cam->width != ctx->cfg.width || cam->height != ctx->cfg.height) return fail(ctx, DPRT_ERR_INVALID, "camera resolution != config");
+    ctx->hp.camera = *cam;
+    return 0;
+}
+
+// ---- stages ------------------------------------------------------------------------------------
+int dprt_reset_frame(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->hp.direct, 0, ctx->buf_bytes[DPRT_BUF_DIRECT], ctx->stream));
+    CK(cudaMemsetAsync(ctx->hp.env, 0, ctx->buf_bytes[DPRT_BUF_ENV], ctx->stream));
+    CK(cudaMemsetAsync(ctx->hp.contribution, 0, ctx->buf_bytes[DPRT_BUF_CONTRIBUTION], ctx->stream));
+    CK(cudaMemsetAsync(ctx->hp.occlusion, 0, ctx->buf_bytes[DPRT_BUF_OCCLUSION], ctx->stream));
+    return 0;
+}
+
+int dprt_begin_sample(dprt_ctx* ctx, int sample) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    ctx->sample = sample;
+    // resetSampleBuffers: offsets to zero. Path buffers are reset by count (slots >= pathSize are never read).
+    CK(cudaMemsetAsync(ctx->hp.transferOffset, 0, 64 * sizeof(int32_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->hp.sceneOffset, 0, 64 * sizeof(int32_t), ctx->stream));
+    const int N = ctx->N, W = ctx->world;
+    if (ctx->cfg.pathGenMode == 1) ctx->pathSize = (N - ctx->rank + W - 1) / W;
+    else ctx->pathSize = ctx->rank == 0 ? N : 0;      // renderer.cpp:1514: only rank 0 generates camera paths
+    ctx->shadowPathSize = 0;
+    ctx->histFresh = false; ctx->qhistFresh = false;
+    sync_params(ctx);
+    return 0;
+}
+
+int dprt_path_gen(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    sync_params(ctx);
+    launch_path_gen(ctx->hp, ctx->pathSize, ctx->stream);
+    ctx->stats.kernel_launches += ctx->pathSize > 0;
+    ctx->histFresh = false;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dprt_traverse(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    sync_params(ctx);
+    CK(cudaMemsetAsync(ctx->hp.pathHist, 0, 32 * sizeof(int32_t), ctx->stream));
+    launch_traverse(ctx->hp, ctx->pathSize, ctx->stream);
+    ctx->stats.kernel_launches += ctx->pathSize > 0;
+    ctx->stats.rays_traverse += ctx->pathSize;
+    ctx->histFresh = true;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dprt_partition(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    sync_params(ctx);
+    if (!ctx->histFresh) {
+        launch_path_histogram(ctx->hp.paths, ctx->pathSize, ctx->world, ctx->hp.pathHist, ctx->stream);
+        ctx->stats.kernel_launches += ctx->pathSize > 0;
+    }
+    launch_partition_paths(ctx->hp.paths, ctx->pathSize, ctx->world, ctx->hp.pathHist, ctx->hp.transfer,
+                           ctx->hp.transferOffset, ctx->scratch, ctx->stream);
+    ctx->stats.kernel_launches += 1;
+    ctx->histFresh = false;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dprt_exchange(dprt_ctx* ctx, int* done) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int W = ctx->world, me = ctx->rank;
+    const size_t R = sizeof(dprt_path_record);
+    if (W == 1) {
+        int r = read_offsets(ctx); if (r) return r;
+        const int cnt = ctx->h_offsets[1];
+        if (cnt > 0) CK(cudaMemcpyAsync(ctx->hp.paths, ctx->hp.transfer, cnt * R, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->pathSize = cnt;
+        if (done) *done = 1;
+        ctx->stats.exchange_iters++;
+        return 0;
+    }
+    if (!ctx->comm) return fail(ctx, DPRT_ERR_STATE, "dprt_exchange on a multi-rank context without an NCCL communicator");
+    // MPI_Alltoall(counts): every rank learns the whole W x (W+1) offset matrix in one all-gather
+    NK(g_nccl.AllGather(ctx->hp.transferOffset, ctx->d_gather, W + 1, ncclInt32, ctx->comm, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_gather, sizeof(int32_t) * W * (W + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int32_t* M = ctx->h_pinned;     // M[s*(W+1)+d] = offset of rank s's segment for destination d
+    ctx->h_offsets.assign(M + me * (W + 1), M + (me + 1) * (W + 1));
+    long offdiag = 0; int recvTotal = 0;
+    std::vector<int> recvOff(W + 1, 0);
+    for (int s = 0; s < W; s++) {
+        for (int d = 0; d < W; d++) {
+            const int c = M[s * (W + 1) + d + 1] - M[s * (W + 1) + d];
+            if (s != d) offdiag += c;
+            if (d == me) recvOff[s + 1] = recvOff[s] + c;
+        }
+    }
+    recvTotal = recvOff[W];
+    if ((size_t)recvTotal > (size_t)ctx->N) return fail(ctx, DPRT_ERR_CAPACITY, "received more paths than the frame holds");
+    // MPI_Alltoallv: grouped send/recv straight from the partitioned device buffer
+    NK(g_nccl.GroupStart());
+    for (int peer = 0; peer < W; peer++) {
+        if (peer == me) continue;
+        const int sc = ctx->h_offsets[peer + 1] - ctx->h_offsets[peer];
+        const int rc = recvOff[peer + 1] - recvOff[peer];
+        if (sc > 0) NK(g_nccl.Send(ctx->hp.transfer + ctx->h_offsets[peer], (size_t)sc * R, ncclUint8, peer, ctx->comm, ctx->stream));
+        if (rc > 0) NK(g_nccl.Recv(ctx->hp.paths + recvOff[peer], (size_t)rc * R, ncclUint8, peer, ctx->comm, ctx->stream));
+        ctx->stats.paths_sent_offrank += sc; ctx->stats.bytes_alltoall += (int64_t)sc * R;
+    }
+    NK(g_nccl.GroupEnd());
+    const int selfc = ctx->h_offsets[me + 1] - ctx->h_offsets[me];
+    if (selfc > 0)
+        CK(cudaMemcpyAsync(ctx->hp.paths + recvOff[me], ctx->hp.transfer + ctx->h_offsets[me], (size_t)selfc * R,
+                           cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->pathSize = recvTotal;
+    if (done) *done = offdiag == 0;     // MPI_Allreduce(LAND) of "nothing crossed ranks" (renderer.cpp:1292-1298)
+    ctx->stats.exchange_iters++;
+    return 0;
+}
+
+int dprt_exchange_group(dprt_ctx** ctxs, int W, int* done) {
+    if (!ctxs || W < 1) return DPRT_ERR_INVALID;
+    const size_t R = sizeof(dprt_path_record);
+    for (int s = 0; s < W; s++) {
+        if (!ctxs[s] || ctxs[s]->world != W || ctxs[s]->rank != s) return DPRT_ERR_INVALID;
+        dprt_ctx* ctx = ctxs[s];
+        CK(cudaSetDevice(ctx->device));
+        int r = read_offsets(ctx); if (r) return r;
+    }
+    long offdiag = 0;
+    for (int d = 0; d < W; d++) {
+        dprt_ctx* ctx = ctxs[d];
+        CK(cudaSetDevice(ctx->device));
+        int roff = 0;
+        for (int s = 0; s < W; s++) {
+            const int c = ctxs[s]->h_offsets[d + 1] - ctxs[s]->h_offsets[d];
+            if (s != d) { offdiag += c; ctxs[s]->stats.paths_sent_offrank += c; ctxs[s]->stats.bytes_alltoall += (int64_t)c * R; }
+            if (roff + c > ctx->N) return fail(ctx, DPRT_ERR_CAPACITY, "received more paths than the frame holds");
+            if (c > 0) {
+                if (ctxs[s]->device == ctx->device)
+                    CK(cudaMemcpyAsync(ctx->hp.paths + roff, ctxs[s]->hp.transfer + ctxs[s]->h_offsets[d], c * R,
+                                       cudaMemcpyDeviceToDevice, ctx->stream));
+                else
+                    CK(cudaMemcpyPeerAsync(ctx->hp.paths + roff, ctx->device, ctxs[s]->hp.transfer + ctxs[s]->h_offsets[d],
+                                           ctxs[s]->device, c * R, ctx->stream));
+            }
+            roff += c;
+        }
+        CK(cudaStreamSynchronize(ctx->stream));   // sources may be re-partitioned next iteration
+        ctx->pathSize = roff;
+        ctx->stats.exchange_iters++;
+    }
+    if (done) *done = offdiag == 0;
+    return 0;
+}
+
+int dprt_shade(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->hp.lightCount < 1) return fail(ctx, DPRT_ERR_STATE, "no lights set");
+    ctx->shadowPathSize = ctx->cfg.shadowPathCount * ctx->pathSize;     // renderer.cpp:1328
+    sync_params(ctx);
+    launch_shade(ctx->hp, ctx->pathSize, ctx->stream);
+    ctx->stats.kernel_launches += ctx->pathSize > 0;
+    ctx->stats.rays_shade += ctx->pathSize;
+    ctx->histFresh = false;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dprt_reset_nn(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    // resetNNBuffers (renderer.cpp:367-414). Query/feature/prediction buffers are reset by count inside the
+    // producing kernels; the per-pixel accumulators are cleared here.
+    CK(cudaMemsetAsync(ctx->hp.occlusion, 0, ctx->buf_bytes[DPRT_BUF_OCCLUSION], ctx->stream));
+    CK(cudaMemsetAsync(ctx->hp.contribution, 0, ctx->buf_bytes[DPRT_BUF_CONTRIBUTION], ctx->stream));
+    if (ctx->cfg.shadowPathCount > 1)
+        CK(cudaMemsetAsync(ctx->hp.direct + (size_t)ctx->N * 3, 0, (size_t)ctx->N * 3 * sizeof(float) * (ctx->cfg.shadowPathCount - 1),
+                           ctx->stream));
+    CK(cudaMemsetAsync(ctx->hp.queryHist, 0, 64 * sizeof(int32_t), ctx->stream));
+    ctx->qhistFresh = false;
+    return 0;
+}
+
+int dprt_shadow_trace(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    sync_params(ctx);
+    CK(cudaMemsetAsync(ctx->hp.queryHist, 0, 64 * sizeof(int32_t), ctx->stream));
+    launch_shadow_trace(ctx->hp, ctx->shadowPathSize, ctx->stream);
+    ctx->stats.kernel_launches += ctx->shadowPathSize > 0;
+    ctx->stats.rays_shadow += ctx->shadowPathSize;
+    ctx->qhistFresh = true; ctx->queryWhich = 0;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dprt_secondary_trace(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->cfg.proxyMode) return fail(ctx, DPRT_ERR_STATE, "secondary stage needs proxyMode=1");
+    sync_params(ctx);
+    CK(cudaMemsetAsync(ctx->hp.queryHist, 0, 64 * sizeof(int32_t), ctx->stream));
+    launch_secondary_trace(ctx->hp, ctx->pathSize, ctx->stream);
+    ctx->stats.kernel_launches += ctx->pathSize > 0;
+    ctx->stats.rays_secondary += ctx->pathSize;
+    ctx->qhistFresh = true; ctx->queryWhich = 1;
+    ctx->histFresh = false;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dprt_bucket_queries(dprt_ctx* ctx, int which, int inside_only, int* total) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->cfg.proxyMode) return fail(ctx, DPRT_ERR_STATE, "query bucketing needs proxyMode=1");
+    sync_params(ctx);
+    const int S = ctx->cfg.sceneSize;
+    const int n = ctx->cfg.maxCount * (which == 0 ? ctx->shadowPathSize : ctx->pathSize);
+    int32_t* hist = ctx->hp.queryHist + (inside_only ? S : 0);
+    if (!ctx->qhistFresh || ctx->queryWhich != which) {
+        hist = ctx->d_hist + 96;
+        launch_query_histogram(ctx->hp.nnQuery, n, S, inside_only ? 1 : 0, hist, ctx->stream);
+        ctx->stats.kernel_launches += n > 0;
+    }
+    launch_partition_queries(ctx->hp.nnQuery, ctx->hp.nnInput, n, S, inside_only ? 1 : 0, hist, ctx->hp.nnPackedQuery,
+                             ctx->hp.nnPackedInput, ctx->hp.sceneOffset, ctx->scratch, ctx->stream);
+    ctx->stats.kernel_launches += 1;
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->hp.sceneOffset, (S + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));      // renderer.cpp:781-787: sceneOffset is read back before the forward loop
+    ctx->h_sceneOffset.assign(ctx->h_pinned, ctx->h_pinned + S + 1);
+    ctx->queryTotal = ctx->h_sceneOffset[S];
+    if (total) *total = ctx->queryTotal;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dprt_proxy_infer(dprt_ctx* ctx, int kind, int pred_offset) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int S = ctx->cfg.sceneSize;
+    if (pred_offset < 0 || (size_t)(pred_offset + ctx->queryTotal) * sizeof(dprt_half) > ctx->buf_bytes[DPRT_BUF_PRED])
+        return fail(ctx, DPRT_ERR_CAPACITY, "prediction range outside predBuffer");
+    if (ctx->queryTotal > 0)
+        CK(cudaMemsetAsync(ctx->hp.pred + pred_offset, 0, (size_t)ctx->queryTotal * sizeof(dprt_half), ctx->stream));
+    for (int i = 0; i < S; i++) {
+        const int start = ctx->h_sceneOffset[i], cnt = ctx->h_sceneOffset[i + 1] - start;
+        if (cnt <= 0) continue;
+        const MlpModel* m = kind == 0 ? ctx->objects[i].vis : ctx->objects[i].depth;
+        if (!m) continue;                                    // "padding" model slot (renderer.cpp:791)
+        if (mlp_forward(m, ctx->hp.nnPackedInput + (size_t)start * 5, ctx->hp.pred + pred_offset + start, cnt, ctx->stream, ctx->err))
+            return DPRT_ERR_CUDA;
+        ctx->stats.kernel_launches += 1;
+        ctx->stats.nn_queries += cnt;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dprt_frame_buffer_update(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    sync_params(ctx);
+    launch_shadow_occlusion(ctx->hp, ctx->cfg.proxyMode ? ctx->queryTotal : 0, ctx->stream);
+    launch_contribution(ctx->hp, ctx->stream);
+    ctx->stats.kernel_launches += 1 + (ctx->queryTotal > 0);
+    CK(cudaGetLastError());
+    return 0;
+}
+int dprt_depth_buffer_update(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    sync_params(ctx);
+    launch_depth_update(ctx->hp, ctx->queryTotal, ctx->stream);
+    ctx->stats.kernel_launches += ctx->queryTotal > 0;
+    ctx->qhistFresh = ctx->qhistFresh;   // normalizedT changes, keys do not
+    CK(cudaGetLastError());
+    return 0;
+}
+int dprt_target_node_update(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    sync_params(ctx);
+    launch_tmax(ctx->hp, ctx->queryTotal, ctx->stream);
+    launch_target_node(ctx->hp, ctx->pathSize, ctx->stream);
+    ctx->stats.kernel_launches += (ctx->queryTotal > 0) + (ctx->pathSize > 0);
+    ctx->histFresh = false;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- composite modules ---------------------------------------------------------------------------
+int dprt_primary_ray_module(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    for (;;) {
+        int r, done = 0;
+        if ((r = dprt_traverse(ctx))) return r;
+        if ((r = dprt_partition(ctx))) return r;
+        if ((r = dprt_exchange(ctx, &done))) return r;
+        if (done) break;
+    }
+    return 0;
+}
+
+int dprt_shadow_ray_module(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    int r;
+    if ((r = dprt_shadow_trace(ctx))) return r;
+    if (ctx->cfg.proxyMode) {
+        int total = 0;
+        if ((r = dprt_bucket_queries(ctx, 0, 1, &total))) return r;       // Work_Efficient_Scan_For_NN_HIT_INSIDE
+        if ((r = dprt_proxy_infer(ctx, 1, 0))) return r;                  // castShadowRaysDepthNN
+        if ((r = dprt_depth_buffer_update(ctx))) return r;
+        if ((r = dprt_bucket_queries(ctx, 0, 0, &total))) return r;       // Work_Efficient_Scan_For_NN
+        if ((r = dprt_proxy_infer(ctx, 0, 0))) return r;                  // castShadowRaysNN
+    } else {
+        ctx->queryTotal = 0;
+    }
+    return dprt_frame_buffer_update(ctx);
+}
+
+int dprt_secondary_ray_module(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    int r, total = 0;
+    if ((r = dprt_secondary_trace(ctx))) return r;
+    if ((r = dprt_bucket_queries(ctx, 1, 0, &total))) return r;
+    if ((r = dprt_proxy_infer(ctx, 0, 0))) return r;                      // vis -> pred[0..total)
+    if ((r = dprt_proxy_infer(ctx, 1, total))) return r;                  // depth -> pred[total..2 total) (renderer.cpp:956)
+    return dprt_target_node_update(ctx);
+}
+
+namespace {
+// one bounce of runSample for one rank, split at the exchange so that a group can interleave ranks
+int bounce_pre(dprt_ctx* ctx, int bounce) {
+    int r;
+    if (bounce > 0 && ctx->cfg.proxyMode) {
+        if ((r = dprt_reset_nn(ctx))) return r;
+        if ((r = dprt_secondary_ray_module(ctx))) return r;
+    }
+    return 0;
+}
+int bounce_post(dprt_ctx* ctx) {
+    int r;
+    if ((r = dprt_shade(ctx))) return r;
+    if ((r = dprt_reset_nn(ctx))) return r;
+    return dprt_shadow_ray_module(ctx);
+}
+}  // namespace
+
+int dprt_render_sample(dprt_ctx* ctx, int sample) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    int r;
+    if ((r = dprt_begin_sample(ctx, sample))) return r;
+    if ((r = dprt_path_gen(ctx))) return r;
+    for (int bounce = 0; bounce <= ctx->cfg.bounces; bounce++) {          // inclusive: renderer.cpp:1530
+        if ((r = bounce_pre(ctx, bounce))) return r;
+        if ((r = dprt_primary_ray_module(ctx))) return r;
+        if ((r = bounce_post(ctx))) return r;
+    }
+    return 0;
+}
+
+int dprt_render_sample_group(dprt_ctx** ctxs, int W, int sample) {
+    if (!ctxs || W < 1) return DPRT_ERR_INVALID;
+    int r;
+    for (int k = 0; k < W; k++) {
+        if ((r = dprt_begin_sample(ctxs[k], sample))) return r;
+        if ((r = dprt_path_gen(ctxs[k]))) return r;
+    }
+    const int bounces = ctxs[0]->cfg.bounces;
+    for (int bounce = 0; bounce <= bounces; bounce++) {
+        for (int k = 0; k < W; k++) if ((r = bounce_pre(ctxs[k], bounce))) return r;
+        for (;;) {
+            int done = 0;
+            for (int k = 0; k < W; k++) {
+                if ((r = dprt_traverse(ctxs[k]))) return r;
+                if ((r = dprt_partition(ctxs[k]))) return r;
+            }
+            if ((r = dprt_exchange_group(ctxs, W, &done))) return r;
+            if (done) break;
+        }
+        for (int k = 0; k < W; k++) if ((r = bounce_post(ctxs[k]))) return r;
+    }
+    return 0;
+}
+
+int dprt_reduce_image(dprt_ctx* ctx, int root, float* out_host) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int n3 = ctx->N * 3;
+    launch_image_average(ctx->hp.direct, ctx->hp.env, ctx->d_image, n3, (float)ctx->cfg.spp, ctx->stream);
+    ctx->stats.kernel_launches += 1;
+    const float* src = ctx->d_image;
+    if (ctx->world > 1) {
+        if (!ctx->comm) return fail(ctx, DPRT_ERR_STATE, "dprt_reduce_image on a multi-rank context without an NCCL communicator");
+        NK(g_nccl.Reduce(ctx->d_image, ctx->d_image_sum, n3, ncclFloat32, ncclSum, root, ctx->comm, ctx->stream));
+        src = ctx->d_image_sum;
+    }
+    if (ctx->rank == root && out_host)
+        CK(cudaMemcpyAsync(out_host, src, sizeof(float) * n3, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int dprt_reduce_image_group(dprt_ctx** ctxs, int W, int root, float* out_host) {
+    if (!ctxs || W < 1 || root < 0 || root >= W || !out_host) return DPRT_ERR_INVALID;
+    // rank-ordered fp32 sum on the host side of the harness; the NCCL path is dprt_reduce_image
+    dprt_ctx* ctx = ctxs[0];
+    const int n3 = ctx->N * 3;
+    std::vector<float> tmp(n3);
+    std::fill(out_host, out_host + n3, 0.f);
+    for (int k = 0; k < W; k++) {
+        ctx = ctxs[k];
+        CK(cudaSetDevice(ctx->device));
+        launch_image_average(ctx->hp.direct, ctx->hp.env, ctx->d_image, n3, (float)ctx->cfg.spp, ctx->stream);
+        CK(cudaMemcpyAsync(tmp.data(), ctx->d_image, sizeof(float) * n3, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < n3; i++) out_host[i] += tmp[i];
+    }
+    return 0;
+}
+
+// ---- state access ----------------------------------------------------------------------------------
+int dprt_get_path_size(const dprt_ctx* ctx, int* ps, int* sps) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    if (ps) *ps = ctx->pathSize;
+    if (sps) *sps = ctx->shadowPathSize;
+    return 0;
+}
+int dprt_set_path_size(dprt_ctx* ctx, int ps) {
+    if (!ctx || ps < 0 || ps > ctx->N) return DPRT_ERR_INVALID;
+    ctx->pathSize = ps; ctx->histFresh = false; ctx->qhistFresh = false;
+    return 0;
+}
+int dprt_buffer_bytes(const dprt_ctx* ctx, int id, size_t* bytes) {
+    if (!ctx || id < 0 || id >= DPRT_BUF_COUNT || !bytes) return DPRT_ERR_INVALID;
+    *bytes = ctx->buf_bytes[id]; return 0;
+}
+int dprt_download(dprt_ctx* ctx, int id, size_t off, void* host, size_t bytes) {
+    if (!ctx || id < 0 || id >= DPRT_BUF_COUNT || !host) return DPRT_ERR_INVALID;
+    if (!ctx->buf_ptr[id] || off + bytes > ctx->buf_bytes[id]) return fail(ctx, DPRT_ERR_CAPACITY, "download range outside buffer");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(host, (const char*)ctx->buf_ptr[id] + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int dprt_upload(dprt_ctx* ctx, int id, size_t off, const void* host, size_t bytes) {
+    if (!ctx || id < 0 || id >= DPRT_BUF_COUNT || !host) return DPRT_ERR_INVALID;
+    if (!ctx->buf_ptr[id] || off + bytes > ctx->buf_bytes[id]) return fail(ctx, DPRT_ERR_CAPACITY, "upload range outside buffer");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync((char*)ctx->buf_ptr[id] + off, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->histFresh = false; ctx->qhistFresh = false;
+    return 0;
+}
+int dprt_enable_hit_prim(dprt_ctx* ctx, int enable) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (enable && !ctx->buf_ptr[DPRT_BUF_HIT_PRIM]) {
+        int r = alloc_buf(ctx, DPRT_BUF_HIT_PRIM, (size_t)(1 + ctx->cfg.shadowPathCount) * ctx->N * sizeof(int32_t));
+        if (r) return r;
+    }
+    ctx->hp.hitPrim = enable ? (int32_t*)ctx->buf_ptr[DPRT_BUF_HIT_PRIM] : nullptr;
+    return 0;
+}
+
+// ---- standalone operators ----------------------------------------------------------------------------
+int dprt_trace_closest_device(dprt_ctx* ctx, const void* rays_dev, int64_t n, void* hits_dev) {
+    if (!ctx || !rays_dev || !hits_dev || n < 0) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    launch_trace_closest(ctx->d_objects, ctx->cfg.sceneSize, (const dprt_ray*)rays_dev, (dprt_hit*)hits_dev, n, ctx->stream);
+    ctx->stats.kernel_launches += n > 0;
+    ctx->stats.rays_traverse += n;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dprt_trace_closest(dprt_ctx* ctx, const dprt_ray* rays_host, int64_t n, dprt_hit* hits_host) {
+    if (!ctx || !rays_host || !hits_host || n < 0) return DPRT_ERR_INVALID;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const size_t rb = (size_t)n * sizeof(dprt_ray), hb = (size_t)n * sizeof(dprt_hit);
+    int r = ensure_io(ctx, rb + hb); if (r) return r;
+    char* d = (char*)ctx->d_io;
+    CK(cudaMemcpyAsync(d, rays_host, rb, cudaMemcpyHostToDevice, ctx->stream));
+    if ((r = dprt_trace_closest_device(ctx, d, n, d + rb))) return r;
+    CK(cudaMemcpyAsync(hits_host, d + rb, hb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int dprt_mlp_infer_device(dprt_ctx* ctx, int si, int kind, const void* x_dev, int64_t n, void* y_dev) {
+    if (!ctx || si < 0 || si >= ctx->cfg.sceneSize || !x_dev || !y_dev || n < 0) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const MlpModel* m = kind == 0 ? ctx->objects[si].vis : ctx->objects[si].depth;
+    if (!m) return fail(ctx, DPRT_ERR_STATE, "no proxy model uploaded for this scene object");
+    if (n == 0) return 0;
+    if (mlp_forward(m, (const dprt_half*)x_dev, (dprt_half*)y_dev, n, ctx->stream, ctx->err)) return DPRT_ERR_CUDA;
+    ctx->stats.kernel_launches += 1; ctx->stats.nn_queries += n;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dprt_mlp_infer(dprt_ctx* ctx, int si, int kind, const dprt_half* x_host, int64_t n, dprt_half* y_host) {
+    if (!ctx || !x_host || !y_host || n < 0) return DPRT_ERR_INVALID;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const size_t xb = ((size_t)n * 5 * sizeof(dprt_half) + 255) & ~(size_t)255, yb = (size_t)n * sizeof(dprt_half);
+    int r = ensure_io(ctx, xb + yb + 256); if (r) return r;
+    char* d = (char*)ctx->d_io;
+    CK(cudaMemcpyAsync(d, x_host, (size_t)n * 5 * sizeof(dprt_half), cudaMemcpyHostToDevice, ctx->stream));
+    if ((r = dprt_mlp_infer_device(ctx, si, kind, d, n, d + xb))) return r;
+    CK(cudaMemcpyAsync(y_host, d + xb, yb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int dprt_device_alloc(dprt_ctx* ctx, size_t bytes, void** dev_ptr) {
+    if (!ctx || !dev_ptr) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMalloc(dev_ptr, std::max<size_t>(bytes, 256)));
+    ctx->user_allocs.push_back(*dev_ptr);
+    return 0;
+}
+int dprt_device_free(dprt_ctx* ctx, void* dev_ptr) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    auto it = std::find(ctx->user_allocs.begin(), ctx->user_allocs.end(), dev_ptr);
+    if (it == ctx->user_allocs.end()) return DPRT_ERR_INVALID;
+    ctx->user_allocs.erase(it);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaFree(dev_ptr));
+    return 0;
+}
+int dprt_memcpy_h2d(dprt_ctx* ctx, void* dev, const void* host, size_t bytes) {
+    if (!ctx || !dev || !host) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int dprt_memcpy_d2h(dprt_ctx* ctx, void* host, const void* dev, size_t bytes) {
+    if (!ctx || !dev || !host) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int dprt_timer_start(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    return 0;
+}
+int dprt_timer_stop(dprt_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return 0;
+}
+int dprt_flush_l2(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->d_flush) { ctx->flush_bytes = (size_t)256 << 20; CK(cudaMalloc(&ctx->d_flush, ctx->flush_bytes)); }
+    CK(cudaMemsetAsync(ctx->d_flush, 0, ctx->flush_bytes, ctx->stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// dprt_internal.cuh -- device-side parameter block and launch prototypes shared by the .cu files.
+// DevParams is the equivalent of the reference's Renderer::Params, passed by value.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "dprt_types.h"
+
+namespace dprt {
+
+struct DevObject {                 // AccelerationStructure (renderer.cpp:1812-1842) as the kernels see it
+    int32_t nodeID;
+    int32_t isProxy;
+    float   aabbMin[3];
+    float   aabbMax[3];
+    float   maxLength;
+    float   w2o[12];
+    const uint4*  nodes;           // BVH8 nodes, 5 x uint4 each (local objects only)
+    const float4* tris;            // leaf-ordered triangles, 3 x float4 each
+    const float*  normals;         // 9 floats per original triangle (vertex normals), may be null
+};
+
+struct DevParams {
+    int32_t pathSize;
+    int32_t shadowPathSize;
+    int32_t spc;                   // shadowPathCount
+    int32_t mc;                    // maxCount
+    int32_t sceneSize;
+    int32_t worldID;
+    int32_t worldSize;
+    int32_t sampleCount;
+    int32_t frameBufferSize;       // N = width*height
+    int32_t lightCount;
+    int32_t proxyMode;
+    int32_t pathGenMode;
+    float   envColor[3];
+    dprt_camera camera;
+
+    const DevObject*      objects;
+    const dprt_material*  materials;
+    const dprt_light_tri* lights;
+
+    dprt_path_record* paths;       // pathDataBuffer: slot 0 live paths, pathSize + i*spc + s shadow paths
+    dprt_path_record* transfer;    // transferPathDataBuffer
+    int32_t* transferOffset;       // W+1
+    int32_t* pathHist;             // W counters: valid paths per targetNode (by-product of traverse)
+    float*   direct;               // directLightingBuffer, spc planes of 3N
+    float*   env;                  // envLightingBuffer 3N
+    float*   contribution;         // 3N*spc
+    float*   occlusion;            // shadowOcclusionFloatTypeBuffer N*mc*spc
+    dprt_half*     nnInput;        // inputDataBuffer
+    dprt_half*     nnPackedInput;
+    dprt_nn_query* nnQuery;        // NNPathDataBuffer
+    dprt_nn_query* nnPackedQuery;
+    int32_t* sceneOffset;          // sceneSize+1
+    int32_t* queryHist;            // sceneSize counters (all queries), then sceneSize (inside only)
+    dprt_half* pred;               // predBuffer
+    int32_t* hitPrim;              // parity aid, may be null
+};
+
+// stage launches (all asynchronous on `stream`)
+void launch_path_gen(const DevParams& p, int n, cudaStream_t stream);
+void launch_traverse(const DevParams& p, int n, cudaStream_t stream);
+void launch_shade(const DevParams& p, int n, cudaStream_t stream);
+void launch_shadow_trace(const DevParams& p, int nShadow, cudaStream_t stream);
+void launch_secondary_trace(const DevParams& p, int n, cudaStream_t stream);
+void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ray* rays, dprt_hit* hits, int64_t n,
+                          cudaStream_t stream);
+
+// partition / bucketing (partition.cu)
+struct PartitionScratch {
+    uint32_t* tileState;           // tiles * 32 words
+    int32_t*  tileCounter;         // dynamic tile id
+    int32_t   maxTiles;
+};
+void launch_path_histogram(const dprt_path_record* paths, int n, int W, int32_t* hist, cudaStream_t stream);
+void launch_partition_paths(const dprt_path_record* paths, int n, int W, const int32_t* hist,
+                            dprt_path_record* out, int32_t* offsets, const PartitionScratch& s, cudaStream_t stream);
+void launch_query_histogram(const dprt_nn_query* q, int n, int S, int insideOnly, int32_t* hist, cudaStream_t stream);
+void launch_partition_queries(const dprt_nn_query* q, const dprt_half* in, int n, int S, int insideOnly,
+                              const int32_t* hist, dprt_nn_query* outQ, dprt_half* outIn, int32_t* offsets,
+                              const PartitionScratch& s, cudaStream_t stream);
+
+// NN epilogues (epilogue.cu): frame_buffer_update.cu equivalents
+void launch_shadow_occlusion(const DevParams& p, int size, cudaStream_t stream);
+void launch_contribution(const DevParams& p, cudaStream_t stream);
+void launch_depth_update(const DevParams& p, int size, cudaStream_t stream);
+void launch_tmax(const DevParams& p, int size, cudaStream_t stream);
+void launch_target_node(const DevParams& p, int n, cudaStream_t stream);
+void launch_image_average(const float* direct, const float* env, float* out, int n3, float invSpp, cudaStream_t stream);
+
+}  // namespace dprt

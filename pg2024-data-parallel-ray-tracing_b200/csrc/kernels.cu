@@ -1,0 +1,484 @@
+// kernels.cu -- the ray-tracing stage kernels of the per-bounce loop (sm_100a).
+//
+//   path_gen_kernel        <- optix/path_gen_kernel.cu:46-105           (PathGen raygen)
+//   traverse_kernel        <- optix/distributed_traversal_kernel.cu:215-340 (TraRay raygen + ch/ms)
+//   shade_kernel           <- optix/kernel.cu:362-466 + closest hit :171-300 (MainRay)
+//   shadow_trace_kernel    <- optix/shadow_ray_kernel.cu:150-355        (ShadowRay)
+//   secondary_trace_kernel <- optix/secondary_ray_kernel.cu:172-369     (SecondaryRay)
+//   trace_closest_kernel   <- a bare optixTrace closest-hit launch (BASELINE config 2)
+//
+// One thread per path; rays walk a compressed BVH8 per local scene object (bvh_traverse.cuh).
+// Compiled with --fmad=false: the arithmetic is the specification in dprt_math.cuh.
+#include "dprt_internal.cuh"
+#include "bvh_traverse.cuh"
+
+namespace dprt {
+
+namespace {
+
+constexpr int kBlock = 128;
+
+struct PathRegs {
+    V3 origin, direction; float tMax; V3 throughput;
+    int pixelIndex, shadowPathID; uint32_t visitedMask; int currentNode, targetNode; uint32_t flags;
+};
+// flag bytes: isShadowRay | isDelta<<8 | isValid<<16 | isHit<<24
+constexpr uint32_t F_SHADOW = 1u, F_DELTA = 1u << 8, F_VALID = 1u << 16, F_HIT = 1u << 24;
+
+DPRT_D PathRegs load_path(const dprt_path_record* p) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+    float4 a = q[0], b = q[1], c = q[2], d = q[3];
+    PathRegs r;
+    r.origin = v3(a.x, a.y, a.z); r.direction = v3(a.w, b.x, b.y); r.tMax = b.z;
+    r.throughput = v3(b.w, c.x, c.y);
+    r.pixelIndex = __float_as_int(c.z); r.shadowPathID = __float_as_int(c.w);
+    r.visitedMask = __float_as_uint(d.x); r.currentNode = __float_as_int(d.y);
+    r.targetNode = __float_as_int(d.z); r.flags = __float_as_uint(d.w);
+    return r;
+}
+DPRT_D void store_path(dprt_path_record* p, const PathRegs& r) {
+    float4* q = reinterpret_cast<float4*>(p);
+    q[0] = make_float4(r.origin.x, r.origin.y, r.origin.z, r.direction.x);
+    q[1] = make_float4(r.direction.y, r.direction.z, r.tMax, r.throughput.x);
+    q[2] = make_float4(r.throughput.y, r.throughput.z, __int_as_float(r.pixelIndex), __int_as_float(r.shadowPathID));
+    q[3] = make_float4(__uint_as_float(r.visitedMask), __int_as_float(r.currentNode), __int_as_float(r.targetNode),
+                       __uint_as_float(r.flags));
+}
+DPRT_D void store_zero_path(dprt_path_record* p) {
+    float4* q = reinterpret_cast<float4*>(p);
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    q[0] = z; q[1] = z; q[2] = z; q[3] = z;
+}
+
+// calculateEnvironmentLighting (distributed_traversal_kernel.cu:82-103): the reference looks a lat-long
+// texture up at (phi/2pi, theta/pi); the synthetic scenes use the analytic sky Le = envColor*(0.5+0.5*d.z).
+DPRT_D V3 env_radiance(const DevParams& p, V3 d) {
+    float w = fmaf(0.5f, d.z, 0.5f);
+    return v3(p.envColor[0] * w, p.envColor[1] * w, p.envColor[2] * w);
+}
+DPRT_D void add_env(const DevParams& p, PathRegs& path) {
+    path.throughput = v3mul(path.throughput, env_radiance(p, path.direction));
+    const int px = path.pixelIndex * 3;
+    p.env[px + 0] += path.throughput.x;   // one live path per pixel per rank: non-atomic like the reference (:332-334)
+    p.env[px + 1] += path.throughput.y;
+    p.env[px + 2] += path.throughput.z;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) path_gen_kernel(DevParams p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int width = p.camera.width;
+    const int pixel = p.pathGenMode == 1 ? i * p.worldSize + p.worldID : i;
+    const int row = pixel / width, col = pixel - row * width;
+    uint32_t seed = tea4((uint32_t)pixel, (uint32_t)p.sampleCount);
+    const float xi1 = rnd(seed), xi2 = rnd(seed);
+    // Camera::generateRay(row, col, xi): pinhole through the jittered pixel position
+    const float a = fmaf(2.0f, ((float)col + xi1) / (float)width, -1.0f);
+    const float b = fmaf(-2.0f, ((float)row + xi2) / (float)p.camera.height, 1.0f);
+    const dprt_camera& c = p.camera;
+    V3 dir = v3(fmaf(c.U[0], a, fmaf(c.V[0], b, c.W[0])), fmaf(c.U[1], a, fmaf(c.V[1], b, c.W[1])),
+                fmaf(c.U[2], a, fmaf(c.V[2], b, c.W[2])));
+    PathRegs r;
+    r.origin = v3(c.origin[0], c.origin[1], c.origin[2]);
+    r.direction = v3normalized(dir);
+    r.tMax = FLT_MAX;
+    r.throughput = v3(1.f, 1.f, 1.f);
+    r.pixelIndex = pixel; r.shadowPathID = -1; r.visitedMask = 0u; r.currentNode = -1; r.targetNode = -1;
+    r.flags = F_VALID;
+    store_path(p.paths + i, r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// closest hit over all local (non-proxy) objects; `skipVisited`: TraRay skips objects whose owner bit is set.
+DPRT_D bool trace_local_closest(const DevParams& p, V3 o, V3 d, float tmin, float& tMax, uint32_t visitedMask,
+                                bool skipVisited, TraceHit& best, int& bestObj) {
+    bool any = false;
+    for (int i = 0; i < p.sceneSize; i++) {
+        const DevObject& ob = p.objects[i];
+        if (ob.isProxy) continue;
+        if (skipVisited && ((visitedMask >> ob.nodeID) & 1u)) continue;
+        TraceHit h;
+        if (bvh8_trace<false>(ob.nodes, ob.tris, o, d, tmin, tMax, h)) {
+            tMax = h.t; best = h; bestObj = i; any = true;
+        }
+    }
+    return any;
+}
+
+__global__ void __launch_bounds__(kBlock) traverse_kernel(DevParams p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool outValid = false; int target = -1;
+    if (i < n) {
+        PathRegs path = load_path(p.paths + i);
+        if (path.flags & F_VALID) {
+            const V3 o = path.origin, d = path.direction;
+            TraceHit h; int hobj = -1; h.prim = -1;
+            float tMax = path.tMax;
+            if (trace_local_closest(p, o, d, DPRT_EPSILON, tMax, path.visitedMask, true, h, hobj)) {
+                path.tMax = tMax; path.flags |= F_HIT; path.currentNode = p.worldID;
+            }
+            if (p.hitPrim) p.hitPrim[i] = h.prim;
+            path.visitedMask |= (1u << p.worldID);
+            // nearest unvisited proxy AABB within tMax decides the next owner (:280-314)
+            float tProxy = path.tMax; bool proxyHit = false;
+            for (int k = 0; k < p.sceneSize; k++) {
+                const DevObject& ob = p.objects[k];
+                if (ob.isProxy != 1) continue;
+                if ((path.visitedMask >> ob.nodeID) & 1u) continue;
+                const V3 ol = xform_point(ob.w2o, o), dl = xform_vector(ob.w2o, d);
+                float t; bool inside;
+                if (aabb_intersect(ol, dl, ob.aabbMin, ob.aabbMax, DPRT_EPSILON, tProxy, &t, &inside)) {
+                    tProxy = t; proxyHit = true; path.targetNode = ob.nodeID;
+                }
+            }
+            if (!proxyHit) path.targetNode = path.currentNode;
+            if (!proxyHit && !(path.flags & F_HIT)) {
+                add_env(p, path);
+                path.flags &= ~F_VALID;
+            }
+            store_path(p.paths + i, path);
+            outValid = (path.flags & F_VALID) != 0;
+            target = path.targetNode;
+        } else if (p.hitPrim) {
+            p.hitPrim[i] = -1;
+        }
+    }
+    // by-product for the partition stage: valid paths per destination (warp-aggregated)
+    outValid = outValid && target >= 0 && target < p.worldSize;
+    const unsigned m = __ballot_sync(0xffffffffu, outValid);
+    if (outValid) {
+        const unsigned peers = __match_any_sync(m, target);
+        if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(p.pathHist + target, __popc(peers));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct BsdfSample { V3 wiLocal; float weight; bool isDelta; };
+
+DPRT_D BsdfSample sample_lambertian(float xi1, float xi2) {           // bsdfs/lambertian.hpp:10-32
+    BsdfSample s; s.wiLocal = uniform_hemisphere(xi1, xi2); s.weight = 2.0f; s.isDelta = false; return s;
+}
+DPRT_D float fresnel_dielectric(float cosI, float etaI, float etaT) { // moana Fresnel::dielectricReflectance (PBRT)
+    const float eta = etaI / etaT;
+    const float sin2t = (eta * eta) * fmaxf(0.0f, fmaf(-cosI, cosI, 1.0f));
+    if (sin2t >= 1.0f) return 1.0f;
+    const float cosT = sqrtf(1.0f - sin2t);
+    const float rParl = (etaT * cosI - etaI * cosT) / (etaT * cosI + etaI * cosT);
+    const float rPerp = (etaI * cosI - etaT * cosT) / (etaI * cosI + etaT * cosT);
+    return 0.5f * (rParl * rParl + rPerp * rPerp);
+}
+DPRT_D BsdfSample sample_water(float xi1, V3 normal, V3 woWorld, bool isInside) {   // bsdfs/water.hpp:12-94
+    const V3 wo = frame_to_local(normal, woWorld);
+    float etaI = 1.0f, etaT = 1.33f;
+    if (isInside) { float t = etaI; etaI = etaT; etaT = t; }
+    V3 wi = v3(0.f, 0.f, 0.f);
+    {   // Snell::refract about the local +z normal
+        const float eta = etaI / etaT;
+        const float sin2t = (eta * eta) * fmaxf(0.0f, fmaf(-wo.z, wo.z, 1.0f));
+        if (sin2t < 1.0f) { const float cosT = sqrtf(1.0f - sin2t); wi = v3(-(eta * wo.x), -(eta * wo.y), -cosT); }
+    }
+    const float fr = fresnel_dielectric(fabsf(wo.z), etaI, etaT);
+    BsdfSample s; s.isDelta = true;
+    if (xi1 < fr) {
+        wi = v3(-wo.x, -wo.y, wo.z);                                   // wo.reflect((0,0,1))
+        const float cosTheta = fabsf(wi.z);
+        const float thr = cosTheta == 0.0f ? 0.0f : fr / cosTheta;
+        s.wiLocal = wi; s.weight = thr / fr;
+    } else {
+        const float ft = 1.0f - fr;
+        const float cosTheta = fabsf(wi.z);
+        const float thr = cosTheta == 0.0f ? 0.0f : ft / cosTheta;
+        const float corr = (etaI / etaT) * (etaI / etaT);
+        s.wiLocal = wi; s.weight = thr * corr / ft;
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(kBlock) shade_kernel(DevParams p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PathRegs path = load_path(p.paths + i);
+    if (!(path.flags & F_VALID)) return;
+    const V3 o = path.origin, d = path.direction;
+
+    TraceHit h; int hobj = -1; float tMax = FLT_MAX;
+    const bool isHit = trace_local_closest(p, o, d, DPRT_EPSILON, tMax, 0u, false, h, hobj);
+    if (p.hitPrim) p.hitPrim[i] = isHit ? h.prim : -1;
+    if (!isHit) {
+        // kernel.cu:416-423: environment light, path dies. The reference then writes an invalid record built
+        // from an uninitialised sampling record; the defined behaviour here is the all-zero (invalid) record.
+        add_env(p, path);
+        store_zero_path(p.paths + i);
+        for (int s = 0; s < p.spc; s++) store_zero_path(p.paths + (size_t)i * p.spc + s + p.pathSize);
+        return;
+    }
+    const DevObject& ob = p.objects[hobj];
+    // closest-hit program (kernel.cu:171-300): interpolated vertex normal, base colour, face-forward
+    const float4 tb = __ldg(ob.tris + 3 * (size_t)h.tri + 1);
+    const int matID = __float_as_int(tb.w);
+    const dprt_material mat = p.materials[matID];
+    const V3 albedo = v3(mat.baseColor[0], mat.baseColor[1], mat.baseColor[2]);
+    const V3 point = v3at(o, d, h.t);
+    const V3 woWorld = v3neg(d);
+    V3 normal;
+    {
+        const float* nn = ob.normals + 9 * (size_t)h.prim;
+        const V3 n0 = v3normalized(v3(nn[0], nn[1], nn[2]));
+        const V3 n1 = v3normalized(v3(nn[3], nn[4], nn[5]));
+        const V3 n2 = v3normalized(v3(nn[6], nn[7], nn[8]));
+        const float alpha = h.alpha, beta = h.beta, gamma = 1.0f - alpha - beta;
+        normal = v3(fmaf(beta, n2.x, fmaf(alpha, n1.x, gamma * n0.x)), fmaf(beta, n2.y, fmaf(alpha, n1.y, gamma * n0.y)),
+                    fmaf(beta, n2.z, fmaf(alpha, n1.z, gamma * n0.z)));
+        normal = v3normalized(normal);
+    }
+    bool isInside = false;
+    if (v3dot(normal, woWorld) < 0.0f) { normal = v3neg(normal); isInside = true; }
+
+    // createSamplingRecord (kernel.cu:50-64): the seed ignores the bounce, as in the reference
+    uint32_t seed = tea4((uint32_t)path.pixelIndex, (uint32_t)p.sampleCount);
+    const float xi1 = rnd(seed), xi2 = rnd(seed);
+    const BsdfSample bs = mat.bsdfType == 1 ? sample_water(xi1, normal, woWorld, isInside) : sample_lambertian(xi1, xi2);
+
+    // generateNextNewPath (kernel.cu:134-162)
+    PathRegs next;
+    next.origin = point;
+    next.direction = v3normalized(frame_to_world(normal, bs.wiLocal));
+    next.tMax = FLT_MAX;
+    const float cosThetaWi = fabsf(bs.wiLocal.z);
+    next.throughput = v3mul(v3scale(v3scale(path.throughput, bs.weight), cosThetaWi), albedo);
+    next.pixelIndex = path.pixelIndex; next.shadowPathID = -1; next.visitedMask = 0u;
+    next.currentNode = -1; next.targetNode = -1; next.flags = F_VALID;
+    store_path(p.paths + i, next);
+
+    // generateShadowPath x spc (kernel.cu:66-132, 442-465)
+    for (int s = 0; s < p.spc; s++) {
+        dprt_path_record* slot = p.paths + (size_t)i * p.spc + s + p.pathSize;
+        if (bs.isDelta) { store_zero_path(slot); continue; }      // reference leaves the reset (zero) slot
+        uint32_t sseed = tea4((uint32_t)(path.pixelIndex * p.spc + s), (uint32_t)p.sampleCount);
+        const float x1 = rnd(sseed), x2 = rnd(sseed), x3 = rnd(sseed);
+        int li = (int)floorf(x1 * (float)p.lightCount);
+        const dprt_light_tri L = p.lights[li];
+        // Triangle::sample(xi2, xi3): uniform area sampling, areaPDF = 1/area
+        const V3 p0 = v3(L.p0[0], L.p0[1], L.p0[2]), p1 = v3(L.p1[0], L.p1[1], L.p1[2]), p2 = v3(L.p2[0], L.p2[1], L.p2[2]);
+        const float su = sqrtf(x2);
+        const float b0 = 1.0f - su, b1 = x3 * su, b2 = 1.0f - b0 - b1;
+        const V3 lp = v3(fmaf(b2, p2.x, fmaf(b1, p1.x, b0 * p0.x)), fmaf(b2, p2.y, fmaf(b1, p1.y, b0 * p0.y)),
+                         fmaf(b2, p2.z, fmaf(b1, p1.z, b0 * p0.z)));
+        const V3 cr = v3cross(v3sub(p1, p0), v3sub(p2, p0));
+        const float crl = v3length(cr);
+        const V3 ln = v3scale(cr, 1.0f / crl);
+        float areaPDF = 1.0f / (0.5f * crl);
+        areaPDF = areaPDF * (1.0f / (float)p.lightCount);
+        const V3 ldir = v3sub(lp, point);
+        const V3 wi = v3normalized(ldir);
+        const float stMax = v3length(ldir);
+        const float f1 = fmaxf(0.0f, v3dot(ln, v3neg(wi)));
+        const float f2 = fmaxf(0.0f, v3dot(wi, normal));
+        V3 c = v3mul(v3mul(v3(L.Le[0], L.Le[1], L.Le[2]), path.throughput), albedo);
+        c = v3scale(v3scale(c, f1), f2);
+        const float tt = stMax * stMax;
+        c = v3(c.x / areaPDF / tt, c.y / areaPDF / tt, c.z / areaPDF / tt);
+        c = v3scale(c, 0.318309886183790671538f);
+        PathRegs sh;
+        sh.origin = point; sh.direction = wi; sh.tMax = stMax; sh.throughput = c;
+        sh.pixelIndex = path.pixelIndex; sh.shadowPathID = s; sh.visitedMask = 0u; sh.currentNode = -1; sh.targetNode = -1;
+        sh.flags = F_SHADOW | F_VALID;
+        store_path(slot, sh);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Proxy-AABB march shared by the shadow and secondary stages (shadow_ray_kernel.cu:198-350,
+// secondary_ray_kernel.cu:226-362). Emits <= mc queries into slot base `q0 = threadIndex*mc`.
+struct MarchOut { int count; bool envMiss; };
+
+DPRT_D void clear_query_slots(const DevParams& p, int threadIndex, int from) {
+    for (int q = from; q < p.mc; q++) p.nnQuery[(size_t)threadIndex * p.mc + q].hitAABBID = 0;   // reset by count, not memset
+}
+
+template <bool SECONDARY>
+DPRT_D int proxy_march(const DevParams& p, const PathRegs& path, int threadIndex, float tMaxPath, int* shHist) {
+    const V3 o = path.origin, d = path.direction;
+    const int mc = p.mc;
+    bool isHit = true; bool isInside = false; float tMin = 0.0f; int count = 0; int hitIdx = -1;
+    bool addedDirect = false;
+    while (isHit && count < mc) {
+        isHit = false;
+        float tMax = tMaxPath;
+        V3 pl = v3(0, 0, 0), oloc = v3(0, 0, 0), dloc = v3(0, 0, 0);
+        for (int k = 0; k < p.sceneSize; k++) {
+            const DevObject& ob = p.objects[k];
+            if (ob.isProxy != 1) continue;
+            const V3 ol = xform_point(ob.w2o, o), dl = xform_vector(ob.w2o, d);
+            float t; bool ins;
+            if (aabb_intersect(ol, dl, ob.aabbMin, ob.aabbMax, tMin + DPRT_EPSILON, tMax, &t, &ins)) {
+                tMax = t; isHit = true; hitIdx = k; isInside = ins;
+                oloc = ol; dloc = dl;
+                pl = xform_point(ob.w2o, v3at(o, d, t));   // optixTransformPointFromWorldToObjectSpace(getHitPoint())
+            }
+        }
+        if (isHit) tMin = tMax;
+        if (isHit) {
+            const DevObject& ob = p.objects[hitIdx];
+            if (isInside) {
+                bool skip = false;
+                for (int q = 0; q < count; q++) {
+                    const dprt_nn_query& e = p.nnQuery[(size_t)threadIndex * mc + q];
+                    if (e.hitAABBID == hitIdx + 1 && e.instanceID == hitIdx) skip = true;
+                }
+                if (skip && count) continue;
+            }
+            V3 dirL = isInside ? v3neg(dloc) : dloc;
+            float phi, theta;
+            det_cartesian_to_spherical(v3normalized(dirL), &phi, &theta);
+            dprt_half* in = p.nnInput + ((size_t)threadIndex * mc + count) * 5;
+            in[0] = f32_to_f16_bits((pl.x - ob.aabbMin[0]) / (ob.aabbMax[0] - ob.aabbMin[0]));
+            in[1] = f32_to_f16_bits((pl.y - ob.aabbMin[1]) / (ob.aabbMax[1] - ob.aabbMin[1]));
+            in[2] = f32_to_f16_bits((pl.z - ob.aabbMin[2]) / (ob.aabbMax[2] - ob.aabbMin[2]));
+            in[3] = f32_to_f16_bits(phi / 6.28318530717958647692f);
+            in[4] = f32_to_f16_bits(theta / 3.14159265358979323846f);
+            dprt_nn_query e;
+            e.pixelIndex = path.pixelIndex; e.hitSequence = count; e.hitAABBID = hitIdx + 1;
+            e.isValid = 1; e.instanceID = hitIdx; e.isInside = isInside ? 1 : 0; e.pad_[0] = e.pad_[1] = 0; e.reserved_ = 0;
+            const float dist = v3length(v3sub(oloc, pl));
+            if (SECONDARY) {
+                e.throughput[0] = tMax; e.throughput[1] = ob.maxLength; e.throughput[2] = tMax / dist;
+                e.shadowPathID = 0; e.pathIndex = ob.nodeID;
+                e.normalizedT = isInside ? tMax / ob.maxLength : 0.0f;
+            } else {
+                e.throughput[0] = path.throughput.x; e.throughput[1] = path.throughput.y; e.throughput[2] = path.throughput.z;
+                e.shadowPathID = path.shadowPathID;
+                e.pathIndex = isInside ? threadIndex * mc + count : 0;
+                e.normalizedT = isInside ? dist / ob.maxLength : 0.0f;
+            }
+            p.nnQuery[(size_t)threadIndex * mc + count] = e;
+            // histogram by-product for the bucketing stage: all queries, and inside-only
+            atomicAdd(shHist + hitIdx, 1);
+            if (isInside) atomicAdd(shHist + 32 + hitIdx, 1);
+            count++;
+        } else if (count == 0) {
+            addedDirect = true;
+        }
+    }
+    clear_query_slots(p, threadIndex, count);
+    return addedDirect ? -1 : count;   // -1: nothing in the way at all
+}
+
+DPRT_D void flush_query_hist(const DevParams& p, const int* shHist) {
+    const int t = threadIdx.x;
+    if (t < p.sceneSize) { if (shHist[t]) atomicAdd(p.queryHist + t, shHist[t]); }
+    else if (t >= 32 && t < 32 + p.sceneSize) { if (shHist[t]) atomicAdd(p.queryHist + p.sceneSize + (t - 32), shHist[t]); }
+}
+
+DPRT_D void shadow_body(const DevParams& p, int i, int* shHist) {
+    dprt_path_record* rec = p.paths + (size_t)p.pathSize + i;
+    PathRegs path = load_path(rec);
+    if (!(path.flags & F_VALID)) { clear_query_slots(p, i, 0); return; }
+    // any local occluder within tMax kills the shadow path (:169-195)
+    bool occluded = false;
+    for (int k = 0; k < p.sceneSize && !occluded; k++) {
+        const DevObject& ob = p.objects[k];
+        if (ob.isProxy) continue;
+        TraceHit h;
+        if (bvh8_trace<true>(ob.nodes, ob.tris, path.origin, path.direction, DPRT_EPSILON, path.tMax, h)) occluded = true;
+    }
+    if (occluded) {
+        path.flags |= F_HIT; path.flags &= ~F_VALID;
+        reinterpret_cast<float4*>(rec)[3] = make_float4(__uint_as_float(path.visitedMask), __int_as_float(path.currentNode),
+                                                        __int_as_float(path.targetNode), __uint_as_float(path.flags));
+        clear_query_slots(p, i, 0);
+        return;
+    }
+    int r;
+    if (p.proxyMode == 0) { r = -1; clear_query_slots(p, i, 0); }   // proxies off: remote chunks are transparent to shadow rays
+    else r = proxy_march<false>(p, path, i, path.tMax, shHist);
+    if (r < 0) {
+        const size_t px = ((size_t)p.frameBufferSize * path.shadowPathID + path.pixelIndex) * 3;
+        const float inv = (float)p.spc;
+        p.direct[px + 0] += path.throughput.x / inv;
+        p.direct[px + 1] += path.throughput.y / inv;
+        p.direct[px + 2] += path.throughput.z / inv;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) shadow_trace_kernel(DevParams p, int nShadow) {
+    __shared__ int shHist[64];
+    if (threadIdx.x < 64) shHist[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nShadow) shadow_body(p, i, shHist);
+    __syncthreads();
+    flush_query_hist(p, shHist);
+}
+
+DPRT_D void secondary_body(const DevParams& p, int i, int* shHist) {
+    PathRegs path = load_path(p.paths + i);
+    if (!(path.flags & F_VALID)) { clear_query_slots(p, i, 0); return; }
+    for (int k = 0; k < p.sceneSize; k++) if (p.objects[k].isProxy != 2) path.visitedMask |= (1u << p.objects[k].nodeID);
+    TraceHit h; int hobj = -1; float tMax = path.tMax;
+    if (trace_local_closest(p, path.origin, path.direction, DPRT_EPSILON, tMax, 0u, false, h, hobj)) {
+        path.tMax = tMax; path.flags |= F_HIT; path.currentNode = p.worldID;
+    }
+    if (p.hitPrim) p.hitPrim[i] = hobj >= 0 ? h.prim : -1;
+    const int r = proxy_march<true>(p, path, i, path.tMax, shHist);
+    if (r < 0 && !(path.flags & F_HIT)) {
+        add_env(p, path);
+        path.flags &= ~F_VALID;
+    }
+    store_path(p.paths + i, path);
+}
+
+__global__ void __launch_bounds__(kBlock) secondary_trace_kernel(DevParams p, int n) {
+    __shared__ int shHist[64];
+    if (threadIdx.x < 64) shHist[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) secondary_body(p, i, shHist);
+    __syncthreads();
+    flush_query_hist(p, shHist);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) trace_closest_kernel(const DevObject* objects, int sceneSize,
+                                                                const dprt_ray* __restrict__ rays, dprt_hit* __restrict__ hits,
+                                                                int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = reinterpret_cast<const float4*>(rays)[2 * i], b = reinterpret_cast<const float4*>(rays)[2 * i + 1];
+    const V3 o = v3(a.x, a.y, a.z), d = v3(b.x, b.y, b.z);
+    float tMax = b.w; int prim = -1;
+    for (int k = 0; k < sceneSize; k++) {
+        const DevObject& ob = objects[k];
+        if (ob.isProxy) continue;
+        TraceHit h;
+        if (bvh8_trace<false>(ob.nodes, ob.tris, o, d, a.w, tMax, h)) { tMax = h.t; prim = h.prim; }
+    }
+    reinterpret_cast<float2*>(hits)[i] = make_float2(tMax, __int_as_float(prim));
+}
+
+inline int blocks_for(int64_t n) { return (int)((n + kBlock - 1) / kBlock); }
+
+}  // namespace
+
+void launch_path_gen(const DevParams& p, int n, cudaStream_t s) {
+    if (n > 0) path_gen_kernel<<<blocks_for(n), kBlock, 0, s>>>(p, n);
+}
+void launch_traverse(const DevParams& p, int n, cudaStream_t s) {
+    if (n > 0) traverse_kernel<<<blocks_for(n), kBlock, 0, s>>>(p, n);
+}
+void launch_shade(const DevParams& p, int n, cudaStream_t s) {
+    if (n > 0) shade_kernel<<<blocks_for(n), kBlock, 0, s>>>(p, n);
+}
+void launch_shadow_trace(const DevParams& p, int nShadow, cudaStream_t s) {
+    if (nShadow > 0) shadow_trace_kernel<<<blocks_for(nShadow), kBlock, 0, s>>>(p, nShadow);
+}
+void launch_secondary_trace(const DevParams& p, int n, cudaStream_t s) {
+    if (n > 0) secondary_trace_kernel<<<blocks_for(n), kBlock, 0, s>>>(p, n);
+}
+void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ray* rays, dprt_hit* hits, int64_t n,
+                          cudaStream_t s) {
+    if (n > 0) trace_closest_kernel<<<blocks_for(n), kBlock, 0, s>>>(objects, sceneSize, rays, hits, n);
+}
+
+}  // namespace dprt

@@ -1,0 +1,209 @@
+// partition.cu -- single-pass stable multi-bucket partition (sm_100a).
+//
+// Replaces the reference's per-destination loop of {preKernel, 3x prefixSum, 2x prefixFixup, postKernel}
+// (src/cuda/cuda_compaction.cu:8-35,306-439 for paths by targetNode; :140-198,441-617 for NN queries by
+// hitAABBID) -- W (or sceneSize) sequential passes of 7 launches each -- with ONE launch:
+//   * keys are read once (the last 16 B of a path record / the id words of a query),
+//   * in-tile ranks come from warp match/ballot, tile prefixes from a decoupled look-back chain that carries
+//     one counter per bucket (lane b of warp 0 owns bucket b),
+//   * bucket bases come from the histogram the producing kernel already accumulated (traverse / shadow /
+//     secondary), so records are scattered straight to their final, contiguous, bucket-major position.
+// Output order is the reference's: bucket-major, original index order inside a bucket, dead entries dropped.
+#include <algorithm>
+#include "dprt_internal.cuh"
+
+namespace dprt {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kItems = 4;
+constexpr int kTile = kThreads * kItems;      // 1024 records per tile
+constexpr int kWarps = kThreads / 32;
+constexpr int kSteps = kWarps * kItems;       // 32 (warp, item) steps per tile, in index order
+
+constexpr uint32_t ST_AGG = 1u << 30, ST_INC = 2u << 30, ST_MASK = 3u << 30, VAL_MASK = ~ST_MASK;
+
+struct PathOps {
+    const dprt_path_record* in; dprt_path_record* out; int B;
+    __device__ __forceinline__ int key(int i) const {
+        const uint4 w = reinterpret_cast<const uint4*>(in + i)[3];   // visitedMask, currentNode, targetNode, flags
+        const int target = (int)w.z;
+        const bool valid = (w.w >> 16) & 0xffu;
+        return (valid && target >= 0 && target < B) ? target : -1;
+    }
+    __device__ __forceinline__ void copy(int src, int dst) const {
+        const float4* s = reinterpret_cast<const float4*>(in + src);
+        float4* d = reinterpret_cast<float4*>(out + dst);
+        const float4 a = s[0], b = s[1], c = s[2], e = s[3];
+        d[0] = a; d[1] = b; d[2] = c; d[3] = e;
+    }
+};
+
+struct QueryOps {
+    const dprt_nn_query* in; const dprt_half* fin; dprt_nn_query* out; dprt_half* fout; int B; int insideOnly;
+    __device__ __forceinline__ int key(int i) const {
+        const int id = in[i].hitAABBID;                 // preKernelNN: hitAABBID == AABBID (scene index + 1)
+        if (id < 1 || id > B) return -1;
+        if (insideOnly && !in[i].isInside) return -1;   // preKernelNN_HIT_INSIDE
+        return id - 1;
+    }
+    __device__ __forceinline__ void copy(int src, int dst) const {
+        const float4* s = reinterpret_cast<const float4*>(in + src);
+        float4* d = reinterpret_cast<float4*>(out + dst);
+        const float4 a = s[0], b = s[1], c = s[2];
+        d[0] = a; d[1] = b; d[2] = c;
+        const dprt_half* fs = fin + (size_t)src * 5; dprt_half* fd = fout + (size_t)dst * 5;
+#pragma unroll
+        for (int k = 0; k < 5; k++) fd[k] = fs[k];
+    }
+};
+
+template <class Ops>
+__global__ void __launch_bounds__(kThreads) partition_kernel(Ops ops, int n, const int32_t* __restrict__ hist,
+                                                              int32_t* __restrict__ offsets, uint32_t* tileState,
+                                                              int32_t* tileCounter) {
+    __shared__ int s_tile;
+    __shared__ int s_cnt[kSteps][32];
+    __shared__ int s_base[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int B = ops.B;
+
+    if (threadIdx.x == 0) s_tile = atomicAdd(tileCounter, 1);   // launch-order tile ids: predecessors are always running
+    for (int k = threadIdx.x; k < kSteps * 32; k += kThreads) (&s_cnt[0][0])[k] = 0;
+    __syncthreads();
+    const int tile = s_tile;
+
+    int key[kItems], rank[kItems];
+    const int base = tile * kTile + warp * (32 * kItems);
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+        const int idx = base + j * 32 + lane;
+        key[j] = idx < n ? ops.key(idx) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+        const bool v = key[j] >= 0;
+        const unsigned m = __ballot_sync(0xffffffffu, v);
+        rank[j] = 0;
+        if (v) {
+            const unsigned peers = __match_any_sync(m, key[j]);
+            rank[j] = __popc(peers & ((1u << lane) - 1u));
+            if (rank[j] == 0) s_cnt[warp * kItems + j][key[j]] = __popc(peers);
+        }
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // exclusive scan over the 32 in-tile steps, lane = bucket
+        int run = 0;
+#pragma unroll 8
+        for (int s = 0; s < kSteps; s++) { const int c = s_cnt[s][lane]; s_cnt[s][lane] = run; run += c; }
+        // bucket bases = exclusive prefix of the histogram
+        const int h = lane < B ? hist[lane] : 0;
+        int incl = h;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int bucketBase = incl - h;
+        if (tile == 0) {
+            if (lane < B) offsets[lane] = bucketBase;
+            if (lane == B - 1) offsets[B] = incl;
+        }
+        // decoupled look-back, one chain per bucket
+        int excl = 0;
+        if (lane < B) {
+            volatile uint32_t* st = tileState;
+            if (tile == 0) {
+                st[lane] = ST_INC | (uint32_t)run;
+            } else {
+                st[(size_t)tile * 32 + lane] = ST_AGG | (uint32_t)run;
+                __threadfence();
+                int t = tile - 1;
+                for (;;) {
+                    uint32_t v;
+                    do { v = st[(size_t)t * 32 + lane]; } while ((v & ST_MASK) == 0u);
+                    excl += (int)(v & VAL_MASK);
+                    if ((v & ST_MASK) == ST_INC) break;
+                    t--;
+                }
+                st[(size_t)tile * 32 + lane] = ST_INC | (uint32_t)(excl + run);
+            }
+        }
+        s_base[lane] = bucketBase + excl;
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+        if (key[j] >= 0) {
+            const int idx = base + j * 32 + lane;
+            const int dst = s_base[key[j]] + s_cnt[warp * kItems + j][key[j]] + rank[j];
+            ops.copy(idx, dst);
+        }
+    }
+}
+
+__global__ void path_hist_kernel(const dprt_path_record* __restrict__ paths, int n, int W, int32_t* hist) {
+    __shared__ int sh[32];
+    if (threadIdx.x < 32) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 w = reinterpret_cast<const uint4*>(paths + i)[3];
+        const int target = (int)w.z;
+        if (((w.w >> 16) & 0xffu) && target >= 0 && target < W) atomicAdd(&sh[target], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < W && sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, sh[threadIdx.x]);
+}
+
+__global__ void query_hist_kernel(const dprt_nn_query* __restrict__ q, int n, int S, int insideOnly, int32_t* hist) {
+    __shared__ int sh[32];
+    if (threadIdx.x < 32) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int id = q[i].hitAABBID;
+        if (id >= 1 && id <= S && (!insideOnly || q[i].isInside)) atomicAdd(&sh[id - 1], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < S && sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, sh[threadIdx.x]);
+}
+
+__global__ void empty_offsets_kernel(int32_t* offsets, int B) {
+    if (threadIdx.x <= B) offsets[threadIdx.x] = 0;
+}
+
+template <class Ops>
+void run_partition(Ops ops, int n, const int32_t* hist, int32_t* offsets, const PartitionScratch& s, cudaStream_t stream) {
+    if (n <= 0) { empty_offsets_kernel<<<1, 64, 0, stream>>>(offsets, ops.B); return; }
+    const int tiles = (n + kTile - 1) / kTile;
+    cudaMemsetAsync(s.tileState, 0, (size_t)tiles * 32 * sizeof(uint32_t), stream);
+    cudaMemsetAsync(s.tileCounter, 0, sizeof(int32_t), stream);
+    partition_kernel<Ops><<<tiles, kThreads, 0, stream>>>(ops, n, hist, offsets, s.tileState, s.tileCounter);
+}
+
+}  // namespace
+
+void launch_path_histogram(const dprt_path_record* paths, int n, int W, int32_t* hist, cudaStream_t stream) {
+    cudaMemsetAsync(hist, 0, 32 * sizeof(int32_t), stream);
+    if (n > 0) path_hist_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, stream>>>(paths, n, W, hist);
+}
+
+void launch_partition_paths(const dprt_path_record* paths, int n, int W, const int32_t* hist, dprt_path_record* out,
+                            int32_t* offsets, const PartitionScratch& s, cudaStream_t stream) {
+    PathOps ops{paths, out, W};
+    run_partition(ops, n, hist, offsets, s, stream);
+}
+
+void launch_query_histogram(const dprt_nn_query* q, int n, int S, int insideOnly, int32_t* hist, cudaStream_t stream) {
+    cudaMemsetAsync(hist, 0, 32 * sizeof(int32_t), stream);
+    if (n > 0) query_hist_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, stream>>>(q, n, S, insideOnly, hist);
+}
+
+void launch_partition_queries(const dprt_nn_query* q, const dprt_half* in, int n, int S, int insideOnly,
+                              const int32_t* hist, dprt_nn_query* outQ, dprt_half* outIn, int32_t* offsets,
+                              const PartitionScratch& s, cudaStream_t stream) {
+    QueryOps ops{q, in, outQ, outIn, S, insideOnly};
+    run_partition(ops, n, hist, offsets, s, stream);
+}
+
+}  // namespace dprt

@@ -1,0 +1,114 @@
+"""ctypes / numpy mirrors of include/dprt_types.h (shared by the libdprt binding and the oracle binding).
+
+Every structure here restates one POD of ``include/dprt_types.h``; sizes are asserted at import.
+"""
+import ctypes as C
+
+import numpy as np
+
+DPRT_EPSILON = 1e-3
+MAX_WORLD = 32
+
+
+class Config(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("bounces", C.c_int32),
+                ("shadowPathCount", C.c_int32), ("maxCount", C.c_int32), ("sceneSize", C.c_int32),
+                ("proxyMode", C.c_int32), ("pathGenMode", C.c_int32), ("mlpDtype", C.c_int32),
+                ("envColor", C.c_float * 3), ("reserved_", C.c_int32 * 3)]
+
+
+class ObjectDesc(C.Structure):
+    _fields_ = [("nodeID", C.c_int32), ("isProxy", C.c_int32), ("aabbMin", C.c_float * 3), ("aabbMax", C.c_float * 3),
+                ("maxLength", C.c_float), ("worldToObject", C.c_float * 12)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("U", C.c_float * 3), ("V", C.c_float * 3), ("W", C.c_float * 3),
+                ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("rays_traverse", C.c_int64), ("rays_shade", C.c_int64), ("rays_shadow", C.c_int64),
+                ("rays_secondary", C.c_int64), ("nn_queries", C.c_int64), ("paths_sent_offrank", C.c_int64),
+                ("exchange_iters", C.c_int64), ("kernel_launches", C.c_int64), ("bytes_alltoall", C.c_int64),
+                ("reserved_", C.c_int64 * 7)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "reserved_"}
+
+
+PATH_DTYPE = np.dtype([("origin", "<f4", 3), ("direction", "<f4", 3), ("tMax", "<f4"), ("throughput", "<f4", 3),
+                       ("pixelIndex", "<i4"), ("shadowPathID", "<i4"), ("visitedMask", "<u4"), ("currentNode", "<i4"),
+                       ("targetNode", "<i4"), ("isShadowRay", "u1"), ("isDelta", "u1"), ("isValid", "u1"), ("isHit", "u1")])
+QUERY_DTYPE = np.dtype([("throughput", "<f4", 3), ("pixelIndex", "<i4"), ("hitSequence", "<i4"), ("hitAABBID", "<i4"),
+                        ("shadowPathID", "<i4"), ("instanceID", "<i4"), ("pathIndex", "<i4"), ("normalizedT", "<f4"),
+                        ("isValid", "u1"), ("isInside", "u1"), ("pad_", "u1", 2), ("reserved_", "<i4")])
+RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("tMin", "<f4"), ("direction", "<f4", 3), ("tMax", "<f4")])
+HIT_DTYPE = np.dtype([("t", "<f4"), ("primID", "<i4")])
+MATERIAL_DTYPE = np.dtype([("baseColor", "<f4", 3), ("bsdfType", "<i4")])
+LIGHT_DTYPE = np.dtype([("p0", "<f4", 3), ("p1", "<f4", 3), ("p2", "<f4", 3), ("Le", "<f4", 3)])
+NODE_DTYPE = np.dtype([("p", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("childBase", "<u4"), ("triBase", "<u4"),
+                       ("meta", "u1", 8), ("qlox", "u1", 8), ("qloy", "u1", 8), ("qloz", "u1", 8),
+                       ("qhix", "u1", 8), ("qhiy", "u1", 8), ("qhiz", "u1", 8)])
+TRI_DTYPE = np.dtype([("v0", "<f4", 3), ("primID", "<i4"), ("v1", "<f4", 3), ("matID", "<i4"), ("v2", "<f4", 3), ("pad_", "<i4")])
+
+assert PATH_DTYPE.itemsize == 64 and QUERY_DTYPE.itemsize == 48 and RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 8
+assert NODE_DTYPE.itemsize == 80 and TRI_DTYPE.itemsize == 48 and MATERIAL_DTYPE.itemsize == 16 and LIGHT_DTYPE.itemsize == 48
+assert C.sizeof(Config) == 64 and C.sizeof(ObjectDesc) == 84 and C.sizeof(Camera) == 56 and C.sizeof(Stats) == 128
+
+# dprt_buffer_id
+BUF_PATHS, BUF_TRANSFER, BUF_TRANSFER_OFFSET, BUF_DIRECT, BUF_ENV, BUF_NN_INPUT, BUF_NN_QUERY, BUF_NN_PACKED_INPUT, \
+    BUF_NN_PACKED_QUERY, BUF_SCENE_OFFSET, BUF_PRED, BUF_OCCLUSION, BUF_CONTRIBUTION, BUF_HIT_PRIM = range(14)
+
+BUFFER_DTYPES = {
+    BUF_PATHS: PATH_DTYPE, BUF_TRANSFER: PATH_DTYPE, BUF_TRANSFER_OFFSET: np.dtype("<i4"), BUF_DIRECT: np.dtype("<f4"),
+    BUF_ENV: np.dtype("<f4"), BUF_NN_INPUT: np.dtype("<u2"), BUF_NN_QUERY: QUERY_DTYPE, BUF_NN_PACKED_INPUT: np.dtype("<u2"),
+    BUF_NN_PACKED_QUERY: QUERY_DTYPE, BUF_SCENE_OFFSET: np.dtype("<i4"), BUF_PRED: np.dtype("<u2"),
+    BUF_OCCLUSION: np.dtype("<f4"), BUF_CONTRIBUTION: np.dtype("<f4"), BUF_HIT_PRIM: np.dtype("<i4"),
+}
+
+
+def make_config(width, height, spp=1, bounces=4, spc=4, mc=3, scene_size=1, proxy_mode=0, path_gen_mode=0,
+                mlp_dtype=0, env_color=(0.6, 0.7, 0.9)):
+    cfg = Config()
+    cfg.width, cfg.height, cfg.spp, cfg.bounces = width, height, spp, bounces
+    cfg.shadowPathCount, cfg.maxCount, cfg.sceneSize = spc, mc, scene_size
+    cfg.proxyMode, cfg.pathGenMode, cfg.mlpDtype = proxy_mode, path_gen_mode, mlp_dtype
+    cfg.envColor[:] = [float(c) for c in env_color]
+    return cfg
+
+
+def make_object_desc(node_id, aabb_min, aabb_max, is_proxy=0, world_to_object=None):
+    d = ObjectDesc()
+    d.nodeID, d.isProxy = int(node_id), int(is_proxy)
+    mn = np.asarray(aabb_min, np.float32)
+    mx = np.asarray(aabb_max, np.float32)
+    d.aabbMin[:] = mn.tolist()
+    d.aabbMax[:] = mx.tolist()
+    diff = (mx - mn).astype(np.float32)
+    # (aabb.m_max - aabb.m_min).length() in fp32, renderer.cpp:1830: fma(z,z,fma(y,y,x*x)) then sqrt
+    acc = np.float32(diff[0] * diff[0])
+    acc = np.float32(np.float64(diff[1]) * np.float64(diff[1]) + np.float64(acc))
+    acc = np.float32(np.float64(diff[2]) * np.float64(diff[2]) + np.float64(acc))
+    d.maxLength = float(np.sqrt(acc, dtype=np.float32))
+    m = np.eye(4, dtype=np.float32)[:3] if world_to_object is None else np.asarray(world_to_object, np.float32).reshape(3, 4)
+    d.worldToObject[:] = m.reshape(-1).tolist()
+    return d
+
+
+def make_camera(origin, look_at, up, vfov_deg, width, height):
+    """Pinhole camera basis, pre-scaled like dprt_camera documents (computed in float64, stored float32)."""
+    o = np.asarray(origin, np.float64)
+    w = np.asarray(look_at, np.float64) - o
+    w /= np.linalg.norm(w)
+    u = np.cross(w, np.asarray(up, np.float64))
+    u /= np.linalg.norm(u)
+    v = np.cross(u, w)
+    th = np.tan(np.radians(vfov_deg) / 2.0)
+    cam = Camera()
+    cam.origin[:] = o.astype(np.float32).tolist()
+    cam.U[:] = (u * th * (width / height)).astype(np.float32).tolist()
+    cam.V[:] = (v * th).astype(np.float32).tolist()
+    cam.W[:] = w.astype(np.float32).tolist()
+    cam.width, cam.height = int(width), int(height)
+    return cam

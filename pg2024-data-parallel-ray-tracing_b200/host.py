@@ -1,0 +1,391 @@
+"""ctypes binding of libdprt.so -- the reference-side stub a maintainer would write.
+
+``Renderer`` mirrors ``moana::Renderer`` of the reference (src/render/renderer.cpp): ``launch`` ->
+:meth:`Renderer.launch`, ``runSample`` -> :meth:`Renderer.run_sample`, and one method per stage helper
+(``primaryRayModule`` :1212, ``generateSecondaryAndShadowRay`` :1320, ``shadowRayModuleBasedNN`` :1349,
+``secondaryRayModuleBasedNN`` :1407) plus the free functions of src/cuda (``Work_Efficient_Scan`` ->
+:meth:`partition`, ``Frame_Buffer_Update`` -> :meth:`frame_buffer_update`, ...). There is no CPU fallback:
+a missing library or a box without a GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import ctypes_defs as D
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdprt.so")
+
+_PROTOTYPES = {
+    # name: (restype, argtypes)
+    "dprt_get_unique_id": (C.c_int, [C.c_void_p]),
+    "dprt_create": (C.c_int, [C.POINTER(D.Config), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dprt_destroy": (None, [C.c_void_p]),
+    "dprt_last_error": (C.c_char_p, [C.c_void_p]),
+    "dprt_synchronize": (C.c_int, [C.c_void_p]),
+    "dprt_get_stats": (C.c_int, [C.c_void_p, C.POINTER(D.Stats)]),
+    "dprt_reset_stats": (C.c_int, [C.c_void_p]),
+    "dprt_bvh8_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.POINTER(C.c_void_p)]),
+    "dprt_bvh8_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "dprt_bvh8_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dprt_bvh8_free": (None, [C.c_void_p]),
+    "dprt_upload_chunk": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(D.ObjectDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "dprt_upload_proxy": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(D.ObjectDesc), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "dprt_set_materials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "dprt_set_lights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "dprt_set_camera": (C.c_int, [C.c_void_p, C.POINTER(D.Camera)]),
+    "dprt_reset_frame": (C.c_int, [C.c_void_p]),
+    "dprt_begin_sample": (C.c_int, [C.c_void_p, C.c_int]),
+    "dprt_path_gen": (C.c_int, [C.c_void_p]),
+    "dprt_traverse": (C.c_int, [C.c_void_p]),
+    "dprt_partition": (C.c_int, [C.c_void_p]),
+    "dprt_exchange": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "dprt_shade": (C.c_int, [C.c_void_p]),
+    "dprt_reset_nn": (C.c_int, [C.c_void_p]),
+    "dprt_shadow_trace": (C.c_int, [C.c_void_p]),
+    "dprt_secondary_trace": (C.c_int, [C.c_void_p]),
+    "dprt_bucket_queries": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "dprt_proxy_infer": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "dprt_frame_buffer_update": (C.c_int, [C.c_void_p]),
+    "dprt_depth_buffer_update": (C.c_int, [C.c_void_p]),
+    "dprt_target_node_update": (C.c_int, [C.c_void_p]),
+    "dprt_primary_ray_module": (C.c_int, [C.c_void_p]),
+    "dprt_shadow_ray_module": (C.c_int, [C.c_void_p]),
+    "dprt_secondary_ray_module": (C.c_int, [C.c_void_p]),
+    "dprt_render_sample": (C.c_int, [C.c_void_p, C.c_int]),
+    "dprt_reduce_image": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "dprt_exchange_group": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int)]),
+    "dprt_render_sample_group": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
+    "dprt_reduce_image_group": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]),
+    "dprt_get_path_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dprt_set_path_size": (C.c_int, [C.c_void_p, C.c_int]),
+    "dprt_buffer_bytes": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]),
+    "dprt_download": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "dprt_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "dprt_enable_hit_prim": (C.c_int, [C.c_void_p, C.c_int]),
+    "dprt_trace_closest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "dprt_trace_closest_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "dprt_mlp_infer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "dprt_mlp_infer_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "dprt_device_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "dprt_device_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dprt_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "dprt_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "dprt_timer_start": (C.c_int, [C.c_void_p]),
+    "dprt_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "dprt_flush_l2": (C.c_int, [C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+
+_lib = None
+
+
+class DprtError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """dlopen libdprt.so and bind every prototype of include/dprt.h. Raises if the library is absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise DprtError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    lib = C.CDLL(p)
+    for name, (res, args) in _PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def get_unique_id():
+    buf = (C.c_char * 128)()
+    rc = load_library().dprt_get_unique_id(buf)
+    if rc:
+        raise DprtError(f"dprt_get_unique_id failed: {rc}")
+    return bytes(buf)
+
+
+def build_bvh8(verts9, mat_ids=None, pad=-1.0):
+    """Host BVH8 build -> (nodes[NODE_DTYPE], tris[TRI_DTYPE], max_depth). No GPU needed."""
+    lib = load_library()
+    v = np.ascontiguousarray(verts9, np.float32).reshape(-1, 9)
+    m = None if mat_ids is None else np.ascontiguousarray(mat_ids, np.int32)
+    h = C.c_void_p()
+    rc = lib.dprt_bvh8_build(_ptr(v), _ptr(m), v.shape[0], float(pad), C.byref(h))
+    if rc:
+        raise DprtError(f"dprt_bvh8_build failed: {rc}")
+    try:
+        nn, nt, md = C.c_int64(), C.c_int64(), C.c_int32()
+        lib.dprt_bvh8_info(h, C.byref(nn), C.byref(nt), C.byref(md))
+        nodes = np.zeros(nn.value, D.NODE_DTYPE)
+        tris = np.zeros(nt.value, D.TRI_DTYPE)
+        lib.dprt_bvh8_copy(h, _ptr(nodes), _ptr(tris))
+    finally:
+        lib.dprt_bvh8_free(h)
+    return nodes, tris, int(md.value)
+
+
+class Renderer:
+    """One rank of the data-parallel renderer (one GPU, one scene-chunk owner)."""
+
+    def __init__(self, cfg, rank=0, world=1, device=0, nccl_unique_id=None):
+        self.lib = load_library()
+        self.cfg = cfg
+        self.rank, self.world = rank, world
+        self.N = cfg.width * cfg.height
+        h = C.c_void_p()
+        idbuf = None
+        if nccl_unique_id is not None:
+            idbuf = C.create_string_buffer(bytes(nccl_unique_id), 128)
+        rc = self.lib.dprt_create(C.byref(cfg), rank, world, device, idbuf, C.byref(h))
+        if rc:
+            raise DprtError(f"dprt_create failed ({rc}): {self.lib.dprt_last_error(None).decode()}")
+        self.h = h
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _ck(self, rc, what):
+        if rc:
+            raise DprtError(f"{what} failed ({rc}): {self.lib.dprt_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dprt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._ck(self.lib.dprt_synchronize(self.h), "dprt_synchronize")
+
+    def stats(self):
+        s = D.Stats()
+        self._ck(self.lib.dprt_get_stats(self.h, C.byref(s)), "dprt_get_stats")
+        return s.as_dict()
+
+    def reset_stats(self):
+        self._ck(self.lib.dprt_reset_stats(self.h), "dprt_reset_stats")
+
+    # -- scene ------------------------------------------------------------------------------------
+    def upload_chunk(self, scene_index, desc, verts9, normals9, mat_ids):
+        v = np.ascontiguousarray(verts9, np.float32).reshape(-1, 9)
+        n = None if normals9 is None else np.ascontiguousarray(normals9, np.float32).reshape(-1, 9)
+        m = None if mat_ids is None else np.ascontiguousarray(mat_ids, np.int32)
+        self._ck(self.lib.dprt_upload_chunk(self.h, scene_index, C.byref(desc), _ptr(v), _ptr(n), _ptr(m), v.shape[0]),
+                 "dprt_upload_chunk")
+
+    def upload_proxy(self, scene_index, desc, vis_blob=None, depth_blob=None):
+        vb = None if vis_blob is None else np.frombuffer(vis_blob, np.uint8)
+        db = None if depth_blob is None else np.frombuffer(depth_blob, np.uint8)
+        self._ck(self.lib.dprt_upload_proxy(self.h, scene_index, C.byref(desc), _ptr(vb), 0 if vb is None else vb.size,
+                                            _ptr(db), 0 if db is None else db.size), "dprt_upload_proxy")
+
+    def set_materials(self, mats):
+        m = np.ascontiguousarray(mats, D.MATERIAL_DTYPE)
+        self._ck(self.lib.dprt_set_materials(self.h, _ptr(m), m.size), "dprt_set_materials")
+
+    def set_lights(self, lights):
+        l = np.ascontiguousarray(lights, D.LIGHT_DTYPE)
+        self._ck(self.lib.dprt_set_lights(self.h, _ptr(l), l.size), "dprt_set_lights")
+
+    def set_camera(self, cam):
+        self._ck(self.lib.dprt_set_camera(self.h, C.byref(cam)), "dprt_set_camera")
+
+    # -- stages (reference call sites in include/dprt.h) ----------------------------------------------
+    def reset_frame(self):
+        self._ck(self.lib.dprt_reset_frame(self.h), "dprt_reset_frame")
+
+    def begin_sample(self, sample):
+        self._ck(self.lib.dprt_begin_sample(self.h, sample), "dprt_begin_sample")
+
+    def path_gen(self):
+        self._ck(self.lib.dprt_path_gen(self.h), "dprt_path_gen")
+
+    def traverse(self):
+        self._ck(self.lib.dprt_traverse(self.h), "dprt_traverse")
+
+    def partition(self):
+        self._ck(self.lib.dprt_partition(self.h), "dprt_partition")
+
+    def exchange(self):
+        done = C.c_int(0)
+        self._ck(self.lib.dprt_exchange(self.h, C.byref(done)), "dprt_exchange")
+        return bool(done.value)
+
+    def shade(self):
+        self._ck(self.lib.dprt_shade(self.h), "dprt_shade")
+
+    def reset_nn(self):
+        self._ck(self.lib.dprt_reset_nn(self.h), "dprt_reset_nn")
+
+    def shadow_trace(self):
+        self._ck(self.lib.dprt_shadow_trace(self.h), "dprt_shadow_trace")
+
+    def secondary_trace(self):
+        self._ck(self.lib.dprt_secondary_trace(self.h), "dprt_secondary_trace")
+
+    def bucket_queries(self, which, inside_only):
+        total = C.c_int(0)
+        self._ck(self.lib.dprt_bucket_queries(self.h, which, int(inside_only), C.byref(total)), "dprt_bucket_queries")
+        return int(total.value)
+
+    def proxy_infer(self, kind, pred_offset=0):
+        self._ck(self.lib.dprt_proxy_infer(self.h, kind, pred_offset), "dprt_proxy_infer")
+
+    def frame_buffer_update(self):
+        self._ck(self.lib.dprt_frame_buffer_update(self.h), "dprt_frame_buffer_update")
+
+    def depth_buffer_update(self):
+        self._ck(self.lib.dprt_depth_buffer_update(self.h), "dprt_depth_buffer_update")
+
+    def target_node_update(self):
+        self._ck(self.lib.dprt_target_node_update(self.h), "dprt_target_node_update")
+
+    def primary_ray_module(self):
+        self._ck(self.lib.dprt_primary_ray_module(self.h), "dprt_primary_ray_module")
+
+    def shadow_ray_module(self):
+        self._ck(self.lib.dprt_shadow_ray_module(self.h), "dprt_shadow_ray_module")
+
+    def secondary_ray_module(self):
+        self._ck(self.lib.dprt_secondary_ray_module(self.h), "dprt_secondary_ray_module")
+
+    def run_sample(self, sample):
+        self._ck(self.lib.dprt_render_sample(self.h, sample), "dprt_render_sample")
+
+    def reduce_image(self, root=0):
+        out = np.zeros((self.cfg.height, self.cfg.width, 3), np.float32) if self.rank == root else None
+        self._ck(self.lib.dprt_reduce_image(self.h, root, _ptr(out)), "dprt_reduce_image")
+        return out
+
+    def launch(self):
+        """Renderer::launch (renderer.cpp:1576): reset, spp x runSample, average + reduce to rank 0."""
+        self.reset_frame()
+        for s in range(self.cfg.spp):
+            self.run_sample(s)
+        return self.reduce_image(0)
+
+    # -- state access -----------------------------------------------------------------------------------
+    @property
+    def path_size(self):
+        a, b = C.c_int(), C.c_int()
+        self._ck(self.lib.dprt_get_path_size(self.h, C.byref(a), C.byref(b)), "dprt_get_path_size")
+        return int(a.value)
+
+    @property
+    def shadow_path_size(self):
+        a, b = C.c_int(), C.c_int()
+        self._ck(self.lib.dprt_get_path_size(self.h, C.byref(a), C.byref(b)), "dprt_get_path_size")
+        return int(b.value)
+
+    def set_path_size(self, n):
+        self._ck(self.lib.dprt_set_path_size(self.h, int(n)), "dprt_set_path_size")
+
+    def download(self, buf, count=None, offset=0):
+        dt = D.BUFFER_DTYPES[buf]
+        if count is None:
+            nbytes = C.c_size_t()
+            self._ck(self.lib.dprt_buffer_bytes(self.h, buf, C.byref(nbytes)), "dprt_buffer_bytes")
+            count = nbytes.value // dt.itemsize - offset
+        out = np.zeros(count, dt)
+        if count:
+            self._ck(self.lib.dprt_download(self.h, buf, offset * dt.itemsize, _ptr(out), out.nbytes), "dprt_download")
+        return out
+
+    def upload(self, buf, array, offset=0):
+        dt = D.BUFFER_DTYPES[buf]
+        a = np.ascontiguousarray(array, dt)
+        if a.size:
+            self._ck(self.lib.dprt_upload(self.h, buf, offset * dt.itemsize, _ptr(a), a.nbytes), "dprt_upload")
+
+    def enable_hit_prim(self, enable=True):
+        self._ck(self.lib.dprt_enable_hit_prim(self.h, int(enable)), "dprt_enable_hit_prim")
+
+    # -- standalone operators ------------------------------------------------------------------------------
+    def trace_closest(self, rays):
+        r = np.ascontiguousarray(rays, D.RAY_DTYPE)
+        hits = np.zeros(r.size, D.HIT_DTYPE)
+        self._ck(self.lib.dprt_trace_closest(self.h, _ptr(r), r.size, _ptr(hits)), "dprt_trace_closest")
+        return hits
+
+    def mlp_infer(self, scene_index, kind, x_half):
+        x = np.ascontiguousarray(x_half, np.uint16).reshape(-1, 5)
+        y = np.zeros(x.shape[0], np.uint16)
+        self._ck(self.lib.dprt_mlp_infer(self.h, scene_index, kind, _ptr(x), x.shape[0], _ptr(y)), "dprt_mlp_infer")
+        return y
+
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._ck(self.lib.dprt_device_alloc(self.h, nbytes, C.byref(p)), "dprt_device_alloc")
+        return p
+
+    def device_free(self, p):
+        self._ck(self.lib.dprt_device_free(self.h, p), "dprt_device_free")
+
+    def h2d(self, dev, array):
+        a = np.ascontiguousarray(array)
+        self._ck(self.lib.dprt_memcpy_h2d(self.h, dev, _ptr(a), a.nbytes), "dprt_memcpy_h2d")
+
+    def d2h(self, array, dev):
+        self._ck(self.lib.dprt_memcpy_d2h(self.h, _ptr(array), dev, array.nbytes), "dprt_memcpy_d2h")
+
+    def trace_closest_device(self, rays_dev, n, hits_dev):
+        self._ck(self.lib.dprt_trace_closest_device(self.h, rays_dev, n, hits_dev), "dprt_trace_closest_device")
+
+    def mlp_infer_device(self, scene_index, kind, x_dev, n, y_dev):
+        self._ck(self.lib.dprt_mlp_infer_device(self.h, scene_index, kind, x_dev, n, y_dev), "dprt_mlp_infer_device")
+
+    def timer_start(self):
+        self._ck(self.lib.dprt_timer_start(self.h), "dprt_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self.lib.dprt_timer_stop(self.h, C.byref(ms)), "dprt_timer_stop")
+        return float(ms.value)
+
+    def flush_l2(self):
+        self._ck(self.lib.dprt_flush_l2(self.h), "dprt_flush_l2")
+
+
+class RankGroup:
+    """W contexts driven by one thread (dprt_*_group): multi-chunk runs on fewer GPUs than ranks."""
+
+    def __init__(self, renderers):
+        self.rs = list(renderers)
+        self.lib = self.rs[0].lib
+        self.arr = (C.c_void_p * len(self.rs))(*[r.h for r in self.rs])
+
+    def exchange(self):
+        done = C.c_int(0)
+        self.rs[0]._ck(self.lib.dprt_exchange_group(self.arr, len(self.rs), C.byref(done)), "dprt_exchange_group")
+        return bool(done.value)
+
+    def run_sample(self, sample):
+        self.rs[0]._ck(self.lib.dprt_render_sample_group(self.arr, len(self.rs), sample), "dprt_render_sample_group")
+
+    def reduce_image(self, root=0):
+        cfg = self.rs[0].cfg
+        out = np.zeros((cfg.height, cfg.width, 3), np.float32)
+        self.rs[0]._ck(self.lib.dprt_reduce_image_group(self.arr, len(self.rs), root, _ptr(out)), "dprt_reduce_image_group")
+        return out
+
+    def launch(self):
+        for r in self.rs:
+            r.reset_frame()
+        for s in range(self.rs[0].cfg.spp):
+            self.run_sample(s)
+        return self.reduce_image(0)

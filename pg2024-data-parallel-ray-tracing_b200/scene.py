@@ -1,0 +1,167 @@
+"""Synthetic scene / light / camera generators for the BASELINE.json configs.
+
+The reference's scene loader is not in the tree; the benchmark scenes are jittered
+height-field sheets, one per spatial cell of the unit cube, each cell owned by one rank (= one scene chunk,
+``AccelerationStructure.nodeID`` of renderer.cpp:1834-1839). Vertex jitter and material assignment come from
+the reference RNG (``tea<4>`` / ``rnd`` of optix/random.hpp:31-67, vectorised here in uint32 numpy).
+Everything produced here is plain input data for both libdprt and the oracle.
+"""
+import numpy as np
+
+from . import ctypes_defs as D
+
+
+def tea4_np(val0, val1):
+    v0 = np.asarray(val0, np.uint32).copy()
+    v1 = np.broadcast_to(np.asarray(val1, np.uint32), v0.shape).copy()
+    s0 = np.uint32(0)
+    with np.errstate(over="ignore"):
+        for _ in range(4):
+            s0 = np.uint32((int(s0) + 0x9E3779B9) & 0xFFFFFFFF)
+            v0 += ((v1 << np.uint32(4)) + np.uint32(0xA341316C)) ^ (v1 + s0) ^ ((v1 >> np.uint32(5)) + np.uint32(0xC8013EA4))
+            v1 += ((v0 << np.uint32(4)) + np.uint32(0xAD90777D)) ^ (v0 + s0) ^ ((v0 >> np.uint32(5)) + np.uint32(0x7E95761E))
+    return v0
+
+
+def rnd_np(seed):
+    """One LCG step: returns (float32 in [0,1), new seed)."""
+    with np.errstate(over="ignore"):
+        seed = seed * np.uint32(1664525) + np.uint32(1013904223)
+    return ((seed & np.uint32(0x00FFFFFF)).astype(np.float32) / np.float32(0x01000000)), seed
+
+
+def cell_layout(W):
+    """Spatial cells of the unit cube, one per rank: (min, max) per cell."""
+    dims = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(W)
+    if dims is None:
+        dims = (W, 1, 1)
+    cells = []
+    for k in range(W):
+        ix, iy, iz = k % dims[0], (k // dims[0]) % dims[1], k // (dims[0] * dims[1])
+        mn = np.array([ix / dims[0], iy / dims[1], iz / dims[2]], np.float64)
+        mx = np.array([(ix + 1) / dims[0], (iy + 1) / dims[1], (iz + 1) / dims[2]], np.float64)
+        cells.append((mn, mx, iz, dims[2]))
+    return cells
+
+
+def make_heightfield_chunk(cell_min, cell_max, nx, ny, seed, hole_frac=0.0, n_materials=16, water_frac=0.0):
+    """nx*ny quads -> 2*nx*ny triangles (minus holes). Returns verts9, normals9, mat_ids (float32/int32)."""
+    gx, gy = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="ij")
+    x = cell_min[0] + (cell_max[0] - cell_min[0]) * gx / nx
+    y = cell_min[1] + (cell_max[1] - cell_min[1]) * gy / ny
+    vid = (gx * (ny + 1) + gy).astype(np.uint32)
+    s = tea4_np(vid, np.uint32(0xC0FFEE + seed))
+    j, s = rnd_np(s)
+    zr = cell_max[2] - cell_min[2]
+    h = 0.45 + 0.22 * np.sin(7.0 * x + 0.6 * seed) * np.cos(6.0 * y - 0.3 * seed) + 0.08 * np.sin(23.0 * x * y + seed)
+    amp = 0.25 * min((cell_max[0] - cell_min[0]) / nx, (cell_max[1] - cell_min[1]) / ny) / max(zr, 1e-9)
+    z = cell_min[2] + zr * np.clip(h + amp * (j.astype(np.float64) - 0.5), 0.02, 0.98)
+    P = np.stack([x, y, z], -1)                                   # [nx+1, ny+1, 3]
+    # per-vertex normals from central differences
+    dxv = np.gradient(P, axis=0)
+    dyv = np.gradient(P, axis=1)
+    nrm = np.cross(dxv, dyv)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    p00, p10, p01, p11 = P[:-1, :-1], P[1:, :-1], P[:-1, 1:], P[1:, 1:]
+    n00, n10, n01, n11 = nrm[:-1, :-1], nrm[1:, :-1], nrm[:-1, 1:], nrm[1:, 1:]
+    t0 = np.concatenate([p00, p10, p11], -1).reshape(-1, 9)
+    t1 = np.concatenate([p00, p11, p01], -1).reshape(-1, 9)
+    m0 = np.concatenate([n00, n10, n11], -1).reshape(-1, 9)
+    m1 = np.concatenate([n00, n11, n01], -1).reshape(-1, 9)
+    verts = np.stack([t0, t1], 1).reshape(-1, 9)
+    norms = np.stack([m0, m1], 1).reshape(-1, 9)
+    qid = np.arange(nx * ny, dtype=np.uint32)
+    ms = tea4_np(qid, np.uint32(7 + seed))
+    mat = (ms % np.uint32(max(1, n_materials - 1))).astype(np.int32)
+    if water_frac > 0.0:
+        wsel, _ = rnd_np(tea4_np(qid, np.uint32(0x5EA + seed)))
+        mat = np.where(wsel < water_frac, n_materials - 1, mat).astype(np.int32)
+    mats = np.repeat(mat, 2)
+    if hole_frac > 0.0:
+        qx, qy = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+        blob = 0.5 + 0.5 * np.sin(9.0 * qx / nx * np.pi + seed) * np.sin(7.0 * qy / ny * np.pi + 2 * seed)
+        keep = np.repeat((blob.reshape(-1) >= hole_frac), 2)
+        verts, norms, mats = verts[keep], norms[keep], mats[keep]
+    return verts.astype(np.float32), norms.astype(np.float32), mats.astype(np.int32)
+
+
+def make_materials(n=16, water_last=False):
+    m = np.zeros(n, D.MATERIAL_DTYPE)
+    s = tea4_np(np.arange(n, dtype=np.uint32), np.uint32(0xA1BED0))
+    for c in range(3):
+        v, s = rnd_np(s)
+        m["baseColor"][:, c] = 0.25 + 0.7 * v
+    if water_last:
+        m["bsdfType"][n - 1] = 1
+        m["baseColor"][n - 1] = 1.0
+    return m
+
+
+def make_lights(scale=1.0):
+    """Two area-light triangles above the scene, facing down; Le is the reference default (renderer.cpp:1784)."""
+    Le = np.array([891.443777, 505.928150, 154.625939], np.float32) * np.float32(scale)
+    q = np.array([[0.25, 0.25, 2.0], [0.75, 0.25, 2.0], [0.75, 0.75, 2.0], [0.25, 0.75, 2.0]], np.float32)
+    L = np.zeros(2, D.LIGHT_DTYPE)
+    L["p0"][0], L["p1"][0], L["p2"][0] = q[0], q[2], q[1]
+    L["p0"][1], L["p1"][1], L["p2"][1] = q[0], q[3], q[2]
+    L["Le"][:] = Le
+    return L
+
+
+def default_camera(width, height):
+    # SURVEY.md 8(d) proposed (0.5,-1.5,0.8)->(0.5,0.5,0.3) at 40 deg; from there only 12 % of the 16:9 frame
+    # hits the unit-square sheet. This oblique, narrower view keeps ~90 % of the primary rays on geometry.
+    return D.make_camera((0.5, -0.4, 1.0), (0.5, 0.5, 0.45), (0.0, 0.0, 1.0), 28.0, width, height)
+
+
+class Chunk:
+    def __init__(self, index, node_id, verts, normals, mats):
+        self.index, self.node_id = index, node_id
+        self.verts, self.normals, self.mats = verts, normals, mats
+        mn = verts.reshape(-1, 3).min(0).astype(np.float32)
+        mx = verts.reshape(-1, 3).max(0).astype(np.float32)
+        eps = np.float32(1e-4)
+        self.aabb_min, self.aabb_max = mn - eps, mx + eps
+
+    def desc(self, is_proxy):
+        return D.make_object_desc(self.node_id, self.aabb_min, self.aabb_max, is_proxy=int(is_proxy))
+
+    @property
+    def ntris(self):
+        return self.verts.shape[0]
+
+
+def make_scene(W, tris_per_chunk, water_frac=0.0, seed=0):
+    """W chunks (one per rank); ~tris_per_chunk triangles each. Returns (chunks, materials, lights)."""
+    cells = cell_layout(W)
+    chunks = []
+    for k, (mn, mx, iz, nz) in enumerate(cells):
+        hole = 0.35 if (nz > 1 and iz == nz - 1) else 0.0           # upper sheets let rays through to the lower cells
+        quads = tris_per_chunk / 2 / (1.0 - 0.45 * (hole > 0))
+        ax, ay = mx[0] - mn[0], mx[1] - mn[1]
+        nx = max(2, int(round(np.sqrt(quads * ax / ay))))
+        ny = max(2, int(round(quads / nx)))
+        v, n, m = make_heightfield_chunk(mn, mx, nx, ny, seed + k, hole_frac=hole, water_frac=water_frac)
+        chunks.append(Chunk(k, k, v, n, m))
+    return chunks, make_materials(16, water_last=water_frac > 0), make_lights()
+
+
+def camera_rays(cam, sample=0):
+    """The PathGen rays as dprt_ray records (float64 math, for harness use; the parity path is the kernel)."""
+    w, h = cam.width, cam.height
+    pix = np.arange(w * h, dtype=np.uint32)
+    s = tea4_np(pix, np.uint32(sample))
+    x1, s = rnd_np(s)
+    x2, s = rnd_np(s)
+    col, row = (pix % w).astype(np.float64), (pix // w).astype(np.float64)
+    a = 2.0 * (col + x1) / w - 1.0
+    b = 1.0 - 2.0 * (row + x2) / h
+    U, V, Wv = (np.array(list(v), np.float64) for v in (cam.U, cam.V, cam.W))
+    d = a[:, None] * U + b[:, None] * V + Wv
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.zeros(w * h, D.RAY_DTYPE)
+    rays["origin"] = np.array(list(cam.origin), np.float32)
+    rays["direction"] = d.astype(np.float32)
+    rays["tMin"] = D.DPRT_EPSILON
+    rays["tMax"] = np.finfo(np.float32).max
+    return rays
