@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DevParams p, int n) {
 struct MarchOut { int count; bool envMiss; };
 
 DPRT_D void clear_query_slots(const DevParams& p, int threadIndex, int from) {
+    if (!p.proxyMode) return;                     // no query buffers exist when proxies are off
     for (int q = from; q < p.mc; q++) p.nnQuery[(size_t)threadIndex * p.mc + q].hitAABBID = 0;   // reset by count, not memset
 }
 

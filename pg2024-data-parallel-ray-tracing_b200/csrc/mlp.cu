@@ -1,9 +1,481 @@
-// placeholder, replaced by the tcgen05 kernel
+// mlp.cu -- fused neural-proxy MLP inference on the 5th-generation tensor cores (sm_100a).
+//
+// Replaces the batched torch::jit forward loops of src/render/renderer.cpp:768-839, 841-1011, 1014-1159
+// (one cuBLAS HGEMM per layer, activations round-tripping HBM) for the proxy network of
+// trainingcode/module.py:755-837 (NeuralVisNetworkWith{4,6}Res256SingleOutput):
+//     x[:,0:3] -> Lin(3,32) LReLU Lin(32,128) LReLU  \  concat 256 -> nres x LReLU(x + Lin256(x)) -> (+ skip)
+//     x[:,3:5] -> Lin(2,32) LReLU Lin(32,128) LReLU  /  -> Lin(256,64) LReLU -> Lin(64,1) LReLU
+//
+// One CTA owns a tile of 128 queries; the whole chain runs without leaving the SM:
+//   * the two 5->32 input layers and the final 64->1 layer run on CUDA cores (K too small for an MMA),
+//   * every other layer is a tcgen05.mma (M=128, N=256 or 64, K=16 steps) with both operands in shared memory
+//     (128-byte-swizzled K-major tiles) and the fp32 accumulator in TMEM,
+//   * the residual stream stays in fp32 *inside TMEM*: the epilogue writes LReLU(acc+b) back with tcgen05.st
+//     and the next layer's MMAs accumulate on top of it, so only the MMA operands are rounded to 16 bits,
+//   * a second TMEM region keeps the encoder output for the outer skip connection,
+//   * weights are pre-tiled on the host into 32 KiB stages that a dedicated warp streams from L2 with
+//     cp.async.bulk into a 4-deep mbarrier ring (no tensor maps needed: the tiles are already in smem order).
+// Warp roles: warps 0-3 = prologue/epilogue (thread == row == TMEM lane), warp 4 = MMA issuer, warp 5 = loader.
 #include "mlp.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <cstring>
+#include <vector>
+
 namespace dprt {
-struct MlpModel { int dummy; };
-int mlp_create(const void*, size_t, int, MlpModel**, std::string& err) { err = "mlp not built"; return -1; }
-void mlp_destroy(MlpModel*) {}
-int mlp_forward(const MlpModel*, const dprt_half*, dprt_half*, int64_t, cudaStream_t, std::string& err) { err = "mlp not built"; return -1; }
-int64_t mlp_macs_per_row(const MlpModel*) { return 0; }
+
+namespace {
+
+constexpr int kRows = 128;
+constexpr int kWidth = 256;
+constexpr int kStageBytes = 32768;
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+constexpr int kMaxRes = 6;
+constexpr uint32_t kBlobMagic = 0x50524d4cu;
+
+// fp32 side parameters, offsets in floats
+constexpr int kE3W0 = 0, kE3B0 = 96, kE2W0 = 128, kE2B0 = 192, kBEnc = 224, kBRes = 480;
+__host__ __device__ constexpr int small_floats(int nres) { return kBRes + nres * kWidth + 64 + 64 + 1; }
+constexpr int kSmallMax = small_floats(kMaxRes);   // 2145 floats
+
+// shared memory map (bytes from the 1024-aligned base)
+constexpr int kSmemA = 0;                                    // 128 x 256 x 16 bit, 4 K-blocks of 16 KiB
+constexpr int kSmemStages = 65536;
+constexpr int kSmemSmall = kSmemStages + kStages * kStageBytes;          // 196608
+constexpr int kSmemBars = kSmemSmall + ((kSmallMax * 4 + 15) / 16) * 16;  // barriers: full[4], empty[4], mma_done
+constexpr int kSmemTmemPtr = kSmemBars + 9 * 8;
+constexpr int kSmemTotal = kSmemTmemPtr + 16 + 1024;                      // + alignment slack
+
+// ---- PTX helpers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart (SM100 version bit set)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// instruction descriptor, kind::f16: fp32 accumulate, A/B both K-major, fmt 0 = f16 / 1 = bf16
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int fmt) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+#define TMEM_LD32(taddr, v)                                                                                          \
+    asm volatile(                                                                                                    \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                    \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                    \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                    \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), \
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),       \
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),      \
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                    \
+        : "r"(taddr)                                                                                                 \
+        : "memory")
+
+#define TMEM_ST32(taddr, v)                                                                                          \
+    asm volatile(                                                                                                    \
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                              \
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "                                   \
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),             \
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),  \
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),    \
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),    \
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])                                                                \
+        : "memory")
+
+__device__ __forceinline__ float lrelu(float x) { return x > 0.0f ? x : 0.01f * x; }
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    if (BF16) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+
+// byte offset of 16-byte chunk j (0..7) of `row` inside one K-block (128 rows x 128 B, 128B swizzle)
+__device__ __forceinline__ uint32_t a_chunk_off(int row, int j) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((j ^ (row & 7)) << 4));
+}
+
+// writes 32 consecutive activations (columns c32*32 ..) of `row` as 16-bit operands into the A tile
+template <bool BF16>
+__device__ __forceinline__ void store_a32(uint8_t* A, int row, int c32, const float* y) {
+    uint8_t* kb = A + (c32 >> 1) * 16384;
+    const int j0 = (c32 & 1) * 4;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint4 w;
+        w.x = pack2<BF16>(y[q * 8 + 0], y[q * 8 + 1]);
+        w.y = pack2<BF16>(y[q * 8 + 2], y[q * 8 + 3]);
+        w.z = pack2<BF16>(y[q * 8 + 4], y[q * 8 + 5]);
+        w.w = pack2<BF16>(y[q * 8 + 6], y[q * 8 + 7]);
+        *reinterpret_cast<uint4*>(kb + a_chunk_off(row, j0 + q)) = w;
+    }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_kernel(const uint8_t* __restrict__ wstages, const float* __restrict__ small_g, int nres, const uint16_t* __restrict__ x,
+           uint16_t* __restrict__ y, int n) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem + kSmemA;
+    float* sSmall = reinterpret_cast<float*>(smem + kSmemSmall);
+    const uint32_t aBase = smem_u32(sA);
+    const uint32_t stageBase = smem_u32(smem + kSmemStages);
+    const uint32_t barBase = smem_u32(smem + kSmemBars);
+    auto fullBar = [&](int s) { return barBase + 8u * (uint32_t)s; };
+    auto emptyBar = [&](int s) { return barBase + 8u * (uint32_t)(kStages + s); };
+    const uint32_t mmaDone = barBase + 8u * (2 * kStages);
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem + kSmemTmemPtr);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = (n + kRows - 1) / kRows;
+    const int chunksPerTile = 2 + 4 * nres;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) { mbar_init(fullBar(s), 1); mbar_init(emptyBar(s), 1); }
+        mbar_init(mmaDone, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < small_floats(nres); i += kThreads) sSmall[i] = small_g[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *sTmem;
+    const int fmt = BF16 ? 1 : 0;
+
+    if (warp == 5) {
+        // ---------------- weight loader: streams the per-tile stage sequence through the ring ----------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int c = 0; c < chunksPerTile; c++, it++) {
+                    const int s = it % kStages;
+                    if (it >= kStages) mbar_wait(emptyBar(s), ((it / kStages) - 1) & 1);
+                    mbar_expect_tx(fullBar(s), kStageBytes);
+                    bulk_g2s(stageBase + s * kStageBytes, wstages + (size_t)c * kStageBytes, kStageBytes, fullBar(s));
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ---------------- MMA issuer ----------------
+        const uint32_t idesc256 = make_idesc(kRows, 256, fmt), idesc64 = make_idesc(kRows, 64, fmt);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            // encoder second layers as one block-diagonal 64 -> 256 GEMM
+            named_bar_sync(1, 160);
+            tc_fence_after();
+            if (lane == 0) {
+                const int s = it % kStages;
+                mbar_wait(fullBar(s), (it / kStages) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++)
+                    tc_mma(tmem, make_desc(aBase + ks * 32), make_desc(stageBase + s * kStageBytes + ks * 32), idesc256, ks > 0);
+                tc_commit(emptyBar(s));
+                tc_commit(mmaDone);
+            }
+            it++;
+            __syncwarp();
+            // residual layers: acc (already holding the fp32 residual) += A . W^T
+            for (int l = 0; l < nres; l++) {
+                named_bar_sync(1, 160);
+                tc_fence_after();
+                for (int kc = 0; kc < 4; kc++, it++) {
+                    if (lane == 0) {
+                        const int s = it % kStages;
+                        mbar_wait(fullBar(s), (it / kStages) & 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++)
+                            tc_mma(tmem, make_desc(aBase + kc * 16384 + ks * 32), make_desc(stageBase + s * kStageBytes + ks * 32),
+                                   idesc256, 1u);
+                        tc_commit(emptyBar(s));
+                        if (kc == 3) tc_commit(mmaDone);
+                    }
+                }
+                __syncwarp();
+            }
+            // post layer 256 -> 64
+            named_bar_sync(1, 160);
+            tc_fence_after();
+            if (lane == 0) {
+                const int s = it % kStages;
+                mbar_wait(fullBar(s), (it / kStages) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < 16; ks++)
+                    tc_mma(tmem, make_desc(aBase + (ks >> 2) * 16384 + (ks & 3) * 32),
+                           make_desc(stageBase + s * kStageBytes + (ks >> 2) * 8192 + (ks & 3) * 32), idesc64, ks > 0);
+                tc_commit(emptyBar(s));
+                tc_commit(mmaDone);
+            }
+            it++;
+            __syncwarp();
+        }
+    } else {
+        // ---------------- prologue / epilogue warps: thread == row == TMEM lane ----------------
+        const int row = threadIdx.x;
+        const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+        uint32_t phase = 0;
+        const float* bEnc = sSmall + kBEnc;
+        const float* bRes = sSmall + kBRes;
+        const float* bP0 = sSmall + kBRes + nres * kWidth;
+        const float* wP1 = bP0 + 64;
+        const float bP1 = wP1[64];
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int g = tile * kRows + row;
+            // input layers on CUDA cores: h = [LReLU(W3 x[0:3] + b3) | LReLU(W2 x[3:5] + b2)], 64 values -> K-block 0
+            float xin[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) xin[k] = g < n ? __half2float(__ushort_as_half(x[(size_t)g * 5 + k])) : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                float h[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int o = j * 8 + e;
+                    float s;
+                    if (o < 32) s = fmaf(sSmall[kE3W0 + o * 3 + 2], xin[2], fmaf(sSmall[kE3W0 + o * 3 + 1], xin[1], fmaf(sSmall[kE3W0 + o * 3], xin[0], sSmall[kE3B0 + o])));
+                    else s = fmaf(sSmall[kE2W0 + (o - 32) * 2 + 1], xin[4], fmaf(sSmall[kE2W0 + (o - 32) * 2], xin[3], sSmall[kE2B0 + o - 32]));
+                    h[e] = lrelu(s);
+                }
+                uint4 w;
+                w.x = pack2<BF16>(h[0], h[1]); w.y = pack2<BF16>(h[2], h[3]); w.z = pack2<BF16>(h[4], h[5]); w.w = pack2<BF16>(h[6], h[7]);
+                *reinterpret_cast<uint4*>(sA + a_chunk_off(row, j)) = w;
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            named_bar_sync(1, 160);
+
+            // encoder epilogue: out1 = LReLU(acc + b) -> TMEM (residual), TMEM copy (outer skip), A operand
+            mbar_wait(mmaDone, phase); phase ^= 1;
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 8; c++) {
+                uint32_t v[32];
+                TMEM_LD32(tlane + c * 32, v);
+                tc_wait_ld();
+                float yv[32];
+#pragma unroll
+                for (int i = 0; i < 32; i++) { yv[i] = lrelu(__uint_as_float(v[i]) + bEnc[c * 32 + i]); v[i] = __float_as_uint(yv[i]); }
+                TMEM_ST32(tlane + c * 32, v);
+                TMEM_ST32(tlane + 256 + c * 32, v);
+                store_a32<BF16>(sA, row, c, yv);
+            }
+            tc_wait_st();
+            fence_proxy_async();
+            tc_fence_before();
+            named_bar_sync(1, 160);
+
+            for (int l = 0; l < nres; l++) {
+                mbar_wait(mmaDone, phase); phase ^= 1;
+                tc_fence_after();
+                const bool last = l == nres - 1;
+#pragma unroll 1
+                for (int c = 0; c < 8; c++) {
+                    uint32_t v[32];
+                    TMEM_LD32(tlane + c * 32, v);
+                    tc_wait_ld();
+                    float yv[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i++) yv[i] = lrelu(__uint_as_float(v[i]) + bRes[l * kWidth + c * 32 + i]);
+                    if (!last) {
+#pragma unroll
+                        for (int i = 0; i < 32; i++) v[i] = __float_as_uint(yv[i]);
+                        TMEM_ST32(tlane + c * 32, v);
+                    } else {
+                        TMEM_LD32(tlane + 256 + c * 32, v);          // outer skip: out1 + out2
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; i++) yv[i] += __uint_as_float(v[i]);
+                    }
+                    store_a32<BF16>(sA, row, c, yv);
+                }
+                tc_wait_st();
+                fence_proxy_async();
+                tc_fence_before();
+                named_bar_sync(1, 160);
+            }
+
+            // post epilogue: z = LReLU(acc[:,0:64] + b0); out = LReLU(w1 . z + b1) on CUDA cores
+            mbar_wait(mmaDone, phase); phase ^= 1;
+            tc_fence_after();
+            float acc = bP1;
+#pragma unroll 1
+            for (int c = 0; c < 2; c++) {
+                uint32_t v[32];
+                TMEM_LD32(tlane + c * 32, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; i++) acc = fmaf(lrelu(__uint_as_float(v[i]) + bP0[c * 32 + i]), wP1[c * 32 + i], acc);
+            }
+            if (g < n) y[g] = __half_as_ushort(__float2half_rn(lrelu(acc)));
+            tc_fence_before();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+// ---- host side: blob -> device stages ----------------------------------------------------------------------
+inline uint16_t to16(float f, int dtype) {
+    if (dtype == 0) { __nv_bfloat16 h = __float2bfloat16_rn(f); uint16_t u; std::memcpy(&u, &h, 2); return u; }
+    __half h = __float2half_rn(f); uint16_t u; std::memcpy(&u, &h, 2); return u;
+}
+// element (n, kk) of a [rows x 64] K-major tile with 128-byte swizzle
+inline size_t tile_off(int nrow, int kk) { return (size_t)(nrow / 8) * 1024 + (nrow % 8) * 128 + (((kk / 8) ^ (nrow % 8)) * 16) + (kk % 8) * 2; }
+
+}  // namespace
+
+struct MlpModel {
+    int width = 0, nres = 0, dtype = 0;
+    uint8_t* d_stages = nullptr;
+    float* d_small = nullptr;
+    int num_sms = 148;
+};
+
+int mlp_create(const void* blob, size_t bytes, int dtype, MlpModel** out, std::string& err) {
+    *out = nullptr;
+    if (!blob || bytes < 16) { err = "proxy blob: too small"; return -1; }
+    const uint32_t* h = (const uint32_t*)blob;
+    const int width = (int)h[1], nres = (int)h[2];
+    if (h[0] != kBlobMagic) { err = "proxy blob: bad magic"; return -1; }
+    if (width != kWidth || nres < 1 || nres > kMaxRes) { err = "proxy blob: only width 256 with 1..6 residual blocks is built"; return -1; }
+    const int half = width / 2;
+    const size_t need = (size_t)(32 * 3 + 32 + half * 32 + half) + (size_t)(32 * 2 + 32 + half * 32 + half) +
+                        (size_t)nres * ((size_t)width * width + width) + (size_t)(64 * width + 64) + 65;
+    if (bytes != 16 + need * 4) { err = "proxy blob: size does not match header"; return -1; }
+    const float* p = (const float*)(h + 4);
+    const float* e3w0 = p; p += 96; const float* e3b0 = p; p += 32; const float* e3w1 = p; p += half * 32; const float* e3b1 = p; p += half;
+    const float* e2w0 = p; p += 64; const float* e2b0 = p; p += 32; const float* e2w1 = p; p += half * 32; const float* e2b1 = p; p += half;
+    std::vector<const float*> rw(nres), rb(nres);
+    for (int i = 0; i < nres; i++) { rw[i] = p; p += (size_t)width * width; rb[i] = p; p += width; }
+    const float* pw0 = p; p += 64 * width; const float* pb0 = p; p += 64; const float* pw1 = p; p += 64; const float* pb1 = p;
+
+    const int nstages = 2 + 4 * nres;
+    std::vector<uint8_t> stages((size_t)nstages * kStageBytes, 0);
+    auto put = [&](uint8_t* base, int nrow, int kk, float v) { uint16_t u = to16(v, dtype); std::memcpy(base + tile_off(nrow, kk), &u, 2); };
+    // stage 0: block-diagonal encoder second layers, [256 x 64]
+    for (int nrow = 0; nrow < half; nrow++) for (int k = 0; k < 32; k++) put(stages.data(), nrow, k, e3w1[nrow * 32 + k]);
+    for (int nrow = 0; nrow < half; nrow++) for (int k = 0; k < 32; k++) put(stages.data(), half + nrow, 32 + k, e2w1[nrow * 32 + k]);
+    for (int l = 0; l < nres; l++)
+        for (int kc = 0; kc < 4; kc++) {
+            uint8_t* base = stages.data() + (size_t)(1 + l * 4 + kc) * kStageBytes;
+            for (int nrow = 0; nrow < width; nrow++) for (int kk = 0; kk < 64; kk++) put(base, nrow, kk, rw[l][(size_t)nrow * width + kc * 64 + kk]);
+        }
+    {
+        uint8_t* base = stages.data() + (size_t)(1 + 4 * nres) * kStageBytes;
+        for (int kb = 0; kb < 4; kb++) for (int nrow = 0; nrow < 64; nrow++) for (int kk = 0; kk < 64; kk++)
+            put(base + kb * 8192, nrow, kk, pw0[(size_t)nrow * width + kb * 64 + kk]);
+    }
+    std::vector<float> sm(small_floats(nres), 0.f);
+    std::memcpy(&sm[kE3W0], e3w0, 96 * 4); std::memcpy(&sm[kE3B0], e3b0, 32 * 4);
+    std::memcpy(&sm[kE2W0], e2w0, 64 * 4); std::memcpy(&sm[kE2B0], e2b0, 32 * 4);
+    std::memcpy(&sm[kBEnc], e3b1, half * 4); std::memcpy(&sm[kBEnc + half], e2b1, half * 4);
+    for (int l = 0; l < nres; l++) std::memcpy(&sm[kBRes + l * kWidth], rb[l], width * 4);
+    std::memcpy(&sm[kBRes + nres * kWidth], pb0, 64 * 4);
+    std::memcpy(&sm[kBRes + nres * kWidth + 64], pw1, 64 * 4);
+    sm[kBRes + nres * kWidth + 128] = pb1[0];
+
+    MlpModel* m = new MlpModel();
+    m->width = width; m->nres = nres; m->dtype = dtype;
+    cudaError_t e;
+    if ((e = cudaMalloc(&m->d_stages, stages.size())) != cudaSuccess || (e = cudaMalloc(&m->d_small, sm.size() * 4)) != cudaSuccess ||
+        (e = cudaMemcpy(m->d_stages, stages.data(), stages.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(m->d_small, sm.data(), sm.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        err = std::string("mlp_create: ") + cudaGetErrorString(e);
+        mlp_destroy(m);
+        return -1;
+    }
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    cudaFuncSetAttribute(mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    *out = m;
+    return 0;
+}
+
+void mlp_destroy(MlpModel* m) {
+    if (!m) return;
+    if (m->d_stages) cudaFree(m->d_stages);
+    if (m->d_small) cudaFree(m->d_small);
+    delete m;
+}
+
+int mlp_forward(const MlpModel* m, const dprt_half* x_dev, dprt_half* y_dev, int64_t n, cudaStream_t stream, std::string& err) {
+    if (!m) { err = "mlp_forward: no model"; return -1; }
+    if (n <= 0) return 0;
+    if (n > 0x7fffffff) { err = "mlp_forward: batch too large"; return -1; }
+    const int ntiles = (int)((n + kRows - 1) / kRows);
+    const int grid = ntiles < m->num_sms ? ntiles : m->num_sms;
+    if (m->dtype == 0) mlp_kernel<true><<<grid, kThreads, kSmemTotal, stream>>>(m->d_stages, m->d_small, m->nres, x_dev, y_dev, (int)n);
+    else mlp_kernel<false><<<grid, kThreads, kSmemTotal, stream>>>(m->d_stages, m->d_small, m->nres, x_dev, y_dev, (int)n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("mlp_kernel launch: ") + cudaGetErrorString(e); return -1; }
+    return 0;
+}
+
+int64_t mlp_macs_per_row(const MlpModel* m) {
+    if (!m) return 0;
+    const int64_t w = m->width, h = w / 2;
+    return 3 * 32 + 2 * 32 + 2 * 32 * h + (int64_t)m->nres * w * w + 64 * w + 64;
+}
+
+}  // namespace dprt

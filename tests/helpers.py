@@ -45,6 +45,8 @@ def build_pair(O, W, tris_per_chunk, width, height, *, spp=1, bounces=2, proxy_m
 def assert_records_equal(a, b, what):
     """Bitwise comparison of structured record arrays with a readable first-mismatch report."""
     assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    if a.size == 0:
+        return
     ab, bb = a.view(np.uint8).reshape(a.size, -1), b.view(np.uint8).reshape(b.size, -1)
     bad = np.nonzero((ab != bb).any(axis=1))[0]
     if bad.size:
