@@ -115,6 +115,16 @@ int  dprt_memcpy_d2h(dprt_ctx* ctx, void* host, const void* dev, size_t bytes);
 int  dprt_timer_start(dprt_ctx* ctx);
 int  dprt_timer_stop(dprt_ctx* ctx, float* ms);
 int  dprt_flush_l2(dprt_ctx* ctx);
+/* Per-stage device time: when enabled every stage launch is bracketed by a CUDA-event pair on the context's
+ * stream (the Timing::start/end sections of renderer.cpp:1245-1251,1262-1283 as device-side measurements).
+ * ms_out / launches_out hold DPRT_STAGE_COUNT entries, accumulated since the last dprt_reset_stats. */
+int  dprt_stage_profile(dprt_ctx* ctx, int enable);
+int  dprt_get_stage_times(dprt_ctx* ctx, double* ms_out, int64_t* launches_out);
+/* Instrumented traversal: when enabled the traversal kernels run in a counting variant that accumulates BVH8
+ * nodes visited and triangles tested per stage (the algorithmic-byte basis of the roofline).
+ * counts_out holds 2*DPRT_STAGE_COUNT entries {nodes, tris}. Results are unchanged; timing is not representative. */
+int  dprt_enable_counters(dprt_ctx* ctx, int enable);
+int  dprt_get_counters(dprt_ctx* ctx, uint64_t* counts_out);
 
 #ifdef __cplusplus
 }

@@ -180,6 +180,25 @@ enum dprt_buffer_id {
     DPRT_BUF_COUNT = 14
 };
 
+/* Stage identifiers for dprt_get_stage_times / dprt_get_counters: one per reference call site of runSample. */
+enum dprt_stage_id {
+    DPRT_STAGE_PATH_GEN = 0,
+    DPRT_STAGE_TRAVERSE = 1,
+    DPRT_STAGE_PARTITION = 2,
+    DPRT_STAGE_EXCHANGE = 3,
+    DPRT_STAGE_SHADE = 4,
+    DPRT_STAGE_SHADOW_TRACE = 5,
+    DPRT_STAGE_SECONDARY_TRACE = 6,
+    DPRT_STAGE_BUCKET = 7,
+    DPRT_STAGE_PROXY_MLP = 8,
+    DPRT_STAGE_FRAME_UPDATE = 9,
+    DPRT_STAGE_DEPTH_UPDATE = 10,
+    DPRT_STAGE_TARGET_UPDATE = 11,
+    DPRT_STAGE_IMAGE = 12,
+    DPRT_STAGE_TRACE_CLOSEST = 13,
+    DPRT_STAGE_COUNT = 14
+};
+
 enum dprt_error {
     DPRT_OK = 0,
     DPRT_ERR_INVALID = -1,

@@ -23,10 +23,13 @@ DPRT_D float q2f(uint32_t w, uint32_t sel) {
 
 #define DPRT_STACK 40
 
+// instrumentation (dprt_enable_counters): BVH8 nodes fetched and triangles tested by one thread
+struct TraceCount { uint32_t nodes, tris; };
+
 // ANY = true: return as soon as one triangle is hit in (tmin, tmax) (shadow rays).
-template <bool ANY>
+template <bool ANY, bool COUNT>
 DPRT_D bool bvh8_trace(const uint4* __restrict__ nodes, const float4* __restrict__ tris,
-                       V3 o, V3 d, float tmin, float tmax, TraceHit& hit) {
+                       V3 o, V3 d, float tmin, float tmax, TraceHit& hit, TraceCount& cnt) {
     const RayShear rs = ray_shear(d);
     const float dxs = fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x);
     const float dys = fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y);
@@ -51,6 +54,7 @@ DPRT_D bool bvh8_trace(const uint4* __restrict__ nodes, const float4* __restrict
             const uint32_t ni = ng.x + rel;
             if (ng.y & 0xff000000u) { if (sp < DPRT_STACK) stack[sp++] = ng; }
 
+            if (COUNT) cnt.nodes++;
             const uint4 n0 = __ldg(nodes + 5 * (size_t)ni + 0);
             const uint4 n1 = __ldg(nodes + 5 * (size_t)ni + 1);
             const uint4 n2 = __ldg(nodes + 5 * (size_t)ni + 2);
@@ -101,6 +105,7 @@ DPRT_D bool bvh8_trace(const uint4* __restrict__ nodes, const float4* __restrict
             const uint32_t k = __ffs(tg.y) - 1u;
             tg.y &= tg.y - 1u;
             const uint32_t ti = tg.x + k;
+            if (COUNT) cnt.tris++;
             const float4 a = __ldg(tris + 3 * (size_t)ti + 0);
             const float4 b = __ldg(tris + 3 * (size_t)ti + 1);
             const float4 c = __ldg(tris + 3 * (size_t)ti + 2);

@@ -109,6 +109,14 @@ struct dprt_ctx {
     dprt_stats stats{};
     std::string err;
     std::vector<void*> user_allocs;
+    // per-stage device timing (dprt_stage_profile): event pairs recorded around each stage, resolved lazily
+    bool profile = false;
+    std::vector<cudaEvent_t> evPool;
+    struct Pending { int stage; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    double stageMs[DPRT_STAGE_COUNT] = {0};
+    int64_t stageLaunches[DPRT_STAGE_COUNT] = {0};
+    unsigned long long* d_counters = nullptr;   // 2*DPRT_STAGE_COUNT, allocated on first dprt_enable_counters
 };
 
 namespace {
@@ -132,6 +140,38 @@ namespace {
     } while (0)
 
 int fail(dprt_ctx* ctx, int code, const std::string& msg) { ctx->err = msg; return code; }
+
+void resolve_pending(dprt_ctx* ctx) {
+    for (auto& pd : ctx->pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(pd.b) == cudaSuccess && cudaEventElapsedTime(&ms, pd.a, pd.b) == cudaSuccess) {
+            ctx->stageMs[pd.stage] += ms; ctx->stageLaunches[pd.stage] += 1;
+        }
+        ctx->evPool.push_back(pd.a); ctx->evPool.push_back(pd.b);
+    }
+    ctx->pending.clear();
+}
+
+// Brackets one stage with an event pair on the context's stream when profiling is on (a no-op otherwise).
+struct StageScope {
+    dprt_ctx* ctx; int stage; cudaEvent_t a = nullptr, b = nullptr;
+    StageScope(dprt_ctx* c, int st, bool active = true) : ctx(c), stage(st) {
+        if (!ctx->profile || !active) return;
+        if (ctx->pending.size() >= 8192) resolve_pending(ctx);
+        auto get = [&]() {
+            cudaEvent_t e = nullptr;
+            if (!ctx->evPool.empty()) { e = ctx->evPool.back(); ctx->evPool.pop_back(); } else cudaEventCreate(&e);
+            return e;
+        };
+        a = get(); b = get();
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~StageScope() {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->pending.push_back({stage, a, b});
+    }
+};
 
 int alloc_buf(dprt_ctx* ctx, int id, size_t bytes) {
     bytes = std::max<size_t>(bytes, 256);
@@ -272,7 +312,7 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
         p.nnQuery = (dprt_nn_query*)ctx->buf_ptr[DPRT_BUF_NN_QUERY]; p.nnPackedQuery = (dprt_nn_query*)ctx->buf_ptr[DPRT_BUF_NN_PACKED_QUERY];
         p.sceneOffset = (int32_t*)ctx->buf_ptr[DPRT_BUF_SCENE_OFFSET];
         p.pred = (dprt_half*)ctx->buf_ptr[DPRT_BUF_PRED];
-        p.hitPrim = nullptr;
+        p.hitPrim = nullptr; p.counters = nullptr;
         p.camera.width = cfg->width; p.camera.height = cfg->height;
         p.lightCount = 0;
         sync_params(ctx);
@@ -318,6 +358,9 @@ void dprt_destroy(dprt_ctx* ctx) {
     if (ctx->d_image_sum) cudaFree(ctx->d_image_sum);
     if (ctx->d_gather) cudaFree(ctx->d_gather);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    resolve_pending(ctx);
+    for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_flush) cudaFree(ctx->d_flush);
     if (ctx->d_io) cudaFree(ctx->d_io);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -334,7 +377,51 @@ int dprt_synchronize(dprt_ctx* ctx) {
     return 0;
 }
 int dprt_get_stats(const dprt_ctx* ctx, dprt_stats* out) { if (!ctx || !out) return DPRT_ERR_INVALID; *out = ctx->stats; return 0; }
-int dprt_reset_stats(dprt_ctx* ctx) { if (!ctx) return DPRT_ERR_INVALID; ctx->stats = dprt_stats{}; return 0; }
+int dprt_reset_stats(dprt_ctx* ctx) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    ctx->stats = dprt_stats{};
+    cudaSetDevice(ctx->device);
+    resolve_pending(ctx);
+    for (int i = 0; i < DPRT_STAGE_COUNT; i++) { ctx->stageMs[i] = 0.0; ctx->stageLaunches[i] = 0; }
+    if (ctx->d_counters) CK(cudaMemsetAsync(ctx->d_counters, 0, 2 * DPRT_STAGE_COUNT * sizeof(unsigned long long), ctx->stream));
+    return 0;
+}
+
+int dprt_stage_profile(dprt_ctx* ctx, int enable) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    resolve_pending(ctx);
+    ctx->profile = enable != 0;
+    return 0;
+}
+int dprt_get_stage_times(dprt_ctx* ctx, double* ms_out, int64_t* launches_out) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    resolve_pending(ctx);
+    for (int i = 0; i < DPRT_STAGE_COUNT; i++) {
+        if (ms_out) ms_out[i] = ctx->stageMs[i];
+        if (launches_out) launches_out[i] = ctx->stageLaunches[i];
+    }
+    return 0;
+}
+int dprt_enable_counters(dprt_ctx* ctx, int enable) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (enable && !ctx->d_counters) {
+        CK(cudaMalloc(&ctx->d_counters, 2 * DPRT_STAGE_COUNT * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(ctx->d_counters, 0, 2 * DPRT_STAGE_COUNT * sizeof(unsigned long long), ctx->stream));
+    }
+    ctx->hp.counters = enable ? ctx->d_counters : nullptr;
+    return 0;
+}
+int dprt_get_counters(dprt_ctx* ctx, uint64_t* counts_out) {
+    if (!ctx || !counts_out) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->d_counters) { std::memset(counts_out, 0, 2 * DPRT_STAGE_COUNT * sizeof(uint64_t)); return 0; }
+    CK(cudaMemcpyAsync(counts_out, ctx->d_counters, 2 * DPRT_STAGE_COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
 
 // ---- scene -------------------------------------------------------------------------------------
 int dprt_bvh8_build(const float* verts9, const int32_t* mat_ids, int64_t ntris, float pad, dprt_bvh8** out) {
@@ -449,6 +536,7 @@ int dprt_path_gen(dprt_ctx* ctx) {
     if (!ctx) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     sync_params(ctx);
+    StageScope sc_(ctx, DPRT_STAGE_PATH_GEN, ctx->pathSize > 0);
     launch_path_gen(ctx->hp, ctx->pathSize, ctx->stream);
     ctx->stats.kernel_launches += ctx->pathSize > 0;
     ctx->histFresh = false;
@@ -461,6 +549,7 @@ int dprt_traverse(dprt_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     sync_params(ctx);
     CK(cudaMemsetAsync(ctx->hp.pathHist, 0, 32 * sizeof(int32_t), ctx->stream));
+    StageScope sc_(ctx, DPRT_STAGE_TRAVERSE, ctx->pathSize > 0);
     launch_traverse(ctx->hp, ctx->pathSize, ctx->stream);
     ctx->stats.kernel_launches += ctx->pathSize > 0;
     ctx->stats.rays_traverse += ctx->pathSize;
@@ -473,6 +562,7 @@ int dprt_partition(dprt_ctx* ctx) {
     if (!ctx) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     sync_params(ctx);
+    StageScope sc_(ctx, DPRT_STAGE_PARTITION);
     if (!ctx->histFresh) {
         launch_path_histogram(ctx->hp.paths, ctx->pathSize, ctx->world, ctx->hp.pathHist, ctx->stream);
         ctx->stats.kernel_launches += ctx->pathSize > 0;
@@ -490,6 +580,7 @@ int dprt_exchange(dprt_ctx* ctx, int* done) {
     CK(cudaSetDevice(ctx->device));
     const int W = ctx->world, me = ctx->rank;
     const size_t R = sizeof(dprt_path_record);
+    StageScope sc_(ctx, DPRT_STAGE_EXCHANGE);
     if (W == 1) {
         int r = read_offsets(ctx); if (r) return r;
         const int cnt = ctx->h_offsets[1];
@@ -580,6 +671,7 @@ int dprt_shade(dprt_ctx* ctx) {
     if (ctx->hp.lightCount < 1) return fail(ctx, DPRT_ERR_STATE, "no lights set");
     ctx->shadowPathSize = ctx->cfg.shadowPathCount * ctx->pathSize;     // renderer.cpp:1328
     sync_params(ctx);
+    StageScope sc_(ctx, DPRT_STAGE_SHADE, ctx->pathSize > 0);
     launch_shade(ctx->hp, ctx->pathSize, ctx->stream);
     ctx->stats.kernel_launches += ctx->pathSize > 0;
     ctx->stats.rays_shade += ctx->pathSize;
@@ -608,6 +700,7 @@ int dprt_shadow_trace(dprt_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     sync_params(ctx);
     CK(cudaMemsetAsync(ctx->hp.queryHist, 0, 64 * sizeof(int32_t), ctx->stream));
+    StageScope sc_(ctx, DPRT_STAGE_SHADOW_TRACE, ctx->shadowPathSize > 0);
     launch_shadow_trace(ctx->hp, ctx->shadowPathSize, ctx->stream);
     ctx->stats.kernel_launches += ctx->shadowPathSize > 0;
     ctx->stats.rays_shadow += ctx->shadowPathSize;
@@ -622,6 +715,7 @@ int dprt_secondary_trace(dprt_ctx* ctx) {
     if (!ctx->cfg.proxyMode) return fail(ctx, DPRT_ERR_STATE, "secondary stage needs proxyMode=1");
     sync_params(ctx);
     CK(cudaMemsetAsync(ctx->hp.queryHist, 0, 64 * sizeof(int32_t), ctx->stream));
+    StageScope sc_(ctx, DPRT_STAGE_SECONDARY_TRACE, ctx->pathSize > 0);
     launch_secondary_trace(ctx->hp, ctx->pathSize, ctx->stream);
     ctx->stats.kernel_launches += ctx->pathSize > 0;
     ctx->stats.rays_secondary += ctx->pathSize;
@@ -639,6 +733,7 @@ int dprt_bucket_queries(dprt_ctx* ctx, int which, int inside_only, int* total) {
     const int S = ctx->cfg.sceneSize;
     const int n = ctx->cfg.maxCount * (which == 0 ? ctx->shadowPathSize : ctx->pathSize);
     int32_t* hist = ctx->hp.queryHist + (inside_only ? S : 0);
+    StageScope sc_(ctx, DPRT_STAGE_BUCKET);
     if (!ctx->qhistFresh || ctx->queryWhich != which) {
         hist = ctx->d_hist + 96;
         launch_query_histogram(ctx->hp.nnQuery, n, S, inside_only ? 1 : 0, hist, ctx->stream);
@@ -662,6 +757,7 @@ int dprt_proxy_infer(dprt_ctx* ctx, int kind, int pred_offset) {
     const int S = ctx->cfg.sceneSize;
     if (pred_offset < 0 || (size_t)(pred_offset + ctx->queryTotal) * sizeof(dprt_half) > ctx->buf_bytes[DPRT_BUF_PRED])
         return fail(ctx, DPRT_ERR_CAPACITY, "prediction range outside predBuffer");
+    StageScope sc_(ctx, DPRT_STAGE_PROXY_MLP, ctx->queryTotal > 0);
     if (ctx->queryTotal > 0)
         CK(cudaMemsetAsync(ctx->hp.pred + pred_offset, 0, (size_t)ctx->queryTotal * sizeof(dprt_half), ctx->stream));
     for (int i = 0; i < S; i++) {
@@ -682,6 +778,7 @@ int dprt_frame_buffer_update(dprt_ctx* ctx) {
     if (!ctx) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     sync_params(ctx);
+    StageScope sc_(ctx, DPRT_STAGE_FRAME_UPDATE);
     launch_shadow_occlusion(ctx->hp, ctx->cfg.proxyMode ? ctx->queryTotal : 0, ctx->stream);
     launch_contribution(ctx->hp, ctx->stream);
     ctx->stats.kernel_launches += 1 + (ctx->queryTotal > 0);
@@ -692,6 +789,7 @@ int dprt_depth_buffer_update(dprt_ctx* ctx) {
     if (!ctx) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     sync_params(ctx);
+    StageScope sc_(ctx, DPRT_STAGE_DEPTH_UPDATE, ctx->queryTotal > 0);
     launch_depth_update(ctx->hp, ctx->queryTotal, ctx->stream);
     ctx->stats.kernel_launches += ctx->queryTotal > 0;
     ctx->qhistFresh = ctx->qhistFresh;   // normalizedT changes, keys do not
@@ -702,6 +800,7 @@ int dprt_target_node_update(dprt_ctx* ctx) {
     if (!ctx) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     sync_params(ctx);
+    StageScope sc_(ctx, DPRT_STAGE_TARGET_UPDATE);
     launch_tmax(ctx->hp, ctx->queryTotal, ctx->stream);
     launch_target_node(ctx->hp, ctx->pathSize, ctx->stream);
     ctx->stats.kernel_launches += (ctx->queryTotal > 0) + (ctx->pathSize > 0);
@@ -809,6 +908,7 @@ int dprt_reduce_image(dprt_ctx* ctx, int root, float* out_host) {
     if (!ctx) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     const int n3 = ctx->N * 3;
+    StageScope* sc_ = new StageScope(ctx, DPRT_STAGE_IMAGE);
     launch_image_average(ctx->hp.direct, ctx->hp.env, ctx->d_image, n3, (float)ctx->cfg.spp, ctx->stream);
     ctx->stats.kernel_launches += 1;
     const float* src = ctx->d_image;
@@ -817,6 +917,7 @@ int dprt_reduce_image(dprt_ctx* ctx, int root, float* out_host) {
         NK(g_nccl.Reduce(ctx->d_image, ctx->d_image_sum, n3, ncclFloat32, ncclSum, root, ctx->comm, ctx->stream));
         src = ctx->d_image_sum;
     }
+    delete sc_;
     if (ctx->rank == root && out_host)
         CK(cudaMemcpyAsync(out_host, src, sizeof(float) * n3, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -889,7 +990,9 @@ int dprt_enable_hit_prim(dprt_ctx* ctx, int enable) {
 int dprt_trace_closest_device(dprt_ctx* ctx, const void* rays_dev, int64_t n, void* hits_dev) {
     if (!ctx || !rays_dev || !hits_dev || n < 0) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    launch_trace_closest(ctx->d_objects, ctx->cfg.sceneSize, (const dprt_ray*)rays_dev, (dprt_hit*)hits_dev, n, ctx->stream);
+    StageScope sc_(ctx, DPRT_STAGE_TRACE_CLOSEST, n > 0);
+    launch_trace_closest(ctx->d_objects, ctx->cfg.sceneSize, (const dprt_ray*)rays_dev, (dprt_hit*)hits_dev, n, ctx->hp.counters,
+                         ctx->stream);
     ctx->stats.kernel_launches += n > 0;
     ctx->stats.rays_traverse += n;
     CK(cudaGetLastError());

@@ -55,6 +55,7 @@ struct DevParams {
     int32_t* queryHist;            // sceneSize counters (all queries), then sceneSize (inside only)
     dprt_half* pred;               // predBuffer
     int32_t* hitPrim;              // parity aid, may be null
+    unsigned long long* counters;  // instrumentation: {nodes, tris} per dprt_stage_id, null = off
 };
 
 // stage launches (all asynchronous on `stream`)
@@ -64,7 +65,7 @@ void launch_shade(const DevParams& p, int n, cudaStream_t stream);
 void launch_shadow_trace(const DevParams& p, int nShadow, cudaStream_t stream);
 void launch_secondary_trace(const DevParams& p, int n, cudaStream_t stream);
 void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ray* rays, dprt_hit* hits, int64_t n,
-                          cudaStream_t stream);
+                          unsigned long long* counters, cudaStream_t stream);
 
 // partition / bucketing (partition.cu)
 struct PartitionScratch {

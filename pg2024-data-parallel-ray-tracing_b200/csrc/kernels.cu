@@ -91,21 +91,32 @@ __global__ void __launch_bounds__(kBlock) path_gen_kernel(DevParams p, int n) {
 
 // ------------------------------------------------------------------------------------------------
 // closest hit over all local (non-proxy) objects; `skipVisited`: TraRay skips objects whose owner bit is set.
+template <bool COUNT>
 DPRT_D bool trace_local_closest(const DevParams& p, V3 o, V3 d, float tmin, float& tMax, uint32_t visitedMask,
-                                bool skipVisited, TraceHit& best, int& bestObj) {
+                                bool skipVisited, TraceHit& best, int& bestObj, TraceCount& cnt) {
     bool any = false;
     for (int i = 0; i < p.sceneSize; i++) {
         const DevObject& ob = p.objects[i];
         if (ob.isProxy) continue;
         if (skipVisited && ((visitedMask >> ob.nodeID) & 1u)) continue;
         TraceHit h;
-        if (bvh8_trace<false>(ob.nodes, ob.tris, o, d, tmin, tMax, h)) {
+        if (bvh8_trace<false, COUNT>(ob.nodes, ob.tris, o, d, tmin, tMax, h, cnt)) {
             tMax = h.t; best = h; bestObj = i; any = true;
         }
     }
     return any;
 }
 
+// instrumentation flush: per-thread atomics (the counting variants are not timed)
+template <bool COUNT>
+DPRT_D void flush_count(const DevParams& p, int stage, const TraceCount& c) {
+    if (COUNT) {
+        if (c.nodes) atomicAdd(p.counters + 2 * stage, (unsigned long long)c.nodes);
+        if (c.tris) atomicAdd(p.counters + 2 * stage + 1, (unsigned long long)c.tris);
+    }
+}
+
+template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) traverse_kernel(DevParams p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool outValid = false; int target = -1;
@@ -115,9 +126,11 @@ __global__ void __launch_bounds__(kBlock) traverse_kernel(DevParams p, int n) {
             const V3 o = path.origin, d = path.direction;
             TraceHit h; int hobj = -1; h.prim = -1;
             float tMax = path.tMax;
-            if (trace_local_closest(p, o, d, DPRT_EPSILON, tMax, path.visitedMask, true, h, hobj)) {
+            TraceCount cnt = {0u, 0u};
+            if (trace_local_closest<COUNT>(p, o, d, DPRT_EPSILON, tMax, path.visitedMask, true, h, hobj, cnt)) {
                 path.tMax = tMax; path.flags |= F_HIT; path.currentNode = p.worldID;
             }
+            flush_count<COUNT>(p, DPRT_STAGE_TRAVERSE, cnt);
             if (p.hitPrim) p.hitPrim[i] = h.prim;
             path.visitedMask |= (1u << p.worldID);
             // nearest unvisited proxy AABB within tMax decides the next owner (:280-314)
@@ -195,6 +208,7 @@ DPRT_D BsdfSample sample_water(float xi1, V3 normal, V3 woWorld, bool isInside) 
     return s;
 }
 
+template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) shade_kernel(DevParams p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -203,7 +217,9 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DevParams p, int n) {
     const V3 o = path.origin, d = path.direction;
 
     TraceHit h; int hobj = -1; float tMax = FLT_MAX;
-    const bool isHit = trace_local_closest(p, o, d, DPRT_EPSILON, tMax, 0u, false, h, hobj);
+    TraceCount cnt = {0u, 0u};
+    const bool isHit = trace_local_closest<COUNT>(p, o, d, DPRT_EPSILON, tMax, 0u, false, h, hobj, cnt);
+    flush_count<COUNT>(p, DPRT_STAGE_SHADE, cnt);
     if (p.hitPrim) p.hitPrim[i] = isHit ? h.prim : -1;
     if (!isHit) {
         // kernel.cu:416-423: environment light, path dies. The reference then writes an invalid record built
@@ -372,18 +388,21 @@ DPRT_D void flush_query_hist(const DevParams& p, const int* shHist) {
     else if (t >= 32 && t < 32 + p.sceneSize) { if (shHist[t]) atomicAdd(p.queryHist + p.sceneSize + (t - 32), shHist[t]); }
 }
 
+template <bool COUNT>
 DPRT_D void shadow_body(const DevParams& p, int i, int* shHist) {
     dprt_path_record* rec = p.paths + (size_t)p.pathSize + i;
     PathRegs path = load_path(rec);
     if (!(path.flags & F_VALID)) { clear_query_slots(p, i, 0); return; }
     // any local occluder within tMax kills the shadow path (:169-195)
     bool occluded = false;
+    TraceCount cnt = {0u, 0u};
     for (int k = 0; k < p.sceneSize && !occluded; k++) {
         const DevObject& ob = p.objects[k];
         if (ob.isProxy) continue;
         TraceHit h;
-        if (bvh8_trace<true>(ob.nodes, ob.tris, path.origin, path.direction, DPRT_EPSILON, path.tMax, h)) occluded = true;
+        if (bvh8_trace<true, COUNT>(ob.nodes, ob.tris, path.origin, path.direction, DPRT_EPSILON, path.tMax, h, cnt)) occluded = true;
     }
+    flush_count<COUNT>(p, DPRT_STAGE_SHADOW_TRACE, cnt);
     if (occluded) {
         path.flags |= F_HIT; path.flags &= ~F_VALID;
         reinterpret_cast<float4*>(rec)[3] = make_float4(__uint_as_float(path.visitedMask), __int_as_float(path.currentNode),
@@ -403,24 +422,28 @@ DPRT_D void shadow_body(const DevParams& p, int i, int* shHist) {
     }
 }
 
+template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) shadow_trace_kernel(DevParams p, int nShadow) {
     __shared__ int shHist[64];
     if (threadIdx.x < 64) shHist[threadIdx.x] = 0;
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nShadow) shadow_body(p, i, shHist);
+    if (i < nShadow) shadow_body<COUNT>(p, i, shHist);
     __syncthreads();
     flush_query_hist(p, shHist);
 }
 
+template <bool COUNT>
 DPRT_D void secondary_body(const DevParams& p, int i, int* shHist) {
     PathRegs path = load_path(p.paths + i);
     if (!(path.flags & F_VALID)) { clear_query_slots(p, i, 0); return; }
     for (int k = 0; k < p.sceneSize; k++) if (p.objects[k].isProxy != 2) path.visitedMask |= (1u << p.objects[k].nodeID);
     TraceHit h; int hobj = -1; float tMax = path.tMax;
-    if (trace_local_closest(p, path.origin, path.direction, DPRT_EPSILON, tMax, 0u, false, h, hobj)) {
+    TraceCount cnt = {0u, 0u};
+    if (trace_local_closest<COUNT>(p, path.origin, path.direction, DPRT_EPSILON, tMax, 0u, false, h, hobj, cnt)) {
         path.tMax = tMax; path.flags |= F_HIT; path.currentNode = p.worldID;
     }
+    flush_count<COUNT>(p, DPRT_STAGE_SECONDARY_TRACE, cnt);
     if (p.hitPrim) p.hitPrim[i] = hobj >= 0 ? h.prim : -1;
     const int r = proxy_march<true>(p, path, i, path.tMax, shHist);
     if (r < 0 && !(path.flags & F_HIT)) {
@@ -430,30 +453,37 @@ DPRT_D void secondary_body(const DevParams& p, int i, int* shHist) {
     store_path(p.paths + i, path);
 }
 
+template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) secondary_trace_kernel(DevParams p, int n) {
     __shared__ int shHist[64];
     if (threadIdx.x < 64) shHist[threadIdx.x] = 0;
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) secondary_body(p, i, shHist);
+    if (i < n) secondary_body<COUNT>(p, i, shHist);
     __syncthreads();
     flush_query_hist(p, shHist);
 }
 
 // ------------------------------------------------------------------------------------------------
+template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) trace_closest_kernel(const DevObject* objects, int sceneSize,
                                                                 const dprt_ray* __restrict__ rays, dprt_hit* __restrict__ hits,
-                                                                int64_t n) {
+                                                                int64_t n, unsigned long long* counters) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 a = reinterpret_cast<const float4*>(rays)[2 * i], b = reinterpret_cast<const float4*>(rays)[2 * i + 1];
     const V3 o = v3(a.x, a.y, a.z), d = v3(b.x, b.y, b.z);
     float tMax = b.w; int prim = -1;
+    TraceCount cnt = {0u, 0u};
     for (int k = 0; k < sceneSize; k++) {
         const DevObject& ob = objects[k];
         if (ob.isProxy) continue;
         TraceHit h;
-        if (bvh8_trace<false>(ob.nodes, ob.tris, o, d, a.w, tMax, h)) { tMax = h.t; prim = h.prim; }
+        if (bvh8_trace<false, COUNT>(ob.nodes, ob.tris, o, d, a.w, tMax, h, cnt)) { tMax = h.t; prim = h.prim; }
+    }
+    if (COUNT) {
+        atomicAdd(counters + 2 * DPRT_STAGE_TRACE_CLOSEST, (unsigned long long)cnt.nodes);
+        atomicAdd(counters + 2 * DPRT_STAGE_TRACE_CLOSEST + 1, (unsigned long long)cnt.tris);
     }
     reinterpret_cast<float2*>(hits)[i] = make_float2(tMax, __int_as_float(prim));
 }
@@ -466,20 +496,30 @@ void launch_path_gen(const DevParams& p, int n, cudaStream_t s) {
     if (n > 0) path_gen_kernel<<<blocks_for(n), kBlock, 0, s>>>(p, n);
 }
 void launch_traverse(const DevParams& p, int n, cudaStream_t s) {
-    if (n > 0) traverse_kernel<<<blocks_for(n), kBlock, 0, s>>>(p, n);
+    if (n <= 0) return;
+    if (p.counters) traverse_kernel<true><<<blocks_for(n), kBlock, 0, s>>>(p, n);
+    else traverse_kernel<false><<<blocks_for(n), kBlock, 0, s>>>(p, n);
 }
 void launch_shade(const DevParams& p, int n, cudaStream_t s) {
-    if (n > 0) shade_kernel<<<blocks_for(n), kBlock, 0, s>>>(p, n);
+    if (n <= 0) return;
+    if (p.counters) shade_kernel<true><<<blocks_for(n), kBlock, 0, s>>>(p, n);
+    else shade_kernel<false><<<blocks_for(n), kBlock, 0, s>>>(p, n);
 }
 void launch_shadow_trace(const DevParams& p, int nShadow, cudaStream_t s) {
-    if (nShadow > 0) shadow_trace_kernel<<<blocks_for(nShadow), kBlock, 0, s>>>(p, nShadow);
+    if (nShadow <= 0) return;
+    if (p.counters) shadow_trace_kernel<true><<<blocks_for(nShadow), kBlock, 0, s>>>(p, nShadow);
+    else shadow_trace_kernel<false><<<blocks_for(nShadow), kBlock, 0, s>>>(p, nShadow);
 }
 void launch_secondary_trace(const DevParams& p, int n, cudaStream_t s) {
-    if (n > 0) secondary_trace_kernel<<<blocks_for(n), kBlock, 0, s>>>(p, n);
+    if (n <= 0) return;
+    if (p.counters) secondary_trace_kernel<true><<<blocks_for(n), kBlock, 0, s>>>(p, n);
+    else secondary_trace_kernel<false><<<blocks_for(n), kBlock, 0, s>>>(p, n);
 }
 void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ray* rays, dprt_hit* hits, int64_t n,
-                          cudaStream_t s) {
-    if (n > 0) trace_closest_kernel<<<blocks_for(n), kBlock, 0, s>>>(objects, sceneSize, rays, hits, n);
+                          unsigned long long* counters, cudaStream_t s) {
+    if (n <= 0) return;
+    if (counters) trace_closest_kernel<true><<<blocks_for(n), kBlock, 0, s>>>(objects, sceneSize, rays, hits, n, counters);
+    else trace_closest_kernel<false><<<blocks_for(n), kBlock, 0, s>>>(objects, sceneSize, rays, hits, n, nullptr);
 }
 
 }  // namespace dprt

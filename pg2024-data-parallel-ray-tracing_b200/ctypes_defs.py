@@ -60,6 +60,11 @@ assert C.sizeof(Config) == 64 and C.sizeof(ObjectDesc) == 84 and C.sizeof(Camera
 BUF_PATHS, BUF_TRANSFER, BUF_TRANSFER_OFFSET, BUF_DIRECT, BUF_ENV, BUF_NN_INPUT, BUF_NN_QUERY, BUF_NN_PACKED_INPUT, \
     BUF_NN_PACKED_QUERY, BUF_SCENE_OFFSET, BUF_PRED, BUF_OCCLUSION, BUF_CONTRIBUTION, BUF_HIT_PRIM = range(14)
 
+# dprt_stage_id
+STAGE_NAMES = ("path_gen", "traverse", "partition", "exchange", "shade", "shadow_trace", "secondary_trace", "bucket",
+               "proxy_mlp", "frame_update", "depth_update", "target_update", "image", "trace_closest")
+STAGE_COUNT = len(STAGE_NAMES)
+
 BUFFER_DTYPES = {
     BUF_PATHS: PATH_DTYPE, BUF_TRANSFER: PATH_DTYPE, BUF_TRANSFER_OFFSET: np.dtype("<i4"), BUF_DIRECT: np.dtype("<f4"),
     BUF_ENV: np.dtype("<f4"), BUF_NN_INPUT: np.dtype("<u2"), BUF_NN_QUERY: QUERY_DTYPE, BUF_NN_PACKED_INPUT: np.dtype("<u2"),

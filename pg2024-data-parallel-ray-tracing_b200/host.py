@@ -75,6 +75,10 @@ _PROTOTYPES = {
     "dprt_timer_start": (C.c_int, [C.c_void_p]),
     "dprt_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "dprt_flush_l2": (C.c_int, [C.c_void_p]),
+    "dprt_stage_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "dprt_get_stage_times": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dprt_enable_counters": (C.c_int, [C.c_void_p, C.c_int]),
+    "dprt_get_counters": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
@@ -359,6 +363,25 @@ class Renderer:
 
     def flush_l2(self):
         self._ck(self.lib.dprt_flush_l2(self.h), "dprt_flush_l2")
+
+    def stage_profile(self, enable=True):
+        self._ck(self.lib.dprt_stage_profile(self.h, int(enable)), "dprt_stage_profile")
+
+    def stage_times(self):
+        """{stage name: (device ms, launches)} accumulated since the last reset_stats()."""
+        ms = np.zeros(D.STAGE_COUNT, np.float64)
+        ln = np.zeros(D.STAGE_COUNT, np.int64)
+        self._ck(self.lib.dprt_get_stage_times(self.h, _ptr(ms), _ptr(ln)), "dprt_get_stage_times")
+        return {D.STAGE_NAMES[i]: (float(ms[i]), int(ln[i])) for i in range(D.STAGE_COUNT)}
+
+    def enable_counters(self, enable=True):
+        self._ck(self.lib.dprt_enable_counters(self.h, int(enable)), "dprt_enable_counters")
+
+    def counters(self):
+        """{stage name: (bvh8 nodes visited, triangles tested)} of the instrumented traversal variants."""
+        c = np.zeros(2 * D.STAGE_COUNT, np.uint64)
+        self._ck(self.lib.dprt_get_counters(self.h, _ptr(c)), "dprt_get_counters")
+        return {D.STAGE_NAMES[i]: (int(c[2 * i]), int(c[2 * i + 1])) for i in range(D.STAGE_COUNT)}
 
 
 class RankGroup:
