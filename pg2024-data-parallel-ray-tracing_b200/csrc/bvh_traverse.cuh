@@ -1,20 +1,14 @@
-// bvh_traverse.cuh -- per-thread traversal of the 80-byte compressed 8-wide BVH (device).
+// bvh_traverse.cuh -- traversal of the 80-byte compressed 8-wide BVH as a resumable per-lane state machine.
 //
 // This is what replaces optixTrace() (call sites: optix/kernel.cu:394, distributed_traversal_kernel.cu:245,
-// shadow_ray_kernel.cu:177, secondary_ray_kernel.cu:200). Closest-hit results are independent of the BVH:
-// every candidate triangle goes through the watertight test of dprt_math.cuh and ties in t resolve to the
-// lower primitive id, so any conservative traversal order yields the same (t, primID).
+// shadow_ray_kernel.cu:177, secondary_ray_kernel.cu:200). Closest-hit results are independent of the BVH and
+// of the traversal order: every candidate triangle goes through the watertight test of dprt_math.cuh and ties
+// in t resolve to the lower primitive id. That freedom is what lets kernels.cu run the traversal as a
+// persistent wavefront in which a lane that finishes its ray immediately picks up the next one.
 #pragma once
 #include "dprt_math.cuh"
 
 namespace dprt {
-
-struct TraceHit {
-    float t;        // closest accepted t (tmax when nothing was hit)
-    int   prim;     // original primitive id, -1 = none
-    int   tri;      // index into the leaf-ordered triangle array
-    float alpha, beta;
-};
 
 DPRT_D float q2f(uint32_t w, uint32_t sel) {
     // byte `sel & 3` of w -> float, via the 2^23 mantissa trick (exact for 0..255)
@@ -26,106 +20,189 @@ DPRT_D float q2f(uint32_t w, uint32_t sel) {
 // instrumentation (dprt_enable_counters): BVH8 nodes fetched and triangles tested by one thread
 struct TraceCount { uint32_t nodes, tris; };
 
-// ANY = true: return as soon as one triangle is hit in (tmin, tmax) (shadow rays).
-template <bool ANY, bool COUNT>
-DPRT_D bool bvh8_trace(const uint4* __restrict__ nodes, const float4* __restrict__ tris,
-                       V3 o, V3 d, float tmin, float tmax, TraceHit& hit, TraceCount& cnt) {
-    const RayShear rs = ray_shear(d);
+struct Trav {
+    // ray
+    V3 o, d; float tmin;
+    float idx, idy, idz;            // reciprocal direction (zero components nudged to +-1e-20)
+    uint32_t octinv;                // 7 - octant
+    // result so far (over all objects traced for this ray)
+    float tbest;                    // closest accepted t; starts at the ray's tmax
+    int   hitPrim, hitTri, hitObj;  // hitTri < 0: nothing yet
+    float ha, hb;                   // barycentrics of the best hit (weights of v1, v2)
+    // current object
+    float tlimit;                   // strict upper bound for this object = tbest when the object was entered
+    int   tiePrim;                  // lowest primitive id among this object's hits at tbest
+    const uint4* nodes; const float4* tris;
+    uint2 ng;                       // node group: child base, hit bits of internal children | imask
+    uint2 tg;                       // pending triangle group: triangle base, leaf-triangle bits
+    int sp;
+};   // the traversal stack (uint2[DPRT_STACK]) is a separate local array so that this struct stays in registers
+
+DPRT_D void trav_init_ray(Trav& s, V3 o, V3 d, float tmin, float tmax) {
+    s.o = o; s.d = d; s.tmin = tmin;
     const float dxs = fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x);
     const float dys = fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y);
     const float dzs = fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z);
-    const float idx = 1.0f / dxs, idy = 1.0f / dys, idz = 1.0f / dzs;
-    const bool nx = dxs < 0.0f, ny = dys < 0.0f, nz = dzs < 0.0f;
-    const uint32_t octinv = 7u - ((nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u));
+    s.idx = 1.0f / dxs; s.idy = 1.0f / dys; s.idz = 1.0f / dzs;
+    s.octinv = 7u - ((dxs < 0.0f ? 1u : 0u) | (dys < 0.0f ? 2u : 0u) | (dzs < 0.0f ? 4u : 0u));
+    s.tbest = tmax; s.hitPrim = -1; s.hitTri = -1; s.hitObj = -1; s.ha = 0.f; s.hb = 0.f;
+    s.ng = make_uint2(0u, 0u); s.tg = make_uint2(0u, 0u); s.sp = 0;      // no object entered yet: no work of either kind
+}
 
-    float tbest = tmax; int bestPrim = 0x7fffffff; int bestTri = -1; float ba = 0.f, bb = 0.f;
+DPRT_D void trav_enter_object(Trav& s, const uint4* nodes, const float4* tris) {
+    s.nodes = nodes; s.tris = tris;
+    s.tlimit = s.tbest; s.tiePrim = 0x7fffffff;
+    s.ng = make_uint2(0u, 0x80000000u); s.tg = make_uint2(0u, 0u); s.sp = 0;
+}
 
-    uint2 stack[DPRT_STACK];
-    int sp = 0;
-    uint2 ng = make_uint2(0u, 0x80000000u);
+// The traversal is split in two phases. trav_node expands one node (8 child slabs) for the calling lane and
+// leaves the leaf triangles it found in s.tg. Triangles are NOT tested by the lane that found them: the lanes of
+// a warp append their (owner lane, triangle) pairs to a warp-wide queue in shared memory and, once 32 pairs are
+// waiting, the whole warp tests 32 of them at once (tri_round), whichever rays they belong to. Node expansion
+// runs with nearly all lanes busy and triangle tests run 32 wide, instead of 3-4 lanes wide when every lane
+// tests its own leaf. tbest of a lane lags by the queueing delay, which only makes node culling conservative.
+template <bool COUNT>
+DPRT_D void trav_node(Trav& s, uint2* stack, TraceCount& cnt) {
+    const uint32_t octinv = s.octinv;
+    const uint32_t bit = 31u - __clz(s.ng.y);
+    const uint32_t slot = (bit - 24u) ^ octinv;
+    const uint32_t rel = __popc(s.ng.y & 0xffu & ((1u << slot) - 1u));
+    s.ng.y &= ~(1u << bit);
+    const uint32_t ni = s.ng.x + rel;
+    if (s.ng.y & 0xff000000u) { if (s.sp < DPRT_STACK) stack[s.sp++] = s.ng; }
+    if (COUNT) cnt.nodes++;
 
-    for (;;) {
-        uint2 tg = make_uint2(0u, 0u);
-        if (ng.y & 0xff000000u) {
-            const uint32_t bit = 31u - __clz(ng.y);
-            const uint32_t slot = (bit - 24u) ^ octinv;
-            const uint32_t rel = __popc(ng.y & 0xffu & ((1u << slot) - 1u));
-            ng.y &= ~(1u << bit);
-            const uint32_t ni = ng.x + rel;
-            if (ng.y & 0xff000000u) { if (sp < DPRT_STACK) stack[sp++] = ng; }
+    const uint4* np = s.nodes + 5 * (size_t)ni;
+    const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+    const bool nx = !(octinv & 1u), ny = !(octinv & 2u), nz = !(octinv & 4u);
 
-            if (COUNT) cnt.nodes++;
-            const uint4 n0 = __ldg(nodes + 5 * (size_t)ni + 0);
-            const uint4 n1 = __ldg(nodes + 5 * (size_t)ni + 1);
-            const uint4 n2 = __ldg(nodes + 5 * (size_t)ni + 2);
-            const uint4 n3 = __ldg(nodes + 5 * (size_t)ni + 3);
-            const uint4 n4 = __ldg(nodes + 5 * (size_t)ni + 4);
+    const float adjx = __uint_as_float((n0.w & 0xffu) << 23) * s.idx;
+    const float adjy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * s.idy;
+    const float adjz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * s.idz;
+    const float orgx = (__uint_as_float(n0.x) - s.o.x) * s.idx;
+    const float orgy = (__uint_as_float(n0.y) - s.o.y) * s.idy;
+    const float orgz = (__uint_as_float(n0.z) - s.o.z) * s.idz;
+    const float tmin = s.tmin, tbest = s.tbest;
 
-            const float adjx = __uint_as_float((n0.w & 0xffu) << 23) * idx;
-            const float adjy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * idy;
-            const float adjz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * idz;
-            const float orgx = (__uint_as_float(n0.x) - o.x) * idx;
-            const float orgy = (__uint_as_float(n0.y) - o.y) * idy;
-            const float orgz = (__uint_as_float(n0.z) - o.z) * idz;
-
-            uint32_t hitmask = 0;
+    uint32_t hitmask = 0;
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint32_t meta4 = h ? n1.w : n1.z;
-                const uint32_t lox = h ? (nx ? n3.w : n2.y) : (nx ? n3.z : n2.x);
-                const uint32_t hix = h ? (nx ? n2.y : n3.w) : (nx ? n2.x : n3.z);
-                const uint32_t loy = h ? (ny ? n4.y : n2.w) : (ny ? n4.x : n2.z);
-                const uint32_t hiy = h ? (ny ? n2.w : n4.y) : (ny ? n2.z : n4.x);
-                const uint32_t loz = h ? (nz ? n4.w : n3.y) : (nz ? n4.z : n3.x);
-                const uint32_t hiz = h ? (nz ? n3.y : n4.w) : (nz ? n3.x : n4.z);
+    for (int h = 0; h < 2; h++) {
+        const uint32_t meta4 = h ? n1.w : n1.z;
+        const uint32_t lox = h ? (nx ? n3.w : n2.y) : (nx ? n3.z : n2.x);
+        const uint32_t hix = h ? (nx ? n2.y : n3.w) : (nx ? n2.x : n3.z);
+        const uint32_t loy = h ? (ny ? n4.y : n2.w) : (ny ? n4.x : n2.z);
+        const uint32_t hiy = h ? (ny ? n2.w : n4.y) : (ny ? n2.z : n4.x);
+        const uint32_t loz = h ? (nz ? n4.w : n3.y) : (nz ? n4.z : n3.x);
+        const uint32_t hiz = h ? (nz ? n3.y : n4.w) : (nz ? n3.x : n4.z);
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t sel = 0x7650u | (uint32_t)j;
-                    const float tnx = fmaf(q2f(lox, sel), adjx, orgx);
-                    const float tny = fmaf(q2f(loy, sel), adjy, orgy);
-                    const float tnz = fmaf(q2f(loz, sel), adjz, orgz);
-                    const float tfx = fmaf(q2f(hix, sel), adjx, orgx);
-                    const float tfy = fmaf(q2f(hiy, sel), adjy, orgy);
-                    const float tfz = fmaf(q2f(hiz, sel), adjz, orgz);
-                    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-                    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
-                    if (tn <= tf) {
-                        const uint32_t meta = (meta4 >> (8 * j)) & 0xffu;
-                        const uint32_t inner = ((meta & 0x18u) == 0x18u) ? octinv : 0u;
-                        const uint32_t bidx = (meta ^ inner) & 31u;
-                        hitmask |= (meta >> 5) << bidx;
-                    }
-                }
-            }
-            ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
-            tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
-        }
-
-        while (tg.y) {
-            const uint32_t k = __ffs(tg.y) - 1u;
-            tg.y &= tg.y - 1u;
-            const uint32_t ti = tg.x + k;
-            if (COUNT) cnt.tris++;
-            const float4 a = __ldg(tris + 3 * (size_t)ti + 0);
-            const float4 b = __ldg(tris + 3 * (size_t)ti + 1);
-            const float4 c = __ldg(tris + 3 * (size_t)ti + 2);
-            float t, al, be;
-            if (tri_intersect(rs, o, v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), tmin, tmax, &t, &al, &be)) {
-                if (ANY) { hit.t = t; hit.prim = __float_as_int(a.w); hit.tri = (int)ti; hit.alpha = al; hit.beta = be; return true; }
-                const int prim = __float_as_int(a.w);
-                if (t < tbest || (t == tbest && prim < bestPrim)) {
-                    tbest = t; bestPrim = prim; bestTri = (int)ti; ba = al; bb = be;
-                }
-            }
-        }
-
-        if ((ng.y & 0xff000000u) == 0u) {
-            if (sp == 0) break;
-            ng = stack[--sp];
+        for (int j = 0; j < 4; j++) {
+            const uint32_t sel = 0x7650u | (uint32_t)j;
+            const float tnx = fmaf(q2f(lox, sel), adjx, orgx);
+            const float tny = fmaf(q2f(loy, sel), adjy, orgy);
+            const float tnz = fmaf(q2f(loz, sel), adjz, orgz);
+            const float tfx = fmaf(q2f(hix, sel), adjx, orgx);
+            const float tfy = fmaf(q2f(hiy, sel), adjy, orgy);
+            const float tfz = fmaf(q2f(hiz, sel), adjz, orgz);
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
+            // branch-free: child bits are computed for every slot and masked by the slab test
+            const uint32_t meta = (meta4 >> (8 * j)) & 0xffu;
+            const uint32_t inner = ((meta & 0x18u) == 0x18u) ? octinv : 0u;
+            const uint32_t bidx = (meta ^ inner) & 31u;
+            const uint32_t bits = (meta >> 5) << bidx;
+            hitmask |= (tn <= tf) ? bits : 0u;
         }
     }
-    hit.t = tbest; hit.prim = bestTri >= 0 ? bestPrim : -1; hit.tri = bestTri; hit.alpha = ba; hit.beta = bb;
-    return bestTri >= 0;
+    s.ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
+    s.tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
+}
+
+// ---- warp-wide triangle queue -----------------------------------------------------------------------
+#define DPRT_QCAP 128                      // queue capacity per warp (pairs)
+#define DPRT_TRI_BITS 27                   // queue entry = owner lane << 27 | triangle index
+
+struct WarpQueue {
+    float4 rayA[32];                       // per owner lane: origin.xyz, tmin
+    float4 rayB[32];                       // Sx, Sy, Sz, bits(kx | ky << 2 | kz << 4)
+    float4 aux[32];                        // winner of a round: bits(tri index), alpha, beta, -
+    unsigned long long key[32];            // min over a round of (bits(t) << 32 | prim); ~0 = no hit
+    const float4* tris[32];                // triangle array of the owner's current object
+    float  tlimit[32];                     // strict upper bound for the owner's current object
+    int    cnt[32];                        // pairs of this owner tested in the round
+    uint32_t q[DPRT_QCAP];
+};
+
+DPRT_D void wq_set_ray(WarpQueue& w, int lane, const Trav& s) {
+    w.rayA[lane] = make_float4(s.o.x, s.o.y, s.o.z, s.tmin);
+    const RayShear rs = ray_shear(s.d);
+    w.rayB[lane] = make_float4(rs.Sx, rs.Sy, rs.Sz, __uint_as_float((uint32_t)(rs.kx | (rs.ky << 2) | (rs.kz << 4))));
+    w.key[lane] = ~0ull; w.cnt[lane] = 0;
+}
+DPRT_D void wq_set_object(WarpQueue& w, int lane, const Trav& s) { w.tris[lane] = s.tris; w.tlimit[lane] = s.tlimit; }
+
+// Appends the pending triangles of all lanes (s.tg) to the queue, as far as they fit. Warp-synchronous.
+DPRT_D void wq_append(WarpQueue& w, int& qlen, int lane, bool busy, Trav& s, int& pend) {
+    const unsigned FULL = 0xffffffffu;
+    const int c = busy ? __popc(s.tg.y) : 0;
+    if (__ballot_sync(FULL, c > 0) == 0u) return;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(FULL, incl, 31);
+    int pos = qlen + incl - c;
+    while (s.tg.y != 0u && busy && pos < DPRT_QCAP) {
+        const uint32_t k = __ffs(s.tg.y) - 1u;
+        s.tg.y &= s.tg.y - 1u;
+        w.q[pos++] = ((uint32_t)lane << DPRT_TRI_BITS) | (s.tg.x + k);
+        pend++;
+    }
+    qlen = min(DPRT_QCAP, qlen + total);
+}
+
+// Tests the last min(32, qlen) pairs of the queue with all lanes and hands the closest accepted hit of each owner
+// back to it. ANY: the owner keeps the first accepted hit. Warp-synchronous; every lane of the warp must call it.
+template <bool ANY, bool COUNT>
+DPRT_D void tri_round(WarpQueue& w, int& qlen, int lane, Trav& s, int obj, int& pend, TraceCount& cnt) {
+    __syncwarp();
+    const int n = min(32, qlen);
+    const bool valid = lane < n;
+    const int e = qlen - n + lane;
+    qlen -= n;
+    unsigned long long key = ~0ull; int owner = 0; uint32_t ti = 0u; float al = 0.f, be = 0.f;
+    if (valid) {
+        const uint32_t ent = w.q[e];
+        owner = (int)(ent >> DPRT_TRI_BITS); ti = ent & ((1u << DPRT_TRI_BITS) - 1u);
+        const float4 ra = w.rayA[owner], rb = w.rayB[owner];
+        const float4* tp = w.tris[owner] + 3 * (size_t)ti;
+        const float4 a = __ldg(tp + 0), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        RayShear rs; const uint32_t kp = __float_as_uint(rb.w);
+        rs.kx = (int)(kp & 3u); rs.ky = (int)((kp >> 2) & 3u); rs.kz = (int)((kp >> 4) & 3u); rs.Sx = rb.x; rs.Sy = rb.y; rs.Sz = rb.z;
+        if (COUNT) cnt.tris++;
+        float t;
+        if (tri_intersect(rs, v3(ra.x, ra.y, ra.z), v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), ra.w, w.tlimit[owner], &t, &al, &be)) {
+            key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(uint32_t)__float_as_int(a.w);
+            atomicMin(&w.key[owner], key);
+        }
+        atomicAdd(&w.cnt[owner], 1);
+    }
+    __syncwarp();
+    if (valid && key != ~0ull && w.key[owner] == key) w.aux[owner] = make_float4(__uint_as_float(ti), al, be, 0.f);
+    __syncwarp();
+    const int mine = w.cnt[lane];
+    if (mine) {
+        pend -= mine; w.cnt[lane] = 0;
+        const unsigned long long k = w.key[lane];
+        if (k != ~0ull) {
+            w.key[lane] = ~0ull;
+            const float t = __uint_as_float((uint32_t)(k >> 32)); const int prim = (int)(uint32_t)k;
+            const bool take = ANY ? (s.hitTri < 0) : (t < s.tbest || (t == s.tbest && prim < s.tiePrim));
+            if (take) {
+                const float4 x = w.aux[lane];
+                s.tbest = t; s.tiePrim = prim; s.hitPrim = prim; s.hitTri = (int)__float_as_uint(x.x); s.hitObj = obj; s.ha = x.y; s.hb = x.z;
+            }
+        }
+    }
+    __syncwarp();
 }
 
 }  // namespace dprt

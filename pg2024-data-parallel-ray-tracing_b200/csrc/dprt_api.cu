@@ -92,6 +92,8 @@ struct dprt_ctx {
     void* buf_ptr[DPRT_BUF_COUNT] = {nullptr};
     int32_t* d_hist = nullptr;          // 32 path + 64 query counters
     PartitionScratch scratch{};
+    HitRec* d_hits = nullptr;           // N closest-hit records (MainRay)
+    int32_t* d_queue = nullptr;         // ray queue head of the persistent trace kernel
     float* d_image = nullptr;           // averaged image, 3N
     float* d_image_sum = nullptr;       // reduce target, 3N
     int32_t* d_gather = nullptr;        // W*(W+1) offsets of all ranks
@@ -295,6 +297,8 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
         ctx->scratch.maxTiles = (int)((std::max(Q, N) + 1023) / 1024) + 1;
         CK(cudaMalloc(&ctx->scratch.tileState, (size_t)ctx->scratch.maxTiles * 32 * sizeof(uint32_t)));
         CK(cudaMalloc(&ctx->scratch.tileCounter, sizeof(int32_t)));
+        CK(cudaMalloc(&ctx->d_hits, N * sizeof(HitRec)));
+        CK(cudaMalloc(&ctx->d_queue, 64));
         CK(cudaMalloc(&ctx->d_image, 3 * N * sizeof(float)));
         CK(cudaMalloc(&ctx->d_image_sum, 3 * N * sizeof(float)));
         CK(cudaMalloc(&ctx->d_gather, sizeof(int32_t) * (size_t)world * (world + 1)));
@@ -313,6 +317,7 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
         p.sceneOffset = (int32_t*)ctx->buf_ptr[DPRT_BUF_SCENE_OFFSET];
         p.pred = (dprt_half*)ctx->buf_ptr[DPRT_BUF_PRED];
         p.hitPrim = nullptr; p.counters = nullptr;
+        p.hits = ctx->d_hits; p.traceQueue = ctx->d_queue;
         p.camera.width = cfg->width; p.camera.height = cfg->height;
         p.lightCount = 0;
         sync_params(ctx);
@@ -354,6 +359,8 @@ void dprt_destroy(dprt_ctx* ctx) {
     if (ctx->d_hist) cudaFree(ctx->d_hist);
     if (ctx->scratch.tileState) cudaFree(ctx->scratch.tileState);
     if (ctx->scratch.tileCounter) cudaFree(ctx->scratch.tileCounter);
+    if (ctx->d_hits) cudaFree(ctx->d_hits);
+    if (ctx->d_queue) cudaFree(ctx->d_queue);
     if (ctx->d_image) cudaFree(ctx->d_image);
     if (ctx->d_image_sum) cudaFree(ctx->d_image_sum);
     if (ctx->d_gather) cudaFree(ctx->d_gather);
@@ -551,7 +558,7 @@ int dprt_traverse(dprt_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->hp.pathHist, 0, 32 * sizeof(int32_t), ctx->stream));
     StageScope sc_(ctx, DPRT_STAGE_TRAVERSE, ctx->pathSize > 0);
     launch_traverse(ctx->hp, ctx->pathSize, ctx->stream);
-    ctx->stats.kernel_launches += ctx->pathSize > 0;
+    ctx->stats.kernel_launches += 2 * (ctx->pathSize > 0);
     ctx->stats.rays_traverse += ctx->pathSize;
     ctx->histFresh = true;
     CK(cudaGetLastError());
@@ -673,7 +680,7 @@ int dprt_shade(dprt_ctx* ctx) {
     sync_params(ctx);
     StageScope sc_(ctx, DPRT_STAGE_SHADE, ctx->pathSize > 0);
     launch_shade(ctx->hp, ctx->pathSize, ctx->stream);
-    ctx->stats.kernel_launches += ctx->pathSize > 0;
+    ctx->stats.kernel_launches += 2 * (ctx->pathSize > 0);
     ctx->stats.rays_shade += ctx->pathSize;
     ctx->histFresh = false;
     CK(cudaGetLastError());
@@ -702,7 +709,7 @@ int dprt_shadow_trace(dprt_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->hp.queryHist, 0, 64 * sizeof(int32_t), ctx->stream));
     StageScope sc_(ctx, DPRT_STAGE_SHADOW_TRACE, ctx->shadowPathSize > 0);
     launch_shadow_trace(ctx->hp, ctx->shadowPathSize, ctx->stream);
-    ctx->stats.kernel_launches += ctx->shadowPathSize > 0;
+    ctx->stats.kernel_launches += 2 * (ctx->shadowPathSize > 0);
     ctx->stats.rays_shadow += ctx->shadowPathSize;
     ctx->qhistFresh = true; ctx->queryWhich = 0;
     CK(cudaGetLastError());
@@ -717,7 +724,7 @@ int dprt_secondary_trace(dprt_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->hp.queryHist, 0, 64 * sizeof(int32_t), ctx->stream));
     StageScope sc_(ctx, DPRT_STAGE_SECONDARY_TRACE, ctx->pathSize > 0);
     launch_secondary_trace(ctx->hp, ctx->pathSize, ctx->stream);
-    ctx->stats.kernel_launches += ctx->pathSize > 0;
+    ctx->stats.kernel_launches += 2 * (ctx->pathSize > 0);
     ctx->stats.rays_secondary += ctx->pathSize;
     ctx->qhistFresh = true; ctx->queryWhich = 1;
     ctx->histFresh = false;
@@ -991,8 +998,8 @@ int dprt_trace_closest_device(dprt_ctx* ctx, const void* rays_dev, int64_t n, vo
     if (!ctx || !rays_dev || !hits_dev || n < 0) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     StageScope sc_(ctx, DPRT_STAGE_TRACE_CLOSEST, n > 0);
-    launch_trace_closest(ctx->d_objects, ctx->cfg.sceneSize, (const dprt_ray*)rays_dev, (dprt_hit*)hits_dev, n, ctx->hp.counters,
-                         ctx->stream);
+    launch_trace_closest(ctx->d_objects, ctx->cfg.sceneSize, (const dprt_ray*)rays_dev, (dprt_hit*)hits_dev, n, ctx->d_queue,
+                         ctx->hp.counters, ctx->stream);
     ctx->stats.kernel_launches += n > 0;
     ctx->stats.rays_traverse += n;
     CK(cudaGetLastError());

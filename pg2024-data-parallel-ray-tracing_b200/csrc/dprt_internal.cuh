@@ -19,6 +19,15 @@ struct DevObject {                 // AccelerationStructure (renderer.cpp:1812-1
     const float*  normals;         // 9 floats per original triangle (vertex normals), may be null
 };
 
+struct HitRec {                    // closest-hit result handed from the trace to the shading program (32 bytes)
+    float   t;
+    int32_t prim;                  // original primitive id, -1 = miss
+    int32_t tri;                   // index into the leaf-ordered triangle array, -1 = miss
+    int32_t obj;                   // scene index of the object that was hit
+    float   alpha, beta;           // barycentric weights of v1, v2
+    int32_t pad_[2];
+};
+
 struct DevParams {
     int32_t pathSize;
     int32_t shadowPathSize;
@@ -56,6 +65,8 @@ struct DevParams {
     dprt_half* pred;               // predBuffer
     int32_t* hitPrim;              // parity aid, may be null
     unsigned long long* counters;  // instrumentation: {nodes, tris} per dprt_stage_id, null = off
+    HitRec*  hits;                 // N closest-hit records (MainRay trace -> shading program)
+    int32_t* traceQueue;           // head of the persistent trace kernel's ray queue
 };
 
 // stage launches (all asynchronous on `stream`)
@@ -65,7 +76,7 @@ void launch_shade(const DevParams& p, int n, cudaStream_t stream);
 void launch_shadow_trace(const DevParams& p, int nShadow, cudaStream_t stream);
 void launch_secondary_trace(const DevParams& p, int n, cudaStream_t stream);
 void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ray* rays, dprt_hit* hits, int64_t n,
-                          unsigned long long* counters, cudaStream_t stream);
+                          int32_t* queue, unsigned long long* counters, cudaStream_t stream);
 
 // partition / bucketing (partition.cu)
 struct PartitionScratch {

@@ -1,15 +1,20 @@
 // kernels.cu -- the ray-tracing stage kernels of the per-bounce loop (sm_100a).
 //
-//   path_gen_kernel        <- optix/path_gen_kernel.cu:46-105           (PathGen raygen)
-//   traverse_kernel        <- optix/distributed_traversal_kernel.cu:215-340 (TraRay raygen + ch/ms)
-//   shade_kernel           <- optix/kernel.cu:362-466 + closest hit :171-300 (MainRay)
-//   shadow_trace_kernel    <- optix/shadow_ray_kernel.cu:150-355        (ShadowRay)
-//   secondary_trace_kernel <- optix/secondary_ray_kernel.cu:172-369     (SecondaryRay)
-//   trace_closest_kernel   <- a bare optixTrace closest-hit launch (BASELINE config 2)
+//   path_gen_kernel                 <- optix/path_gen_kernel.cu:46-105              (PathGen raygen)
+//   trace_kernel<TM_TRAVERSE>  + traverse_post_kernel   <- optix/distributed_traversal_kernel.cu:215-340 (TraRay)
+//   trace_kernel<TM_SHADE>     + shade_post_kernel      <- optix/kernel.cu:362-466 + closest hit :171-300 (MainRay)
+//   trace_kernel<TM_SHADOW>    + shadow_post_kernel     <- optix/shadow_ray_kernel.cu:150-355            (ShadowRay)
+//   trace_kernel<TM_SECONDARY> + secondary_post_kernel  <- optix/secondary_ray_kernel.cu:172-369         (SecondaryRay)
+//   trace_kernel<TM_RAYS>           <- a bare optixTrace closest-hit launch (BASELINE config 2)
 //
-// One thread per path; rays walk a compressed BVH8 per local scene object (bvh_traverse.cuh).
+// Every stage is split the way the hardware wants it: the optixTrace part runs in ONE persistent wavefront
+// kernel (trace_kernel) whose warps pull rays from a global queue and refill lanes as soon as their ray is done
+// (rays of very different length share a warp without idling it), and the per-path program around the trace
+// (routing, shading, proxy march) runs as a fully coherent one-thread-per-path kernel over the same records.
 // Compiled with --fmad=false: the arithmetic is the specification in dprt_math.cuh.
 #include "dprt_internal.cuh"
+#include <algorithm>
+#include <cstdlib>
 #include "bvh_traverse.cuh"
 
 namespace dprt {
@@ -90,50 +95,200 @@ __global__ void __launch_bounds__(kBlock) path_gen_kernel(DevParams p, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// closest hit over all local (non-proxy) objects; `skipVisited`: TraRay skips objects whose owner bit is set.
-template <bool COUNT>
-DPRT_D bool trace_local_closest(const DevParams& p, V3 o, V3 d, float tmin, float& tMax, uint32_t visitedMask,
-                                bool skipVisited, TraceHit& best, int& bestObj, TraceCount& cnt) {
-    bool any = false;
-    for (int i = 0; i < p.sceneSize; i++) {
-        const DevObject& ob = p.objects[i];
+// ================================================================================================
+// Persistent wavefront trace.
+//
+// begin(i): read what the ray needs from record i (48 of its 64 bytes) and enter the first local object.
+// step:     bvh_traverse.cuh, until the last local object is exhausted (closest hit) or a triangle is accepted (any hit).
+// end(i):   write the few words the stage needs (tMax/currentNode/isHit, or a 32-byte hit record for shading).
+// A warp refills its idle lanes from the queue whenever at least kRefill of them are idle.
+enum TraceMode { TM_TRAVERSE = 0, TM_SHADE = 1, TM_SHADOW = 2, TM_SECONDARY = 3, TM_RAYS = 4 };
+
+constexpr int kTraceBlock = 128;
+constexpr int kTraceBlocksPerSM = 6;
+constexpr int kRefillDefault = 8;
+constexpr int kTriVoteDefault = 8;
+
+template <int MODE> struct StageOf;
+template <> struct StageOf<TM_TRAVERSE> { static constexpr int id = DPRT_STAGE_TRAVERSE; };
+template <> struct StageOf<TM_SHADE> { static constexpr int id = DPRT_STAGE_SHADE; };
+template <> struct StageOf<TM_SHADOW> { static constexpr int id = DPRT_STAGE_SHADOW_TRACE; };
+template <> struct StageOf<TM_SECONDARY> { static constexpr int id = DPRT_STAGE_SECONDARY_TRACE; };
+template <> struct StageOf<TM_RAYS> { static constexpr int id = DPRT_STAGE_TRACE_CLOSEST; };
+
+struct TraceArgs {
+    const DevObject* objects; int sceneSize; int worldID;
+    dprt_path_record* recs;          // first record of the launch (paths, or paths + pathSize for shadow rays)
+    HitRec* hits;                    // TM_SHADE
+    const dprt_ray* rays; dprt_hit* rayHits;   // TM_RAYS
+    int32_t* hitPrim;                // parity aid (may be null)
+    int32_t* queue;                  // ray queue head
+    unsigned long long* counters;
+    int refill;                      // refill a warp when at least this many lanes are idle
+    int triVote;                     // force a triangle round when at least this many busy lanes cannot expand a node
+};
+
+// next local object at or after `from` that the ray still has to visit; sceneSize when none
+DPRT_D int next_object(const TraceArgs& a, int from, uint32_t skipMask) {
+    for (int k = from; k < a.sceneSize; k++) {
+        const DevObject& ob = a.objects[k];
         if (ob.isProxy) continue;
-        if (skipVisited && ((visitedMask >> ob.nodeID) & 1u)) continue;
-        TraceHit h;
-        if (bvh8_trace<false, COUNT>(ob.nodes, ob.tris, o, d, tmin, tMax, h, cnt)) {
-            tMax = h.t; best = h; bestObj = i; any = true;
+        if ((skipMask >> ob.nodeID) & 1u) continue;
+        return k;
+    }
+    return a.sceneSize;
+}
+
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock, kTraceBlocksPerSM) trace_kernel(TraceArgs a, int n) {
+    constexpr bool ANY = MODE == TM_SHADOW;
+    const unsigned FULL = 0xffffffffu;
+    __shared__ WarpQueue s_wq[kTraceBlock / 32];
+    WarpQueue& w = s_wq[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    Trav s;
+    uint2 stack[DPRT_STACK];
+    int idx = -1, obj = 0, pend = 0;
+    bool exh = false;                // the current object has no node work left (triangles may still be queued)
+    uint32_t skipMask = 0u, flags = 0u;
+    bool retry = false;              // TM_SHADE: the bounded trace may be repeated unbounded
+    TraceCount cnt = {0u, 0u};
+    bool exhausted = false;          // warp-uniform: the ray queue has no more rays
+    int qlen = 0;                    // warp-uniform: pairs waiting in the triangle queue
+    const int kRefill = a.refill;
+
+    for (;;) {
+        // ---- refill idle lanes: one atomic per refill reserves exactly the rays the idle lanes need ----
+        const unsigned idle = __ballot_sync(FULL, idx < 0);
+        if (!exhausted && __popc(idle) >= kRefill) {
+            const int leader = __ffs(idle) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(a.queue, __popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (base + __popc(idle) >= n) exhausted = true;
+            const int my = base + __popc(idle & ((1u << lane) - 1u));
+            if (idx < 0 && my < n) {
+                V3 o, d; float tmin = DPRT_EPSILON, tmax; bool live = true;
+                skipMask = 0u; retry = false;
+                if (MODE == TM_RAYS) {
+                    const float4 r0 = __ldg(reinterpret_cast<const float4*>(a.rays) + 2 * (size_t)my);
+                    const float4 r1 = __ldg(reinterpret_cast<const float4*>(a.rays) + 2 * (size_t)my + 1);
+                    o = v3(r0.x, r0.y, r0.z); tmin = r0.w; d = v3(r1.x, r1.y, r1.z); tmax = r1.w;
+                } else {
+                    const float4* q = reinterpret_cast<const float4*>(a.recs + my);
+                    const float4 q0 = q[0], q1 = q[1], q3 = q[3];
+                    o = v3(q0.x, q0.y, q0.z); d = v3(q0.w, q1.x, q1.y); tmax = q1.z;
+                    flags = __float_as_uint(q3.w);
+                    live = (flags & F_VALID) != 0u;
+                    if (MODE == TM_TRAVERSE) skipMask = __float_as_uint(q3.x);
+                    if (MODE == TM_SHADE) {
+                        // The reference re-traces with tMax = infinity (kernel.cu:382-413). When the record says "hit on
+                        // this rank at tMax", the closest local hit is at t <= tMax: a trace bounded by the next float
+                        // above tMax returns the very same (t, prim, barycentrics) while culling part of the BVH.
+                        // A bounded trace that finds nothing is repeated unbounded, so the hint never changes a result.
+                        const int currentNode = __float_as_int(q3.y);
+                        if ((flags & F_HIT) && currentNode == a.worldID && tmax > 0.0f && tmax < FLT_MAX) {
+                            tmax = __uint_as_float(__float_as_uint(tmax) + 1u); retry = true;
+                        } else {
+                            tmax = FLT_MAX;
+                        }
+                    }
+                }
+                if (live) {
+                    idx = my; pend = 0; exh = false;
+                    trav_init_ray(s, o, d, tmin, tmax);
+                    wq_set_ray(w, lane, s);
+                    obj = next_object(a, 0, skipMask);
+                    if (obj < a.sceneSize) { trav_enter_object(s, a.objects[obj].nodes, a.objects[obj].tris); wq_set_object(w, lane, s); }
+                } else if ((MODE == TM_TRAVERSE || MODE == TM_SECONDARY) && a.hitPrim) {
+                    a.hitPrim[my] = -1;
+                }
+            }
         }
-    }
-    return any;
-}
+        const unsigned act = __ballot_sync(FULL, idx >= 0);
+        if (act == 0u) { if (exhausted) break; continue; }
 
-// instrumentation flush: per-thread atomics (the counting variants are not timed)
-template <bool COUNT>
-DPRT_D void flush_count(const DevParams& p, int stage, const TraceCount& c) {
+        // ---- traverse until too few lanes are busy ----
+        const int minBusy = exhausted ? 1 : (32 - kRefill + 1);
+        do {
+            // (1) leaf triangles found by the last node phase go to the warp queue
+            wq_append(w, qlen, lane, idx >= 0, s, pend);
+            // (2) pop / object switch / ray completion
+            if (idx >= 0) {
+                bool done = false;
+                if (obj >= a.sceneSize) {
+                    done = pend == 0;
+                } else {
+                    if (!exh && s.tg.y == 0u && (s.ng.y & 0xff000000u) == 0u) {
+                        if (s.sp == 0) exh = true; else s.ng = stack[--s.sp];
+                    }
+                    if (ANY && s.hitTri >= 0) { exh = true; s.tg.y = 0u; }      // accepted: only wait for queued pairs
+                    if (exh && s.tg.y == 0u && pend == 0) {
+                        if (ANY && s.hitTri >= 0) done = true;
+                        else {
+                            obj = next_object(a, obj + 1, skipMask);
+                            if (obj < a.sceneSize) {
+                                trav_enter_object(s, a.objects[obj].nodes, a.objects[obj].tris); wq_set_object(w, lane, s); exh = false;
+                            } else done = true;
+                        }
+                    }
+                }
+                if (done && MODE == TM_SHADE && retry && s.hitTri < 0) {
+                    retry = false; done = false;
+                    s.tbest = FLT_MAX;
+                    obj = next_object(a, 0, 0u);
+                    if (obj < a.sceneSize) {
+                        trav_enter_object(s, a.objects[obj].nodes, a.objects[obj].tris); wq_set_object(w, lane, s); exh = false;
+                    } else done = true;
+                }
+                if (done) {
+                    // ---- end(idx) ----
+                    const bool hit = s.hitTri >= 0;
+                    if (MODE == TM_TRAVERSE || MODE == TM_SECONDARY) {
+                        dprt_path_record* rec = a.recs + idx;
+                        if (hit) { rec->tMax = s.tbest; rec->currentNode = a.worldID; rec->isHit = 1; }
+                        if (a.hitPrim) a.hitPrim[idx] = hit ? s.hitPrim : -1;
+                    } else if (MODE == TM_SHADE) {
+                        float4* h = reinterpret_cast<float4*>(a.hits + idx);
+                        h[0] = make_float4(s.tbest, __int_as_float(hit ? s.hitPrim : -1), __int_as_float(s.hitTri), __int_as_float(s.hitObj));
+                        h[1] = make_float4(s.ha, s.hb, 0.f, 0.f);
+                    } else if (MODE == TM_SHADOW) {
+                        if (hit) {    // any local occluder kills the shadow path (shadow_ray_kernel.cu:169-195)
+                            flags = (flags | F_HIT) & ~F_VALID;
+                            reinterpret_cast<uint32_t*>(a.recs + idx)[15] = flags;
+                        }
+                    } else {
+                        reinterpret_cast<float2*>(a.rayHits)[idx] = make_float2(s.tbest, __int_as_float(hit ? s.hitPrim : -1));
+                    }
+                    idx = -1;
+                }
+            }
+            // (3) the warp votes: a full (or forced) triangle round, else one node per lane
+            const bool busy = idx >= 0;
+            const bool canNode = busy && obj < a.sceneSize && !exh && s.tg.y == 0u;
+            const unsigned nodeM = __ballot_sync(FULL, canNode);
+            const unsigned waitM = __ballot_sync(FULL, busy && !canNode);
+            if (qlen > 0 && (qlen >= 32 || nodeM == 0u || __popc(waitM) >= a.triVote)) tri_round<ANY, COUNT>(w, qlen, lane, s, obj, pend, cnt);
+            else if (canNode) trav_node<COUNT>(s, stack, cnt);
+        } while (__popc(__ballot_sync(FULL, idx >= 0)) >= minBusy);
+    }
     if (COUNT) {
-        if (c.nodes) atomicAdd(p.counters + 2 * stage, (unsigned long long)c.nodes);
-        if (c.tris) atomicAdd(p.counters + 2 * stage + 1, (unsigned long long)c.tris);
+        if (cnt.nodes) atomicAdd(a.counters + 2 * StageOf<MODE>::id, (unsigned long long)cnt.nodes);
+        if (cnt.tris) atomicAdd(a.counters + 2 * StageOf<MODE>::id + 1, (unsigned long long)cnt.tris);
     }
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) traverse_kernel(DevParams p, int n) {
+// ================================================================================================
+// TraRay program after the trace (distributed_traversal_kernel.cu:266-339): own bit, nearest unvisited proxy AABB
+// within tMax decides the next owner, environment light on a total miss; histogram by-product for the partition.
+__global__ void __launch_bounds__(kBlock) traverse_post_kernel(DevParams p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool outValid = false; int target = -1;
     if (i < n) {
         PathRegs path = load_path(p.paths + i);
         if (path.flags & F_VALID) {
             const V3 o = path.origin, d = path.direction;
-            TraceHit h; int hobj = -1; h.prim = -1;
-            float tMax = path.tMax;
-            TraceCount cnt = {0u, 0u};
-            if (trace_local_closest<COUNT>(p, o, d, DPRT_EPSILON, tMax, path.visitedMask, true, h, hobj, cnt)) {
-                path.tMax = tMax; path.flags |= F_HIT; path.currentNode = p.worldID;
-            }
-            flush_count<COUNT>(p, DPRT_STAGE_TRAVERSE, cnt);
-            if (p.hitPrim) p.hitPrim[i] = h.prim;
             path.visitedMask |= (1u << p.worldID);
-            // nearest unvisited proxy AABB within tMax decides the next owner (:280-314)
             float tProxy = path.tMax; bool proxyHit = false;
             for (int k = 0; k < p.sceneSize; k++) {
                 const DevObject& ob = p.objects[k];
@@ -153,8 +308,6 @@ __global__ void __launch_bounds__(kBlock) traverse_kernel(DevParams p, int n) {
             store_path(p.paths + i, path);
             outValid = (path.flags & F_VALID) != 0;
             target = path.targetNode;
-        } else if (p.hitPrim) {
-            p.hitPrim[i] = -1;
         }
     }
     // by-product for the partition stage: valid paths per destination (warp-aggregated)
@@ -208,19 +361,18 @@ DPRT_D BsdfSample sample_water(float xi1, V3 normal, V3 woWorld, bool isInside) 
     return s;
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) shade_kernel(DevParams p, int n) {
+// MainRay program after the trace: closest-hit program (kernel.cu:171-300), createSamplingRecord (:50-64),
+// generateNextNewPath (:134-162), generateShadowPath x spc (:66-132, :442-465).
+__global__ void __launch_bounds__(kBlock) shade_post_kernel(DevParams p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     PathRegs path = load_path(p.paths + i);
     if (!(path.flags & F_VALID)) return;
     const V3 o = path.origin, d = path.direction;
-
-    TraceHit h; int hobj = -1; float tMax = FLT_MAX;
-    TraceCount cnt = {0u, 0u};
-    const bool isHit = trace_local_closest<COUNT>(p, o, d, DPRT_EPSILON, tMax, 0u, false, h, hobj, cnt);
-    flush_count<COUNT>(p, DPRT_STAGE_SHADE, cnt);
-    if (p.hitPrim) p.hitPrim[i] = isHit ? h.prim : -1;
+    const float4 h0 = reinterpret_cast<const float4*>(p.hits + i)[0], h1 = reinterpret_cast<const float4*>(p.hits + i)[1];
+    const float ht = h0.x; const int hprim = __float_as_int(h0.y), htri = __float_as_int(h0.z), hobj = __float_as_int(h0.w);
+    const bool isHit = htri >= 0;
+    if (p.hitPrim) p.hitPrim[i] = isHit ? hprim : -1;
     if (!isHit) {
         // kernel.cu:416-423: environment light, path dies. The reference then writes an invalid record built
         // from an uninitialised sampling record; the defined behaviour here is the all-zero (invalid) record.
@@ -231,26 +383,25 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DevParams p, int n) {
     }
     const DevObject& ob = p.objects[hobj];
     // closest-hit program (kernel.cu:171-300): interpolated vertex normal, base colour, face-forward
-    const float4 tb = __ldg(ob.tris + 3 * (size_t)h.tri + 1);
+    const float4 tb = __ldg(ob.tris + 3 * (size_t)htri + 1);
     const int matID = __float_as_int(tb.w);
     const dprt_material mat = p.materials[matID];
     const V3 albedo = v3(mat.baseColor[0], mat.baseColor[1], mat.baseColor[2]);
-    const V3 point = v3at(o, d, h.t);
+    const V3 point = v3at(o, d, ht);
     const V3 woWorld = v3neg(d);
     V3 normal;
     {
-        const float* nn = ob.normals + 9 * (size_t)h.prim;
+        const float* nn = ob.normals + 9 * (size_t)hprim;
         const V3 n0 = v3normalized(v3(nn[0], nn[1], nn[2]));
         const V3 n1 = v3normalized(v3(nn[3], nn[4], nn[5]));
         const V3 n2 = v3normalized(v3(nn[6], nn[7], nn[8]));
-        const float alpha = h.alpha, beta = h.beta, gamma = 1.0f - alpha - beta;
+        const float alpha = h1.x, beta = h1.y, gamma = 1.0f - alpha - beta;
         normal = v3(fmaf(beta, n2.x, fmaf(alpha, n1.x, gamma * n0.x)), fmaf(beta, n2.y, fmaf(alpha, n1.y, gamma * n0.y)),
                     fmaf(beta, n2.z, fmaf(alpha, n1.z, gamma * n0.z)));
         normal = v3normalized(normal);
     }
     bool isInside = false;
     if (v3dot(normal, woWorld) < 0.0f) { normal = v3neg(normal); isInside = true; }
-
     // createSamplingRecord (kernel.cu:50-64): the seed ignores the bounce, as in the reference
     uint32_t seed = tea4((uint32_t)path.pixelIndex, (uint32_t)p.sampleCount);
     const float xi1 = rnd(seed), xi2 = rnd(seed);
@@ -304,7 +455,6 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(DevParams p, int n) {
     }
 }
 
-// ------------------------------------------------------------------------------------------------
 // Proxy-AABB march shared by the shadow and secondary stages (shadow_ray_kernel.cu:198-350,
 // secondary_ray_kernel.cu:226-362). Emits <= mc queries into slot base `q0 = threadIndex*mc`.
 struct MarchOut { int count; bool envMiss; };
@@ -388,107 +538,94 @@ DPRT_D void flush_query_hist(const DevParams& p, const int* shHist) {
     else if (t >= 32 && t < 32 + p.sceneSize) { if (shHist[t]) atomicAdd(p.queryHist + p.sceneSize + (t - 32), shHist[t]); }
 }
 
-template <bool COUNT>
-DPRT_D void shadow_body(const DevParams& p, int i, int* shHist) {
-    dprt_path_record* rec = p.paths + (size_t)p.pathSize + i;
-    PathRegs path = load_path(rec);
-    if (!(path.flags & F_VALID)) { clear_query_slots(p, i, 0); return; }
-    // any local occluder within tMax kills the shadow path (:169-195)
-    bool occluded = false;
-    TraceCount cnt = {0u, 0u};
-    for (int k = 0; k < p.sceneSize && !occluded; k++) {
-        const DevObject& ob = p.objects[k];
-        if (ob.isProxy) continue;
-        TraceHit h;
-        if (bvh8_trace<true, COUNT>(ob.nodes, ob.tris, path.origin, path.direction, DPRT_EPSILON, path.tMax, h, cnt)) occluded = true;
-    }
-    flush_count<COUNT>(p, DPRT_STAGE_SHADOW_TRACE, cnt);
-    if (occluded) {
-        path.flags |= F_HIT; path.flags &= ~F_VALID;
-        reinterpret_cast<float4*>(rec)[3] = make_float4(__uint_as_float(path.visitedMask), __int_as_float(path.currentNode),
-                                                        __int_as_float(path.targetNode), __uint_as_float(path.flags));
-        clear_query_slots(p, i, 0);
-        return;
-    }
-    int r;
-    if (p.proxyMode == 0) { r = -1; clear_query_slots(p, i, 0); }   // proxies off: remote chunks are transparent to shadow rays
-    else r = proxy_march<false>(p, path, i, path.tMax, shHist);
-    if (r < 0) {
-        const size_t px = ((size_t)p.frameBufferSize * path.shadowPathID + path.pixelIndex) * 3;
-        const float inv = (float)p.spc;
-        p.direct[px + 0] += path.throughput.x / inv;
-        p.direct[px + 1] += path.throughput.y / inv;
-        p.direct[px + 2] += path.throughput.z / inv;
-    }
-}
-
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) shadow_trace_kernel(DevParams p, int nShadow) {
+// ShadowRay program after the any-hit trace (shadow_ray_kernel.cu:198-350): occluded paths were marked by the trace;
+// the others march through the proxy AABBs or, with nothing in the way, add their contribution.
+__global__ void __launch_bounds__(kBlock) shadow_post_kernel(DevParams p, int nShadow) {
     __shared__ int shHist[64];
     if (threadIdx.x < 64) shHist[threadIdx.x] = 0;
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nShadow) shadow_body<COUNT>(p, i, shHist);
+    if (i < nShadow) {
+        const PathRegs path = load_path(p.paths + (size_t)p.pathSize + i);
+        if (!(path.flags & F_VALID)) {
+            clear_query_slots(p, i, 0);
+        } else {
+            int r;
+            if (p.proxyMode == 0) { r = -1; clear_query_slots(p, i, 0); }   // proxies off: remote chunks are transparent to shadow rays
+            else r = proxy_march<false>(p, path, i, path.tMax, shHist);
+            if (r < 0) {
+                const size_t px = ((size_t)p.frameBufferSize * path.shadowPathID + path.pixelIndex) * 3;
+                const float inv = (float)p.spc;
+                p.direct[px + 0] += path.throughput.x / inv;
+                p.direct[px + 1] += path.throughput.y / inv;
+                p.direct[px + 2] += path.throughput.z / inv;
+            }
+        }
+    }
     __syncthreads();
     flush_query_hist(p, shHist);
 }
 
-template <bool COUNT>
-DPRT_D void secondary_body(const DevParams& p, int i, int* shHist) {
-    PathRegs path = load_path(p.paths + i);
-    if (!(path.flags & F_VALID)) { clear_query_slots(p, i, 0); return; }
-    for (int k = 0; k < p.sceneSize; k++) if (p.objects[k].isProxy != 2) path.visitedMask |= (1u << p.objects[k].nodeID);
-    TraceHit h; int hobj = -1; float tMax = path.tMax;
-    TraceCount cnt = {0u, 0u};
-    if (trace_local_closest<COUNT>(p, path.origin, path.direction, DPRT_EPSILON, tMax, 0u, false, h, hobj, cnt)) {
-        path.tMax = tMax; path.flags |= F_HIT; path.currentNode = p.worldID;
-    }
-    flush_count<COUNT>(p, DPRT_STAGE_SECONDARY_TRACE, cnt);
-    if (p.hitPrim) p.hitPrim[i] = hobj >= 0 ? h.prim : -1;
-    const int r = proxy_march<true>(p, path, i, path.tMax, shHist);
-    if (r < 0 && !(path.flags & F_HIT)) {
-        add_env(p, path);
-        path.flags &= ~F_VALID;
-    }
-    store_path(p.paths + i, path);
-}
-
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) secondary_trace_kernel(DevParams p, int n) {
+// SecondaryRay program after the trace (secondary_ray_kernel.cu:192, :226-362).
+__global__ void __launch_bounds__(kBlock) secondary_post_kernel(DevParams p, int n) {
     __shared__ int shHist[64];
     if (threadIdx.x < 64) shHist[threadIdx.x] = 0;
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) secondary_body<COUNT>(p, i, shHist);
+    if (i < n) {
+        PathRegs path = load_path(p.paths + i);
+        if (!(path.flags & F_VALID)) {
+            clear_query_slots(p, i, 0);
+        } else {
+            for (int k = 0; k < p.sceneSize; k++) if (p.objects[k].isProxy != 2) path.visitedMask |= (1u << p.objects[k].nodeID);
+            const int r = proxy_march<true>(p, path, i, path.tMax, shHist);
+            if (r < 0 && !(path.flags & F_HIT)) {
+                add_env(p, path);
+                path.flags &= ~F_VALID;
+            }
+            store_path(p.paths + i, path);
+        }
+    }
     __syncthreads();
     flush_query_hist(p, shHist);
-}
-
-// ------------------------------------------------------------------------------------------------
-template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) trace_closest_kernel(const DevObject* objects, int sceneSize,
-                                                                const dprt_ray* __restrict__ rays, dprt_hit* __restrict__ hits,
-                                                                int64_t n, unsigned long long* counters) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 a = reinterpret_cast<const float4*>(rays)[2 * i], b = reinterpret_cast<const float4*>(rays)[2 * i + 1];
-    const V3 o = v3(a.x, a.y, a.z), d = v3(b.x, b.y, b.z);
-    float tMax = b.w; int prim = -1;
-    TraceCount cnt = {0u, 0u};
-    for (int k = 0; k < sceneSize; k++) {
-        const DevObject& ob = objects[k];
-        if (ob.isProxy) continue;
-        TraceHit h;
-        if (bvh8_trace<false, COUNT>(ob.nodes, ob.tris, o, d, a.w, tMax, h, cnt)) { tMax = h.t; prim = h.prim; }
-    }
-    if (COUNT) {
-        atomicAdd(counters + 2 * DPRT_STAGE_TRACE_CLOSEST, (unsigned long long)cnt.nodes);
-        atomicAdd(counters + 2 * DPRT_STAGE_TRACE_CLOSEST + 1, (unsigned long long)cnt.tris);
-    }
-    reinterpret_cast<float2*>(hits)[i] = make_float2(tMax, __int_as_float(prim));
 }
 
 inline int blocks_for(int64_t n) { return (int)((n + kBlock - 1) / kBlock); }
+
+int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+    return cached[dev] > 0 ? cached[dev] : 148;
+}
+
+// tuning knobs (defaults measured on B200, see profiles/): environment overrides are for experiments only
+int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* v = getenv(name);
+    if (!v) return dflt;
+    const int x = atoi(v);
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+int tune_refill() { static int v = env_int("DPRT_TRACE_REFILL", kRefillDefault, 1, 32); return v; }
+int tune_trivote() { static int v = env_int("DPRT_TRACE_TRIVOTE", kTriVoteDefault, 1, 32); return v; }
+int tune_blocks() { static int v = env_int("DPRT_TRACE_BLOCKS_PER_SM", kTraceBlocksPerSM, 1, 16); return v; }
+
+template <int MODE>
+void launch_trace(const TraceArgs& a, int64_t n, cudaStream_t s) {
+    cudaMemsetAsync(a.queue, 0, sizeof(int32_t), s);
+    const int blocks = (int)std::min<int64_t>((n + kTraceBlock - 1) / kTraceBlock, (int64_t)num_sms() * tune_blocks());
+    if (a.counters) trace_kernel<MODE, true><<<blocks, kTraceBlock, 0, s>>>(a, (int)n);
+    else trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, s>>>(a, (int)n);
+}
+
+TraceArgs trace_args(const DevParams& p, dprt_path_record* recs) {
+    TraceArgs a;
+    a.objects = p.objects; a.sceneSize = p.sceneSize; a.worldID = p.worldID; a.recs = recs; a.hits = p.hits;
+    a.rays = nullptr; a.rayHits = nullptr; a.hitPrim = p.hitPrim; a.queue = p.traceQueue; a.counters = p.counters;
+    a.refill = tune_refill(); a.triVote = tune_trivote();
+    return a;
+}
 
 }  // namespace
 
@@ -497,29 +634,32 @@ void launch_path_gen(const DevParams& p, int n, cudaStream_t s) {
 }
 void launch_traverse(const DevParams& p, int n, cudaStream_t s) {
     if (n <= 0) return;
-    if (p.counters) traverse_kernel<true><<<blocks_for(n), kBlock, 0, s>>>(p, n);
-    else traverse_kernel<false><<<blocks_for(n), kBlock, 0, s>>>(p, n);
+    launch_trace<TM_TRAVERSE>(trace_args(p, p.paths), n, s);
+    traverse_post_kernel<<<blocks_for(n), kBlock, 0, s>>>(p, n);
 }
 void launch_shade(const DevParams& p, int n, cudaStream_t s) {
     if (n <= 0) return;
-    if (p.counters) shade_kernel<true><<<blocks_for(n), kBlock, 0, s>>>(p, n);
-    else shade_kernel<false><<<blocks_for(n), kBlock, 0, s>>>(p, n);
+    launch_trace<TM_SHADE>(trace_args(p, p.paths), n, s);
+    shade_post_kernel<<<blocks_for(n), kBlock, 0, s>>>(p, n);
 }
 void launch_shadow_trace(const DevParams& p, int nShadow, cudaStream_t s) {
     if (nShadow <= 0) return;
-    if (p.counters) shadow_trace_kernel<true><<<blocks_for(nShadow), kBlock, 0, s>>>(p, nShadow);
-    else shadow_trace_kernel<false><<<blocks_for(nShadow), kBlock, 0, s>>>(p, nShadow);
+    launch_trace<TM_SHADOW>(trace_args(p, p.paths + p.pathSize), nShadow, s);
+    shadow_post_kernel<<<blocks_for(nShadow), kBlock, 0, s>>>(p, nShadow);
 }
 void launch_secondary_trace(const DevParams& p, int n, cudaStream_t s) {
     if (n <= 0) return;
-    if (p.counters) secondary_trace_kernel<true><<<blocks_for(n), kBlock, 0, s>>>(p, n);
-    else secondary_trace_kernel<false><<<blocks_for(n), kBlock, 0, s>>>(p, n);
+    launch_trace<TM_SECONDARY>(trace_args(p, p.paths), n, s);
+    secondary_post_kernel<<<blocks_for(n), kBlock, 0, s>>>(p, n);
 }
 void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ray* rays, dprt_hit* hits, int64_t n,
-                          unsigned long long* counters, cudaStream_t s) {
+                          int32_t* queue, unsigned long long* counters, cudaStream_t s) {
     if (n <= 0) return;
-    if (counters) trace_closest_kernel<true><<<blocks_for(n), kBlock, 0, s>>>(objects, sceneSize, rays, hits, n, counters);
-    else trace_closest_kernel<false><<<blocks_for(n), kBlock, 0, s>>>(objects, sceneSize, rays, hits, n, nullptr);
+    TraceArgs a;
+    a.objects = objects; a.sceneSize = sceneSize; a.worldID = 0; a.recs = nullptr; a.hits = nullptr;
+    a.rays = rays; a.rayHits = hits; a.hitPrim = nullptr; a.queue = queue; a.counters = counters;
+    a.refill = tune_refill(); a.triVote = tune_trivote();
+    launch_trace<TM_RAYS>(a, n, s);
 }
 
 }  // namespace dprt
