@@ -61,6 +61,13 @@ int  dprt_path_gen(dprt_ctx* ctx);                    /* optixLaunch(PathGen)   
 int  dprt_traverse(dprt_ctx* ctx);                    /* optixLaunch(TraRay)          renderer.cpp:1232-1243 */
 int  dprt_partition(dprt_ctx* ctx);                   /* Work_Efficient_Scan          cuda_compaction.cu:352 */
 int  dprt_exchange(dprt_ctx* ctx, int* done);         /* Alltoall+Alltoallv+Allreduce renderer.cpp:1254-1314 */
+/* The host half of dprt_exchange, callable without a device: from the gathered W x (W+1) matrix of every rank's
+ * transferOffset row (row s, column d = where rank s's segment for destination d starts) derive what rank `rank`
+ * sends (send_count[W]), where each source's records land in its path buffer (recv_offset[W+1], recv_count[W]) --
+ * the sendCount/recvCount/recvOffset vectors of renderer.cpp:1256-1277 -- and the termination flag of
+ * renderer.cpp:1292-1298 (all_local = no record crossed ranks anywhere). Output pointers may be NULL. */
+int  dprt_plan_exchange(const int32_t* gathered_offsets, int world, int rank, int32_t* send_count, int32_t* recv_offset,
+                        int32_t* recv_count, int64_t* recv_total, int* all_local);
 int  dprt_shade(dprt_ctx* ctx);                       /* optixLaunch(MainRay)         renderer.cpp:1320-1347 */
 int  dprt_reset_nn(dprt_ctx* ctx);                    /* resetNNBuffers               renderer.cpp:367-414 */
 int  dprt_shadow_trace(dprt_ctx* ctx);                /* optixLaunch(ShadowRay)       renderer.cpp:1366-1379 */

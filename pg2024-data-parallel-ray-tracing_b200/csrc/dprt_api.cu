@@ -582,6 +582,31 @@ int dprt_partition(dprt_ctx* ctx) {
     return 0;
 }
 
+int dprt_plan_exchange(const int32_t* M, int W, int me, int32_t* send_count, int32_t* recv_offset, int32_t* recv_count,
+                       int64_t* recv_total, int* all_local) {
+    if (!M || W < 1 || W > DPRT_MAX_WORLD || me < 0 || me >= W) return DPRT_ERR_INVALID;
+    int64_t offdiag = 0, roff = 0;
+    for (int s = 0; s < W; s++) {
+        if (M[s * (W + 1)] != 0) return DPRT_ERR_INVALID;
+        for (int d = 0; d < W; d++) {
+            const int64_t c = (int64_t)M[s * (W + 1) + d + 1] - M[s * (W + 1) + d];
+            if (c < 0) return DPRT_ERR_INVALID;
+            if (s != d) offdiag += c;
+            if (s == me && send_count) send_count[d] = (int32_t)c;
+            if (d == me) {
+                if (recv_offset) recv_offset[s] = (int32_t)roff;
+                if (recv_count) recv_count[s] = (int32_t)c;
+                roff += c;
+            }
+        }
+    }
+    if (roff > 0x7fffffff) return DPRT_ERR_CAPACITY;
+    if (recv_offset) recv_offset[W] = (int32_t)roff;
+    if (recv_total) *recv_total = roff;
+    if (all_local) *all_local = offdiag == 0;
+    return 0;
+}
+
 int dprt_exchange(dprt_ctx* ctx, int* done) {
     if (!ctx) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
@@ -604,23 +629,19 @@ int dprt_exchange(dprt_ctx* ctx, int* done) {
     CK(cudaStreamSynchronize(ctx->stream));
     const int32_t* M = ctx->h_pinned;     // M[s*(W+1)+d] = offset of rank s's segment for destination d
     ctx->h_offsets.assign(M + me * (W + 1), M + (me + 1) * (W + 1));
-    long offdiag = 0; int recvTotal = 0;
-    std::vector<int> recvOff(W + 1, 0);
-    for (int s = 0; s < W; s++) {
-        for (int d = 0; d < W; d++) {
-            const int c = M[s * (W + 1) + d + 1] - M[s * (W + 1) + d];
-            if (s != d) offdiag += c;
-            if (d == me) recvOff[s + 1] = recvOff[s] + c;
-        }
-    }
-    recvTotal = recvOff[W];
+    std::vector<int32_t> sendCnt(W), recvOff(W + 1, 0), recvCnt(W);
+    int64_t recvTotal64 = 0; int allLocal = 0;
+    if (dprt_plan_exchange(M, W, me, sendCnt.data(), recvOff.data(), recvCnt.data(), &recvTotal64, &allLocal))
+        return fail(ctx, DPRT_ERR_INVALID, "inconsistent offset matrix in the exchange");
+    const int recvTotal = (int)recvTotal64;
+    const long offdiag = allLocal ? 0 : 1;
     if ((size_t)recvTotal > (size_t)ctx->N) return fail(ctx, DPRT_ERR_CAPACITY, "received more paths than the frame holds");
     // MPI_Alltoallv: grouped send/recv straight from the partitioned device buffer
     NK(g_nccl.GroupStart());
     for (int peer = 0; peer < W; peer++) {
         if (peer == me) continue;
-        const int sc = ctx->h_offsets[peer + 1] - ctx->h_offsets[peer];
-        const int rc = recvOff[peer + 1] - recvOff[peer];
+        const int sc = sendCnt[peer];
+        const int rc = recvCnt[peer];
         if (sc > 0) NK(g_nccl.Send(ctx->hp.transfer + ctx->h_offsets[peer], (size_t)sc * R, ncclUint8, peer, ctx->comm, ctx->stream));
         if (rc > 0) NK(g_nccl.Recv(ctx->hp.paths + recvOff[peer], (size_t)rc * R, ncclUint8, peer, ctx->comm, ctx->stream));
         ctx->stats.paths_sent_offrank += sc; ctx->stats.bytes_alltoall += (int64_t)sc * R;

@@ -41,6 +41,8 @@ _PROTOTYPES = {
     "dprt_traverse": (C.c_int, [C.c_void_p]),
     "dprt_partition": (C.c_int, [C.c_void_p]),
     "dprt_exchange": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "dprt_plan_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64),
+                                    C.POINTER(C.c_int)]),
     "dprt_shade": (C.c_int, [C.c_void_p]),
     "dprt_reset_nn": (C.c_int, [C.c_void_p]),
     "dprt_shadow_trace": (C.c_int, [C.c_void_p]),
@@ -138,6 +140,56 @@ def build_bvh8(verts9, mat_ids=None, pad=-1.0):
     finally:
         lib.dprt_bvh8_free(h)
     return nodes, tris, int(md.value)
+
+
+def plan_exchange(gathered_offsets, rank):
+    """dprt_plan_exchange: gathered [W, W+1] int32 offset matrix -> (send_count[W], recv_offset[W+1], recv_count[W],
+    recv_total, all_local). Host only; this is the plan dprt_exchange executes with ncclSend/ncclRecv."""
+    M = np.ascontiguousarray(gathered_offsets, np.int32)
+    W = M.shape[0]
+    if M.shape != (W, W + 1):
+        raise DprtError(f"offset matrix must be [W, W+1], got {M.shape}")
+    sc, ro, rc = np.zeros(W, np.int32), np.zeros(W + 1, np.int32), np.zeros(W, np.int32)
+    tot, loc = C.c_int64(0), C.c_int(0)
+    r = load_library().dprt_plan_exchange(_ptr(M), W, int(rank), _ptr(sc), _ptr(ro), _ptr(rc), C.byref(tot), C.byref(loc))
+    if r:
+        raise DprtError(f"dprt_plan_exchange failed ({r})")
+    return sc, ro, rc, int(tot.value), bool(loc.value)
+
+
+def exchange_host_records(transfer, offsets, rank, world, dist):
+    """The exchange protocol of dprt_exchange on HOST record arrays over a torch.distributed process group
+    (any backend: this is how the protocol is exercised with gloo on CPU-only machines; the product path moves
+    device buffers with NCCL inside libdprt). transfer: bucket-major PATH_DTYPE records of this rank, offsets:
+    its transferOffset row [W+1]. Returns (received records in source-rank order, done)."""
+    import torch
+    row = torch.from_numpy(np.ascontiguousarray(offsets[: world + 1], np.int32).copy())
+    rows = [torch.zeros(world + 1, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(rows, row)                                            # MPI_Alltoall(counts), renderer.cpp:1272
+    M = torch.stack(rows).numpy()
+    sc, ro, rc, total, all_local = plan_exchange(M, rank)
+    out = np.zeros(total, D.PATH_DTYPE)
+    R = D.PATH_DTYPE.itemsize
+    reqs, keep = [], []
+    for peer in range(world):                                             # MPI_Alltoallv, renderer.cpp:1280
+        if peer == rank:
+            continue
+        if sc[peer] > 0:
+            seg = np.ascontiguousarray(transfer[offsets[peer]:offsets[peer] + sc[peer]]).view(np.uint8).copy()
+            t = torch.from_numpy(seg); keep.append(t)
+            reqs.append(dist.isend(t, peer))
+        if rc[peer] > 0:
+            t = torch.zeros(int(rc[peer]) * R, dtype=torch.uint8); keep.append((peer, t))
+            reqs.append(dist.irecv(t, peer))
+    for q in reqs:
+        q.wait()
+    for k in keep:
+        if isinstance(k, tuple):
+            peer, t = k
+            out[ro[peer]:ro[peer] + rc[peer]] = t.numpy().view(D.PATH_DTYPE)
+    if sc[rank] > 0:
+        out[ro[rank]:ro[rank] + sc[rank]] = transfer[offsets[rank]:offsets[rank] + sc[rank]]
+    return out, all_local
 
 
 class Renderer:
