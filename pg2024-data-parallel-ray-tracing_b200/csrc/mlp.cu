@@ -31,8 +31,9 @@ namespace {
 constexpr int kRows = 128;
 constexpr int kWidth = 256;
 constexpr int kStageBytes = 32768;
-constexpr int kStages = 4;
-constexpr int kThreads = 192;
+constexpr int kStages = 3;
+constexpr int kSlots = 2;                 // query tiles in flight per CTA (ping-pong: MMA of one overlaps the epilogue of the other)
+constexpr int kThreads = 384;             // warpgroup 0/1 = epilogue of slot 0/1, warpgroup 2 = MMA issuer + weight loader
 constexpr int kMaxRes = 6;
 constexpr uint32_t kBlobMagic = 0x50524d4cu;
 
@@ -40,14 +41,19 @@ constexpr uint32_t kBlobMagic = 0x50524d4cu;
 constexpr int kE3W0 = 0, kE3B0 = 96, kE2W0 = 128, kE2B0 = 192, kBEnc = 224, kBRes = 480;
 __host__ __device__ constexpr int small_floats(int nres) { return kBRes + nres * kWidth + 64 + 64 + 1; }
 constexpr int kSmallMax = small_floats(kMaxRes);   // 2145 floats
+// The fp32 side parameters (input layers, all biases, the 64->1 output layer: 8.6 KB) travel as a
+// __grid_constant__ kernel parameter: every access is warp-uniform, which is what the constant bank is for,
+// and shared memory is left to the two A tiles and the weight ring.
+struct SmallParams { float v[kSmallMax + 3]; };
 
 // shared memory map (bytes from the 1024-aligned base)
-constexpr int kSmemA = 0;                                    // 128 x 256 x 16 bit, 4 K-blocks of 16 KiB
-constexpr int kSmemStages = 65536;
-constexpr int kSmemSmall = kSmemStages + kStages * kStageBytes;          // 196608
-constexpr int kSmemBars = kSmemSmall + ((kSmallMax * 4 + 15) / 16) * 16;  // barriers: full[4], empty[4], mma_done
-constexpr int kSmemTmemPtr = kSmemBars + 9 * 8;
+constexpr int kSmemA = 0;                                    // 2 slots x (128 x 256 x 16 bit = 4 K-blocks of 16 KiB)
+constexpr int kSmemStages = kSlots * 65536;                  // 131072
+constexpr int kSmemBars = kSmemStages + kStages * kStageBytes;            // 229376: full[3], empty[3], mmaDone[2], aReady[2]
+constexpr int kNumBars = 2 * kStages + 2 * kSlots;
+constexpr int kSmemTmemPtr = kSmemBars + kNumBars * 8;
 constexpr int kSmemTotal = kSmemTmemPtr + 16 + 1024;                      // + alignment slack
+static_assert(kSmemTotal <= 232448, "shared memory budget");
 
 // ---- PTX helpers ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -161,121 +167,153 @@ __device__ __forceinline__ void store_a32(uint8_t* A, int row, int c32, const fl
 }
 
 template <bool BF16>
+__device__ __forceinline__ void unpack2(uint32_t w, float& a, float& b) {
+    if (BF16) { a = __uint_as_float(w << 16); b = __uint_as_float(w & 0xffff0000u); }
+    else { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w)); a = f.x; b = f.y; }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// One CTA keeps TWO 128-query tiles in flight (slot 0 / slot 1). The single MMA-issuing thread walks
+//   enc(s0) enc(s1) | res0(s0) res0(s1) | ... | post(s0) post(s1)
+// so that while the tensor pipe runs a layer of one slot, the 4 epilogue warps of the other slot turn its finished
+// accumulator into the next layer's operand. TMEM: slot s owns columns [256 s, 256 s + 256) -- the fp32 residual
+// stream lives there across the residual layers (the epilogue writes LReLU(acc + b) back, the next layer's MMAs
+// accumulate on top). The outer skip (out1) is kept by the row's own thread as 128 packed 16-bit pairs in
+// registers (the very words it wrote into the A tile), which is what the 208-register epilogue budget
+// (setmaxnreg) is for.
+template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1)
-mlp_kernel(const uint8_t* __restrict__ wstages, const float* __restrict__ small_g, int nres, const uint16_t* __restrict__ x,
+mlp_kernel(const uint8_t* __restrict__ wstages, const __grid_constant__ SmallParams sp, int nres, const uint16_t* __restrict__ x,
            uint16_t* __restrict__ y, int n) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem + kSmemA;
-    float* sSmall = reinterpret_cast<float*>(smem + kSmemSmall);
-    const uint32_t aBase = smem_u32(sA);
+    const uint32_t aBase0 = smem_u32(smem + kSmemA);
     const uint32_t stageBase = smem_u32(smem + kSmemStages);
     const uint32_t barBase = smem_u32(smem + kSmemBars);
     auto fullBar = [&](int s) { return barBase + 8u * (uint32_t)s; };
     auto emptyBar = [&](int s) { return barBase + 8u * (uint32_t)(kStages + s); };
-    const uint32_t mmaDone = barBase + 8u * (2 * kStages);
+    auto mmaDoneBar = [&](int slot) { return barBase + 8u * (uint32_t)(2 * kStages + slot); };
+    auto aReadyBar = [&](int slot) { return barBase + 8u * (uint32_t)(2 * kStages + kSlots + slot); };
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem + kSmemTmemPtr);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = (n + kRows - 1) / kRows;
-    const int chunksPerTile = 2 + 4 * nres;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) { mbar_init(fullBar(s), 1); mbar_init(emptyBar(s), 1); }
-        mbar_init(mmaDone, 1);
+        for (int s = 0; s < kSlots; s++) { mbar_init(mmaDoneBar(s), 1); mbar_init(aReadyBar(s), kRows); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < small_floats(nres); i += kThreads) sSmall[i] = small_g[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *sTmem;
     const int fmt = BF16 ? 1 : 0;
 
-    if (warp == 5) {
-        // ---------------- weight loader: streams the per-tile stage sequence through the ring ----------------
-        if (lane == 0) {
+    if (warp >= 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        if (warp == 9 && lane == 0) {
+            // ---------------- weight loader: the stage sequence the MMA thread consumes, through a 3-deep ring ----------------
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int c = 0; c < chunksPerTile; c++, it++) {
-                    const int s = it % kStages;
-                    if (it >= kStages) mbar_wait(emptyBar(s), ((it / kStages) - 1) & 1);
-                    mbar_expect_tx(fullBar(s), kStageBytes);
-                    bulk_g2s(stageBase + s * kStageBytes, wstages + (size_t)c * kStageBytes, kStageBytes, fullBar(s));
-                }
+            auto load = [&](int chunk) {
+                const int s = it % kStages;
+                if (it >= kStages) mbar_wait(emptyBar(s), ((it / kStages) - 1) & 1);
+                mbar_expect_tx(fullBar(s), kStageBytes);
+                bulk_g2s(stageBase + s * kStageBytes, wstages + (size_t)chunk * kStageBytes, kStageBytes, fullBar(s));
+                it++;
+            };
+            for (int t0 = blockIdx.x * kSlots; t0 < ntiles; t0 += gridDim.x * kSlots) {
+                const int nact = t0 + 1 < ntiles ? 2 : 1;
+                for (int s = 0; s < nact; s++) load(0);
+                for (int l = 0; l < nres; l++)
+                    for (int s = 0; s < nact; s++)
+                        for (int kc = 0; kc < 4; kc++) load(1 + l * 4 + kc);
+                for (int s = 0; s < nact; s++) load(1 + 4 * nres);
             }
-        }
-    } else if (warp == 4) {
-        // ---------------- MMA issuer ----------------
-        const uint32_t idesc256 = make_idesc(kRows, 256, fmt), idesc64 = make_idesc(kRows, 64, fmt);
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            // encoder second layers as one block-diagonal 64 -> 256 GEMM
-            named_bar_sync(1, 160);
-            tc_fence_after();
-            if (lane == 0) {
+        } else if (warp == 8 && lane == 0) {
+            // ---------------- MMA issuer ----------------
+            const uint32_t idesc256 = make_idesc(kRows, 256, fmt), idesc64 = make_idesc(kRows, 64, fmt);
+            uint32_t it = 0;
+            uint32_t rdy[kSlots] = {0u, 0u};
+            auto wait_stage = [&]() {
                 const int s = it % kStages;
                 mbar_wait(fullBar(s), (it / kStages) & 1);
                 tc_fence_after();
+                return s;
+            };
+            for (int t0 = blockIdx.x * kSlots; t0 < ntiles; t0 += gridDim.x * kSlots) {
+                const int nact = t0 + 1 < ntiles ? 2 : 1;
+                // encoder second layers as one block-diagonal 64 -> 256 GEMM
+                for (int sl = 0; sl < nact; sl++) {
+                    mbar_wait(aReadyBar(sl), rdy[sl]); rdy[sl] ^= 1u;
+                    tc_fence_after();
+                    const int s = wait_stage();
+                    const uint32_t aB = aBase0 + sl * 65536, acc = tmem + sl * 256;
 #pragma unroll
-                for (int ks = 0; ks < 4; ks++)
-                    tc_mma(tmem, make_desc(aBase + ks * 32), make_desc(stageBase + s * kStageBytes + ks * 32), idesc256, ks > 0);
-                tc_commit(emptyBar(s));
-                tc_commit(mmaDone);
-            }
-            it++;
-            __syncwarp();
-            // residual layers: acc (already holding the fp32 residual) += A . W^T
-            for (int l = 0; l < nres; l++) {
-                named_bar_sync(1, 160);
-                tc_fence_after();
-                for (int kc = 0; kc < 4; kc++, it++) {
-                    if (lane == 0) {
-                        const int s = it % kStages;
-                        mbar_wait(fullBar(s), (it / kStages) & 1);
+                    for (int ks = 0; ks < 4; ks++)
+                        tc_mma(acc, make_desc(aB + ks * 32), make_desc(stageBase + s * kStageBytes + ks * 32), idesc256, ks > 0);
+                    tc_commit(emptyBar(s));
+                    tc_commit(mmaDoneBar(sl));
+                    it++;
+                }
+                // residual layers: acc (already holding the fp32 residual) += A . W^T
+                for (int l = 0; l < nres; l++) {
+                    for (int sl = 0; sl < nact; sl++) {
+                        mbar_wait(aReadyBar(sl), rdy[sl]); rdy[sl] ^= 1u;
                         tc_fence_after();
+                        const uint32_t aB = aBase0 + sl * 65536, acc = tmem + sl * 256;
+                        for (int kc = 0; kc < 4; kc++, it++) {
+                            const int s = wait_stage();
 #pragma unroll
-                        for (int ks = 0; ks < 4; ks++)
-                            tc_mma(tmem, make_desc(aBase + kc * 16384 + ks * 32), make_desc(stageBase + s * kStageBytes + ks * 32),
-                                   idesc256, 1u);
-                        tc_commit(emptyBar(s));
-                        if (kc == 3) tc_commit(mmaDone);
+                            for (int ks = 0; ks < 4; ks++)
+                                tc_mma(acc, make_desc(aB + kc * 16384 + ks * 32), make_desc(stageBase + s * kStageBytes + ks * 32), idesc256, 1u);
+                            tc_commit(emptyBar(s));
+                        }
+                        tc_commit(mmaDoneBar(sl));
                     }
                 }
-                __syncwarp();
-            }
-            // post layer 256 -> 64
-            named_bar_sync(1, 160);
-            tc_fence_after();
-            if (lane == 0) {
-                const int s = it % kStages;
-                mbar_wait(fullBar(s), (it / kStages) & 1);
-                tc_fence_after();
+                // post layer 256 -> 64
+                for (int sl = 0; sl < nact; sl++) {
+                    mbar_wait(aReadyBar(sl), rdy[sl]); rdy[sl] ^= 1u;
+                    tc_fence_after();
+                    const int s = wait_stage();
+                    const uint32_t aB = aBase0 + sl * 65536, acc = tmem + sl * 256;
 #pragma unroll
-                for (int ks = 0; ks < 16; ks++)
-                    tc_mma(tmem, make_desc(aBase + (ks >> 2) * 16384 + (ks & 3) * 32),
-                           make_desc(stageBase + s * kStageBytes + (ks >> 2) * 8192 + (ks & 3) * 32), idesc64, ks > 0);
-                tc_commit(emptyBar(s));
-                tc_commit(mmaDone);
+                    for (int ks = 0; ks < 16; ks++)
+                        tc_mma(acc, make_desc(aB + (ks >> 2) * 16384 + (ks & 3) * 32),
+                               make_desc(stageBase + s * kStageBytes + (ks >> 2) * 8192 + (ks & 3) * 32), idesc64, ks > 0);
+                    tc_commit(emptyBar(s));
+                    tc_commit(mmaDoneBar(sl));
+                    it++;
+                }
             }
-            it++;
-            __syncwarp();
         }
     } else {
-        // ---------------- prologue / epilogue warps: thread == row == TMEM lane ----------------
-        const int row = threadIdx.x;
-        const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        // ---------------- prologue / epilogue warps: slot = warpgroup, thread == row == TMEM lane ----------------
+        const int slot = warp >> 2;
+        const int row = threadIdx.x & 127;
+        uint8_t* sA = smem + kSmemA + slot * 65536;
+        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(slot * 256);
+        const uint32_t doneBar = mmaDoneBar(slot), readyBar = aReadyBar(slot);
         uint32_t phase = 0;
-        const float* bEnc = sSmall + kBEnc;
-        const float* bRes = sSmall + kBRes;
-        const float* bP0 = sSmall + kBRes + nres * kWidth;
+        const float* P = sp.v;
+        const float* bRes = P + kBRes;
+        const float* bP0 = P + kBRes + nres * kWidth;
         const float* wP1 = bP0 + 64;
         const float bP1 = wP1[64];
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        auto publish = [&]() {           // operand (and residual) of this slot are in place: hand over to the MMA thread
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(readyBar);
+        };
+        for (int tile = blockIdx.x * kSlots + slot; tile < ntiles; tile += gridDim.x * kSlots) {
             const int g = tile * kRows + row;
             // input layers on CUDA cores: h = [LReLU(W3 x[0:3] + b3) | LReLU(W2 x[3:5] + b2)], 64 values -> K-block 0
             float xin[5];
@@ -288,73 +326,84 @@ mlp_kernel(const uint8_t* __restrict__ wstages, const float* __restrict__ small_
                 for (int e = 0; e < 8; e++) {
                     const int o = j * 8 + e;
                     float s;
-                    if (o < 32) s = fmaf(sSmall[kE3W0 + o * 3 + 2], xin[2], fmaf(sSmall[kE3W0 + o * 3 + 1], xin[1], fmaf(sSmall[kE3W0 + o * 3], xin[0], sSmall[kE3B0 + o])));
-                    else s = fmaf(sSmall[kE2W0 + (o - 32) * 2 + 1], xin[4], fmaf(sSmall[kE2W0 + (o - 32) * 2], xin[3], sSmall[kE2B0 + o - 32]));
+                    if (o < 32) s = fmaf(P[kE3W0 + o * 3 + 2], xin[2], fmaf(P[kE3W0 + o * 3 + 1], xin[1], fmaf(P[kE3W0 + o * 3], xin[0], P[kE3B0 + o])));
+                    else s = fmaf(P[kE2W0 + (o - 32) * 2 + 1], xin[4], fmaf(P[kE2W0 + (o - 32) * 2], xin[3], P[kE2B0 + o - 32]));
                     h[e] = lrelu(s);
                 }
                 uint4 w;
                 w.x = pack2<BF16>(h[0], h[1]); w.y = pack2<BF16>(h[2], h[3]); w.z = pack2<BF16>(h[4], h[5]); w.w = pack2<BF16>(h[6], h[7]);
                 *reinterpret_cast<uint4*>(sA + a_chunk_off(row, j)) = w;
             }
-            fence_proxy_async();
-            tc_fence_before();
-            named_bar_sync(1, 160);
+            publish();
 
-            // encoder epilogue: out1 = LReLU(acc + b) -> TMEM (residual), TMEM copy (outer skip), A operand
-            mbar_wait(mmaDone, phase); phase ^= 1;
+            // encoder epilogue: out1 = LReLU(acc + b) -> TMEM (residual), registers (outer skip, 16 bit), A operand
+            uint32_t skip[128];
+            mbar_wait(doneBar, phase); phase ^= 1;
             tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < 8; c++) {
                 uint32_t v[32];
                 TMEM_LD32(tlane + c * 32, v);
                 tc_wait_ld();
-                float yv[32];
 #pragma unroll
-                for (int i = 0; i < 32; i++) { yv[i] = lrelu(__uint_as_float(v[i]) + bEnc[c * 32 + i]); v[i] = __float_as_uint(yv[i]); }
+                for (int i = 0; i < 32; i++) v[i] = __float_as_uint(lrelu(__uint_as_float(v[i]) + P[kBEnc + c * 32 + i]));
                 TMEM_ST32(tlane + c * 32, v);
-                TMEM_ST32(tlane + 256 + c * 32, v);
-                store_a32<BF16>(sA, row, c, yv);
+#pragma unroll
+                for (int i = 0; i < 16; i++) skip[c * 16 + i] = pack2<BF16>(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                uint8_t* kb = sA + (c >> 1) * 16384;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    *reinterpret_cast<uint4*>(kb + a_chunk_off(row, (c & 1) * 4 + q)) =
+                        make_uint4(skip[c * 16 + q * 4], skip[c * 16 + q * 4 + 1], skip[c * 16 + q * 4 + 2], skip[c * 16 + q * 4 + 3]);
             }
             tc_wait_st();
-            fence_proxy_async();
-            tc_fence_before();
-            named_bar_sync(1, 160);
+            publish();
 
-            for (int l = 0; l < nres; l++) {
-                mbar_wait(mmaDone, phase); phase ^= 1;
+            for (int l = 0; l < nres - 1; l++) {
+                mbar_wait(doneBar, phase); phase ^= 1;
                 tc_fence_after();
-                const bool last = l == nres - 1;
-#pragma unroll 1
+                const float* b = bRes + l * kWidth;
+#pragma unroll 2
                 for (int c = 0; c < 8; c++) {
                     uint32_t v[32];
                     TMEM_LD32(tlane + c * 32, v);
                     tc_wait_ld();
                     float yv[32];
 #pragma unroll
-                    for (int i = 0; i < 32; i++) yv[i] = lrelu(__uint_as_float(v[i]) + bRes[l * kWidth + c * 32 + i]);
-                    if (!last) {
-#pragma unroll
-                        for (int i = 0; i < 32; i++) v[i] = __float_as_uint(yv[i]);
-                        TMEM_ST32(tlane + c * 32, v);
-                    } else {
-                        TMEM_LD32(tlane + 256 + c * 32, v);          // outer skip: out1 + out2
-                        tc_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 32; i++) yv[i] += __uint_as_float(v[i]);
-                    }
+                    for (int i = 0; i < 32; i++) { yv[i] = lrelu(__uint_as_float(v[i]) + b[c * 32 + i]); v[i] = __float_as_uint(yv[i]); }
+                    TMEM_ST32(tlane + c * 32, v);
                     store_a32<BF16>(sA, row, c, yv);
                 }
                 tc_wait_st();
-                fence_proxy_async();
-                tc_fence_before();
-                named_bar_sync(1, 160);
+                publish();
+            }
+            {   // last residual layer: add the outer skip (out1 + out2), no residual write-back
+                mbar_wait(doneBar, phase); phase ^= 1;
+                tc_fence_after();
+                const float* b = bRes + (nres - 1) * kWidth;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    uint32_t v[32];
+                    TMEM_LD32(tlane + c * 32, v);
+                    tc_wait_ld();
+                    float yv[32];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        float s0, s1;
+                        unpack2<BF16>(skip[c * 16 + i], s0, s1);
+                        yv[2 * i] = lrelu(__uint_as_float(v[2 * i]) + b[c * 32 + 2 * i]) + s0;
+                        yv[2 * i + 1] = lrelu(__uint_as_float(v[2 * i + 1]) + b[c * 32 + 2 * i + 1]) + s1;
+                    }
+                    store_a32<BF16>(sA, row, c, yv);
+                }
+                publish();
             }
 
             // post epilogue: z = LReLU(acc[:,0:64] + b0); out = LReLU(w1 . z + b1) on CUDA cores
-            mbar_wait(mmaDone, phase); phase ^= 1;
+            mbar_wait(doneBar, phase); phase ^= 1;
             tc_fence_after();
             float acc = bP1;
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < 2; c++) {
                 uint32_t v[32];
                 TMEM_LD32(tlane + c * 32, v);
@@ -369,7 +418,7 @@ mlp_kernel(const uint8_t* __restrict__ wstages, const float* __restrict__ small_
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
     }
 }
@@ -387,7 +436,7 @@ inline size_t tile_off(int nrow, int kk) { return (size_t)(nrow / 8) * 1024 + (n
 struct MlpModel {
     int width = 0, nres = 0, dtype = 0;
     uint8_t* d_stages = nullptr;
-    float* d_small = nullptr;
+    SmallParams small;                     // fp32 side parameters, passed by value at every launch
     int num_sms = 148;
 };
 
@@ -437,9 +486,10 @@ int mlp_create(const void* blob, size_t bytes, int dtype, MlpModel** out, std::s
     MlpModel* m = new MlpModel();
     m->width = width; m->nres = nres; m->dtype = dtype;
     cudaError_t e;
-    if ((e = cudaMalloc(&m->d_stages, stages.size())) != cudaSuccess || (e = cudaMalloc(&m->d_small, sm.size() * 4)) != cudaSuccess ||
-        (e = cudaMemcpy(m->d_stages, stages.data(), stages.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(m->d_small, sm.data(), sm.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+    std::memset(&m->small, 0, sizeof(SmallParams));
+    std::memcpy(m->small.v, sm.data(), sm.size() * 4);
+    if ((e = cudaMalloc(&m->d_stages, stages.size())) != cudaSuccess ||
+        (e = cudaMemcpy(m->d_stages, stages.data(), stages.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
         err = std::string("mlp_create: ") + cudaGetErrorString(e);
         mlp_destroy(m);
         return -1;
@@ -455,7 +505,6 @@ int mlp_create(const void* blob, size_t bytes, int dtype, MlpModel** out, std::s
 void mlp_destroy(MlpModel* m) {
     if (!m) return;
     if (m->d_stages) cudaFree(m->d_stages);
-    if (m->d_small) cudaFree(m->d_small);
     delete m;
 }
 
@@ -464,9 +513,10 @@ int mlp_forward(const MlpModel* m, const dprt_half* x_dev, dprt_half* y_dev, int
     if (n <= 0) return 0;
     if (n > 0x7fffffff) { err = "mlp_forward: batch too large"; return -1; }
     const int ntiles = (int)((n + kRows - 1) / kRows);
-    const int grid = ntiles < m->num_sms ? ntiles : m->num_sms;
-    if (m->dtype == 0) mlp_kernel<true><<<grid, kThreads, kSmemTotal, stream>>>(m->d_stages, m->d_small, m->nres, x_dev, y_dev, (int)n);
-    else mlp_kernel<false><<<grid, kThreads, kSmemTotal, stream>>>(m->d_stages, m->d_small, m->nres, x_dev, y_dev, (int)n);
+    const int npairs = (ntiles + kSlots - 1) / kSlots;
+    const int grid = npairs < m->num_sms ? npairs : m->num_sms;
+    if (m->dtype == 0) mlp_kernel<true><<<grid, kThreads, kSmemTotal, stream>>>(m->d_stages, m->small, m->nres, x_dev, y_dev, (int)n);
+    else mlp_kernel<false><<<grid, kThreads, kSmemTotal, stream>>>(m->d_stages, m->small, m->nres, x_dev, y_dev, (int)n);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("mlp_kernel launch: ") + cudaGetErrorString(e); return -1; }
     return 0;
