@@ -198,8 +198,13 @@ int bvh8_build(const float* verts, const int32_t* mat_ids, int64_t ntris64, floa
         // node frame
         Box nb; nb.reset();
         for (int i = 0; i < nch; i++) nb.grow(n2[ch[i]].box);
+        // The frame is padded by a little more than any child will be (children get pad + 2^-7 of a quantisation step,
+        // the slack the traversal kernel's folded dequantisation needs, bvh_traverse.cuh), so no child bound clamps.
         Box padded = nb;
-        for (int a = 0; a < 3; a++) { padded.lo[a] -= pad; padded.hi[a] += pad; }
+        for (int a = 0; a < 3; a++) {
+            const float fp = pad * 1.01f + (nb.hi[a] - nb.lo[a]) * (1.0f / 8192.0f);
+            padded.lo[a] -= fp; padded.hi[a] += fp;
+        }
 
         // slot assignment (greedy on the octant cost table)
         float cost[8][8]; int slot_of[8]; bool slot_used[8] = {false}; bool child_done[8] = {false};
@@ -274,7 +279,8 @@ int bvh8_build(const float* verts, const int32_t* mat_ids, int64_t ntris64, floa
             uint8_t* qhi[3] = {&node.qhix[s], &node.qhiy[s], &node.qhiz[s]};
             for (int a = 0; a < 3; a++) {
                 double sc = std::ldexp(1.0, (int)node.e[a] - 127);
-                double lo = (double)cn.box.lo[a] - pad, hi = (double)cn.box.hi[a] + pad;
+                const double cpad = (double)pad + sc * (1.0 / 128.0);
+                double lo = (double)cn.box.lo[a] - cpad, hi = (double)cn.box.hi[a] + cpad;
                 double p0 = (double)node.p[a];
                 int ql = (int)std::floor((lo - p0) / sc);
                 int qh2 = (int)std::ceil((hi - p0) / sc);

@@ -10,9 +10,15 @@
 
 namespace dprt {
 
-DPRT_D float q2f(uint32_t w, uint32_t sel) {
-    // byte `sel & 3` of w -> float, via the 2^23 mantissa trick (exact for 0..255)
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
+// Byte j of a packed plane word -> the float 32768 + q, exactly: the byte lands in mantissa bits 8..15 of 2^15
+// (ulp 2^-8). One PRMT with an immediate selector; `magic` = 0x47000000 arrives as a kernel argument so that ptxas
+// cannot fold it: PRMT takes one immediate, and it has to be the selector -- with the constant in that slot the
+// compiler spends a move per PRMT fetching the four selectors from uniform registers (48 moves per node).
+template <int J>
+DPRT_D float qbias(uint32_t w, uint32_t magic) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(magic), "n"(0x7604 | (J << 4)));
+    return __uint_as_float(r);
 }
 
 #define DPRT_STACK 40
@@ -62,7 +68,7 @@ DPRT_D void trav_enter_object(Trav& s, const uint4* nodes, const float4* tris) {
 // runs with nearly all lanes busy and triangle tests run 32 wide, instead of 3-4 lanes wide when every lane
 // tests its own leaf. tbest of a lane lags by the queueing delay, which only makes node culling conservative.
 template <bool COUNT>
-DPRT_D void trav_node(Trav& s, uint2* stack, TraceCount& cnt) {
+DPRT_D void trav_node(Trav& s, uint2* stack, TraceCount& cnt, const uint32_t magic) {
     const uint32_t octinv = s.octinv;
     const uint32_t bit = 31u - __clz(s.ng.y);
     const uint32_t slot = (bit - 24u) ^ octinv;
@@ -79,9 +85,14 @@ DPRT_D void trav_node(Trav& s, uint2* stack, TraceCount& cnt) {
     const float adjx = __uint_as_float((n0.w & 0xffu) << 23) * s.idx;
     const float adjy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * s.idy;
     const float adjz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * s.idz;
-    const float orgx = (__uint_as_float(n0.x) - s.o.x) * s.idx;
-    const float orgy = (__uint_as_float(n0.y) - s.o.y) * s.idy;
-    const float orgz = (__uint_as_float(n0.z) - s.o.z) * s.idz;
+    // plane distance t = (p + q 2^e - o) / d = q adj + org. The byte is dequantised as F = 32768 + q (qbias), so the
+    // constant term carries the bias: t = F adj + (org - 32768 adj), one FFMA per plane. The folded constant is
+    // rounded at magnitude 2^15 |adj|, i.e. to 2^-9 of a quantisation step: the builder pads every child box by
+    // 2^-7 of a step for it (bvh_build.cpp), so the slab test stays conservative. Culling only -- accepted hits go
+    // through the exact triangle test, results do not depend on this arithmetic.
+    const float orgx = fmaf(-32768.0f, adjx, (__uint_as_float(n0.x) - s.o.x) * s.idx);
+    const float orgy = fmaf(-32768.0f, adjy, (__uint_as_float(n0.y) - s.o.y) * s.idy);
+    const float orgz = fmaf(-32768.0f, adjz, (__uint_as_float(n0.z) - s.o.z) * s.idz);
     const float tmin = s.tmin, tbest = s.tbest;
 
     uint32_t hitmask = 0;
@@ -94,24 +105,25 @@ DPRT_D void trav_node(Trav& s, uint2* stack, TraceCount& cnt) {
         const uint32_t hiy = h ? (ny ? n2.w : n4.y) : (ny ? n2.z : n4.x);
         const uint32_t loz = h ? (nz ? n4.w : n3.y) : (nz ? n4.z : n3.x);
         const uint32_t hiz = h ? (nz ? n3.y : n4.w) : (nz ? n3.x : n4.z);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t sel = 0x7650u | (uint32_t)j;
-            const float tnx = fmaf(q2f(lox, sel), adjx, orgx);
-            const float tny = fmaf(q2f(loy, sel), adjy, orgy);
-            const float tnz = fmaf(q2f(loz, sel), adjz, orgz);
-            const float tfx = fmaf(q2f(hix, sel), adjx, orgx);
-            const float tfy = fmaf(q2f(hiy, sel), adjy, orgy);
-            const float tfz = fmaf(q2f(hiz, sel), adjz, orgz);
-            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
-            // branch-free: child bits are computed for every slot and masked by the slab test
-            const uint32_t meta = (meta4 >> (8 * j)) & 0xffu;
-            const uint32_t inner = ((meta & 0x18u) == 0x18u) ? octinv : 0u;
-            const uint32_t bidx = (meta ^ inner) & 31u;
-            const uint32_t bits = (meta >> 5) << bidx;
-            hitmask |= (tn <= tf) ? bits : 0u;
+#define DPRT_CHILD(J)                                                                                   \
+        {                                                                                               \
+            const float tnx = fmaf(qbias<J>(lox, magic), adjx, orgx);                                   \
+            const float tny = fmaf(qbias<J>(loy, magic), adjy, orgy);                                   \
+            const float tnz = fmaf(qbias<J>(loz, magic), adjz, orgz);                                   \
+            const float tfx = fmaf(qbias<J>(hix, magic), adjx, orgx);                                   \
+            const float tfy = fmaf(qbias<J>(hiy, magic), adjy, orgy);                                   \
+            const float tfz = fmaf(qbias<J>(hiz, magic), adjz, orgz);                                   \
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                  \
+            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));                                 \
+            /* branch-free: child bits are computed for every slot and masked by the slab test */      \
+            const uint32_t meta = (meta4 >> (8 * J)) & 0xffu;                                           \
+            const uint32_t inner = ((meta & 0x18u) == 0x18u) ? octinv : 0u;                             \
+            const uint32_t bidx = (meta ^ inner) & 31u;                                                 \
+            const uint32_t bits = (meta >> 5) << bidx;                                                  \
+            hitmask |= (tn <= tf) ? bits : 0u;                                                          \
         }
+        DPRT_CHILD(0) DPRT_CHILD(1) DPRT_CHILD(2) DPRT_CHILD(3)
+#undef DPRT_CHILD
     }
     s.ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
     s.tg = make_uint2(n1.y, hitmask & 0x00ffffffu);

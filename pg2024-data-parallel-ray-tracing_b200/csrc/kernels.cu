@@ -126,6 +126,7 @@ struct TraceArgs {
     unsigned long long* counters;
     int refill;                      // refill a warp when at least this many lanes are idle
     int triVote;                     // force a triangle round when at least this many busy lanes cannot expand a node
+    uint32_t prmtMagic;              // 0x47000000 (bvh_traverse.cuh qbias): a run-time value on purpose
 };
 
 // next local object at or after `from` that the ray still has to visit; sceneSize when none
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceBlocksPerSM) trace_kernel(T
             const unsigned nodeM = __ballot_sync(FULL, canNode);
             const unsigned waitM = __ballot_sync(FULL, busy && !canNode);
             if (qlen > 0 && (qlen >= 32 || nodeM == 0u || __popc(waitM) >= a.triVote)) tri_round<ANY, COUNT>(w, qlen, lane, s, obj, pend, cnt);
-            else if (canNode) trav_node<COUNT>(s, stack, cnt);
+            else if (canNode) trav_node<COUNT>(s, stack, cnt, a.prmtMagic);
         } while (__popc(__ballot_sync(FULL, idx >= 0)) >= minBusy);
     }
     if (COUNT) {
@@ -623,7 +624,7 @@ TraceArgs trace_args(const DevParams& p, dprt_path_record* recs) {
     TraceArgs a;
     a.objects = p.objects; a.sceneSize = p.sceneSize; a.worldID = p.worldID; a.recs = recs; a.hits = p.hits;
     a.rays = nullptr; a.rayHits = nullptr; a.hitPrim = p.hitPrim; a.queue = p.traceQueue; a.counters = p.counters;
-    a.refill = tune_refill(); a.triVote = tune_trivote();
+    a.refill = tune_refill(); a.triVote = tune_trivote(); a.prmtMagic = 0x47000000u;
     return a;
 }
 
@@ -658,7 +659,7 @@ void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ra
     TraceArgs a;
     a.objects = objects; a.sceneSize = sceneSize; a.worldID = 0; a.recs = nullptr; a.hits = nullptr;
     a.rays = rays; a.rayHits = hits; a.hitPrim = nullptr; a.queue = queue; a.counters = counters;
-    a.refill = tune_refill(); a.triVote = tune_trivote();
+    a.refill = tune_refill(); a.triVote = tune_trivote(); a.prmtMagic = 0x47000000u;
     launch_trace<TM_RAYS>(a, n, s);
 }
 
