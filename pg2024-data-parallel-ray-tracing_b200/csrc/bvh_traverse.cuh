@@ -67,33 +67,25 @@ DPRT_D void trav_enter_object(Trav& s, const uint4* nodes, const float4* tris) {
 // waiting, the whole warp tests 32 of them at once (tri_round), whichever rays they belong to. Node expansion
 // runs with nearly all lanes busy and triangle tests run 32 wide, instead of 3-4 lanes wide when every lane
 // tests its own leaf. tbest of a lane lags by the queueing delay, which only makes node culling conservative.
-template <bool COUNT>
-DPRT_D void trav_node(Trav& s, uint2* stack, TraceCount& cnt, const uint32_t magic) {
-    const uint32_t octinv = s.octinv;
-    const uint32_t bit = 31u - __clz(s.ng.y);
-    const uint32_t slot = (bit - 24u) ^ octinv;
-    const uint32_t rel = __popc(s.ng.y & 0xffu & ((1u << slot) - 1u));
-    s.ng.y &= ~(1u << bit);
-    const uint32_t ni = s.ng.x + rel;
-    if (s.ng.y & 0xff000000u) { if (s.sp < DPRT_STACK) stack[s.sp++] = s.ng; }
-    if (COUNT) cnt.nodes++;
-
-    const uint4* np = s.nodes + 5 * (size_t)ni;
+// Slab test of the 8 children of node `ni` against one ray: returns the node's child base / triangle base and the
+// hit bits of its internal children (bits 24..31, octant order: higher bit = nearer) and of its leaf triangles (0..23).
+DPRT_D void expand_node(const uint4* __restrict__ nodes, uint32_t ni, float ox, float oy, float oz, float idx, float idy, float idz,
+                        uint32_t octinv, float tmin, float tbest, uint32_t magic, uint2& ng, uint2& tg) {
+    const uint4* np = nodes + 5 * (size_t)ni;
     const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
     const bool nx = !(octinv & 1u), ny = !(octinv & 2u), nz = !(octinv & 4u);
 
-    const float adjx = __uint_as_float((n0.w & 0xffu) << 23) * s.idx;
-    const float adjy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * s.idy;
-    const float adjz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * s.idz;
+    const float adjx = __uint_as_float((n0.w & 0xffu) << 23) * idx;
+    const float adjy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23) * idy;
+    const float adjz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23) * idz;
     // plane distance t = (p + q 2^e - o) / d = q adj + org. The byte is dequantised as F = 32768 + q (qbias), so the
     // constant term carries the bias: t = F adj + (org - 32768 adj), one FFMA per plane. The folded constant is
     // rounded at magnitude 2^15 |adj|, i.e. to 2^-9 of a quantisation step: the builder pads every child box by
     // 2^-7 of a step for it (bvh_build.cpp), so the slab test stays conservative. Culling only -- accepted hits go
     // through the exact triangle test, results do not depend on this arithmetic.
-    const float orgx = fmaf(-32768.0f, adjx, (__uint_as_float(n0.x) - s.o.x) * s.idx);
-    const float orgy = fmaf(-32768.0f, adjy, (__uint_as_float(n0.y) - s.o.y) * s.idy);
-    const float orgz = fmaf(-32768.0f, adjz, (__uint_as_float(n0.z) - s.o.z) * s.idz);
-    const float tmin = s.tmin, tbest = s.tbest;
+    const float orgx = fmaf(-32768.0f, adjx, (__uint_as_float(n0.x) - ox) * idx);
+    const float orgy = fmaf(-32768.0f, adjy, (__uint_as_float(n0.y) - oy) * idy);
+    const float orgz = fmaf(-32768.0f, adjz, (__uint_as_float(n0.z) - oz) * idz);
 
     uint32_t hitmask = 0;
 #pragma unroll
@@ -125,13 +117,32 @@ DPRT_D void trav_node(Trav& s, uint2* stack, TraceCount& cnt, const uint32_t mag
         DPRT_CHILD(0) DPRT_CHILD(1) DPRT_CHILD(2) DPRT_CHILD(3)
 #undef DPRT_CHILD
     }
-    s.ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
-    s.tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
+    ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
+    tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
+}
+
+// index of the node that bit `bit` (24..31) of node group g stands for
+DPRT_D uint32_t group_node(uint2 g, uint32_t bit, uint32_t octinv) {
+    const uint32_t slot = (bit - 24u) ^ octinv;
+    return g.x + __popc(g.y & 0xffu & ((1u << slot) - 1u));
+}
+
+template <bool COUNT>
+DPRT_D void trav_node(Trav& s, uint2* stack, TraceCount& cnt, const uint32_t magic) {
+    const uint32_t bit = 31u - __clz(s.ng.y);
+    const uint32_t ni = group_node(s.ng, bit, s.octinv);
+    s.ng.y &= ~(1u << bit);
+    if (s.ng.y & 0xff000000u) { if (s.sp < DPRT_STACK) stack[s.sp++] = s.ng; }
+    if (COUNT) cnt.nodes++;
+    expand_node(s.nodes, ni, s.o.x, s.o.y, s.o.z, s.idx, s.idy, s.idz, s.octinv, s.tmin, s.tbest, magic, s.ng, s.tg);
 }
 
 // ---- warp-wide triangle queue -----------------------------------------------------------------------
 #define DPRT_QCAP 128                      // queue capacity per warp (pairs)
 #define DPRT_TRI_BITS 27                   // queue entry = owner lane << 27 | triangle index
+#define DPRT_POOLCAP 1024                  // cooperative-mode node pool per warp (global scratch: shared memory is L1 capacity)
+#define DPRT_POOLLIM 760                   // wide steps keep the pool below this; above it one node per step (DFS), which adds
+                                           // at most 7 entries per tree level: 760 + 7 * 36 (deepest BVH accepted at upload) < 1024
 
 struct WarpQueue {
     float4 rayA[32];                       // per owner lane: origin.xyz, tmin
@@ -142,6 +153,7 @@ struct WarpQueue {
     float  tlimit[32];                     // strict upper bound for the owner's current object
     int    cnt[32];                        // pairs of this owner tested in the round
     uint32_t q[DPRT_QCAP];
+    int    plen;                           // cooperative tail mode: pool length hand-over
 };
 
 DPRT_D void wq_set_ray(WarpQueue& w, int lane, const Trav& s) {
@@ -215,6 +227,102 @@ DPRT_D void tri_round(WarpQueue& w, int& qlen, int lane, Trav& s, int obj, int& 
         }
     }
     __syncwarp();
+}
+
+
+// ---- cooperative tail mode ----------------------------------------------------------------------------
+// Once the ray queue is exhausted a warp is left with a few rays, and its running time is the node count of the
+// longest one at one node per loop iteration (a grazing ray over the height field visits hundreds of nodes while 31
+// lanes idle). coop_run() finishes the current object of ONE ray (owner lane L) with all 32 lanes: the owner's
+// traversal stack becomes a shared pool of node indices, every lane expands one node per step, hit children go back
+// to the pool, leaf triangles to the warp triangle queue (owner L), whose rounds feed the shrinking tbest back.
+// Valid because the closest hit is the minimum over all accepted triangle tests in (t, primitive id) order and the
+// any-hit answer is a flag: neither depends on the order in which nodes are visited.
+
+// appends the pending triangles of all lanes (tg) to the queue on behalf of `owner`, as far as they fit; returns the
+// number appended (warp-uniform)
+DPRT_D int coop_append(WarpQueue& w, int& qlen, int lane, int owner, uint2& tg) {
+    const unsigned FULL = 0xffffffffu;
+    const int c = __popc(tg.y);
+    if (__ballot_sync(FULL, c > 0) == 0u) return 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(FULL, incl, 31);
+    int pos = qlen + incl - c;
+    while (tg.y != 0u && pos < DPRT_QCAP) {
+        const uint32_t k = __ffs(tg.y) - 1u;
+        tg.y &= tg.y - 1u;
+        w.q[pos++] = ((uint32_t)owner << DPRT_TRI_BITS) | (tg.x + k);
+    }
+    const int before = qlen;
+    qlen = min(DPRT_QCAP, qlen + total);
+    return qlen - before;
+}
+
+template <bool ANY, bool COUNT>
+DPRT_D void coop_run(WarpQueue& w, uint32_t* __restrict__ pool, int& qlen, int lane, int L, Trav& s, uint2* stack, int obj, int& pend,
+                     bool& exh, TraceCount& cnt, const uint32_t magic) {
+    const unsigned FULL = 0xffffffffu;
+    while (qlen > 0) tri_round<ANY, COUNT>(w, qlen, lane, s, obj, pend, cnt);     // every owner's queued pairs first
+    // the owner's ray, in every lane's registers
+    const float ox = __shfl_sync(FULL, s.o.x, L), oy = __shfl_sync(FULL, s.o.y, L), oz = __shfl_sync(FULL, s.o.z, L);
+    const float idx = __shfl_sync(FULL, s.idx, L), idy = __shfl_sync(FULL, s.idy, L), idz = __shfl_sync(FULL, s.idz, L);
+    const float tmin = __shfl_sync(FULL, s.tmin, L);
+    const uint32_t octinv = __shfl_sync(FULL, s.octinv, L);
+    const uint4* nodes = (const uint4*)(uintptr_t)__shfl_sync(FULL, (unsigned long long)(uintptr_t)s.nodes, L);
+    float ct = __shfl_sync(FULL, s.tbest, L);
+    uint2 ctg = make_uint2(0u, 0u);
+    if (lane == L) {
+        int n = 0;
+        for (int i = 0; i <= s.sp; i++) {                 // bottom of the stack first, the current group last (on top)
+            const uint2 g = i < s.sp ? stack[i] : s.ng;
+            uint32_t m = g.y & 0xff000000u;
+            while (m) { const uint32_t bit = __ffs(m) - 1u; m &= m - 1u; pool[n++] = group_node(g, bit, octinv); }   // far first
+        }
+        w.plen = n;
+        ctg = s.tg;
+        s.ng = make_uint2(0u, 0u); s.tg = make_uint2(0u, 0u); s.sp = 0;
+    }
+    __syncwarp();
+    int plen = w.plen;
+    for (;;) {
+        const int added = coop_append(w, qlen, lane, L, ctg);
+        if (lane == L) pend += added;
+        const bool more = __ballot_sync(FULL, ctg.y != 0u) != 0u;
+        if (qlen > 0 && (qlen >= 32 || more || plen == 0)) {
+            tri_round<ANY, COUNT>(w, qlen, lane, s, obj, pend, cnt);
+            ct = __shfl_sync(FULL, s.tbest, L);
+            if (ANY && __shfl_sync(FULL, (int)(s.hitTri >= 0), L)) {          // accepted: drop what is left of this ray
+                qlen = 0; plen = 0; ctg.y = 0u;
+                if (lane == L) pend = 0;
+                break;
+            }
+            continue;
+        }
+        if (plen == 0) break;                                                  // pool, queue and pending groups are empty
+        // every lane takes one node off the top of the pool (lane 0 the nearest), as many as are sure to fit back
+        const int np = max(1, min(min(32, plen), (DPRT_POOLLIM - plen) >> 3));
+        uint2 cg = make_uint2(0u, 0u);
+        if (lane < np) {
+            const uint32_t ni = pool[plen - 1 - lane];
+            if (COUNT) cnt.nodes++;
+            expand_node(nodes, ni, ox, oy, oz, idx, idy, idz, octinv, tmin, ct, magic, cg, ctg);
+        }
+        plen -= np;
+        __syncwarp();
+        const int c = __popc(cg.y >> 24);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(FULL, incl, 31);
+        int pos = plen + total - incl;                                          // lane 0's children end up on top
+        uint32_t m = cg.y & 0xff000000u;
+        while (m) { const uint32_t bit = __ffs(m) - 1u; m &= m - 1u; pool[pos++] = group_node(cg, bit, octinv); }
+        plen += total;
+        __syncwarp();
+    }
+    if (lane == L) exh = true;          // object exhausted: the caller's step (2) moves on to the next object / completes the ray
 }
 
 }  // namespace dprt

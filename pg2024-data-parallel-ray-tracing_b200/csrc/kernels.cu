@@ -108,6 +108,8 @@ constexpr int kTraceBlock = 128;
 constexpr int kTraceBlocksPerSM = 6;
 constexpr int kRefillDefault = 8;
 constexpr int kTriVoteDefault = 8;
+constexpr int kCoopDefault = 8;
+constexpr int kRaysPerLaneDefault = 1;
 
 template <int MODE> struct StageOf;
 template <> struct StageOf<TM_TRAVERSE> { static constexpr int id = DPRT_STAGE_TRAVERSE; };
@@ -127,6 +129,8 @@ struct TraceArgs {
     int refill;                      // refill a warp when at least this many lanes are idle
     int triVote;                     // force a triangle round when at least this many busy lanes cannot expand a node
     uint32_t prmtMagic;              // 0x47000000 (bvh_traverse.cuh qbias): a run-time value on purpose
+    uint32_t* coopPool;              // DPRT_POOLCAP words per resident warp
+    int coop;                        // tail: a warp left with at most this many rays finishes them one at a time, 32 lanes per ray
 };
 
 // next local object at or after `from` that the ray still has to visit; sceneSize when none
@@ -262,6 +266,15 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceBlocksPerSM) trace_kernel(T
                         reinterpret_cast<float2*>(a.rayHits)[idx] = make_float2(s.tbest, __int_as_float(hit ? s.hitPrim : -1));
                     }
                     idx = -1;
+                }
+            }
+            // (2.5) tail of the launch: few rays left in this warp -> all lanes work on one of them (bvh_traverse.cuh)
+            if (exhausted && a.coop > 0) {
+                const unsigned workM = __ballot_sync(FULL, idx >= 0 && obj < a.sceneSize && !exh);
+                if (workM != 0u && __popc(__ballot_sync(FULL, idx >= 0)) <= a.coop) {
+                    coop_run<ANY, COUNT>(w, a.coopPool + (size_t)(blockIdx.x * (kTraceBlock / 32) + (threadIdx.x >> 5)) * DPRT_POOLCAP, qlen, lane,
+                                         __ffs(workM) - 1, s, stack, obj, pend, exh, cnt, a.prmtMagic);
+                    continue;
                 }
             }
             // (3) the warp votes: a full (or forced) triangle round, else one node per lane
@@ -610,12 +623,31 @@ int env_int(const char* name, int dflt, int lo, int hi) {
 }
 int tune_refill() { static int v = env_int("DPRT_TRACE_REFILL", kRefillDefault, 1, 32); return v; }
 int tune_trivote() { static int v = env_int("DPRT_TRACE_TRIVOTE", kTriVoteDefault, 1, 32); return v; }
+int tune_coop() { static int v = env_int("DPRT_TRACE_COOP", kCoopDefault, 0, 32); return v; }
+int tune_rpl() { static int v = env_int("DPRT_TRACE_RPL", kRaysPerLaneDefault, 1, 64); return v; }
 int tune_blocks() { static int v = env_int("DPRT_TRACE_BLOCKS_PER_SM", kTraceBlocksPerSM, 1, 16); return v; }
 
+// scratch for the cooperative tail mode: one node pool per warp that can be resident (allocated once per device)
+uint32_t* coop_pool() {
+    static uint32_t* pools[64] = {nullptr};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return nullptr;
+    if (!pools[dev]) {
+        const size_t warps = (size_t)num_sms() * 16 * (kTraceBlock / 32);
+        if (cudaMalloc(&pools[dev], warps * DPRT_POOLCAP * sizeof(uint32_t)) != cudaSuccess) { pools[dev] = nullptr; cudaGetLastError(); }
+    }
+    return pools[dev];
+}
+
 template <int MODE>
-void launch_trace(const TraceArgs& a, int64_t n, cudaStream_t s) {
+void launch_trace(TraceArgs a, int64_t n, cudaStream_t s) {
     cudaMemsetAsync(a.queue, 0, sizeof(int32_t), s);
-    const int blocks = (int)std::min<int64_t>((n + kTraceBlock - 1) / kTraceBlock, (int64_t)num_sms() * tune_blocks());
+    a.coopPool = coop_pool();
+    if (!a.coopPool) a.coop = 0;
+    // Grid: never more warps than keep every lane supplied with ~tune_rpl() rays. A warp runs until its longest ray is
+    // done, so with one ray per lane its efficiency is mean/max ray length; with a few rays per lane the refill evens it out.
+    const int64_t want = (n + (int64_t)kTraceBlock * tune_rpl() - 1) / ((int64_t)kTraceBlock * tune_rpl());
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms() * tune_blocks()));
     if (a.counters) trace_kernel<MODE, true><<<blocks, kTraceBlock, 0, s>>>(a, (int)n);
     else trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, s>>>(a, (int)n);
 }
@@ -624,7 +656,7 @@ TraceArgs trace_args(const DevParams& p, dprt_path_record* recs) {
     TraceArgs a;
     a.objects = p.objects; a.sceneSize = p.sceneSize; a.worldID = p.worldID; a.recs = recs; a.hits = p.hits;
     a.rays = nullptr; a.rayHits = nullptr; a.hitPrim = p.hitPrim; a.queue = p.traceQueue; a.counters = p.counters;
-    a.refill = tune_refill(); a.triVote = tune_trivote(); a.prmtMagic = 0x47000000u;
+    a.refill = tune_refill(); a.triVote = tune_trivote(); a.prmtMagic = 0x47000000u; a.coop = tune_coop();
     return a;
 }
 
@@ -659,7 +691,7 @@ void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ra
     TraceArgs a;
     a.objects = objects; a.sceneSize = sceneSize; a.worldID = 0; a.recs = nullptr; a.hits = nullptr;
     a.rays = rays; a.rayHits = hits; a.hitPrim = nullptr; a.queue = queue; a.counters = counters;
-    a.refill = tune_refill(); a.triVote = tune_trivote(); a.prmtMagic = 0x47000000u;
+    a.refill = tune_refill(); a.triVote = tune_trivote(); a.prmtMagic = 0x47000000u; a.coop = tune_coop();
     launch_trace<TM_RAYS>(a, n, s);
 }
 
