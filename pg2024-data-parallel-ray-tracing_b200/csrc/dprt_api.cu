@@ -298,7 +298,7 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
         CK(cudaMalloc(&ctx->scratch.tileState, (size_t)ctx->scratch.maxTiles * 32 * sizeof(uint32_t)));
         CK(cudaMalloc(&ctx->scratch.tileCounter, sizeof(int32_t)));
         CK(cudaMalloc(&ctx->d_hits, N * sizeof(HitRec)));
-        CK(cudaMalloc(&ctx->d_queue, 64));
+        CK(cudaMalloc(&ctx->d_queue, trace_scratch_bytes()));
         CK(cudaMalloc(&ctx->d_image, 3 * N * sizeof(float)));
         CK(cudaMalloc(&ctx->d_image_sum, 3 * N * sizeof(float)));
         CK(cudaMalloc(&ctx->d_gather, sizeof(int32_t) * (size_t)world * (world + 1)));

@@ -75,6 +75,7 @@ void launch_traverse(const DevParams& p, int n, cudaStream_t stream);
 void launch_shade(const DevParams& p, int n, cudaStream_t stream);
 void launch_shadow_trace(const DevParams& p, int nShadow, cudaStream_t stream);
 void launch_secondary_trace(const DevParams& p, int n, cudaStream_t stream);
+size_t trace_scratch_bytes();   // per-context scratch of the persistent trace kernel (queue head + cooperative-mode pools)
 void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ray* rays, dprt_hit* hits, int64_t n,
                           int32_t* queue, unsigned long long* counters, cudaStream_t stream);
 

@@ -627,23 +627,10 @@ int tune_coop() { static int v = env_int("DPRT_TRACE_COOP", kCoopDefault, 0, 32)
 int tune_rpl() { static int v = env_int("DPRT_TRACE_RPL", kRaysPerLaneDefault, 1, 64); return v; }
 int tune_blocks() { static int v = env_int("DPRT_TRACE_BLOCKS_PER_SM", kTraceBlocksPerSM, 1, 16); return v; }
 
-// scratch for the cooperative tail mode: one node pool per warp that can be resident (allocated once per device)
-uint32_t* coop_pool() {
-    static uint32_t* pools[64] = {nullptr};
-    int dev = 0; cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return nullptr;
-    if (!pools[dev]) {
-        const size_t warps = (size_t)num_sms() * 16 * (kTraceBlock / 32);
-        if (cudaMalloc(&pools[dev], warps * DPRT_POOLCAP * sizeof(uint32_t)) != cudaSuccess) { pools[dev] = nullptr; cudaGetLastError(); }
-    }
-    return pools[dev];
-}
-
 template <int MODE>
 void launch_trace(TraceArgs a, int64_t n, cudaStream_t s) {
     cudaMemsetAsync(a.queue, 0, sizeof(int32_t), s);
-    a.coopPool = coop_pool();
-    if (!a.coopPool) a.coop = 0;
+    a.coopPool = reinterpret_cast<uint32_t*>(a.queue + 16);      // the context's trace scratch: queue head, then the node pools
     // Grid: never more warps than keep every lane supplied with ~tune_rpl() rays. A warp runs until its longest ray is
     // done, so with one ray per lane its efficiency is mean/max ray length; with a few rays per lane the refill evens it out.
     const int64_t want = (n + (int64_t)kTraceBlock * tune_rpl() - 1) / ((int64_t)kTraceBlock * tune_rpl());
@@ -661,6 +648,11 @@ TraceArgs trace_args(const DevParams& p, dprt_path_record* recs) {
 }
 
 }  // namespace
+
+size_t trace_scratch_bytes() {
+    // 64 B for the ray-queue head + one cooperative-mode node pool per warp that can be resident
+    return 64 + (size_t)num_sms() * tune_blocks() * (kTraceBlock / 32) * DPRT_POOLCAP * sizeof(uint32_t);
+}
 
 void launch_path_gen(const DevParams& p, int n, cudaStream_t s) {
     if (n > 0) path_gen_kernel<<<blocks_for(n), kBlock, 0, s>>>(p, n);
