@@ -189,7 +189,7 @@ def workload_config(args, W, fw, fh):
     return {"workload": f"configs[1] scene per GPU: synthetic {args.tris}-triangle chunk x {W} chunk(s), {fw}x{fh} frame "
                         f"(1920x1080 pixels per GPU), 1 spp per step, full per-sample loop with bounces={args.bounces}, spc=4, mc=3",
             "chunks": W, "tris_per_chunk": args.tris, "width": fw, "height": fh, "bounces": args.bounces,
-            "proxy": bool(args.proxy and W > 1), "path_gen": "rank0" if (args.path_gen_mode == 0 or W == 1) else "striped",
+            "proxy": bool(args.proxy and W > 1), "main_ray": "re-trace" if args.retrace else "hit cache", "path_gen": "rank0" if (args.path_gen_mode == 0 or W == 1) else "striped",
             "l2": "inputs larger than L2: 5 x 64 B path records per pixel (663 MB at 1080p) are rewritten every bounce",
             "parallelism": f"scene-chunk x{W}"}
 
@@ -336,7 +336,7 @@ def run_dprt(args):
     N = fw * fh
     proxy = 1 if (args.proxy and W > 1) else 0
     cfg = dprt.make_config(fw, fh, spp=1, bounces=args.bounces, scene_size=W, proxy_mode=proxy,
-                           path_gen_mode=args.path_gen_mode if W > 1 else 0, mlp_dtype=0)
+                           path_gen_mode=args.path_gen_mode if W > 1 else 0, mlp_dtype=0, main_ray_retrace=args.retrace)
     chunks, mats, lights = build_world_scene(dprt, W, args.tris)
     blobs = proxy_blobs(dprt, W, proxy)
     cam = dprt.scene.default_camera(fw, fh)
@@ -382,8 +382,11 @@ def run_dprt(args):
     stage = R.stage_times()
     R.stage_profile(False)
     ms = allreduce(ms, dist.ReduceOp.MAX if W > 1 else None)
-    my_rays = st["rays_traverse"] + st["rays_shade"] + st["rays_shadow"] + st["rays_secondary"]
+    # rays = BVH walks actually performed: MainRay queries answered from the hit cache (the closest hit TraRay already
+    # found for the same ray) are reported separately and are NOT counted in `value`
+    my_rays = st["rays_traverse"] + st["rays_shade"] - st["rays_shade_cached"] + st["rays_shadow"] + st["rays_secondary"]
     rays = allreduce(float(my_rays), dist.ReduceOp.SUM if W > 1 else None)
+    cached = allreduce(float(st["rays_shade_cached"]), dist.ReduceOp.SUM if W > 1 else None)
     launches = allreduce(float(st["kernel_launches"]), dist.ReduceOp.SUM if W > 1 else None)
     sent = allreduce(float(st["bytes_alltoall"]), dist.ReduceOp.SUM if W > 1 else None)
     value = rays / (ms * 1e-3) / 1e6
@@ -395,7 +398,7 @@ def run_dprt(args):
     R.synchronize()
     cnt = R.counters(); cst = R.stats()
     R.enable_counters(False)
-    nrays = {"traverse": cst["rays_traverse"], "shade": cst["rays_shade"], "shadow_trace": cst["rays_shadow"], "secondary_trace": cst["rays_secondary"]}
+    nrays = {"traverse": cst["rays_traverse"], "shade": cst["rays_shade"] - cst["rays_shade_cached"], "shadow_trace": cst["rays_shadow"], "secondary_trace": cst["rays_secondary"]}
     stages_out = {}
     for name in TRAVERSAL_STAGES:
         t_ms, ln = stage[name]
@@ -443,6 +446,7 @@ def run_dprt(args):
     st1 = R.stats()
     e2e_s = allreduce(e2e_s, dist.ReduceOp.MAX if W > 1 else None)
     e_rays = sum(st1[k] - st0[k] for k in ("rays_traverse", "rays_shade", "rays_shadow", "rays_secondary"))
+    e_rays -= st1["rays_shade_cached"] - st0["rays_shade_cached"]
     e_rays = allreduce(float(e_rays), dist.ReduceOp.SUM if W > 1 else None)
     e2e = {"value": e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(N * 12),
            "ms_per_step": e2e_s / args.steps * 1e3, "samples_per_s": N * args.steps / e2e_s,
@@ -453,6 +457,7 @@ def run_dprt(args):
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": W, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "samples_per_s": N * args.steps / (ms * 1e-3), "rays_per_step": rays / args.steps,
+                "main_ray_queries_from_hit_cache_per_step": cached / args.steps,
                 "config": workload_config(args, W, fw, fh), "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clk, "stages": stages_out,
                 "alltoall": {"bytes_per_step": sent / args.steps, "exchange_iters_per_step": st["exchange_iters"] / args.steps}}
@@ -483,6 +488,7 @@ def main():
     ap.add_argument("--proxy", type=int, default=0, help="neural proxies for shadow/secondary rays at remote chunks (N>1)")
     ap.add_argument("--path-gen-mode", type=int, default=1, help="N>1: 0 = rank 0 generates all camera paths (reference), 1 = striped")
     ap.add_argument("--ref-scale", type=int, default=4, help="reference/cpu_baseline arm: frame reduced by this factor per side")
+    ap.add_argument("--retrace", type=int, default=0, help="1 = MainRay always re-traces (no hit cache), for A/B")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")
     args = ap.parse_args()

@@ -112,7 +112,9 @@ typedef struct dprt_config {
     int32_t pathGenMode;      /* 0 = rank 0 generates all camera paths (renderer.cpp:1514), 1 = striped */
     int32_t mlpDtype;         /* 0 = bf16 operands, 1 = fp16 operands (fp32 accumulate either way) */
     float   envColor[3];      /* analytic environment: Le = envColor * (0.5 + 0.5*dir.z) */
-    int32_t reserved_[3];
+    int32_t mainRayRetrace;   /* 0 = MainRay reuses the closest hit TraRay / SecondaryRay found for the same ray on this rank
+                                 (identical result, see DESIGN.md "hit cache"); 1 = always re-trace like kernel.cu:382-413 */
+    int32_t reserved_[2];
 } dprt_config;
 
 /* Standalone closest-hit query (the optixTrace equivalent used by BASELINE config 2). */
@@ -158,7 +160,8 @@ typedef struct dprt_stats {
     int64_t exchange_iters;
     int64_t kernel_launches;
     int64_t bytes_alltoall;
-    int64_t reserved_[7];
+    int64_t rays_shade_cached; /* subset of rays_shade answered from the hit cache instead of a second BVH walk */
+    int64_t reserved_[6];
 } dprt_stats;
 
 /* Buffer identifiers for dprt_download/dprt_upload (parity harness access to Params buffers). */

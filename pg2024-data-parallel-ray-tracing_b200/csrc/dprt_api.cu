@@ -93,6 +93,9 @@ struct dprt_ctx {
     int32_t* d_hist = nullptr;          // 32 path + 64 query counters
     PartitionScratch scratch{};
     HitRec* d_hits = nullptr;           // N closest-hit records (MainRay)
+    HitRec* d_hitCache = nullptr;       // N per-pixel closest hits of the current epoch (null when cfg.mainRayRetrace)
+    unsigned long long* d_cacheHits = nullptr;   // MainRay queries answered from the cache since the last reset_stats
+    uint32_t epoch = 1;                 // bumped whenever the rays behind the path records change (new bounce, new paths)
     int32_t* d_queue = nullptr;         // ray queue head of the persistent trace kernel
     float* d_image = nullptr;           // averaged image, 3N
     float* d_image_sum = nullptr;       // reduce target, 3N
@@ -190,6 +193,7 @@ void sync_params(dprt_ctx* ctx) {
     p.worldID = ctx->rank; p.worldSize = ctx->world; p.sampleCount = ctx->sample;
     p.frameBufferSize = ctx->N; p.proxyMode = ctx->cfg.proxyMode; p.pathGenMode = ctx->cfg.pathGenMode;
     for (int k = 0; k < 3; k++) p.envColor[k] = ctx->cfg.envColor[k];
+    p.hitCache = ctx->d_hitCache; p.hitEpoch = ctx->epoch; p.cacheHits = ctx->d_cacheHits;
 }
 
 int upload_objects(dprt_ctx* ctx) {
@@ -298,6 +302,12 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
         CK(cudaMalloc(&ctx->scratch.tileState, (size_t)ctx->scratch.maxTiles * 32 * sizeof(uint32_t)));
         CK(cudaMalloc(&ctx->scratch.tileCounter, sizeof(int32_t)));
         CK(cudaMalloc(&ctx->d_hits, N * sizeof(HitRec)));
+        if (!cfg->mainRayRetrace) {
+            CK(cudaMalloc(&ctx->d_hitCache, N * sizeof(HitRec)));
+            CK(cudaMemsetAsync(ctx->d_hitCache, 0, N * sizeof(HitRec), ctx->stream));      // epoch 0 = never written
+            CK(cudaMalloc(&ctx->d_cacheHits, sizeof(unsigned long long)));
+            CK(cudaMemsetAsync(ctx->d_cacheHits, 0, sizeof(unsigned long long), ctx->stream));
+        }
         CK(cudaMalloc(&ctx->d_queue, trace_scratch_bytes()));
         CK(cudaMalloc(&ctx->d_image, 3 * N * sizeof(float)));
         CK(cudaMalloc(&ctx->d_image_sum, 3 * N * sizeof(float)));
@@ -360,6 +370,8 @@ void dprt_destroy(dprt_ctx* ctx) {
     if (ctx->scratch.tileState) cudaFree(ctx->scratch.tileState);
     if (ctx->scratch.tileCounter) cudaFree(ctx->scratch.tileCounter);
     if (ctx->d_hits) cudaFree(ctx->d_hits);
+    if (ctx->d_hitCache) cudaFree(ctx->d_hitCache);
+    if (ctx->d_cacheHits) cudaFree(ctx->d_cacheHits);
     if (ctx->d_queue) cudaFree(ctx->d_queue);
     if (ctx->d_image) cudaFree(ctx->d_image);
     if (ctx->d_image_sum) cudaFree(ctx->d_image_sum);
@@ -383,7 +395,17 @@ int dprt_synchronize(dprt_ctx* ctx) {
     CK(cudaGetLastError());
     return 0;
 }
-int dprt_get_stats(const dprt_ctx* ctx, dprt_stats* out) { if (!ctx || !out) return DPRT_ERR_INVALID; *out = ctx->stats; return 0; }
+int dprt_get_stats(const dprt_ctx* ctx, dprt_stats* out) {
+    if (!ctx || !out) return DPRT_ERR_INVALID;
+    *out = ctx->stats;
+    if (ctx->d_cacheHits) {            // the one statistic that is only known on the device
+        unsigned long long v = 0;
+        if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+            cudaMemcpy(&v, ctx->d_cacheHits, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return DPRT_ERR_CUDA;
+        out->rays_shade_cached = (int64_t)v;
+    }
+    return 0;
+}
 int dprt_reset_stats(dprt_ctx* ctx) {
     if (!ctx) return DPRT_ERR_INVALID;
     ctx->stats = dprt_stats{};
@@ -391,6 +413,7 @@ int dprt_reset_stats(dprt_ctx* ctx) {
     resolve_pending(ctx);
     for (int i = 0; i < DPRT_STAGE_COUNT; i++) { ctx->stageMs[i] = 0.0; ctx->stageLaunches[i] = 0; }
     if (ctx->d_counters) CK(cudaMemsetAsync(ctx->d_counters, 0, 2 * DPRT_STAGE_COUNT * sizeof(unsigned long long), ctx->stream));
+    if (ctx->d_cacheHits) CK(cudaMemsetAsync(ctx->d_cacheHits, 0, sizeof(unsigned long long), ctx->stream));
     return 0;
 }
 
@@ -527,6 +550,7 @@ int dprt_begin_sample(dprt_ctx* ctx, int sample) {
     if (!ctx) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     ctx->sample = sample;
+    ctx->epoch++;
     // resetSampleBuffers: offsets to zero. Path buffers are reset by count (slots >= pathSize are never read).
     CK(cudaMemsetAsync(ctx->hp.transferOffset, 0, 64 * sizeof(int32_t), ctx->stream));
     CK(cudaMemsetAsync(ctx->hp.sceneOffset, 0, 64 * sizeof(int32_t), ctx->stream));
@@ -542,6 +566,7 @@ int dprt_begin_sample(dprt_ctx* ctx, int sample) {
 int dprt_path_gen(dprt_ctx* ctx) {
     if (!ctx) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    ctx->epoch++;
     sync_params(ctx);
     StageScope sc_(ctx, DPRT_STAGE_PATH_GEN, ctx->pathSize > 0);
     launch_path_gen(ctx->hp, ctx->pathSize, ctx->stream);
@@ -703,6 +728,7 @@ int dprt_shade(dprt_ctx* ctx) {
     launch_shade(ctx->hp, ctx->pathSize, ctx->stream);
     ctx->stats.kernel_launches += 2 * (ctx->pathSize > 0);
     ctx->stats.rays_shade += ctx->pathSize;
+    ctx->epoch++;                       // the records now hold the next bounce's rays: cached hits are stale
     ctx->histFresh = false;
     CK(cudaGetLastError());
     return 0;
@@ -980,6 +1006,7 @@ int dprt_get_path_size(const dprt_ctx* ctx, int* ps, int* sps) {
 int dprt_set_path_size(dprt_ctx* ctx, int ps) {
     if (!ctx || ps < 0 || ps > ctx->N) return DPRT_ERR_INVALID;
     ctx->pathSize = ps; ctx->histFresh = false; ctx->qhistFresh = false;
+    ctx->epoch++;                       // the harness is about to install its own paths
     return 0;
 }
 int dprt_buffer_bytes(const dprt_ctx* ctx, int id, size_t* bytes) {
@@ -1001,6 +1028,7 @@ int dprt_upload(dprt_ctx* ctx, int id, size_t off, const void* host, size_t byte
     CK(cudaMemcpyAsync((char*)ctx->buf_ptr[id] + off, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->histFresh = false; ctx->qhistFresh = false;
+    if (id == DPRT_BUF_PATHS) ctx->epoch++;
     return 0;
 }
 int dprt_enable_hit_prim(dprt_ctx* ctx, int enable) {

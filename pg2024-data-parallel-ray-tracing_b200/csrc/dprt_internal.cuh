@@ -25,7 +25,8 @@ struct HitRec {                    // closest-hit result handed from the trace t
     int32_t tri;                   // index into the leaf-ordered triangle array, -1 = miss
     int32_t obj;                   // scene index of the object that was hit
     float   alpha, beta;           // barycentric weights of v1, v2
-    int32_t pad_[2];
+    uint32_t epoch;                // hit cache only: trace epoch the entry was written in (0 = never)
+    int32_t pixel;                 // hit cache only: pixelIndex of the path
 };
 
 struct DevParams {
@@ -67,6 +68,9 @@ struct DevParams {
     unsigned long long* counters;  // instrumentation: {nodes, tris} per dprt_stage_id, null = off
     HitRec*  hits;                 // N closest-hit records (MainRay trace -> shading program)
     int32_t* traceQueue;           // head of the persistent trace kernel's ray queue
+    HitRec*  hitCache;             // per pixel: closest local hit of the pixel's path in the current epoch (null = off)
+    uint32_t hitEpoch;             // one epoch per bounce of a sample: entries of older epochs are stale
+    unsigned long long* cacheHits; // device counter: MainRay queries answered from the cache
 };
 
 // stage launches (all asynchronous on `stream`)

@@ -105,7 +105,11 @@ __global__ void __launch_bounds__(kBlock) path_gen_kernel(DevParams p, int n) {
 enum TraceMode { TM_TRAVERSE = 0, TM_SHADE = 1, TM_SHADOW = 2, TM_SECONDARY = 3, TM_RAYS = 4 };
 
 constexpr int kTraceBlock = 128;
-constexpr int kTraceBlocksPerSM = 6;
+#ifndef DPRT_TRACE_MINBLOCKS
+#define DPRT_TRACE_MINBLOCKS 6
+#endif
+constexpr int kTraceBlocksPerSM = DPRT_TRACE_MINBLOCKS;
+constexpr int kNodesPerStepDefault = 1;
 constexpr int kRefillDefault = 8;
 constexpr int kTriVoteDefault = 8;
 constexpr int kCoopDefault = 8;
@@ -131,6 +135,8 @@ struct TraceArgs {
     uint32_t prmtMagic;              // 0x47000000 (bvh_traverse.cuh qbias): a run-time value on purpose
     uint32_t* coopPool;              // DPRT_POOLCAP words per resident warp
     int coop;                        // tail: a warp left with at most this many rays finishes them one at a time, 32 lanes per ray
+    int nodesPerStep;                // a lane expands up to this many nodes per warp step while it finds no leaf triangles
+    HitRec* hitCache; uint32_t epoch; unsigned long long* cacheHits;   // DevParams::hitCache (null = off)
 };
 
 // next local object at or after `from` that the ray still has to visit; sceneSize when none
@@ -157,6 +163,7 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceBlocksPerSM) trace_kernel(T
     bool exh = false;                // the current object has no node work left (triangles may still be queued)
     uint32_t skipMask = 0u, flags = 0u;
     bool retry = false;              // TM_SHADE: the bounded trace may be repeated unbounded
+    uint32_t cached = 0u;            // TM_SHADE: queries answered from the hit cache
     TraceCount cnt = {0u, 0u};
     bool exhausted = false;          // warp-uniform: the ray queue has no more rays
     int qlen = 0;                    // warp-uniform: pairs waiting in the triangle queue
@@ -186,6 +193,19 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceBlocksPerSM) trace_kernel(T
                     flags = __float_as_uint(q3.w);
                     live = (flags & F_VALID) != 0u;
                     if (MODE == TM_TRAVERSE) skipMask = __float_as_uint(q3.x);
+                    if (MODE == TM_SHADE && live && a.hitCache) {
+                        // Hit cache: when TraRay / SecondaryRay already found the closest hit of this very ray (same pixel,
+                        // same bounce of the same sample = same epoch) on this rank's geometry, the re-trace of kernel.cu:382-413
+                        // would return exactly that record (same candidates, same arithmetic, same tie rule): reuse it.
+                        const int pixel = __float_as_int(q[2].z);
+                        const float4* c = reinterpret_cast<const float4*>(a.hitCache + pixel);
+                        const float4 c1 = c[1];
+                        if (__float_as_uint(c1.z) == a.epoch) {
+                            float4* h = reinterpret_cast<float4*>(a.hits + my);
+                            h[0] = c[0]; h[1] = c1;
+                            live = false; cached++;
+                        }
+                    }
                     if (MODE == TM_SHADE) {
                         // The reference re-traces with tMax = infinity (kernel.cu:382-413). When the record says "hit on
                         // this rank at tMax", the closest local hit is at t <= tMax: a trace bounded by the next float
@@ -251,7 +271,15 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceBlocksPerSM) trace_kernel(T
                     const bool hit = s.hitTri >= 0;
                     if (MODE == TM_TRAVERSE || MODE == TM_SECONDARY) {
                         dprt_path_record* rec = a.recs + idx;
-                        if (hit) { rec->tMax = s.tbest; rec->currentNode = a.worldID; rec->isHit = 1; }
+                        if (hit) {
+                            rec->tMax = s.tbest; rec->currentNode = a.worldID; rec->isHit = 1;
+                            if (a.hitCache) {
+                                const int pixel = rec->pixelIndex;
+                                float4* c = reinterpret_cast<float4*>(a.hitCache + pixel);
+                                c[0] = make_float4(s.tbest, __int_as_float(s.hitPrim), __int_as_float(s.hitTri), __int_as_float(s.hitObj));
+                                c[1] = make_float4(s.ha, s.hb, __uint_as_float(a.epoch), __int_as_float(pixel));
+                            }
+                        }
                         if (a.hitPrim) a.hitPrim[idx] = hit ? s.hitPrim : -1;
                     } else if (MODE == TM_SHADE) {
                         float4* h = reinterpret_cast<float4*>(a.hits + idx);
@@ -283,8 +311,22 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceBlocksPerSM) trace_kernel(T
             const unsigned nodeM = __ballot_sync(FULL, canNode);
             const unsigned waitM = __ballot_sync(FULL, busy && !canNode);
             if (qlen > 0 && (qlen >= 32 || nodeM == 0u || __popc(waitM) >= a.triVote)) tri_round<ANY, COUNT>(w, qlen, lane, s, obj, pend, cnt);
-            else if (canNode) trav_node<COUNT>(s, stack, cnt, a.prmtMagic);
+            else if (canNode) {
+                // Up to nodesPerStep nodes per warp step: most nodes yield no leaf triangles, and the warp-level bookkeeping
+                // around a step costs as much as the slab tests of a node. A lane stops early when it has triangles to queue.
+                int left = a.nodesPerStep;
+#pragma unroll 1
+                for (;;) {
+                    trav_node<COUNT>(s, stack, cnt, a.prmtMagic);
+                    if (--left == 0 || s.tg.y != 0u) break;
+                    if ((s.ng.y & 0xff000000u) == 0u) { if (s.sp == 0) break; s.ng = stack[--s.sp]; }
+                }
+            }
         } while (__popc(__ballot_sync(FULL, idx >= 0)) >= minBusy);
+    }
+    if (MODE == TM_SHADE && a.hitCache) {
+        cached = __reduce_add_sync(FULL, cached);
+        if (lane == 0 && cached) atomicAdd(a.cacheHits, (unsigned long long)cached);
     }
     if (COUNT) {
         if (cnt.nodes) atomicAdd(a.counters + 2 * StageOf<MODE>::id, (unsigned long long)cnt.nodes);
@@ -625,6 +667,7 @@ int tune_refill() { static int v = env_int("DPRT_TRACE_REFILL", kRefillDefault, 
 int tune_trivote() { static int v = env_int("DPRT_TRACE_TRIVOTE", kTriVoteDefault, 1, 32); return v; }
 int tune_coop() { static int v = env_int("DPRT_TRACE_COOP", kCoopDefault, 0, 32); return v; }
 int tune_rpl() { static int v = env_int("DPRT_TRACE_RPL", kRaysPerLaneDefault, 1, 64); return v; }
+int tune_nodes() { static int v = env_int("DPRT_TRACE_NODES", kNodesPerStepDefault, 1, 16); return v; }
 int tune_blocks() { static int v = env_int("DPRT_TRACE_BLOCKS_PER_SM", kTraceBlocksPerSM, 1, 16); return v; }
 
 template <int MODE>
@@ -643,7 +686,8 @@ TraceArgs trace_args(const DevParams& p, dprt_path_record* recs) {
     TraceArgs a;
     a.objects = p.objects; a.sceneSize = p.sceneSize; a.worldID = p.worldID; a.recs = recs; a.hits = p.hits;
     a.rays = nullptr; a.rayHits = nullptr; a.hitPrim = p.hitPrim; a.queue = p.traceQueue; a.counters = p.counters;
-    a.refill = tune_refill(); a.triVote = tune_trivote(); a.prmtMagic = 0x47000000u; a.coop = tune_coop();
+    a.refill = tune_refill(); a.triVote = tune_trivote(); a.prmtMagic = 0x47000000u; a.coop = tune_coop(); a.nodesPerStep = tune_nodes();
+    a.hitCache = p.hitCache; a.epoch = p.hitEpoch; a.cacheHits = p.cacheHits;
     return a;
 }
 
@@ -683,7 +727,8 @@ void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ra
     TraceArgs a;
     a.objects = objects; a.sceneSize = sceneSize; a.worldID = 0; a.recs = nullptr; a.hits = nullptr;
     a.rays = rays; a.rayHits = hits; a.hitPrim = nullptr; a.queue = queue; a.counters = counters;
-    a.refill = tune_refill(); a.triVote = tune_trivote(); a.prmtMagic = 0x47000000u; a.coop = tune_coop();
+    a.refill = tune_refill(); a.triVote = tune_trivote(); a.prmtMagic = 0x47000000u; a.coop = tune_coop(); a.nodesPerStep = tune_nodes();
+    a.hitCache = nullptr; a.epoch = 0u; a.cacheHits = nullptr;
     launch_trace<TM_RAYS>(a, n, s);
 }
 

@@ -97,7 +97,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("DPRT_LIB") or LIB_PATH      # DPRT_LIB: A/B builds of the same ABI (profiles/)
     if not os.path.exists(p):
         raise DprtError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(there is no CPU fallback)")

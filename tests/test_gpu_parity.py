@@ -67,6 +67,30 @@ def test_single_rank_image_bit_exact(gpu_required, oracle):
         assert sg[k] == so[k], k
 
 
+@pytest.mark.parametrize("W,proxy", [(1, 0), (4, 0)])
+def test_hit_cache_equals_retrace(gpu_required, oracle, W, proxy):
+    """MainRay answered from the hit cache (default) and MainRay re-traced like kernel.cu:382-413 (mainRayRetrace=1)
+    give the same bits as the oracle, which always re-traces; the cache must actually be exercised."""
+    imgs = []
+    for retrace in (0, 1):
+        rs, world, _ = build_pair(oracle, W, 8000, 128, 72, spp=2, bounces=3, proxy_mode=proxy, main_ray_retrace=retrace)
+        G = dprt.RankGroup(rs)
+        imgs.append(G.launch())
+        cached = sum(R.stats()["rays_shade_cached"] for R in rs)
+        shaded = sum(R.stats()["rays_shade"] for R in rs)
+        assert shaded > 0
+        if retrace:
+            assert cached == 0
+        else:
+            assert 0 < cached <= shaded
+            if W == 1:
+                assert cached == shaded      # one rank: every path that reaches MainRay was traced here in the same bounce
+        if not retrace:
+            img_o = world.launch()
+    assert_bits_equal(imgs[0], img_o, "image with hit cache vs oracle")
+    assert_bits_equal(imgs[1], img_o, "image with re-trace vs oracle")
+
+
 @pytest.mark.parametrize("W", [2, 4, 8])
 def test_multi_rank_group_migration_bit_exact(gpu_required, oracle, W):
     """W chunk owners emulated as W contexts on one GPU; exchange through dprt_exchange_group."""
