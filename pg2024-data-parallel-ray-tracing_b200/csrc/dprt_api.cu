@@ -95,6 +95,13 @@ struct dprt_ctx {
     HitRec* d_hits = nullptr;           // N closest-hit records (MainRay)
     HitRec* d_hitCache = nullptr;       // N per-pixel closest hits of the current epoch (null when cfg.mainRayRetrace)
     unsigned long long* d_cacheHits = nullptr;   // MainRay queries answered from the cache since the last reset_stats
+    // "reset by count" of the shadow planes of directLightingBuffer: MainRay records which pixels get shadow paths
+    // (two lists, ping-pong: one describes the planes that are dirty now, the other is free for the next MainRay)
+    int32_t* d_live[2] = {nullptr, nullptr};
+    int liveCount[2] = {0, 0};
+    int shadeIdx = -1;                  // list written by the last dprt_shade whose shadow paths are still in place; -1 = none
+    int dirtyIdx = -1;                  // which list covers the dirty planes; -1 = planes are clean, -2 = unknown (full memset)
+    bool nnScratchDirty = false;        // occlusion / contribution may hold non-zero data
     uint32_t epoch = 1;                 // bumped whenever the rays behind the path records change (new bounce, new paths)
     int32_t* d_queue = nullptr;         // ray queue head of the persistent trace kernel
     float* d_image = nullptr;           // averaged image, 3N
@@ -302,6 +309,7 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
         CK(cudaMalloc(&ctx->scratch.tileState, (size_t)ctx->scratch.maxTiles * 32 * sizeof(uint32_t)));
         CK(cudaMalloc(&ctx->scratch.tileCounter, sizeof(int32_t)));
         CK(cudaMalloc(&ctx->d_hits, N * sizeof(HitRec)));
+        for (int k = 0; k < 2; k++) CK(cudaMalloc(&ctx->d_live[k], N * sizeof(int32_t)));
         if (!cfg->mainRayRetrace) {
             CK(cudaMalloc(&ctx->d_hitCache, N * sizeof(HitRec)));
             CK(cudaMemsetAsync(ctx->d_hitCache, 0, N * sizeof(HitRec), ctx->stream));      // epoch 0 = never written
@@ -370,6 +378,7 @@ void dprt_destroy(dprt_ctx* ctx) {
     if (ctx->scratch.tileState) cudaFree(ctx->scratch.tileState);
     if (ctx->scratch.tileCounter) cudaFree(ctx->scratch.tileCounter);
     if (ctx->d_hits) cudaFree(ctx->d_hits);
+    for (int k = 0; k < 2; k++) if (ctx->d_live[k]) cudaFree(ctx->d_live[k]);
     if (ctx->d_hitCache) cudaFree(ctx->d_hitCache);
     if (ctx->d_cacheHits) cudaFree(ctx->d_cacheHits);
     if (ctx->d_queue) cudaFree(ctx->d_queue);
@@ -543,6 +552,7 @@ int dprt_reset_frame(dprt_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->hp.env, 0, ctx->buf_bytes[DPRT_BUF_ENV], ctx->stream));
     CK(cudaMemsetAsync(ctx->hp.contribution, 0, ctx->buf_bytes[DPRT_BUF_CONTRIBUTION], ctx->stream));
     CK(cudaMemsetAsync(ctx->hp.occlusion, 0, ctx->buf_bytes[DPRT_BUF_OCCLUSION], ctx->stream));
+    ctx->dirtyIdx = -1; ctx->nnScratchDirty = false;
     return 0;
 }
 
@@ -723,6 +733,8 @@ int dprt_shade(dprt_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->hp.lightCount < 1) return fail(ctx, DPRT_ERR_STATE, "no lights set");
     ctx->shadowPathSize = ctx->cfg.shadowPathCount * ctx->pathSize;     // renderer.cpp:1328
+    const int w = ctx->dirtyIdx == 0 ? 1 : 0;                           // the list that does not describe dirty planes
+    ctx->hp.livePixel = ctx->d_live[w]; ctx->liveCount[w] = ctx->pathSize; ctx->shadeIdx = w;
     sync_params(ctx);
     StageScope sc_(ctx, DPRT_STAGE_SHADE, ctx->pathSize > 0);
     launch_shade(ctx->hp, ctx->pathSize, ctx->stream);
@@ -737,13 +749,26 @@ int dprt_shade(dprt_ctx* ctx) {
 int dprt_reset_nn(dprt_ctx* ctx) {
     if (!ctx) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    // resetNNBuffers (renderer.cpp:367-414). Query/feature/prediction buffers are reset by count inside the
-    // producing kernels; the per-pixel accumulators are cleared here.
-    CK(cudaMemsetAsync(ctx->hp.occlusion, 0, ctx->buf_bytes[DPRT_BUF_OCCLUSION], ctx->stream));
-    CK(cudaMemsetAsync(ctx->hp.contribution, 0, ctx->buf_bytes[DPRT_BUF_CONTRIBUTION], ctx->stream));
-    if (ctx->cfg.shadowPathCount > 1)
-        CK(cudaMemsetAsync(ctx->hp.direct + (size_t)ctx->N * 3, 0, (size_t)ctx->N * 3 * sizeof(float) * (ctx->cfg.shadowPathCount - 1),
-                           ctx->stream));
+    // resetNNBuffers (renderer.cpp:367-414), by count instead of by capacity. Query/feature/prediction buffers are
+    // reset inside the producing kernels. occlusion / contribution are only ever written by the proxy epilogues.
+    // The shadow planes 1..spc-1 of directLightingBuffer are only written by the ShadowRay program, for pixels of the
+    // paths the preceding MainRay shaded: those pixels are zeroed, the rest of the planes is zero already.
+    if (ctx->cfg.proxyMode || ctx->nnScratchDirty) {
+        CK(cudaMemsetAsync(ctx->hp.occlusion, 0, ctx->buf_bytes[DPRT_BUF_OCCLUSION], ctx->stream));
+        CK(cudaMemsetAsync(ctx->hp.contribution, 0, ctx->buf_bytes[DPRT_BUF_CONTRIBUTION], ctx->stream));
+        ctx->nnScratchDirty = false;
+    }
+    if (ctx->cfg.shadowPathCount > 1) {
+        if (ctx->dirtyIdx == -2)
+            CK(cudaMemsetAsync(ctx->hp.direct + (size_t)ctx->N * 3, 0, (size_t)ctx->N * 3 * sizeof(float) * (ctx->cfg.shadowPathCount - 1),
+                               ctx->stream));
+        else if (ctx->dirtyIdx >= 0) {
+            sync_params(ctx);
+            launch_reset_planes(ctx->hp, ctx->d_live[ctx->dirtyIdx], ctx->liveCount[ctx->dirtyIdx], ctx->stream);
+            ctx->stats.kernel_launches += ctx->liveCount[ctx->dirtyIdx] > 0;
+        }
+    }
+    ctx->dirtyIdx = -1;
     CK(cudaMemsetAsync(ctx->hp.queryHist, 0, 64 * sizeof(int32_t), ctx->stream));
     ctx->qhistFresh = false;
     return 0;
@@ -758,6 +783,9 @@ int dprt_shadow_trace(dprt_ctx* ctx) {
     launch_shadow_trace(ctx->hp, ctx->shadowPathSize, ctx->stream);
     ctx->stats.kernel_launches += 2 * (ctx->shadowPathSize > 0);
     ctx->stats.rays_shadow += ctx->shadowPathSize;
+    // planes now hold this bounce's terms: covered by the MainRay list if nothing else was dirty, else unknown
+    if (ctx->shadowPathSize > 0)
+        ctx->dirtyIdx = (ctx->shadeIdx >= 0 && (ctx->dirtyIdx == -1 || ctx->dirtyIdx == ctx->shadeIdx)) ? ctx->shadeIdx : -2;
     ctx->qhistFresh = true; ctx->queryWhich = 0;
     CK(cudaGetLastError());
     return 0;
@@ -834,8 +862,10 @@ int dprt_frame_buffer_update(dprt_ctx* ctx) {
     sync_params(ctx);
     StageScope sc_(ctx, DPRT_STAGE_FRAME_UPDATE);
     launch_shadow_occlusion(ctx->hp, ctx->cfg.proxyMode ? ctx->queryTotal : 0, ctx->stream);
-    launch_contribution(ctx->hp, ctx->stream);
-    ctx->stats.kernel_launches += 1 + (ctx->queryTotal > 0);
+    const bool sparse = ctx->dirtyIdx >= 0 && ctx->dirtyIdx == ctx->shadeIdx;     // else: every pixel (reference behaviour)
+    if (ctx->dirtyIdx != -1)
+        launch_contribution(ctx->hp, sparse ? ctx->d_live[ctx->dirtyIdx] : nullptr, sparse ? ctx->liveCount[ctx->dirtyIdx] : 0, ctx->stream);
+    ctx->stats.kernel_launches += (ctx->dirtyIdx != -1) + (ctx->queryTotal > 0);
     CK(cudaGetLastError());
     return 0;
 }
@@ -1007,6 +1037,7 @@ int dprt_set_path_size(dprt_ctx* ctx, int ps) {
     if (!ctx || ps < 0 || ps > ctx->N) return DPRT_ERR_INVALID;
     ctx->pathSize = ps; ctx->histFresh = false; ctx->qhistFresh = false;
     ctx->epoch++;                       // the harness is about to install its own paths
+    ctx->shadeIdx = -1;
     return 0;
 }
 int dprt_buffer_bytes(const dprt_ctx* ctx, int id, size_t* bytes) {
@@ -1028,7 +1059,9 @@ int dprt_upload(dprt_ctx* ctx, int id, size_t off, const void* host, size_t byte
     CK(cudaMemcpyAsync((char*)ctx->buf_ptr[id] + off, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->histFresh = false; ctx->qhistFresh = false;
-    if (id == DPRT_BUF_PATHS) ctx->epoch++;
+    if (id == DPRT_BUF_PATHS) { ctx->epoch++; ctx->shadeIdx = -1; }
+    if (id == DPRT_BUF_DIRECT) ctx->dirtyIdx = -2;
+    if (id == DPRT_BUF_OCCLUSION || id == DPRT_BUF_CONTRIBUTION) { ctx->nnScratchDirty = true; ctx->dirtyIdx = -2; }
     return 0;
 }
 int dprt_enable_hit_prim(dprt_ctx* ctx, int enable) {

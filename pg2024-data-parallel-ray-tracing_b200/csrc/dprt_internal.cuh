@@ -71,6 +71,7 @@ struct DevParams {
     HitRec*  hitCache;             // per pixel: closest local hit of the pixel's path in the current epoch (null = off)
     uint32_t hitEpoch;             // one epoch per bounce of a sample: entries of older epochs are stale
     unsigned long long* cacheHits; // device counter: MainRay queries answered from the cache
+    int32_t* livePixel;            // per path slot of the last MainRay launch: pixel that got shadow paths, or -1
 };
 
 // stage launches (all asynchronous on `stream`)
@@ -99,7 +100,10 @@ void launch_partition_queries(const dprt_nn_query* q, const dprt_half* in, int n
 
 // NN epilogues (epilogue.cu): frame_buffer_update.cu equivalents
 void launch_shadow_occlusion(const DevParams& p, int size, cudaStream_t stream);
-void launch_contribution(const DevParams& p, cudaStream_t stream);
+// live != null: only the `liveCount` pixels listed there can hold non-zero terms (the others fold to a bitwise no-op)
+void launch_contribution(const DevParams& p, const int32_t* live, int liveCount, cudaStream_t stream);
+// zero the shadow planes 1..spc-1 of directLightingBuffer for the listed pixels (resetNNBuffers by count)
+void launch_reset_planes(const DevParams& p, const int32_t* live, int liveCount, cudaStream_t stream);
 void launch_depth_update(const DevParams& p, int size, cudaStream_t stream);
 void launch_tmax(const DevParams& p, int size, cudaStream_t stream);
 void launch_target_node(const DevParams& p, int n, cudaStream_t stream);

@@ -33,24 +33,46 @@ __global__ void shadow_occlusion_kernel(DevParams p, int size) {
     }
 }
 
-__global__ void contribution_kernel(DevParams p) {
+// NN = false (proxies off): occlusion and contribution are never written and stay all-zero, so their terms are
+// computed from literal zeros (same arithmetic, same bits) instead of being read.
+// live != null: the fold runs over the pixels of the paths MainRay just shaded. For any other pixel the shadow planes
+// and the contribution terms are +0, and d + (+0) leaves d unchanged bit for bit (d is a sum of non-negative terms
+// that starts at +0, so it is never -0): skipping those pixels gives the reference's result.
+template <bool NN>
+__global__ void contribution_kernel(DevParams p, const int32_t* __restrict__ live, int count) {
     const int N = p.frameBufferSize, spc = p.spc, mc = p.mc;
-    for (int px = blockIdx.x * blockDim.x + threadIdx.x; px < N; px += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const int px = live ? live[i] : i;
+        if (px < 0) continue;
         float d0 = p.direct[(size_t)px * 3 + 0], d1 = p.direct[(size_t)px * 3 + 1], d2 = p.direct[(size_t)px * 3 + 2];
         for (int s = 0; s < spc; s++) {
             const size_t slot = (size_t)px * spc + s;
             float maxOcc = 0.0f;
-            for (int j = 0; j < mc; j++) { const float o = p.occlusion[slot * mc + j]; maxOcc = maxOcc > o ? maxOcc : o; }
+            if (NN) for (int j = 0; j < mc; j++) { const float o = p.occlusion[slot * mc + j]; maxOcc = maxOcc > o ? maxOcc : o; }
             const float w = 1.0f - maxOcc;
-            d0 += p.contribution[slot * 3 + 0] * w / (float)spc;
-            d1 += p.contribution[slot * 3 + 1] * w / (float)spc;
-            d2 += p.contribution[slot * 3 + 2] * w / (float)spc;
+            const float c0 = NN ? p.contribution[slot * 3 + 0] : 0.0f, c1 = NN ? p.contribution[slot * 3 + 1] : 0.0f,
+                        c2 = NN ? p.contribution[slot * 3 + 2] : 0.0f;
+            d0 += c0 * w / (float)spc;
+            d1 += c1 * w / (float)spc;
+            d2 += c2 * w / (float)spc;
         }
         for (int s = 1; s < spc; s++) {
             const size_t pl = ((size_t)N * s + px) * 3;
             d0 += p.direct[pl + 0]; d1 += p.direct[pl + 1]; d2 += p.direct[pl + 2];
         }
         p.direct[(size_t)px * 3 + 0] = d0; p.direct[(size_t)px * 3 + 1] = d1; p.direct[(size_t)px * 3 + 2] = d2;
+    }
+}
+
+__global__ void reset_planes_kernel(DevParams p, const int32_t* __restrict__ live, int count) {
+    const int N = p.frameBufferSize;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const int px = live[i];
+        if (px < 0) continue;
+        for (int s = 1; s < p.spc; s++) {
+            const size_t pl = ((size_t)N * s + px) * 3;
+            p.direct[pl + 0] = 0.0f; p.direct[pl + 1] = 0.0f; p.direct[pl + 2] = 0.0f;
+        }
     }
 }
 
@@ -109,8 +131,14 @@ __global__ void image_average_kernel(const float* __restrict__ direct, const flo
 void launch_shadow_occlusion(const DevParams& p, int size, cudaStream_t s) {
     if (size > 0) shadow_occlusion_kernel<<<grid_for(size), kBlock, 0, s>>>(p, size);
 }
-void launch_contribution(const DevParams& p, cudaStream_t s) {
-    contribution_kernel<<<grid_for(p.frameBufferSize), kBlock, 0, s>>>(p);
+void launch_contribution(const DevParams& p, const int32_t* live, int liveCount, cudaStream_t s) {
+    const int count = live ? liveCount : p.frameBufferSize;
+    if (count <= 0) return;
+    if (p.proxyMode) contribution_kernel<true><<<grid_for(count), kBlock, 0, s>>>(p, live, count);
+    else contribution_kernel<false><<<grid_for(count), kBlock, 0, s>>>(p, live, count);
+}
+void launch_reset_planes(const DevParams& p, const int32_t* live, int liveCount, cudaStream_t s) {
+    if (liveCount > 0 && p.spc > 1) reset_planes_kernel<<<grid_for(liveCount), kBlock, 0, s>>>(p, live, liveCount);
 }
 void launch_depth_update(const DevParams& p, int size, cudaStream_t s) {
     if (size > 0) depth_update_kernel<<<grid_for(size), kBlock, 0, s>>>(p, size);

@@ -423,12 +423,13 @@ __global__ void __launch_bounds__(kBlock) shade_post_kernel(DevParams p, int n) 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     PathRegs path = load_path(p.paths + i);
-    if (!(path.flags & F_VALID)) return;
+    if (!(path.flags & F_VALID)) { if (p.livePixel) p.livePixel[i] = -1; return; }
     const V3 o = path.origin, d = path.direction;
     const float4 h0 = reinterpret_cast<const float4*>(p.hits + i)[0], h1 = reinterpret_cast<const float4*>(p.hits + i)[1];
     const float ht = h0.x; const int hprim = __float_as_int(h0.y), htri = __float_as_int(h0.z), hobj = __float_as_int(h0.w);
     const bool isHit = htri >= 0;
     if (p.hitPrim) p.hitPrim[i] = isHit ? hprim : -1;
+    if (p.livePixel) p.livePixel[i] = isHit ? path.pixelIndex : -1;     // pixels whose shadow planes this bounce can touch
     if (!isHit) {
         // kernel.cu:416-423: environment light, path dies. The reference then writes an invalid record built
         // from an uninitialised sampling record; the defined behaviour here is the all-zero (invalid) record.
