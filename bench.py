@@ -189,7 +189,8 @@ def workload_config(args, W, fw, fh):
     return {"workload": f"configs[1] scene per GPU: synthetic {args.tris}-triangle chunk x {W} chunk(s), {fw}x{fh} frame "
                         f"(1920x1080 pixels per GPU), 1 spp per step, full per-sample loop with bounces={args.bounces}, spc=4, mc=3",
             "chunks": W, "tris_per_chunk": args.tris, "width": fw, "height": fh, "bounces": args.bounces,
-            "proxy": bool(args.proxy and W > 1), "main_ray": "re-trace" if args.retrace else "hit cache", "path_gen": "rank0" if (args.path_gen_mode == 0 or W == 1) else "striped",
+            "proxy": bool(args.proxy and W > 1), "main_ray": "re-trace" if args.retrace else "hit cache",
+            "stage_overlap": bool(not args.serial and not (args.proxy and W > 1)), "path_gen": "rank0" if (args.path_gen_mode == 0 or W == 1) else "striped",
             "l2": "inputs larger than L2: 5 x 64 B path records per pixel (663 MB at 1080p) are rewritten every bounce",
             "parallelism": f"scene-chunk x{W}"}
 
@@ -336,7 +337,8 @@ def run_dprt(args):
     N = fw * fh
     proxy = 1 if (args.proxy and W > 1) else 0
     cfg = dprt.make_config(fw, fh, spp=1, bounces=args.bounces, scene_size=W, proxy_mode=proxy,
-                           path_gen_mode=args.path_gen_mode if W > 1 else 0, mlp_dtype=0, main_ray_retrace=args.retrace)
+                           path_gen_mode=args.path_gen_mode if W > 1 else 0, mlp_dtype=0, main_ray_retrace=args.retrace,
+                           serial_stages=args.serial)
     chunks, mats, lights = build_world_scene(dprt, W, args.tris)
     blobs = proxy_blobs(dprt, W, proxy)
     cam = dprt.scene.default_camera(fw, fh)
@@ -368,7 +370,7 @@ def run_dprt(args):
     for s in range(args.warmup):
         R.run_sample(s)
     barrier()
-    R.reset_stats(); R.stage_profile(True)
+    R.reset_stats()
     clocks = ClockSampler(local if "CUDA_VISIBLE_DEVICES" not in os.environ else os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local])
     if rank == 0:
         clocks.start()
@@ -379,9 +381,18 @@ def run_dprt(args):
     barrier()
     clk = clocks.stop() if rank == 0 else None
     st = R.stats()
+    ms = allreduce(ms, dist.ReduceOp.MAX if W > 1 else None)
+    # ---- per-stage pass over the same samples: CUDA-event pairs around every stage launch on the stream it is launched
+    # on. Stage profiling forces strictly serial single-stream execution (no shadow/traverse overlap), so each kernel's
+    # duration is its own; the step time of this pass is reported beside it (share_of_step refers to it).
+    R.reset_stats(); R.stage_profile(True)
+    R.timer_start()
+    for s in range(args.steps):
+        R.run_sample(args.warmup + s)
+    ms_serial = R.timer_stop()
+    barrier()
     stage = R.stage_times()
     R.stage_profile(False)
-    ms = allreduce(ms, dist.ReduceOp.MAX if W > 1 else None)
     # rays = BVH walks actually performed: MainRay queries answered from the hit cache (the closest hit TraRay already
     # found for the same ray) are reported separately and are NOT counted in `value`
     my_rays = st["rays_traverse"] + st["rays_shade"] - st["rays_shade_cached"] + st["rays_shadow"] + st["rays_secondary"]
@@ -422,7 +433,7 @@ def run_dprt(args):
             traffic = tj.get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": d["GBps"], "peak": pk["hbm"], "unit": "GB/s",
                 "frac": d["GBps"] / pk["hbm"], "traffic": traffic, "alg_bytes_per_launch": d["alg_bytes"] / d["launches"],
-                "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / ms, "peak_source": pk["source"],
+                "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / ms_serial, "serial_pass_ms_per_step": ms_serial / args.steps, "peak_source": pk["source"],
                 "note": "working set of a 1 M-triangle chunk (48 MB triangles + 12 MB BVH8) is L2-resident: achieved counts bytes the kernel "
                         "must touch per ray, served mostly by L2/L1; see profiles/ for the ncu DRAM figure"}
 
@@ -489,6 +500,7 @@ def main():
     ap.add_argument("--path-gen-mode", type=int, default=1, help="N>1: 0 = rank 0 generates all camera paths (reference), 1 = striped")
     ap.add_argument("--ref-scale", type=int, default=4, help="reference/cpu_baseline arm: frame reduced by this factor per side")
     ap.add_argument("--retrace", type=int, default=0, help="1 = MainRay always re-traces (no hit cache), for A/B")
+    ap.add_argument("--serial", type=int, default=0, help="1 = no shadow/traverse stream overlap inside dprt_render_sample, for A/B")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")
     args = ap.parse_args()

@@ -114,7 +114,10 @@ typedef struct dprt_config {
     float   envColor[3];      /* analytic environment: Le = envColor * (0.5 + 0.5*dir.z) */
     int32_t mainRayRetrace;   /* 0 = MainRay reuses the closest hit TraRay / SecondaryRay found for the same ray on this rank
                                  (identical result, see DESIGN.md "hit cache"); 1 = always re-trace like kernel.cu:382-413 */
-    int32_t reserved_[2];
+    int32_t serialStages;     /* 0 = dprt_render_sample may run the ShadowRay module of bounce b on a second CUDA stream beside
+                                 the TraRay loop of bounce b+1 (independent data, same results; proxyMode 0 only);
+                                 1 = every stage strictly in order on one stream */
+    int32_t reserved_[1];
 } dprt_config;
 
 /* Standalone closest-hit query (the optixTrace equivalent used by BASELINE config 2). */

@@ -104,6 +104,12 @@ struct dprt_ctx {
     bool nnScratchDirty = false;        // occlusion / contribution may hold non-zero data
     uint32_t epoch = 1;                 // bumped whenever the rays behind the path records change (new bounce, new paths)
     int32_t* d_queue = nullptr;         // ray queue head of the persistent trace kernel
+    // second stream for the ShadowRay module of dprt_render_sample (cfg.serialStages == 0, proxies off)
+    cudaStream_t aux = nullptr;
+    cudaEvent_t evShade = nullptr, evAux = nullptr;
+    int32_t* d_queue_aux = nullptr;     // trace scratch of launches on the aux stream
+    bool auxPending = false;            // aux work not yet joined into `stream`
+    int auxGuardBase = 0;               // first path slot the pending aux work reads (its shadow paths start there)
     float* d_image = nullptr;           // averaged image, 3N
     float* d_image_sum = nullptr;       // reduce target, 3N
     int32_t* d_gather = nullptr;        // W*(W+1) offsets of all ranks
@@ -152,6 +158,15 @@ namespace {
     } while (0)
 
 int fail(dprt_ctx* ctx, int code, const std::string& msg) { ctx->err = msg; return code; }
+
+// makes `stream` wait for the ShadowRay module that dprt_render_sample left running on the aux stream
+int join_aux(dprt_ctx* ctx) {
+    if (ctx->auxPending) {
+        ctx->auxPending = false;
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->evAux, 0));
+    }
+    return 0;
+}
 
 void resolve_pending(dprt_ctx* ctx) {
     for (auto& pd : ctx->pending) {
@@ -317,6 +332,14 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
             CK(cudaMemsetAsync(ctx->d_cacheHits, 0, sizeof(unsigned long long), ctx->stream));
         }
         CK(cudaMalloc(&ctx->d_queue, trace_scratch_bytes()));
+        if (!cfg->serialStages && !cfg->proxyMode) {
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // the main stream carries the critical path: aux gets the lowest priority
+            CK(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, lo));
+            CK(cudaEventCreateWithFlags(&ctx->evShade, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->evAux, cudaEventDisableTiming));
+            CK(cudaMalloc(&ctx->d_queue_aux, trace_scratch_bytes()));
+        }
         CK(cudaMalloc(&ctx->d_image, 3 * N * sizeof(float)));
         CK(cudaMalloc(&ctx->d_image_sum, 3 * N * sizeof(float)));
         CK(cudaMalloc(&ctx->d_gather, sizeof(int32_t) * (size_t)world * (world + 1)));
@@ -379,6 +402,10 @@ void dprt_destroy(dprt_ctx* ctx) {
     if (ctx->scratch.tileCounter) cudaFree(ctx->scratch.tileCounter);
     if (ctx->d_hits) cudaFree(ctx->d_hits);
     for (int k = 0; k < 2; k++) if (ctx->d_live[k]) cudaFree(ctx->d_live[k]);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
+    if (ctx->evShade) cudaEventDestroy(ctx->evShade);
+    if (ctx->evAux) cudaEventDestroy(ctx->evAux);
+    if (ctx->d_queue_aux) cudaFree(ctx->d_queue_aux);
     if (ctx->d_hitCache) cudaFree(ctx->d_hitCache);
     if (ctx->d_cacheHits) cudaFree(ctx->d_cacheHits);
     if (ctx->d_queue) cudaFree(ctx->d_queue);
@@ -671,6 +698,7 @@ int dprt_exchange(dprt_ctx* ctx, int* done) {
     const int recvTotal = (int)recvTotal64;
     const long offdiag = allLocal ? 0 : 1;
     if ((size_t)recvTotal > (size_t)ctx->N) return fail(ctx, DPRT_ERR_CAPACITY, "received more paths than the frame holds");
+    if (ctx->auxPending && recvTotal > ctx->auxGuardBase) { int jr = join_aux(ctx); if (jr) return jr; }   // would land on shadow paths still in use
     // MPI_Alltoallv: grouped send/recv straight from the partitioned device buffer
     NK(g_nccl.GroupStart());
     for (int peer = 0; peer < W; peer++) {
@@ -956,12 +984,29 @@ int dprt_render_sample(dprt_ctx* ctx, int sample) {
     int r;
     if ((r = dprt_begin_sample(ctx, sample))) return r;
     if ((r = dprt_path_gen(ctx))) return r;
+    // The ShadowRay module of bounce b only reads the shadow paths MainRay(b) wrote (slots >= pathSize) and only writes
+    // directLightingBuffer; the TraRay loop of bounce b+1 works on slots < pathSize, the transfer buffer and
+    // envLightingBuffer. With proxies off (no shared NN buffers, no host round trip in the shadow module) the two run
+    // side by side: shadow(b) on the low-priority aux stream fills the SMs that the tail of the migrate loop leaves idle.
+    const bool overlap = ctx->aux && !ctx->profile;
     for (int bounce = 0; bounce <= ctx->cfg.bounces; bounce++) {          // inclusive: renderer.cpp:1530
         if ((r = bounce_pre(ctx, bounce))) return r;
         if ((r = dprt_primary_ray_module(ctx))) return r;
-        if ((r = bounce_post(ctx))) return r;
+        if (!overlap) { if ((r = bounce_post(ctx))) return r; continue; }
+        if ((r = join_aux(ctx))) return r;                                // MainRay rewrites the shadow slots and the pixel lists
+        if ((r = dprt_shade(ctx))) return r;
+        CK(cudaEventRecord(ctx->evShade, ctx->stream));
+        cudaStream_t mainStream = ctx->stream; int32_t* mainQueue = ctx->hp.traceQueue;
+        ctx->stream = ctx->aux; ctx->hp.traceQueue = ctx->d_queue_aux;
+        cudaError_t ce = cudaStreamWaitEvent(ctx->aux, ctx->evShade, 0);
+        r = ce != cudaSuccess ? DPRT_ERR_CUDA : dprt_reset_nn(ctx);
+        if (!r) r = dprt_shadow_ray_module(ctx);
+        if (!r && cudaEventRecord(ctx->evAux, ctx->aux) != cudaSuccess) r = DPRT_ERR_CUDA;
+        ctx->stream = mainStream; ctx->hp.traceQueue = mainQueue;
+        if (r) return r;
+        ctx->auxPending = true; ctx->auxGuardBase = ctx->pathSize;
     }
-    return 0;
+    return join_aux(ctx);
 }
 
 int dprt_render_sample_group(dprt_ctx** ctxs, int W, int sample) {

@@ -14,7 +14,8 @@ class Config(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("bounces", C.c_int32),
                 ("shadowPathCount", C.c_int32), ("maxCount", C.c_int32), ("sceneSize", C.c_int32),
                 ("proxyMode", C.c_int32), ("pathGenMode", C.c_int32), ("mlpDtype", C.c_int32),
-                ("envColor", C.c_float * 3), ("mainRayRetrace", C.c_int32), ("reserved_", C.c_int32 * 2)]
+                ("envColor", C.c_float * 3), ("mainRayRetrace", C.c_int32), ("serialStages", C.c_int32),
+                ("reserved_", C.c_int32 * 1)]
 
 
 class ObjectDesc(C.Structure):
@@ -74,9 +75,9 @@ BUFFER_DTYPES = {
 
 
 def make_config(width, height, spp=1, bounces=4, spc=4, mc=3, scene_size=1, proxy_mode=0, path_gen_mode=0,
-                mlp_dtype=0, env_color=(0.6, 0.7, 0.9), main_ray_retrace=0):
+                mlp_dtype=0, env_color=(0.6, 0.7, 0.9), main_ray_retrace=0, serial_stages=0):
     cfg = Config()
-    cfg.mainRayRetrace = int(main_ray_retrace)
+    cfg.mainRayRetrace, cfg.serialStages = int(main_ray_retrace), int(serial_stages)
     cfg.width, cfg.height, cfg.spp, cfg.bounces = width, height, spp, bounces
     cfg.shadowPathCount, cfg.maxCount, cfg.sceneSize = spc, mc, scene_size
     cfg.proxyMode, cfg.pathGenMode, cfg.mlpDtype = proxy_mode, path_gen_mode, mlp_dtype

@@ -1,7 +1,8 @@
 #!/bin/bash
-# quick A/B of trace-kernel knobs: bash profiles/quick_bench.sh "VAR=val VAR2=val" ...   (one bench run per argument)
+# quick A/B of trace-kernel knobs: bash profiles/quick_bench.sh "VAR=val VAR2=val" ...   (one bench run per argument;
+# BENCH_ARGS="--serial 1" inside an argument adds bench.py flags to that run)
 for envs in "$@"; do
-  env $envs timeout 200 python bench.py --steps 4 --skip-cpu --skip-extras 2>/dev/null | tail -1 > /tmp/qb.json
+  env $envs bash -c 'timeout 200 python bench.py --steps 4 --skip-cpu --skip-extras $BENCH_ARGS 2>/dev/null' | tail -1 > /tmp/qb.json
   python - "$envs" <<'PY'
 import json, sys
 j = json.loads(open("/tmp/qb.json").read())

@@ -67,6 +67,21 @@ def test_single_rank_image_bit_exact(gpu_required, oracle):
         assert sg[k] == so[k], k
 
 
+@pytest.mark.parametrize("serial", [0, 1])
+def test_stage_overlap_same_bits(gpu_required, oracle, serial):
+    """dprt_render_sample with the ShadowRay module of bounce b on the aux stream beside the TraRay loop of bounce b+1
+    (serialStages=0, default) and strictly serial (serialStages=1): same image and path records as the oracle."""
+    rs, world, _ = build_pair(oracle, 1, 30000, 256, 144, spp=3, bounces=4, proxy_mode=0, water_frac=0.03, serial_stages=serial)
+    R = rs[0]
+    img_g, img_o = R.launch(), world.launch()
+    assert_bits_equal(img_g, img_o, f"image, serialStages={serial}")
+    n = R.path_size
+    assert n == world.path_size(0)
+    tot = n * (1 + R.cfg.shadowPathCount)
+    assert_records_equal(R.download(D.BUF_PATHS, tot), world.download(0, D.BUF_PATHS, tot), "paths + shadow paths after the last bounce")
+    assert_bits_equal(R.download(D.BUF_DIRECT), world.download(0, D.BUF_DIRECT, 3 * 256 * 144 * R.cfg.shadowPathCount), "direct planes")
+
+
 @pytest.mark.parametrize("W,proxy", [(1, 0), (4, 0)])
 def test_hit_cache_equals_retrace(gpu_required, oracle, W, proxy):
     """MainRay answered from the hit cache (default) and MainRay re-traced like kernel.cu:382-413 (mainRayRetrace=1)
