@@ -111,8 +111,11 @@ class ClockSampler:
         return out
 
 
-def build_world_scene(dprt, world, tris):
-    chunks, mats, lights = dprt.scene.make_scene(world, tris)
+def build_world_scene(dprt, world, tris, layout="slabs"):
+    """N > 1: the unit cube is cut into load-balanced x-slabs for the benchmark camera (scene.balanced_slab_layout), one
+    1 M-triangle height-field chunk per slab; --layout cells gives the 2x2x1 / 2x2x2 cells the parity tests use."""
+    fw, fh = frame_for(world)
+    chunks, mats, lights = dprt.scene.make_scene(world, tris, layout=layout, camera=dprt.scene.default_camera(fw, fh))
     return chunks, mats, lights
 
 
@@ -145,7 +148,7 @@ def run_reference(args):
     W = args.gpus
     fw, fh = frame_for(W)
     w, h = max(16, fw // args.ref_scale), max(9, fh // args.ref_scale)
-    chunks, mats, lights = build_world_scene(dprt, W, args.tris)
+    chunks, mats, lights = build_world_scene(dprt, W, args.tris, args.layout)
     cfg = dprt.make_config(w, h, spp=1, bounces=args.bounces, scene_size=W, proxy_mode=1 if (args.proxy and W > 1) else 0,
                            path_gen_mode=args.path_gen_mode if W > 1 else 0, mlp_dtype=1)
     world = O.World(cfg, W)
@@ -159,11 +162,7 @@ def run_reference(args):
     for s in range(args.warmup):
         world.render_sample(s)
     def rays_total():
-        t = 0
-        for r in range(W):
-            st = world.stats(r)
-            t += st["rays_traverse"] + st["rays_shade"] + st["rays_shadow"] + st["rays_secondary"]
-        return t
+        return sum(world.stats(r)["rays_walked"] for r in range(W))
     r0 = rays_total()
     t0 = time.perf_counter()
     for s in range(args.steps):
@@ -188,7 +187,8 @@ def run_reference(args):
 def workload_config(args, W, fw, fh):
     return {"workload": f"configs[1] scene per GPU: synthetic {args.tris}-triangle chunk x {W} chunk(s), {fw}x{fh} frame "
                         f"(1920x1080 pixels per GPU), 1 spp per step, full per-sample loop with bounces={args.bounces}, spc=4, mc=3",
-            "chunks": W, "tris_per_chunk": args.tris, "width": fw, "height": fh, "bounces": args.bounces,
+            "chunks": W, "tris_per_chunk": args.tris, "chunk_layout": "single chunk" if W == 1 else
+            ("load-balanced x-slabs (k/W quantiles of the primary-ray footprint)" if args.layout == "slabs" else "2x1x1 / 2x2x1 / 2x2x2 cells"), "width": fw, "height": fh, "bounces": args.bounces,
             "proxy": bool(args.proxy and W > 1), "main_ray": "re-trace" if args.retrace else "hit cache",
             "stage_overlap": bool(not args.serial and not (args.proxy and W > 1)), "path_gen": "rank0" if (args.path_gen_mode == 0 or W == 1) else "striped",
             "l2": "inputs larger than L2: 5 x 64 B path records per pixel (663 MB at 1080p) are rewritten every bounce",
@@ -220,7 +220,7 @@ def cpu_baseline(dprt, args, seconds_target=15.0):
             break
     dt = time.perf_counter() - t0
     st = world.stats(0)
-    rays = sum(st[k] - st0[k] for k in ("rays_traverse", "rays_shade", "rays_shadow", "rays_secondary"))
+    rays = st["rays_walked"] - st0["rays_walked"]
     return {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": O.num_threads(), "kind": "port",
             "sample": f"{n} x runSample over a {w}x{h} frame (1/{args.ref_scale} per side) of the same 1-chunk scene, {dt:.1f} s",
             "samples_per_s": w * h * n / dt}
@@ -339,7 +339,7 @@ def run_dprt(args):
     cfg = dprt.make_config(fw, fh, spp=1, bounces=args.bounces, scene_size=W, proxy_mode=proxy,
                            path_gen_mode=args.path_gen_mode if W > 1 else 0, mlp_dtype=0, main_ray_retrace=args.retrace,
                            serial_stages=args.serial)
-    chunks, mats, lights = build_world_scene(dprt, W, args.tris)
+    chunks, mats, lights = build_world_scene(dprt, W, args.tris, args.layout)
     blobs = proxy_blobs(dprt, W, proxy)
     cam = dprt.scene.default_camera(fw, fh)
     R = dprt.Renderer(cfg, rank=rank, world=W, device=local, nccl_unique_id=uid)
@@ -381,6 +381,7 @@ def run_dprt(args):
     barrier()
     clk = clocks.stop() if rank == 0 else None
     st = R.stats()
+    my_rays_walked = st["rays_walked"]
     ms = allreduce(ms, dist.ReduceOp.MAX if W > 1 else None)
     # ---- per-stage pass over the same samples: CUDA-event pairs around every stage launch on the stream it is launched
     # on. Stage profiling forces strictly serial single-stream execution (no shadow/traverse overlap), so each kernel's
@@ -393,9 +394,18 @@ def run_dprt(args):
     barrier()
     stage = R.stage_times()
     R.stage_profile(False)
-    # rays = BVH walks actually performed: MainRay queries answered from the hit cache (the closest hit TraRay already
-    # found for the same ray) are reported separately and are NOT counted in `value`
-    my_rays = st["rays_traverse"] + st["rays_shade"] - st["rays_shade_cached"] + st["rays_shadow"] + st["rays_secondary"]
+    # per-rank view of the serial pass: time inside the exchange stage is mostly waiting for the slowest chunk owner
+    mine = {"rank": rank, "rays_walked_per_step": my_rays_walked / args.steps,
+            "busy_ms_per_step": sum(t for k, (t, _) in stage.items() if k != "exchange") / args.steps,
+            "exchange_ms_per_step": stage["exchange"][0] / args.steps}
+    per_rank = [mine]
+    if W > 1:
+        per_rank = [None] * W
+        dist.all_gather_object(per_rank, mine)
+    # rays = BVH walks actually performed (dprt_stats.rays_walked, counted on the device): a live record with at least one
+    # local object it has not visited yet. Records that only ride along in a TraRay launch (their chunk is already
+    # visited) and MainRay queries answered from the hit cache are NOT counted in `value`.
+    my_rays = st["rays_walked"]
     rays = allreduce(float(my_rays), dist.ReduceOp.SUM if W > 1 else None)
     cached = allreduce(float(st["rays_shade_cached"]), dist.ReduceOp.SUM if W > 1 else None)
     launches = allreduce(float(st["kernel_launches"]), dist.ReduceOp.SUM if W > 1 else None)
@@ -456,8 +466,7 @@ def run_dprt(args):
     e2e_s = time.perf_counter() - t0
     st1 = R.stats()
     e2e_s = allreduce(e2e_s, dist.ReduceOp.MAX if W > 1 else None)
-    e_rays = sum(st1[k] - st0[k] for k in ("rays_traverse", "rays_shade", "rays_shadow", "rays_secondary"))
-    e_rays -= st1["rays_shade_cached"] - st0["rays_shade_cached"]
+    e_rays = st1["rays_walked"] - st0["rays_walked"]
     e_rays = allreduce(float(e_rays), dist.ReduceOp.SUM if W > 1 else None)
     e2e = {"value": e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(N * 12),
            "ms_per_step": e2e_s / args.steps * 1e3, "samples_per_s": N * args.steps / e2e_s,
@@ -470,7 +479,7 @@ def run_dprt(args):
                 "data": "synthetic", "samples_per_s": N * args.steps / (ms * 1e-3), "rays_per_step": rays / args.steps,
                 "main_ray_queries_from_hit_cache_per_step": cached / args.steps,
                 "config": workload_config(args, W, fw, fh), "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clk, "stages": stages_out,
+                "clocks": clk, "stages": stages_out, "ranks": per_rank,
                 "alltoall": {"bytes_per_step": sent / args.steps, "exchange_iters_per_step": st["exchange_iters"] / args.steps}}
     if W == 1:
         if not args.skip_extras:
@@ -500,6 +509,7 @@ def main():
     ap.add_argument("--path-gen-mode", type=int, default=1, help="N>1: 0 = rank 0 generates all camera paths (reference), 1 = striped")
     ap.add_argument("--ref-scale", type=int, default=4, help="reference/cpu_baseline arm: frame reduced by this factor per side")
     ap.add_argument("--retrace", type=int, default=0, help="1 = MainRay always re-traces (no hit cache), for A/B")
+    ap.add_argument("--layout", choices=("slabs", "cells"), default="slabs", help="N>1: how the unit cube is cut into chunks")
     ap.add_argument("--serial", type=int, default=0, help="1 = no shadow/traverse stream overlap inside dprt_render_sample, for A/B")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")

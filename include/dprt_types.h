@@ -117,7 +117,10 @@ typedef struct dprt_config {
     int32_t serialStages;     /* 0 = dprt_render_sample may run the ShadowRay module of bounce b on a second CUDA stream beside
                                  the TraRay loop of bounce b+1 (independent data, same results; proxyMode 0 only);
                                  1 = every stage strictly in order on one stream */
-    int32_t reserved_[1];
+    int32_t referenceMigrate; /* 0 = the migrate loop of dprt_primary_ray_module keeps paths that have reached their final rank in
+                                 a double-ended buffer and only traces / partitions / sends the ones still travelling (same
+                                 final buffers, DESIGN.md "settled deque"); 1 = every iteration handles every path, as
+                                 Work_Efficient_Scan + MPI_Alltoallv do (renderer.cpp:1212-1318) */
 } dprt_config;
 
 /* Standalone closest-hit query (the optixTrace equivalent used by BASELINE config 2). */
@@ -164,7 +167,10 @@ typedef struct dprt_stats {
     int64_t kernel_launches;
     int64_t bytes_alltoall;
     int64_t rays_shade_cached; /* subset of rays_shade answered from the hit cache instead of a second BVH walk */
-    int64_t reserved_[6];
+    int64_t rays_walked;       /* rays of all four stages that actually walked a local BVH: live record, at least one local
+                                  object not yet visited, not answered from the hit cache (rays_* count launch sizes, like
+                                  the reference's optixLaunch dimensions) */
+    int64_t reserved_[5];
 } dprt_stats;
 
 /* Buffer identifiers for dprt_download/dprt_upload (parity harness access to Params buffers). */

@@ -408,6 +408,17 @@ void add_env(World& w, Rank& r, dprt_path_record& p) {
     r.env[px + 0] += p.throughput[0]; r.env[px + 1] += p.throughput[1]; r.env[px + 2] += p.throughput[2];
 }
 
+// does a ray with this visited set walk any local BVH on this rank? (dprt_stats.rays_walked)
+bool has_local_work(const World& w, int rank, uint32_t visited, bool skipVisited) {
+    for (int i = 0; i < (int)w.objects.size(); i++) {
+        const Object& ob = w.objects[i];
+        if (!ob.present || w.is_proxy(rank, i)) continue;
+        if (skipVisited && ((visited >> ob.desc.nodeID) & 1u)) continue;
+        return true;
+    }
+    return false;
+}
+
 // closest hit over the rank's local objects, in scene order, tMax shrinking (strict < across objects)
 bool trace_local(const World& w, int rank, V3 o, V3 d, float tmin, float& tMax, uint32_t visited, bool skipVisited, Hit& best,
                  int& bestObj) {
@@ -449,11 +460,13 @@ void path_gen(World& w, Rank& r) {
 
 void traverse(World& w, Rank& r) {
     const int n = r.pathSize;
-#pragma omp parallel for schedule(dynamic, 256)
+    int64_t walked = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : walked)
     for (int i = 0; i < n; i++) {
         dprt_path_record p = r.paths[i];
         if (!r.hitPrim.empty()) r.hitPrim[i] = -1;
         if (!p.isValid) continue;
+        walked += has_local_work(w, r.id, p.visitedMask, true);
         const V3 o = v3(p.origin[0], p.origin[1], p.origin[2]), d = v3(p.direction[0], p.direction[1], p.direction[2]);
         Hit h; h.prim = -1; int hobj = -1; float tMax = p.tMax;
         if (trace_local(w, r.id, o, d, DPRT_EPSILON, tMax, p.visitedMask, true, h, hobj)) {
@@ -476,7 +489,7 @@ void traverse(World& w, Rank& r) {
         if (!proxyHit && !p.isHit) { add_env(w, r, p); p.isValid = 0; }
         r.paths[i] = p;
     }
-    r.stats.rays_traverse += n;
+    r.stats.rays_traverse += n; r.stats.rays_walked += walked;
 }
 
 // Work_Efficient_Scan: stable partition of valid paths by targetNode (bucket-major, index order inside)
@@ -554,11 +567,13 @@ void shade(World& w, Rank& r) {
     const int n = r.pathSize, spc = w.cfg.shadowPathCount;
     r.shadowPathSize = spc * n;
     const dprt_path_record zero{};
-#pragma omp parallel for schedule(dynamic, 256)
+    int64_t walked = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : walked)
     for (int i = 0; i < n; i++) {
         dprt_path_record path = r.paths[i];
         if (!r.hitPrim.empty()) r.hitPrim[i] = -1;
         if (!path.isValid) continue;
+        walked += has_local_work(w, r.id, 0u, false);     // the oracle always re-traces (kernel.cu:382-413)
         const V3 o = v3(path.origin[0], path.origin[1], path.origin[2]), d = v3(path.direction[0], path.direction[1], path.direction[2]);
         Hit h; int hobj = -1; float tMax = FLT_MAX;
         const bool isHit = trace_local(w, r.id, o, d, DPRT_EPSILON, tMax, 0u, false, h, hobj);
@@ -634,7 +649,7 @@ void shade(World& w, Rank& r) {
             slot = sh;
         }
     }
-    r.stats.rays_shade += n;
+    r.stats.rays_shade += n; r.stats.rays_walked += walked;
 }
 
 // proxy-AABB march shared by ShadowRay / SecondaryRay; returns -1 when nothing was in the way
@@ -706,10 +721,12 @@ void clear_slots(World& w, Rank& r, int threadIndex) {
 
 void shadow_trace(World& w, Rank& r) {
     const int n = r.shadowPathSize, spc = w.cfg.shadowPathCount;
-#pragma omp parallel for schedule(dynamic, 256)
+    int64_t walked = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : walked)
     for (int i = 0; i < n; i++) {
         dprt_path_record& path = r.paths[(size_t)r.pathSize + i];
         if (!path.isValid) { if (w.cfg.proxyMode) clear_slots(w, r, i); continue; }
+        walked += has_local_work(w, r.id, 0u, false);
         const V3 o = v3(path.origin[0], path.origin[1], path.origin[2]), d = v3(path.direction[0], path.direction[1], path.direction[2]);
         bool occluded = false;
         for (int k = 0; k < (int)w.objects.size() && !occluded; k++) {
@@ -730,16 +747,18 @@ void shadow_trace(World& w, Rank& r) {
             r.direct[px + 2] += path.throughput[2] / inv;
         }
     }
-    r.stats.rays_shadow += n;
+    r.stats.rays_shadow += n; r.stats.rays_walked += walked;
 }
 
 void secondary_trace(World& w, Rank& r) {
     const int n = r.pathSize;
-#pragma omp parallel for schedule(dynamic, 256)
+    int64_t walked = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : walked)
     for (int i = 0; i < n; i++) {
         dprt_path_record path = r.paths[i];
         if (!r.hitPrim.empty()) r.hitPrim[i] = -1;
         if (!path.isValid) { clear_slots(w, r, i); continue; }
+        walked += has_local_work(w, r.id, 0u, false);
         for (size_t k = 0; k < w.objects.size(); k++) if (w.objects[k].present) path.visitedMask |= (1u << w.objects[k].desc.nodeID);
         const V3 o = v3(path.origin[0], path.origin[1], path.origin[2]), d = v3(path.direction[0], path.direction[1], path.direction[2]);
         Hit h; int hobj = -1; float tMax = path.tMax;
@@ -749,7 +768,7 @@ void secondary_trace(World& w, Rank& r) {
         if (res < 0 && !path.isHit) { add_env(w, r, path); path.isValid = 0; }
         r.paths[i] = path;
     }
-    r.stats.rays_secondary += n;
+    r.stats.rays_secondary += n; r.stats.rays_walked += walked;
 }
 
 // Work_Efficient_Scan_For_NN(_HIT_INSIDE): stable bucket of queries by hitAABBID

@@ -94,13 +94,17 @@ struct dprt_ctx {
     PartitionScratch scratch{};
     HitRec* d_hits = nullptr;           // N closest-hit records (MainRay)
     HitRec* d_hitCache = nullptr;       // N per-pixel closest hits of the current epoch (null when cfg.mainRayRetrace)
-    unsigned long long* d_cacheHits = nullptr;   // MainRay queries answered from the cache since the last reset_stats
+    unsigned long long* d_cacheHits = nullptr;   // [0] MainRay queries answered from the cache, [1] rays that walked a BVH (since reset_stats)
     // "reset by count" of the shadow planes of directLightingBuffer: MainRay records which pixels get shadow paths
     // (two lists, ping-pong: one describes the planes that are dirty now, the other is free for the next MainRay)
     int32_t* d_live[2] = {nullptr, nullptr};
     int liveCount[2] = {0, 0};
     int shadeIdx = -1;                  // list written by the last dprt_shade whose shadow paths are still in place; -1 = none
     int dirtyIdx = -1;                  // which list covers the dirty planes; -1 = planes are clean, -2 = unknown (full memset)
+    // settled deque of the migrate loop (cfg.referenceMigrate == 0, W > 1): paths that have reached their final rank
+    dprt_path_record* d_settled = nullptr;   // 2N records; the block [front, back) grows at both ends from the middle
+    int front = 0, back = 0;
+    int nL = 0;                         // active records [0, nL) came from lower ranks, [nL, pathSize) from higher ones
     bool nnScratchDirty = false;        // occlusion / contribution may hold non-zero data
     uint32_t epoch = 1;                 // bumped whenever the rays behind the path records change (new bounce, new paths)
     int32_t* d_queue = nullptr;         // ray queue head of the persistent trace kernel
@@ -215,6 +219,7 @@ void sync_params(dprt_ctx* ctx) {
     p.worldID = ctx->rank; p.worldSize = ctx->world; p.sampleCount = ctx->sample;
     p.frameBufferSize = ctx->N; p.proxyMode = ctx->cfg.proxyMode; p.pathGenMode = ctx->cfg.pathGenMode;
     for (int k = 0; k < 3; k++) p.envColor[k] = ctx->cfg.envColor[k];
+    p.splitL = 0x7fffffff;
     p.hitCache = ctx->d_hitCache; p.hitEpoch = ctx->epoch; p.cacheHits = ctx->d_cacheHits;
 }
 
@@ -328,9 +333,9 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
         if (!cfg->mainRayRetrace) {
             CK(cudaMalloc(&ctx->d_hitCache, N * sizeof(HitRec)));
             CK(cudaMemsetAsync(ctx->d_hitCache, 0, N * sizeof(HitRec), ctx->stream));      // epoch 0 = never written
-            CK(cudaMalloc(&ctx->d_cacheHits, sizeof(unsigned long long)));
-            CK(cudaMemsetAsync(ctx->d_cacheHits, 0, sizeof(unsigned long long), ctx->stream));
         }
+        CK(cudaMalloc(&ctx->d_cacheHits, 2 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(ctx->d_cacheHits, 0, 2 * sizeof(unsigned long long), ctx->stream));
         CK(cudaMalloc(&ctx->d_queue, trace_scratch_bytes()));
         if (!cfg->serialStages && !cfg->proxyMode) {
             int lo = 0, hi = 0;
@@ -342,8 +347,9 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
         }
         CK(cudaMalloc(&ctx->d_image, 3 * N * sizeof(float)));
         CK(cudaMalloc(&ctx->d_image_sum, 3 * N * sizeof(float)));
-        CK(cudaMalloc(&ctx->d_gather, sizeof(int32_t) * (size_t)world * (world + 1)));
-        CK(cudaMallocHost(&ctx->h_pinned, sizeof(int32_t) * std::max<size_t>(256, (size_t)world * (world + 1))));
+        CK(cudaMalloc(&ctx->d_gather, sizeof(int32_t) * (size_t)world * (world + 2)));
+        CK(cudaMallocHost(&ctx->h_pinned, sizeof(int32_t) * std::max<size_t>(256, (size_t)world * (world + 2))));
+        if (world > 1 && world < 32 && !cfg->referenceMigrate) CK(cudaMalloc(&ctx->d_settled, 2 * N * sizeof(dprt_path_record)));
 
         DevParams& p = ctx->hp;
         p.objects = ctx->d_objects; p.materials = ctx->d_materials; p.lights = ctx->d_lights;
@@ -412,6 +418,7 @@ void dprt_destroy(dprt_ctx* ctx) {
     if (ctx->d_image) cudaFree(ctx->d_image);
     if (ctx->d_image_sum) cudaFree(ctx->d_image_sum);
     if (ctx->d_gather) cudaFree(ctx->d_gather);
+    if (ctx->d_settled) cudaFree(ctx->d_settled);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     resolve_pending(ctx);
     for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
@@ -435,10 +442,10 @@ int dprt_get_stats(const dprt_ctx* ctx, dprt_stats* out) {
     if (!ctx || !out) return DPRT_ERR_INVALID;
     *out = ctx->stats;
     if (ctx->d_cacheHits) {            // the one statistic that is only known on the device
-        unsigned long long v = 0;
+        unsigned long long v[2] = {0, 0};
         if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
-            cudaMemcpy(&v, ctx->d_cacheHits, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return DPRT_ERR_CUDA;
-        out->rays_shade_cached = (int64_t)v;
+            cudaMemcpy(v, ctx->d_cacheHits, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return DPRT_ERR_CUDA;
+        out->rays_shade_cached = (int64_t)v[0]; out->rays_walked = (int64_t)v[1];
     }
     return 0;
 }
@@ -449,7 +456,7 @@ int dprt_reset_stats(dprt_ctx* ctx) {
     resolve_pending(ctx);
     for (int i = 0; i < DPRT_STAGE_COUNT; i++) { ctx->stageMs[i] = 0.0; ctx->stageLaunches[i] = 0; }
     if (ctx->d_counters) CK(cudaMemsetAsync(ctx->d_counters, 0, 2 * DPRT_STAGE_COUNT * sizeof(unsigned long long), ctx->stream));
-    if (ctx->d_cacheHits) CK(cudaMemsetAsync(ctx->d_cacheHits, 0, sizeof(unsigned long long), ctx->stream));
+    if (ctx->d_cacheHits) CK(cudaMemsetAsync(ctx->d_cacheHits, 0, 2 * sizeof(unsigned long long), ctx->stream));
     return 0;
 }
 
@@ -636,7 +643,7 @@ int dprt_partition(dprt_ctx* ctx) {
         launch_path_histogram(ctx->hp.paths, ctx->pathSize, ctx->world, ctx->hp.pathHist, ctx->stream);
         ctx->stats.kernel_launches += ctx->pathSize > 0;
     }
-    launch_partition_paths(ctx->hp.paths, ctx->pathSize, ctx->world, ctx->hp.pathHist, ctx->hp.transfer,
+    launch_partition_paths(ctx->hp.paths, ctx->pathSize, ctx->world, ctx->world, ctx->rank, 0x7fffffff, ctx->hp.pathHist, ctx->hp.transfer,
                            ctx->hp.transferOffset, ctx->scratch, ctx->stream);
     ctx->stats.kernel_launches += 1;
     ctx->histFresh = false;
@@ -921,9 +928,177 @@ int dprt_target_node_update(dprt_ctx* ctx) {
     return 0;
 }
 
+// ---- settled deque: the migrate loop without the riders ---------------------------------------------
+// In the reference every iteration of primaryRayModule runs TraRay, Work_Efficient_Scan and MPI_Alltoallv over ALL paths
+// of the rank, although a path that has reached the rank of its closest hit (targetNode == rank, own bit visited) comes
+// out of each of those steps unchanged. The buffer of rank r after an iteration is  L ++ M ++ R : records received from
+// lower ranks, the rank's own segment, records received from higher ranks; the own segment of the NEXT iteration is
+// stay(L) ++ M ++ stay(R), because the partition is stable and nothing in M moves or dies. So M is kept in the middle of
+// a 2N-record buffer and grows at both ends, and only L ++ R (what arrived in the last exchange) is traced, partitioned
+// (W + 1 buckets: the self bucket in its two pieces) and sent on. When the loop ends the active set is empty and M is
+// the rank's path buffer, record for record what the reference would hold.
+namespace {
+
+bool deque_enabled(const dprt_ctx* ctx) { return ctx->d_settled && !ctx->hp.hitPrim; }
+
+int deque_begin(dprt_ctx* ctx) { ctx->front = ctx->back = ctx->N; ctx->nL = 0; return 0; }
+
+int deque_traverse(dprt_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    sync_params(ctx);
+    ctx->hp.splitL = ctx->nL;
+    CK(cudaMemsetAsync(ctx->hp.pathHist, 0, 32 * sizeof(int32_t), ctx->stream));   // W + 1 <= 32 buckets
+    {
+        StageScope sc_(ctx, DPRT_STAGE_TRAVERSE, ctx->pathSize > 0);
+        launch_traverse(ctx->hp, ctx->pathSize, ctx->stream);
+    }
+    ctx->hp.splitL = 0x7fffffff;
+    ctx->stats.kernel_launches += 2 * (ctx->pathSize > 0);
+    ctx->stats.rays_traverse += ctx->pathSize + (ctx->back - ctx->front);          // the reference launches over the riders too
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int deque_partition(dprt_ctx* ctx) {
+    StageScope sc_(ctx, DPRT_STAGE_PARTITION);
+    launch_partition_paths(ctx->hp.paths, ctx->pathSize, ctx->world, ctx->world + 1, ctx->rank, ctx->nL, ctx->hp.pathHist,
+                           ctx->hp.transfer, ctx->hp.transferOffset, ctx->scratch, ctx->stream);
+    ctx->stats.kernel_launches += 1;
+    ctx->histFresh = false;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// rows: W rows of W + 2 offsets (row s = transferOffset of rank s: buckets 0..W-1 by destination, bucket W = second self piece)
+struct DequePlan { std::vector<int> sendCnt, recvCnt; int cL = 0, cR = 0, offL = 0, offR = 0, newNL = 0, newActive = 0; bool allLocal = true; };
+int deque_plan(const int32_t* rows, int W, int me, DequePlan& p) {
+    p.sendCnt.assign(W, 0); p.recvCnt.assign(W, 0);
+    for (int s = 0; s < W; s++) {
+        const int32_t* r = rows + (size_t)s * (W + 2);
+        if (r[0] != 0) return DPRT_ERR_INVALID;
+        for (int d = 0; d <= W; d++) if (r[d + 1] < r[d]) return DPRT_ERR_INVALID;
+        for (int d = 0; d < W; d++) {
+            const int c = r[d + 1] - r[d];
+            if (s != d && c > 0) p.allLocal = false;
+            if (s == me && d != me) p.sendCnt[d] = c;
+            if (d == me && s != me) { p.recvCnt[s] = c; p.newActive += c; if (s < me) p.newNL += c; }
+        }
+        if (s == me) { p.offL = r[me]; p.cL = r[me + 1] - r[me]; p.offR = r[W]; p.cR = r[W + 1] - r[W]; }
+    }
+    return 0;
+}
+
+// moves the two pieces of the self segment from the transfer buffer to the ends of the settled block
+int deque_absorb(dprt_ctx* ctx, const DequePlan& p) {
+    const size_t R = sizeof(dprt_path_record);
+    if (ctx->front - p.cL < 0 || ctx->back + p.cR > 2 * ctx->N || (ctx->back - ctx->front) + p.cL + p.cR > ctx->N)
+        return fail(ctx, DPRT_ERR_CAPACITY, "more settled paths than the frame holds");
+    if (p.cL > 0) CK(cudaMemcpyAsync(ctx->d_settled + ctx->front - p.cL, ctx->hp.transfer + p.offL, p.cL * R, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (p.cR > 0) CK(cudaMemcpyAsync(ctx->d_settled + ctx->back, ctx->hp.transfer + p.offR, p.cR * R, cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->front -= p.cL; ctx->back += p.cR;
+    return 0;
+}
+
+int deque_exchange(dprt_ctx* ctx, int* done) {
+    CK(cudaSetDevice(ctx->device));
+    const int W = ctx->world, me = ctx->rank;
+    const size_t R = sizeof(dprt_path_record);
+    StageScope sc_(ctx, DPRT_STAGE_EXCHANGE);
+    if (!ctx->comm) return fail(ctx, DPRT_ERR_STATE, "dprt_exchange on a multi-rank context without an NCCL communicator");
+    NK(g_nccl.AllGather(ctx->hp.transferOffset, ctx->d_gather, W + 2, ncclInt32, ctx->comm, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->d_gather, sizeof(int32_t) * W * (W + 2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    DequePlan p;
+    if (deque_plan(ctx->h_pinned, W, me, p)) return fail(ctx, DPRT_ERR_INVALID, "inconsistent offset matrix in the exchange");
+    if (p.newActive > ctx->N) return fail(ctx, DPRT_ERR_CAPACITY, "received more paths than the frame holds");
+    if (ctx->auxPending && p.newActive > ctx->auxGuardBase) { int jr = join_aux(ctx); if (jr) return jr; }
+    const int32_t* row = ctx->h_pinned + (size_t)me * (W + 2);
+    NK(g_nccl.GroupStart());
+    int roff = 0;
+    for (int peer = 0; peer < W; peer++) {
+        if (peer == me) continue;
+        const int sc = p.sendCnt[peer], rc = p.recvCnt[peer];
+        if (sc > 0) NK(g_nccl.Send(ctx->hp.transfer + row[peer], (size_t)sc * R, ncclUint8, peer, ctx->comm, ctx->stream));
+        if (rc > 0) NK(g_nccl.Recv(ctx->hp.paths + roff, (size_t)rc * R, ncclUint8, peer, ctx->comm, ctx->stream));
+        roff += rc;
+        ctx->stats.paths_sent_offrank += sc; ctx->stats.bytes_alltoall += (int64_t)sc * R;
+    }
+    NK(g_nccl.GroupEnd());
+    int r = deque_absorb(ctx, p); if (r) return r;
+    ctx->pathSize = p.newActive; ctx->nL = p.newNL;
+    if (done) *done = p.allLocal;
+    ctx->stats.exchange_iters++;
+    return 0;
+}
+
+int deque_exchange_group(dprt_ctx** ctxs, int W, int* done) {
+    const size_t R = sizeof(dprt_path_record);
+    std::vector<int32_t> rows((size_t)W * (W + 2));
+    for (int s = 0; s < W; s++) {
+        dprt_ctx* ctx = ctxs[s];
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaMemcpyAsync(ctx->h_pinned, ctx->hp.transferOffset, (W + 2) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::copy(ctx->h_pinned, ctx->h_pinned + W + 2, rows.begin() + (size_t)s * (W + 2));
+    }
+    bool allLocal = true;
+    for (int d = 0; d < W; d++) {
+        dprt_ctx* ctx = ctxs[d];
+        CK(cudaSetDevice(ctx->device));
+        DequePlan p;
+        if (deque_plan(rows.data(), W, d, p)) return fail(ctx, DPRT_ERR_INVALID, "inconsistent offset matrix in the exchange");
+        if (p.newActive > ctx->N) return fail(ctx, DPRT_ERR_CAPACITY, "received more paths than the frame holds");
+        allLocal = allLocal && p.allLocal;
+        int roff = 0;
+        for (int s = 0; s < W; s++) {
+            if (s == d) continue;
+            const int c = p.recvCnt[s];
+            const int32_t* srow = rows.data() + (size_t)s * (W + 2);
+            ctxs[s]->stats.paths_sent_offrank += c; ctxs[s]->stats.bytes_alltoall += (int64_t)c * R;
+            if (c > 0) {
+                if (ctxs[s]->device == ctx->device)
+                    CK(cudaMemcpyAsync(ctx->hp.paths + roff, ctxs[s]->hp.transfer + srow[d], c * R, cudaMemcpyDeviceToDevice, ctx->stream));
+                else
+                    CK(cudaMemcpyPeerAsync(ctx->hp.paths + roff, ctx->device, ctxs[s]->hp.transfer + srow[d], ctxs[s]->device, c * R, ctx->stream));
+            }
+            roff += c;
+        }
+        int r = deque_absorb(ctx, p); if (r) return r;
+        CK(cudaStreamSynchronize(ctx->stream));   // sources are re-partitioned next iteration
+        ctx->pathSize = p.newActive; ctx->nL = p.newNL;
+        ctx->stats.exchange_iters++;
+    }
+    if (done) *done = allLocal;
+    return 0;
+}
+
+// the active set is empty: the settled block is the path buffer
+int deque_finish(dprt_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->back - ctx->front;
+    if (ctx->auxPending && n > ctx->auxGuardBase) { int jr = join_aux(ctx); if (jr) return jr; }
+    StageScope sc_(ctx, DPRT_STAGE_EXCHANGE);
+    if (n > 0) CK(cudaMemcpyAsync(ctx->hp.paths, ctx->d_settled + ctx->front, (size_t)n * sizeof(dprt_path_record), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->pathSize = n; ctx->nL = 0;
+    return 0;
+}
+
+}  // namespace
+
 // ---- composite modules ---------------------------------------------------------------------------
 int dprt_primary_ray_module(dprt_ctx* ctx) {
     if (!ctx) return DPRT_ERR_INVALID;
+    if (deque_enabled(ctx)) {
+        int r = deque_begin(ctx);
+        for (;;) {
+            int done = 0;
+            if ((r = deque_traverse(ctx))) return r;
+            if ((r = deque_partition(ctx))) return r;
+            if ((r = deque_exchange(ctx, &done))) return r;
+            if (done) break;
+        }
+        return deque_finish(ctx);
+    }
     for (;;) {
         int r, done = 0;
         if ((r = dprt_traverse(ctx))) return r;
@@ -1017,17 +1192,21 @@ int dprt_render_sample_group(dprt_ctx** ctxs, int W, int sample) {
         if ((r = dprt_path_gen(ctxs[k]))) return r;
     }
     const int bounces = ctxs[0]->cfg.bounces;
+    bool deque = true;
+    for (int k = 0; k < W; k++) deque = deque && ctxs[k] && deque_enabled(ctxs[k]) && ctxs[k]->world == W && ctxs[k]->rank == k;
     for (int bounce = 0; bounce <= bounces; bounce++) {
         for (int k = 0; k < W; k++) if ((r = bounce_pre(ctxs[k], bounce))) return r;
+        if (deque) for (int k = 0; k < W; k++) deque_begin(ctxs[k]);
         for (;;) {
             int done = 0;
             for (int k = 0; k < W; k++) {
-                if ((r = dprt_traverse(ctxs[k]))) return r;
-                if ((r = dprt_partition(ctxs[k]))) return r;
+                if ((r = deque ? deque_traverse(ctxs[k]) : dprt_traverse(ctxs[k]))) return r;
+                if ((r = deque ? deque_partition(ctxs[k]) : dprt_partition(ctxs[k]))) return r;
             }
-            if ((r = dprt_exchange_group(ctxs, W, &done))) return r;
+            if ((r = deque ? deque_exchange_group(ctxs, W, &done) : dprt_exchange_group(ctxs, W, &done))) return r;
             if (done) break;
         }
+        if (deque) for (int k = 0; k < W; k++) if ((r = deque_finish(ctxs[k]))) return r;
         for (int k = 0; k < W; k++) if ((r = bounce_post(ctxs[k]))) return r;
     }
     return 0;

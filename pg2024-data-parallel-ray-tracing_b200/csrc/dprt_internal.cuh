@@ -71,6 +71,8 @@ struct DevParams {
     HitRec*  hitCache;             // per pixel: closest local hit of the pixel's path in the current epoch (null = off)
     uint32_t hitEpoch;             // one epoch per bounce of a sample: entries of older epochs are stale
     unsigned long long* cacheHits; // device counter: MainRay queries answered from the cache
+    int32_t  splitL;               // settled-deque mode of the migrate loop: records at index >= splitL that stay on this
+                                   // rank are counted in bucket worldSize instead of bucket worldID (INT_MAX: reference)
     int32_t* livePixel;            // per path slot of the last MainRay launch: pixel that got shadow paths, or -1
 };
 
@@ -91,7 +93,9 @@ struct PartitionScratch {
     int32_t   maxTiles;
 };
 void launch_path_histogram(const dprt_path_record* paths, int n, int W, int32_t* hist, cudaStream_t stream);
-void launch_partition_paths(const dprt_path_record* paths, int n, int W, const int32_t* hist,
+// B buckets. B == W: bucket = targetNode (reference). B == W + 1 (settled-deque mode): records that stay on rank `me` and
+// sit at index >= splitL go to bucket W, so that the self segment comes out in two pieces (before / after the old own block).
+void launch_partition_paths(const dprt_path_record* paths, int n, int W, int B, int me, int splitL, const int32_t* hist,
                             dprt_path_record* out, int32_t* offsets, const PartitionScratch& s, cudaStream_t stream);
 void launch_query_histogram(const dprt_nn_query* q, int n, int S, int insideOnly, int32_t* hist, cudaStream_t stream);
 void launch_partition_queries(const dprt_nn_query* q, const dprt_half* in, int n, int S, int insideOnly,

@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceBlocksPerSM) trace_kernel(T
     uint32_t skipMask = 0u, flags = 0u;
     bool retry = false;              // TM_SHADE: the bounded trace may be repeated unbounded
     uint32_t cached = 0u;            // TM_SHADE: queries answered from the hit cache
+    uint32_t walked = 0u;            // rays of this lane that entered at least one local object
     TraceCount cnt = {0u, 0u};
     bool exhausted = false;          // warp-uniform: the ray queue has no more rays
     int qlen = 0;                    // warp-uniform: pairs waiting in the triangle queue
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceBlocksPerSM) trace_kernel(T
                     trav_init_ray(s, o, d, tmin, tmax);
                     wq_set_ray(w, lane, s);
                     obj = next_object(a, 0, skipMask);
-                    if (obj < a.sceneSize) { trav_enter_object(s, a.objects[obj].nodes, a.objects[obj].tris); wq_set_object(w, lane, s); }
+                    if (obj < a.sceneSize) { trav_enter_object(s, a.objects[obj].nodes, a.objects[obj].tris); wq_set_object(w, lane, s); walked++; }
                 } else if ((MODE == TM_TRAVERSE || MODE == TM_SECONDARY) && a.hitPrim) {
                     a.hitPrim[my] = -1;
                 }
@@ -324,9 +325,13 @@ __global__ void __launch_bounds__(kTraceBlock, kTraceBlocksPerSM) trace_kernel(T
             }
         } while (__popc(__ballot_sync(FULL, idx >= 0)) >= minBusy);
     }
-    if (MODE == TM_SHADE && a.hitCache) {
-        cached = __reduce_add_sync(FULL, cached);
-        if (lane == 0 && cached) atomicAdd(a.cacheHits, (unsigned long long)cached);
+    if (a.cacheHits) {               // device-side statistics: [0] MainRay queries answered from the cache, [1] rays that walked a BVH
+        if (MODE == TM_SHADE) {
+            cached = __reduce_add_sync(FULL, cached);
+            if (lane == 0 && cached) atomicAdd(a.cacheHits, (unsigned long long)cached);
+        }
+        walked = __reduce_add_sync(FULL, walked);
+        if (lane == 0 && walked) atomicAdd(a.cacheHits + 1, (unsigned long long)walked);
     }
     if (COUNT) {
         if (cnt.nodes) atomicAdd(a.counters + 2 * StageOf<MODE>::id, (unsigned long long)cnt.nodes);
@@ -368,6 +373,7 @@ __global__ void __launch_bounds__(kBlock) traverse_post_kernel(DevParams p, int 
     }
     // by-product for the partition stage: valid paths per destination (warp-aggregated)
     outValid = outValid && target >= 0 && target < p.worldSize;
+    if (target == p.worldID && i >= p.splitL) target = p.worldSize;      // settled-deque mode: second piece of the self segment
     const unsigned m = __ballot_sync(0xffffffffu, outValid);
     if (outValid) {
         const unsigned peers = __match_any_sync(m, target);

@@ -25,12 +25,13 @@ constexpr int kSteps = kWarps * kItems;       // 32 (warp, item) steps per tile,
 constexpr uint32_t ST_AGG = 1u << 30, ST_INC = 2u << 30, ST_MASK = 3u << 30, VAL_MASK = ~ST_MASK;
 
 struct PathOps {
-    const dprt_path_record* in; dprt_path_record* out; int B;
+    const dprt_path_record* in; dprt_path_record* out; int B; int W; int me; int splitL;
     __device__ __forceinline__ int key(int i) const {
         const uint4 w = reinterpret_cast<const uint4*>(in + i)[3];   // visitedMask, currentNode, targetNode, flags
         const int target = (int)w.z;
         const bool valid = (w.w >> 16) & 0xffu;
-        return (valid && target >= 0 && target < B) ? target : -1;
+        if (!(valid && target >= 0 && target < W)) return -1;
+        return (target == me && i >= splitL) ? W : target;           // bucket W only exists in settled-deque mode (B == W + 1)
     }
     __device__ __forceinline__ void copy(int src, int dst) const {
         const float4* s = reinterpret_cast<const float4*>(in + src);
@@ -188,9 +189,9 @@ void launch_path_histogram(const dprt_path_record* paths, int n, int W, int32_t*
     if (n > 0) path_hist_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, stream>>>(paths, n, W, hist);
 }
 
-void launch_partition_paths(const dprt_path_record* paths, int n, int W, const int32_t* hist, dprt_path_record* out,
-                            int32_t* offsets, const PartitionScratch& s, cudaStream_t stream) {
-    PathOps ops{paths, out, W};
+void launch_partition_paths(const dprt_path_record* paths, int n, int W, int B, int me, int splitL, const int32_t* hist,
+                            dprt_path_record* out, int32_t* offsets, const PartitionScratch& s, cudaStream_t stream) {
+    PathOps ops{paths, out, B, W, B > W ? me : -1, splitL};
     run_partition(ops, n, hist, offsets, s, stream);
 }
 

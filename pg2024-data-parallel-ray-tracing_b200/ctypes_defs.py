@@ -15,7 +15,7 @@ class Config(C.Structure):
                 ("shadowPathCount", C.c_int32), ("maxCount", C.c_int32), ("sceneSize", C.c_int32),
                 ("proxyMode", C.c_int32), ("pathGenMode", C.c_int32), ("mlpDtype", C.c_int32),
                 ("envColor", C.c_float * 3), ("mainRayRetrace", C.c_int32), ("serialStages", C.c_int32),
-                ("reserved_", C.c_int32 * 1)]
+                ("referenceMigrate", C.c_int32)]
 
 
 class ObjectDesc(C.Structure):
@@ -32,7 +32,7 @@ class Stats(C.Structure):
     _fields_ = [("rays_traverse", C.c_int64), ("rays_shade", C.c_int64), ("rays_shadow", C.c_int64),
                 ("rays_secondary", C.c_int64), ("nn_queries", C.c_int64), ("paths_sent_offrank", C.c_int64),
                 ("exchange_iters", C.c_int64), ("kernel_launches", C.c_int64), ("bytes_alltoall", C.c_int64),
-                ("rays_shade_cached", C.c_int64), ("reserved_", C.c_int64 * 6)]
+                ("rays_shade_cached", C.c_int64), ("rays_walked", C.c_int64), ("reserved_", C.c_int64 * 5)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "reserved_"}
@@ -75,9 +75,9 @@ BUFFER_DTYPES = {
 
 
 def make_config(width, height, spp=1, bounces=4, spc=4, mc=3, scene_size=1, proxy_mode=0, path_gen_mode=0,
-                mlp_dtype=0, env_color=(0.6, 0.7, 0.9), main_ray_retrace=0, serial_stages=0):
+                mlp_dtype=0, env_color=(0.6, 0.7, 0.9), main_ray_retrace=0, serial_stages=0, reference_migrate=0):
     cfg = Config()
-    cfg.mainRayRetrace, cfg.serialStages = int(main_ray_retrace), int(serial_stages)
+    cfg.mainRayRetrace, cfg.serialStages, cfg.referenceMigrate = int(main_ray_retrace), int(serial_stages), int(reference_migrate)
     cfg.width, cfg.height, cfg.spp, cfg.bounces = width, height, spp, bounces
     cfg.shadowPathCount, cfg.maxCount, cfg.sceneSize = spc, mc, scene_size
     cfg.proxyMode, cfg.pathGenMode, cfg.mlpDtype = proxy_mode, path_gen_mode, mlp_dtype

@@ -44,6 +44,27 @@ def cell_layout(W):
     return cells
 
 
+def balanced_slab_layout(W, cam, plane_z=0.45):
+    """Load-balanced k-d partition of the unit cube along x: W slabs whose boundaries are the k/W quantiles of where the
+    camera's primary rays meet the mean terrain plane z = plane_z (the usual way a data-parallel renderer places its
+    cuts: by expected load, not by volume). Every slab still gets the same number of triangles."""
+    n = 512
+    a = (np.arange(n) + 0.5) / n * 2.0 - 1.0
+    A, B = np.meshgrid(a, a, indexing="xy")
+    U, V, Wv, O = (np.array(list(v), np.float64) for v in (cam.U, cam.V, cam.W, cam.origin))
+    d = A[..., None] * U + B[..., None] * V + Wv
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = (plane_z - O[2]) / d[..., 2]
+    hx, hy = O[0] + t * d[..., 0], O[1] + t * d[..., 1]
+    ok = (t > 0) & (hx >= 0) & (hx <= 1) & (hy >= 0) & (hy <= 1)
+    xs = np.sort(hx[ok])
+    cuts = [0.0] + [float(xs[int(len(xs) * k / W)]) for k in range(1, W)] + [1.0]
+    cells = []
+    for k in range(W):
+        cells.append((np.array([cuts[k], 0.0, 0.0]), np.array([cuts[k + 1], 1.0, 1.0]), 0, 1))
+    return cells
+
+
 def make_heightfield_chunk(cell_min, cell_max, nx, ny, seed, hole_frac=0.0, n_materials=16, water_frac=0.0):
     """nx*ny quads -> 2*nx*ny triangles (minus holes). Returns verts9, normals9, mat_ids (float32/int32)."""
     gx, gy = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="ij")
@@ -131,9 +152,10 @@ class Chunk:
         return self.verts.shape[0]
 
 
-def make_scene(W, tris_per_chunk, water_frac=0.0, seed=0):
-    """W chunks (one per rank); ~tris_per_chunk triangles each. Returns (chunks, materials, lights)."""
-    cells = cell_layout(W)
+def make_scene(W, tris_per_chunk, water_frac=0.0, seed=0, layout="cells", camera=None):
+    """W chunks (one per rank); ~tris_per_chunk triangles each. Returns (chunks, materials, lights).
+    layout "cells": 2x1x1 / 2x2x1 / 2x2x2 spatial cells (upper cells perforated); "slabs": load-balanced x-slabs for `camera`."""
+    cells = balanced_slab_layout(W, camera) if (layout == "slabs" and W > 1) else cell_layout(W)
     chunks = []
     for k, (mn, mx, iz, nz) in enumerate(cells):
         hole = 0.35 if (nz > 1 and iz == nz - 1) else 0.0           # upper sheets let rays through to the lower cells

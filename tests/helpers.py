@@ -8,12 +8,12 @@ D = dprt.ctypes_defs
 
 
 def build_pair(O, W, tris_per_chunk, width, height, *, spp=1, bounces=2, proxy_mode=0, path_gen_mode=0, water_frac=0.0,
-               group=True, models=None, mlp_dtype=1, device=0, main_ray_retrace=0, serial_stages=0):
+               group=True, models=None, mlp_dtype=1, device=0, main_ray_retrace=0, serial_stages=0, reference_migrate=0):
     """Returns (renderers[list of W Renderer], oracle World, chunks). models: {scene_index: (vis_blob, depth_blob)}."""
     chunks, mats, lights = dprt.scene.make_scene(W, tris_per_chunk, water_frac=water_frac)
     cfg = dprt.make_config(width, height, spp=spp, bounces=bounces, scene_size=W, proxy_mode=proxy_mode,
                            path_gen_mode=path_gen_mode, mlp_dtype=mlp_dtype, main_ray_retrace=main_ray_retrace,
-                           serial_stages=serial_stages)
+                           serial_stages=serial_stages, reference_migrate=reference_migrate)
     cam = dprt.scene.default_camera(width, height)
     world = O.World(cfg, W)
     for c in chunks:

@@ -67,6 +67,7 @@ def main():
     assert_bits_equal(R.download(D.BUF_ENV), world.download(rank, D.BUF_ENV, 3 * N), f"rank {rank} env")
     assert_bits_equal(R.download(D.BUF_DIRECT), world.download(rank, D.BUF_DIRECT, 3 * N * spc), f"rank {rank} direct")
     sg, so = R.stats(), world.stats(rank)
+    assert sg["rays_walked"] + sg["rays_shade_cached"] == so["rays_walked"], (sg, so)
     for k in ("rays_traverse", "rays_shade", "rays_shadow", "paths_sent_offrank", "exchange_iters"):
         assert sg[k] == so[k], (rank, k, sg[k], so[k])
     sent = torch.tensor([sg["paths_sent_offrank"]], dtype=torch.int64, device="cuda")

@@ -65,6 +65,9 @@ def test_single_rank_image_bit_exact(gpu_required, oracle):
     sg, so = rs[0].stats(), world.stats(0)
     for k in ("rays_traverse", "rays_shade", "rays_shadow"):
         assert sg[k] == so[k], k
+    # BVH walks: the oracle re-traces every MainRay query, libdprt answers them from the hit cache
+    assert sg["rays_walked"] + sg["rays_shade_cached"] == so["rays_walked"]
+    assert 0 < sg["rays_walked"] < so["rays_walked"]
 
 
 @pytest.mark.parametrize("serial", [0, 1])
@@ -106,10 +109,11 @@ def test_hit_cache_equals_retrace(gpu_required, oracle, W, proxy):
     assert_bits_equal(imgs[1], img_o, "image with re-trace vs oracle")
 
 
-@pytest.mark.parametrize("W", [2, 4, 8])
-def test_multi_rank_group_migration_bit_exact(gpu_required, oracle, W):
-    """W chunk owners emulated as W contexts on one GPU; exchange through dprt_exchange_group."""
-    rs, world, _ = build_pair(oracle, W, 6000, 128, 72, spp=1, bounces=2, proxy_mode=0)
+@pytest.mark.parametrize("W,refmig", [(2, 0), (4, 0), (8, 0), (4, 1), (3, 0)])
+def test_multi_rank_group_migration_bit_exact(gpu_required, oracle, W, refmig):
+    """W chunk owners emulated as W contexts on one GPU; exchange through dprt_exchange_group. refmig=0: migrate loop with
+    the settled deque (only travelling paths are traced / partitioned / sent); refmig=1: every iteration over every path."""
+    rs, world, _ = build_pair(oracle, W, 6000, 128, 72, spp=1, bounces=2, proxy_mode=0, reference_migrate=refmig)
     G = dprt.RankGroup(rs)
     for R in rs:
         R.reset_frame()
@@ -126,6 +130,7 @@ def test_multi_rank_group_migration_bit_exact(gpu_required, oracle, W):
         assert_bits_equal(R.download(D.BUF_DIRECT), world.download(r, D.BUF_DIRECT, 3 * N * spc), f"rank {r} direct")
         sg, so = R.stats(), world.stats(r)
         assert sg["paths_sent_offrank"] == so["paths_sent_offrank"] and sg["exchange_iters"] == so["exchange_iters"]
+        assert sg["rays_traverse"] == so["rays_traverse"] and sg["rays_walked"] + sg["rays_shade_cached"] == so["rays_walked"]
         sent += sg["paths_sent_offrank"]
     assert sent > 0, "no path migrated: the scene does not exercise the exchange"
     assert_bits_equal(G.reduce_image(0), world.image(), "reduced image")
