@@ -439,8 +439,8 @@ def run_dprt(args):
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
-        if tj.get("kernel") == dom and tj.get("n_gpus") == W:
-            traffic = tj.get("dram_bytes_per_launch")
+        if tj.get("n_gpus") == W and dom in tj.get("kernels", {}):
+            traffic = tj["kernels"][dom]["dram_bytes_per_launch"]
     roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": d["GBps"], "peak": pk["hbm"], "unit": "GB/s",
                 "frac": d["GBps"] / pk["hbm"], "traffic": traffic, "alg_bytes_per_launch": d["alg_bytes"] / d["launches"],
                 "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / ms_serial, "serial_pass_ms_per_step": ms_serial / args.steps, "peak_source": pk["source"],
