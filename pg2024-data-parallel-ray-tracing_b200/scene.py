@@ -187,3 +187,37 @@ def camera_rays(cam, sample=0):
     rays["tMin"] = D.DPRT_EPSILON
     rays["tMax"] = np.finfo(np.float32).max
     return rays
+
+
+def save_scene(path, chunks, materials, lights, cam, models=None):
+    """Scene file of the C++ host csrc/dprt_render.cpp (layout documented there). models: {scene_index: (vis_blob, depth_blob)}."""
+    import ctypes as C
+    with open(path, "wb") as f:
+        f.write(b"DPRTSCN1")
+        f.write(np.array([len(chunks), len(materials), len(lights)], np.int32).tobytes())
+        f.write(bytes(C.string_at(C.addressof(cam), C.sizeof(cam))))
+        f.write(np.ascontiguousarray(materials).tobytes())
+        f.write(np.ascontiguousarray(lights).tobytes())
+        for c in chunks:
+            d = c.desc(False)
+            f.write(bytes(C.string_at(C.addressof(d), C.sizeof(d))))
+            f.write(np.array([c.ntris], np.int64).tobytes())
+            f.write(np.ascontiguousarray(c.verts, np.float32).tobytes())
+            f.write(np.ascontiguousarray(c.normals, np.float32).tobytes())
+            f.write(np.ascontiguousarray(c.mats, np.int32).tobytes())
+            vb, db = (models or {}).get(c.index, (None, None))
+            for blob in (vb, db):
+                b = bytes(blob) if blob is not None else b""
+                f.write(np.array([len(b)], np.int64).tobytes())
+                f.write(b)
+
+
+def load_pfm(path):
+    """RGB float32 PFM as written by dprt_render (little endian, bottom-up) -> [h, w, 3] top-down."""
+    with open(path, "rb") as f:
+        assert f.readline().strip() == b"PF"
+        w, h = (int(x) for x in f.readline().split())
+        scale = float(f.readline())
+        assert scale < 0
+        img = np.frombuffer(f.read(), "<f4").reshape(h, w, 3)
+    return img[::-1].copy()

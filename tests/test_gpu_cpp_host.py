@@ -1,0 +1,59 @@
+"""The C++ host (csrc/dprt_render.cpp, the Renderer::launch equivalent) against the oracle: the binary reads a scene
+file, drives libdprt.so through the C ABI only, writes a PFM; the image must carry the oracle's bits."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import assert_bits_equal, dprt
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(os.path.dirname(dprt.host.LIB_PATH), "dprt_render")
+
+
+def _scene_and_oracle(oracle, tmp_path, W, tris, w, h, spp, bounces, path_gen_mode):
+    chunks, mats, lights = dprt.scene.make_scene(W, tris, water_frac=0.02)
+    cam = dprt.scene.default_camera(w, h)
+    path = str(tmp_path / f"scene_w{W}.dprt")
+    dprt.scene.save_scene(path, chunks, mats, lights, cam)
+    cfg = dprt.make_config(w, h, spp=spp, bounces=bounces, scene_size=W, proxy_mode=0, path_gen_mode=path_gen_mode)
+    world = oracle.World(cfg, W)
+    for c in chunks:
+        world.add_object(c.index, c.desc(False), c.verts, c.normals, c.mats)
+    world.set_materials(mats); world.set_lights(lights); world.set_camera(cam)
+    return path, world.launch()
+
+
+@pytest.mark.parametrize("W", [1, 3])
+def test_dprt_render_binary_matches_oracle(gpu_required, oracle, tmp_path, W):
+    assert os.path.exists(BIN), "build() did not produce dprt_render"
+    scene, img_o = _scene_and_oracle(oracle, tmp_path, W, 8000, 160, 90, 2, 3, 1 if W > 1 else 0)
+    out = str(tmp_path / "img.pfm")
+    p = subprocess.run([BIN, "--scene", scene, "--out", out, "--spp", "2", "--bounces", "3", "--world", str(W)],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert '"rays_walked"' in p.stdout
+    img = dprt.scene.load_pfm(out)
+    assert img.shape == (90, 160, 3) and img.max() > 0
+    assert_bits_equal(img.reshape(-1), np.asarray(img_o, np.float32).reshape(-1), f"dprt_render image, W={W}")
+
+
+def test_dprt_render_one_process_per_gpu(gpu_required, oracle, tmp_path):
+    """Two dprt_render processes, one per GPU, NCCL unique id through a file: the reference's deployment."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    scene, img_o = _scene_and_oracle(oracle, tmp_path, 2, 8000, 160, 90, 2, 3, 1)
+    out, idf = str(tmp_path / "img2.pfm"), str(tmp_path / "nccl.id")
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r))
+        procs.append(subprocess.Popen([BIN, "--scene", scene, "--out", out, "--spp", "2", "--bounces", "3", "--nccl-id-file", idf],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-2000:]
+    img = dprt.scene.load_pfm(out)
+    err = np.abs(img.reshape(-1) - np.asarray(img_o, np.float32).reshape(-1)).max() / max(1e-30, float(np.abs(img_o).max()))
+    assert err <= 1e-6, f"ncclReduce image differs: {err}"      # the reduce sums ranks in an order NCCL chooses

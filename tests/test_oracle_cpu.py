@@ -222,6 +222,26 @@ def test_no_cpu_fallback_without_gpu():
     assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
 
 
+def test_cpp_host_binary_builds_and_fails_loudly_without_gpu(tmp_path):
+    """csrc/dprt_render.cpp (the Renderer::launch equivalent) is built by build(); it parses the scene file format that
+    scene.save_scene writes and, like the library, has no CPU fallback."""
+    import subprocess
+    import torch
+    binp = os.path.join(os.path.dirname(dprt.host.LIB_PATH), "dprt_render")
+    assert os.path.exists(binp)
+    assert subprocess.run([binp], capture_output=True).returncode == 2          # usage
+    chunks, mats, lights = dprt.scene.make_scene(2, 500)
+    scene = str(tmp_path / "s.dprt")
+    dprt.scene.save_scene(scene, chunks, mats, lights, dprt.scene.default_camera(32, 18))
+    bad = str(tmp_path / "bad.dprt")
+    open(bad, "wb").write(open(scene, "rb").read()[:1000])
+    p = subprocess.run([binp, "--scene", bad], capture_output=True, text=True)
+    assert p.returncode == 1 and "malformed" in p.stderr
+    if not torch.cuda.is_available():
+        p = subprocess.run([binp, "--scene", scene, "--out", str(tmp_path / "o.pfm")], capture_output=True, text=True)
+        assert p.returncode == 1 and "no CUDA device" in p.stderr and not os.path.exists(str(tmp_path / "o.pfm"))
+
+
 def test_bvh8_build_host_only_properties():
     chunks, _, _ = dprt.scene.make_scene(1, 5000)
     nodes, tris, depth = dprt.build_bvh8(chunks[0].verts, chunks[0].mats)
