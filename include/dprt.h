@@ -114,6 +114,14 @@ int  dprt_trace_closest_device(dprt_ctx* ctx, const void* rays_dev, int64_t n, v
 int  dprt_mlp_infer(dprt_ctx* ctx, int scene_index, int kind, const dprt_half* x_host, int64_t n, dprt_half* y_host);
 int  dprt_mlp_infer_device(dprt_ctx* ctx, int scene_index, int kind, const void* x_dev, int64_t n, void* y_dev);
 
+/* Training samples of the proxy of scene object `scene_index` (a LOCAL object of this rank): the Vis pipeline,
+ * optix/vis_ray_kernel.cu:98-161 + copyOutputBuffersForTrainData renderer.cpp:264-285. Closest hit of each ray
+ * against that object only (the reference uses tMin 1e-5, tMax inf: put them in the ray records);
+ * features_host[5n] = ((o - aabbMin) / (aabbMax - aabbMin), phi / 2pi, theta / pi) of the ray in object space,
+ * labels_host[n] = t / maxLength for a hit, exactly 1.0 for a miss -- the encoding trainingcode/datasets.py:149-227 reads. */
+int  dprt_gen_train_data(dprt_ctx* ctx, int scene_index, const dprt_ray* rays_host, int64_t n, float* features_host,
+                         float* labels_host);
+
 int  dprt_device_alloc(dprt_ctx* ctx, size_t bytes, void** dev_ptr);
 int  dprt_device_free(dprt_ctx* ctx, void* dev_ptr);
 int  dprt_memcpy_h2d(dprt_ctx* ctx, void* dev, const void* host, size_t bytes);

@@ -1149,6 +1149,32 @@ int orc_trace_closest(void* wp, int rank, const dprt_ray* rays, int64_t n, dprt_
     return 0;
 }
 
+// Vis pipeline (optix/vis_ray_kernel.cu:98-161): training samples of scene object si -- closest hit against that object
+// only, features ((o - aabbMin)/(aabbMax - aabbMin), phi/2pi, theta/pi) in object space, label t/maxLength or 1.0 (miss).
+int orc_gen_train_data(void* wp, int si, const dprt_ray* rays, int64_t n, float* feat, float* label) {
+    World* w = (World*)wp;
+    if (!w || si < 0 || si >= (int)w->objects.size() || !w->objects[si].present) return -1;
+    const Object& ob = w->objects[si];
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; i++) {
+        const dprt_ray& ry = rays[i];
+        const V3 o = v3(ry.origin[0], ry.origin[1], ry.origin[2]), d = v3(ry.direction[0], ry.direction[1], ry.direction[2]);
+        Hit h;
+        const bool hit = ob.mesh.trace(o, d, ry.tMin, ry.tMax, false, h);
+        const V3 ol = xform_point(ob.desc.worldToObject, o), dl = xform_vector(ob.desc.worldToObject, d);
+        float phi, theta;
+        cartesian_to_spherical(normalized(dl), &phi, &theta);
+        float* f = feat + 5 * i;
+        f[0] = (ol.x - ob.desc.aabbMin[0]) / (ob.desc.aabbMax[0] - ob.desc.aabbMin[0]);
+        f[1] = (ol.y - ob.desc.aabbMin[1]) / (ob.desc.aabbMax[1] - ob.desc.aabbMin[1]);
+        f[2] = (ol.z - ob.desc.aabbMin[2]) / (ob.desc.aabbMax[2] - ob.desc.aabbMin[2]);
+        f[3] = phi / 6.28318530717958647692f;
+        f[4] = theta / 3.14159265358979323846f;
+        label[i] = hit ? h.t / ob.desc.maxLength : 1.0f;
+    }
+    return 0;
+}
+
 // walk the product's BVH8 blob: hits + per-ray counters (nodes fetched, triangles tested)
 int orc_bvh8_trace(const dprt_bvh8_node* nodes, const dprt_bvh8_tri* tris, const dprt_ray* rays, int64_t n, dprt_hit* hits,
                    int64_t* nodes_visited, int64_t* tris_tested) {

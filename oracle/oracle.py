@@ -49,6 +49,7 @@ def lib():
         L.orc_download.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]
         L.orc_upload.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]
         L.orc_trace_closest.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+        L.orc_gen_train_data.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_bvh8_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.orc_mlp_forward.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_tea4.restype = C.c_uint32
@@ -243,6 +244,12 @@ class World:
         a = np.ascontiguousarray(array, dt)
         if a.size:
             assert self.L.orc_upload(self.h, rank, buf, offset * dt.itemsize, _p(a), a.nbytes) == 0, "oracle upload range"
+
+    def gen_train_data(self, scene_index, rays):
+        r = np.ascontiguousarray(rays, D.RAY_DTYPE)
+        feat, lab = np.zeros((r.size, 5), np.float32), np.zeros(r.size, np.float32)
+        assert self.L.orc_gen_train_data(self.h, scene_index, _p(r), r.size, _p(feat), _p(lab)) == 0
+        return feat, lab
 
     def trace_closest(self, rank, rays, brute=False):
         r = np.ascontiguousarray(rays, D.RAY_DTYPE)

@@ -1326,6 +1326,29 @@ int dprt_trace_closest(dprt_ctx* ctx, const dprt_ray* rays_host, int64_t n, dprt
     return 0;
 }
 
+int dprt_gen_train_data(dprt_ctx* ctx, int si, const dprt_ray* rays_host, int64_t n, float* features_host, float* labels_host) {
+    if (!ctx || !rays_host || !features_host || !labels_host || n < 0) return DPRT_ERR_INVALID;
+    if (si < 0 || si >= ctx->cfg.sceneSize || !ctx->objects[si].present || ctx->objects[si].desc.isProxy || !ctx->objects[si].d_nodes)
+        return fail(ctx, DPRT_ERR_STATE, "training data can only be generated for an object whose geometry is on this rank");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const size_t rb = (size_t)n * sizeof(dprt_ray), hb = (size_t)n * sizeof(dprt_hit), fb = (size_t)n * 5 * sizeof(float), lb = (size_t)n * sizeof(float);
+    int r = ensure_io(ctx, rb + hb + fb + lb); if (r) return r;
+    char* d = (char*)ctx->d_io;
+    CK(cudaMemcpyAsync(d, rays_host, rb, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        StageScope sc_(ctx, DPRT_STAGE_TRACE_CLOSEST);
+        launch_trace_closest(ctx->d_objects + si, 1, (const dprt_ray*)d, (dprt_hit*)(d + rb), n, ctx->d_queue, ctx->hp.counters, ctx->stream);   // startObj only
+        launch_train_features(ctx->d_objects + si, (const dprt_ray*)d, (const dprt_hit*)(d + rb), n, (float*)(d + rb + hb), (float*)(d + rb + hb + fb), ctx->stream);
+    }
+    ctx->stats.kernel_launches += 2;
+    CK(cudaMemcpyAsync(features_host, d + rb + hb, fb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(labels_host, d + rb + hb + fb, lb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int dprt_mlp_infer_device(dprt_ctx* ctx, int si, int kind, const void* x_dev, int64_t n, void* y_dev) {
     if (!ctx || si < 0 || si >= ctx->cfg.sceneSize || !x_dev || !y_dev || n < 0) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));

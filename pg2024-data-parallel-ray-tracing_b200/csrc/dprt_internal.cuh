@@ -86,6 +86,10 @@ size_t trace_scratch_bytes();   // per-context scratch of the persistent trace k
 void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ray* rays, dprt_hit* hits, int64_t n,
                           int32_t* queue, unsigned long long* counters, cudaStream_t stream);
 
+// Vis pipeline epilogue (vis_ray_kernel.cu:145-160): features and label of every traced training ray of object `obj`
+void launch_train_features(const DevObject* obj, const dprt_ray* rays, const dprt_hit* hits, int64_t n, float* features,
+                           float* labels, cudaStream_t stream);
+
 // partition / bucketing (partition.cu)
 struct PartitionScratch {
     uint32_t* tileState;           // tiles * 32 words

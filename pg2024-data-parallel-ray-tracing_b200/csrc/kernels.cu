@@ -653,6 +653,28 @@ __global__ void __launch_bounds__(kBlock) secondary_post_kernel(DevParams p, int
     flush_query_hist(p, shHist);
 }
 
+// Vis pipeline after its trace (vis_ray_kernel.cu:145-160): the encoding the proxy MLPs are trained on, the same one the
+// ShadowRay / SecondaryRay programs feed them with (proxy_march above).
+__global__ void __launch_bounds__(kBlock) train_features_kernel(const DevObject* __restrict__ obj, const dprt_ray* __restrict__ rays,
+                                                                 const dprt_hit* __restrict__ hits, int64_t n, float* __restrict__ feat,
+                                                                 float* __restrict__ label) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevObject& ob = *obj;
+    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rays) + 2 * i), r1 = __ldg(reinterpret_cast<const float4*>(rays) + 2 * i + 1);
+    const V3 ol = xform_point(ob.w2o, v3(r0.x, r0.y, r0.z)), dl = xform_vector(ob.w2o, v3(r1.x, r1.y, r1.z));
+    float phi, theta;
+    det_cartesian_to_spherical(v3normalized(dl), &phi, &theta);
+    float* f = feat + 5 * i;
+    f[0] = (ol.x - ob.aabbMin[0]) / (ob.aabbMax[0] - ob.aabbMin[0]);
+    f[1] = (ol.y - ob.aabbMin[1]) / (ob.aabbMax[1] - ob.aabbMin[1]);
+    f[2] = (ol.z - ob.aabbMin[2]) / (ob.aabbMax[2] - ob.aabbMin[2]);
+    f[3] = phi / 6.28318530717958647692f;
+    f[4] = theta / 3.14159265358979323846f;
+    const float2 h = reinterpret_cast<const float2*>(hits)[i];
+    label[i] = __float_as_int(h.y) >= 0 ? h.x / ob.maxLength : 1.0f;
+}
+
 inline int blocks_for(int64_t n) { return (int)((n + kBlock - 1) / kBlock); }
 
 int num_sms() {
@@ -727,6 +749,10 @@ void launch_secondary_trace(const DevParams& p, int n, cudaStream_t s) {
     if (n <= 0) return;
     launch_trace<TM_SECONDARY>(trace_args(p, p.paths), n, s);
     secondary_post_kernel<<<blocks_for(n), kBlock, 0, s>>>(p, n);
+}
+void launch_train_features(const DevObject* obj, const dprt_ray* rays, const dprt_hit* hits, int64_t n, float* features,
+                           float* labels, cudaStream_t s) {
+    if (n > 0) train_features_kernel<<<blocks_for(n), kBlock, 0, s>>>(obj, rays, hits, n, features, labels);
 }
 void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ray* rays, dprt_hit* hits, int64_t n,
                           int32_t* queue, unsigned long long* counters, cudaStream_t s) {

@@ -68,6 +68,7 @@ _PROTOTYPES = {
     "dprt_enable_hit_prim": (C.c_int, [C.c_void_p, C.c_int]),
     "dprt_trace_closest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "dprt_trace_closest_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "dprt_gen_train_data": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "dprt_mlp_infer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "dprt_mlp_infer_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "dprt_device_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -377,6 +378,13 @@ class Renderer:
         hits = np.zeros(r.size, D.HIT_DTYPE)
         self._ck(self.lib.dprt_trace_closest(self.h, _ptr(r), r.size, _ptr(hits)), "dprt_trace_closest")
         return hits
+
+    def gen_train_data(self, scene_index, rays):
+        """Vis pipeline (vis_ray_kernel.cu:98-161): (features [n,5] f32, labels [n] f32; 1.0 = miss) for a local object."""
+        r = np.ascontiguousarray(rays, D.RAY_DTYPE)
+        feat, lab = np.zeros((r.size, 5), np.float32), np.zeros(r.size, np.float32)
+        self._ck(self.lib.dprt_gen_train_data(self.h, scene_index, _ptr(r), r.size, _ptr(feat), _ptr(lab)), "dprt_gen_train_data")
+        return feat, lab
 
     def mlp_infer(self, scene_index, kind, x_half):
         x = np.ascontiguousarray(x_half, np.uint16).reshape(-1, 5)
