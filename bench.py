@@ -439,7 +439,7 @@ def run_dprt(args):
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
-        if tj.get("n_gpus") == W and dom in tj.get("kernels", {}):
+        if tj.get("n_gpus") == W and args.tris == 1000000 and dom in tj.get("kernels", {}):     # captured on the default workload
             traffic = tj["kernels"][dom]["dram_bytes_per_launch"]
     roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": d["GBps"], "peak": pk["hbm"], "unit": "GB/s",
                 "frac": d["GBps"] / pk["hbm"], "traffic": traffic, "alg_bytes_per_launch": d["alg_bytes"] / d["launches"],
