@@ -92,6 +92,7 @@ struct dprt_ctx {
     void* buf_ptr[DPRT_BUF_COUNT] = {nullptr};
     int32_t* d_hist = nullptr;          // 32 path + 64 query counters
     PartitionScratch scratch{};
+    uint8_t* d_nnKey = nullptr;         // one key byte per NN query slot
     HitRec* d_hits = nullptr;           // N closest-hit records (MainRay)
     HitRec* d_hitCache = nullptr;       // N per-pixel closest hits of the current epoch (null when cfg.mainRayRetrace)
     unsigned long long* d_cacheHits = nullptr;   // [0] MainRay queries answered from the cache, [1] rays that walked a BVH (since reset_stats)
@@ -105,6 +106,8 @@ struct dprt_ctx {
     dprt_path_record* d_settled = nullptr;   // 2N records; the block [front, back) grows at both ends from the middle
     int front = 0, back = 0;
     int nL = 0;                         // active records [0, nL) came from lower ranks, [nL, pathSize) from higher ones
+    int32_t* d_secLive = nullptr;       // pixels whose tMax scratch the last Target_Node_Update used
+    int secDirty = 0;                   // entries of d_secLive to clear at the next resetNNBuffers
     bool nnScratchDirty = false;        // occlusion / contribution may hold non-zero data
     uint32_t epoch = 1;                 // bumped whenever the rays behind the path records change (new bounce, new paths)
     int32_t* d_queue = nullptr;         // ray queue head of the persistent trace kernel
@@ -330,6 +333,7 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
         CK(cudaMalloc(&ctx->scratch.tileCounter, sizeof(int32_t)));
         CK(cudaMalloc(&ctx->d_hits, N * sizeof(HitRec)));
         for (int k = 0; k < 2; k++) CK(cudaMalloc(&ctx->d_live[k], N * sizeof(int32_t)));
+        if (cfg->proxyMode) CK(cudaMalloc(&ctx->d_secLive, N * sizeof(int32_t)));
         if (!cfg->mainRayRetrace) {
             CK(cudaMalloc(&ctx->d_hitCache, N * sizeof(HitRec)));
             CK(cudaMemsetAsync(ctx->d_hitCache, 0, N * sizeof(HitRec), ctx->stream));      // epoch 0 = never written
@@ -360,6 +364,8 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
         p.direct = (float*)ctx->buf_ptr[DPRT_BUF_DIRECT]; p.env = (float*)ctx->buf_ptr[DPRT_BUF_ENV];
         p.contribution = (float*)ctx->buf_ptr[DPRT_BUF_CONTRIBUTION]; p.occlusion = (float*)ctx->buf_ptr[DPRT_BUF_OCCLUSION];
         p.nnInput = (dprt_half*)ctx->buf_ptr[DPRT_BUF_NN_INPUT]; p.nnPackedInput = (dprt_half*)ctx->buf_ptr[DPRT_BUF_NN_PACKED_INPUT];
+        CK(cudaMalloc(&ctx->d_nnKey, Q));
+        p.nnKey = ctx->d_nnKey;
         p.nnQuery = (dprt_nn_query*)ctx->buf_ptr[DPRT_BUF_NN_QUERY]; p.nnPackedQuery = (dprt_nn_query*)ctx->buf_ptr[DPRT_BUF_NN_PACKED_QUERY];
         p.sceneOffset = (int32_t*)ctx->buf_ptr[DPRT_BUF_SCENE_OFFSET];
         p.pred = (dprt_half*)ctx->buf_ptr[DPRT_BUF_PRED];
@@ -407,7 +413,9 @@ void dprt_destroy(dprt_ctx* ctx) {
     if (ctx->scratch.tileState) cudaFree(ctx->scratch.tileState);
     if (ctx->scratch.tileCounter) cudaFree(ctx->scratch.tileCounter);
     if (ctx->d_hits) cudaFree(ctx->d_hits);
+    if (ctx->d_nnKey) cudaFree(ctx->d_nnKey);
     for (int k = 0; k < 2; k++) if (ctx->d_live[k]) cudaFree(ctx->d_live[k]);
+    if (ctx->d_secLive) cudaFree(ctx->d_secLive);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->evShade) cudaEventDestroy(ctx->evShade);
     if (ctx->evAux) cudaEventDestroy(ctx->evAux);
@@ -586,7 +594,7 @@ int dprt_reset_frame(dprt_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->hp.env, 0, ctx->buf_bytes[DPRT_BUF_ENV], ctx->stream));
     CK(cudaMemsetAsync(ctx->hp.contribution, 0, ctx->buf_bytes[DPRT_BUF_CONTRIBUTION], ctx->stream));
     CK(cudaMemsetAsync(ctx->hp.occlusion, 0, ctx->buf_bytes[DPRT_BUF_OCCLUSION], ctx->stream));
-    ctx->dirtyIdx = -1; ctx->nnScratchDirty = false;
+    ctx->dirtyIdx = -1; ctx->nnScratchDirty = false; ctx->secDirty = 0;
     return 0;
 }
 
@@ -788,20 +796,25 @@ int dprt_reset_nn(dprt_ctx* ctx) {
     // reset inside the producing kernels. occlusion / contribution are only ever written by the proxy epilogues.
     // The shadow planes 1..spc-1 of directLightingBuffer are only written by the ShadowRay program, for pixels of the
     // paths the preceding MainRay shaded: those pixels are zeroed, the rest of the planes is zero already.
-    if (ctx->cfg.proxyMode || ctx->nnScratchDirty) {
+    const bool nnAll = ctx->nnScratchDirty || (ctx->cfg.proxyMode && ctx->dirtyIdx == -2);   // contents unknown: clear everything
+    if (nnAll) {
         CK(cudaMemsetAsync(ctx->hp.occlusion, 0, ctx->buf_bytes[DPRT_BUF_OCCLUSION], ctx->stream));
         CK(cudaMemsetAsync(ctx->hp.contribution, 0, ctx->buf_bytes[DPRT_BUF_CONTRIBUTION], ctx->stream));
         ctx->nnScratchDirty = false;
+    } else if (ctx->cfg.proxyMode && ctx->secDirty > 0) {
+        sync_params(ctx);
+        launch_reset_sec(ctx->hp, ctx->d_secLive, ctx->secDirty, ctx->stream);     // what Target_Node_Update left behind
+        ctx->stats.kernel_launches += 1;
     }
-    if (ctx->cfg.shadowPathCount > 1) {
-        if (ctx->dirtyIdx == -2)
+    ctx->secDirty = 0;
+    if (ctx->dirtyIdx == -2) {
+        if (ctx->cfg.shadowPathCount > 1)
             CK(cudaMemsetAsync(ctx->hp.direct + (size_t)ctx->N * 3, 0, (size_t)ctx->N * 3 * sizeof(float) * (ctx->cfg.shadowPathCount - 1),
                                ctx->stream));
-        else if (ctx->dirtyIdx >= 0) {
-            sync_params(ctx);
-            launch_reset_planes(ctx->hp, ctx->d_live[ctx->dirtyIdx], ctx->liveCount[ctx->dirtyIdx], ctx->stream);
-            ctx->stats.kernel_launches += ctx->liveCount[ctx->dirtyIdx] > 0;
-        }
+    } else if (ctx->dirtyIdx >= 0) {
+        sync_params(ctx);
+        launch_reset_planes(ctx->hp, ctx->d_live[ctx->dirtyIdx], ctx->liveCount[ctx->dirtyIdx], ctx->cfg.proxyMode && !nnAll, ctx->stream);
+        ctx->stats.kernel_launches += ctx->liveCount[ctx->dirtyIdx] > 0;
     }
     ctx->dirtyIdx = -1;
     CK(cudaMemsetAsync(ctx->hp.queryHist, 0, 64 * sizeof(int32_t), ctx->stream));
@@ -856,7 +869,8 @@ int dprt_bucket_queries(dprt_ctx* ctx, int which, int inside_only, int* total) {
         launch_query_histogram(ctx->hp.nnQuery, n, S, inside_only ? 1 : 0, hist, ctx->stream);
         ctx->stats.kernel_launches += n > 0;
     }
-    launch_partition_queries(ctx->hp.nnQuery, ctx->hp.nnInput, n, S, inside_only ? 1 : 0, hist, ctx->hp.nnPackedQuery,
+    const bool keysFresh = ctx->qhistFresh && ctx->queryWhich == which;      // same launch wrote records, histogram and keys
+    launch_partition_queries(ctx->hp.nnQuery, keysFresh ? ctx->hp.nnKey : nullptr, ctx->hp.nnInput, n, S, inside_only ? 1 : 0, hist, ctx->hp.nnPackedQuery,
                              ctx->hp.nnPackedInput, ctx->hp.sceneOffset, ctx->scratch, ctx->stream);
     ctx->stats.kernel_launches += 1;
     CK(cudaMemcpyAsync(ctx->h_pinned, ctx->hp.sceneOffset, (S + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -898,6 +912,7 @@ int dprt_frame_buffer_update(dprt_ctx* ctx) {
     StageScope sc_(ctx, DPRT_STAGE_FRAME_UPDATE);
     launch_shadow_occlusion(ctx->hp, ctx->cfg.proxyMode ? ctx->queryTotal : 0, ctx->stream);
     const bool sparse = ctx->dirtyIdx >= 0 && ctx->dirtyIdx == ctx->shadeIdx;     // else: every pixel (reference behaviour)
+    if (!sparse && ctx->cfg.proxyMode && ctx->queryTotal > 0) ctx->nnScratchDirty = true;   // entries outside any pixel list
     if (ctx->dirtyIdx != -1)
         launch_contribution(ctx->hp, sparse ? ctx->d_live[ctx->dirtyIdx] : nullptr, sparse ? ctx->liveCount[ctx->dirtyIdx] : 0, ctx->stream);
     ctx->stats.kernel_launches += (ctx->dirtyIdx != -1) + (ctx->queryTotal > 0);
@@ -920,8 +935,11 @@ int dprt_target_node_update(dprt_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     sync_params(ctx);
     StageScope sc_(ctx, DPRT_STAGE_TARGET_UPDATE);
+    ctx->hp.secLive = ctx->d_secLive;
     launch_tmax(ctx->hp, ctx->queryTotal, ctx->stream);
     launch_target_node(ctx->hp, ctx->pathSize, ctx->stream);
+    if (ctx->secDirty > 0 || !ctx->d_secLive) ctx->nnScratchDirty = true;       // two updates without a reset in between: unknown
+    else ctx->secDirty = ctx->pathSize;
     ctx->stats.kernel_launches += (ctx->queryTotal > 0) + (ctx->pathSize > 0);
     ctx->histFresh = false;
     CK(cudaGetLastError());

@@ -61,6 +61,8 @@ struct DevParams {
     dprt_half*     nnPackedInput;
     dprt_nn_query* nnQuery;        // NNPathDataBuffer
     dprt_nn_query* nnPackedQuery;
+    uint8_t* nnKey;                // per query slot: hitAABBID | isInside << 7 (0 = empty): what the bucketing reads instead of
+                                   // the 48-byte records, most of which are empty
     int32_t* sceneOffset;          // sceneSize+1
     int32_t* queryHist;            // sceneSize counters (all queries), then sceneSize (inside only)
     dprt_half* pred;               // predBuffer
@@ -73,6 +75,7 @@ struct DevParams {
     unsigned long long* cacheHits; // device counter: MainRay queries answered from the cache
     int32_t  splitL;               // settled-deque mode of the migrate loop: records at index >= splitL that stay on this
                                    // rank are counted in bucket worldSize instead of bucket worldID (INT_MAX: reference)
+    int32_t* secLive;              // per path slot of the last Target_Node_Update: pixel whose tMax scratch it used, or -1
     int32_t* livePixel;            // per path slot of the last MainRay launch: pixel that got shadow paths, or -1
 };
 
@@ -102,7 +105,8 @@ void launch_path_histogram(const dprt_path_record* paths, int n, int W, int32_t*
 void launch_partition_paths(const dprt_path_record* paths, int n, int W, int B, int me, int splitL, const int32_t* hist,
                             dprt_path_record* out, int32_t* offsets, const PartitionScratch& s, cudaStream_t stream);
 void launch_query_histogram(const dprt_nn_query* q, int n, int S, int insideOnly, int32_t* hist, cudaStream_t stream);
-void launch_partition_queries(const dprt_nn_query* q, const dprt_half* in, int n, int S, int insideOnly,
+// keys: DevParams::nnKey when it is known to mirror q (written by the same launch that wrote q), else null
+void launch_partition_queries(const dprt_nn_query* q, const uint8_t* keys, const dprt_half* in, int n, int S, int insideOnly,
                               const int32_t* hist, dprt_nn_query* outQ, dprt_half* outIn, int32_t* offsets,
                               const PartitionScratch& s, cudaStream_t stream);
 
@@ -110,8 +114,11 @@ void launch_partition_queries(const dprt_nn_query* q, const dprt_half* in, int n
 void launch_shadow_occlusion(const DevParams& p, int size, cudaStream_t stream);
 // live != null: only the `liveCount` pixels listed there can hold non-zero terms (the others fold to a bitwise no-op)
 void launch_contribution(const DevParams& p, const int32_t* live, int liveCount, cudaStream_t stream);
-// zero the shadow planes 1..spc-1 of directLightingBuffer for the listed pixels (resetNNBuffers by count)
-void launch_reset_planes(const DevParams& p, const int32_t* live, int liveCount, cudaStream_t stream);
+// zero the shadow planes 1..spc-1 of directLightingBuffer for the listed pixels (resetNNBuffers by count); nn != 0: also
+// their shadowOcclusion / contribution entries (what Frame_Buffer_Update read for them)
+void launch_reset_planes(const DevParams& p, const int32_t* live, int liveCount, int nn, cudaStream_t stream);
+// zero the tMax scratch Target_Node_Update used for the listed pixels (2*mc floats each in the occlusion buffer)
+void launch_reset_sec(const DevParams& p, const int32_t* live, int liveCount, cudaStream_t stream);
 void launch_depth_update(const DevParams& p, int size, cudaStream_t stream);
 void launch_tmax(const DevParams& p, int size, cudaStream_t stream);
 void launch_target_node(const DevParams& p, int n, cudaStream_t stream);

@@ -64,7 +64,7 @@ __global__ void contribution_kernel(DevParams p, const int32_t* __restrict__ liv
     }
 }
 
-__global__ void reset_planes_kernel(DevParams p, const int32_t* __restrict__ live, int count) {
+__global__ void reset_planes_kernel(DevParams p, const int32_t* __restrict__ live, int count, int nn) {
     const int N = p.frameBufferSize;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         const int px = live[i];
@@ -73,6 +73,21 @@ __global__ void reset_planes_kernel(DevParams p, const int32_t* __restrict__ liv
             const size_t pl = ((size_t)N * s + px) * 3;
             p.direct[pl + 0] = 0.0f; p.direct[pl + 1] = 0.0f; p.direct[pl + 2] = 0.0f;
         }
+        if (nn) {
+            float* oc = p.occlusion + (size_t)px * p.spc * p.mc;
+            for (int k = 0; k < p.spc * p.mc; k++) oc[k] = 0.0f;
+            float* co = p.contribution + (size_t)px * p.spc * 3;
+            for (int k = 0; k < p.spc * 3; k++) co[k] = 0.0f;
+        }
+    }
+}
+
+__global__ void reset_sec_kernel(DevParams p, const int32_t* __restrict__ live, int count) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const int px = live[i];
+        if (px < 0) continue;
+        float* oc = p.occlusion + (size_t)px * p.mc * 2;
+        for (int k = 0; k < p.mc * 2; k++) oc[k] = 0.0f;
     }
 }
 
@@ -103,9 +118,10 @@ __global__ void tmax_kernel(DevParams p, int size) {
 __global__ void target_node_kernel(DevParams p, int n) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         dprt_path_record* rec = p.paths + i;
-        if (!rec->isValid) continue;
+        if (!rec->isValid) { if (p.secLive) p.secLive[i] = -1; continue; }
         float tMax = rec->tMax; int currentNode = rec->currentNode;
         const int pixel = rec->pixelIndex;
+        if (p.secLive) p.secLive[i] = pixel;
         for (int j = 0; j < p.mc; j++) {
             const size_t ti = ((size_t)pixel * p.mc + j) * 2;
             const float t = p.occlusion[ti];
@@ -137,8 +153,11 @@ void launch_contribution(const DevParams& p, const int32_t* live, int liveCount,
     if (p.proxyMode) contribution_kernel<true><<<grid_for(count), kBlock, 0, s>>>(p, live, count);
     else contribution_kernel<false><<<grid_for(count), kBlock, 0, s>>>(p, live, count);
 }
-void launch_reset_planes(const DevParams& p, const int32_t* live, int liveCount, cudaStream_t s) {
-    if (liveCount > 0 && p.spc > 1) reset_planes_kernel<<<grid_for(liveCount), kBlock, 0, s>>>(p, live, liveCount);
+void launch_reset_planes(const DevParams& p, const int32_t* live, int liveCount, int nn, cudaStream_t s) {
+    if (liveCount > 0 && (p.spc > 1 || nn)) reset_planes_kernel<<<grid_for(liveCount), kBlock, 0, s>>>(p, live, liveCount, nn);
+}
+void launch_reset_sec(const DevParams& p, const int32_t* live, int liveCount, cudaStream_t s) {
+    if (liveCount > 0) reset_sec_kernel<<<grid_for(liveCount), kBlock, 0, s>>>(p, live, liveCount);
 }
 void launch_depth_update(const DevParams& p, int size, cudaStream_t s) {
     if (size > 0) depth_update_kernel<<<grid_for(size), kBlock, 0, s>>>(p, size);

@@ -524,7 +524,10 @@ struct MarchOut { int count; bool envMiss; };
 
 DPRT_D void clear_query_slots(const DevParams& p, int threadIndex, int from) {
     if (!p.proxyMode) return;                     // no query buffers exist when proxies are off
-    for (int q = from; q < p.mc; q++) p.nnQuery[(size_t)threadIndex * p.mc + q].hitAABBID = 0;   // reset by count, not memset
+    for (int q = from; q < p.mc; q++) {                                                          // reset by count, not memset
+        p.nnQuery[(size_t)threadIndex * p.mc + q].hitAABBID = 0;
+        p.nnKey[(size_t)threadIndex * p.mc + q] = 0;
+    }
 }
 
 template <bool SECONDARY>
@@ -583,6 +586,7 @@ DPRT_D int proxy_march(const DevParams& p, const PathRegs& path, int threadIndex
                 e.normalizedT = isInside ? dist / ob.maxLength : 0.0f;
             }
             p.nnQuery[(size_t)threadIndex * mc + count] = e;
+            p.nnKey[(size_t)threadIndex * mc + count] = (uint8_t)((hitIdx + 1) | (isInside ? 0x80 : 0));
             // histogram by-product for the bucketing stage: all queries, and inside-only
             atomicAdd(shHist + hitIdx, 1);
             if (isInside) atomicAdd(shHist + 32 + hitIdx, 1);

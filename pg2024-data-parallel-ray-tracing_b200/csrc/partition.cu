@@ -42,11 +42,13 @@ struct PathOps {
 };
 
 struct QueryOps {
-    const dprt_nn_query* in; const dprt_half* fin; dprt_nn_query* out; dprt_half* fout; int B; int insideOnly;
+    const dprt_nn_query* in; const uint8_t* keys; const dprt_half* fin; dprt_nn_query* out; dprt_half* fout; int B; int insideOnly;
     __device__ __forceinline__ int key(int i) const {
-        const int id = in[i].hitAABBID;                 // preKernelNN: hitAABBID == AABBID (scene index + 1)
-        if (id < 1 || id > B) return -1;
-        if (insideOnly && !in[i].isInside) return -1;   // preKernelNN_HIT_INSIDE
+        int id; bool inside;
+        if (keys) { const uint32_t k = keys[i]; id = (int)(k & 0x7fu); inside = (k >> 7) != 0u; }   // 1 byte instead of a 48-byte record
+        else { id = in[i].hitAABBID; inside = in[i].isInside != 0; }
+        if (id < 1 || id > B) return -1;                // preKernelNN: hitAABBID == AABBID (scene index + 1)
+        if (insideOnly && !inside) return -1;           // preKernelNN_HIT_INSIDE
         return id - 1;
     }
     __device__ __forceinline__ void copy(int src, int dst) const {
@@ -200,10 +202,10 @@ void launch_query_histogram(const dprt_nn_query* q, int n, int S, int insideOnly
     if (n > 0) query_hist_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, stream>>>(q, n, S, insideOnly, hist);
 }
 
-void launch_partition_queries(const dprt_nn_query* q, const dprt_half* in, int n, int S, int insideOnly,
+void launch_partition_queries(const dprt_nn_query* q, const uint8_t* keys, const dprt_half* in, int n, int S, int insideOnly,
                               const int32_t* hist, dprt_nn_query* outQ, dprt_half* outIn, int32_t* offsets,
                               const PartitionScratch& s, cudaStream_t stream) {
-    QueryOps ops{q, in, outQ, outIn, S, insideOnly};
+    QueryOps ops{q, keys, in, outQ, outIn, S, insideOnly};
     run_partition(ops, n, hist, offsets, s, stream);
 }
 
