@@ -150,8 +150,13 @@ DPRT_D int next_object(const TraceArgs& a, int from, uint32_t skipMask) {
     return a.sceneSize;
 }
 
+// Resident blocks per SM = register budget. The any-hit (shadow) trace has the shortest dependency chains per ray and gains
+// from a seventh block (72 registers, ~70 bytes of spills); the closest-hit modes lose more to the spills than they gain
+// (profiles/ab_r1d_regs.txt).
+template <int MODE> constexpr int trace_min_blocks() { return MODE == 2 ? (kTraceBlocksPerSM == 6 ? 7 : kTraceBlocksPerSM) : kTraceBlocksPerSM; }
+
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock, kTraceBlocksPerSM) trace_kernel(TraceArgs a, int n) {
+__global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_kernel(TraceArgs a, int n) {
     constexpr bool ANY = MODE == TM_SHADOW;
     const unsigned FULL = 0xffffffffu;
     __shared__ WarpQueue s_wq[kTraceBlock / 32];
@@ -701,7 +706,7 @@ int tune_trivote() { static int v = env_int("DPRT_TRACE_TRIVOTE", kTriVoteDefaul
 int tune_coop() { static int v = env_int("DPRT_TRACE_COOP", kCoopDefault, 0, 32); return v; }
 int tune_rpl() { static int v = env_int("DPRT_TRACE_RPL", kRaysPerLaneDefault, 1, 64); return v; }
 int tune_nodes() { static int v = env_int("DPRT_TRACE_NODES", kNodesPerStepDefault, 1, 16); return v; }
-int tune_blocks() { static int v = env_int("DPRT_TRACE_BLOCKS_PER_SM", kTraceBlocksPerSM, 1, 16); return v; }
+int tune_blocks() { static int v = env_int("DPRT_TRACE_BLOCKS_PER_SM", 0, 0, 16); return v; }     // 0 = the launch bound of the mode
 
 template <int MODE>
 void launch_trace(TraceArgs a, int64_t n, cudaStream_t s) {
@@ -710,7 +715,8 @@ void launch_trace(TraceArgs a, int64_t n, cudaStream_t s) {
     // Grid: never more warps than keep every lane supplied with ~tune_rpl() rays. A warp runs until its longest ray is
     // done, so with one ray per lane its efficiency is mean/max ray length; with a few rays per lane the refill evens it out.
     const int64_t want = (n + (int64_t)kTraceBlock * tune_rpl() - 1) / ((int64_t)kTraceBlock * tune_rpl());
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms() * tune_blocks()));
+    const int perSM = tune_blocks() > 0 ? tune_blocks() : trace_min_blocks<MODE>();
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms() * perSM));
     if (a.counters) trace_kernel<MODE, true><<<blocks, kTraceBlock, 0, s>>>(a, (int)n);
     else trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, s>>>(a, (int)n);
 }
@@ -728,7 +734,7 @@ TraceArgs trace_args(const DevParams& p, dprt_path_record* recs) {
 
 size_t trace_scratch_bytes() {
     // 64 B for the ray-queue head + one cooperative-mode node pool per warp that can be resident
-    return 64 + (size_t)num_sms() * tune_blocks() * (kTraceBlock / 32) * DPRT_POOLCAP * sizeof(uint32_t);
+    return 64 + (size_t)num_sms() * std::max(tune_blocks(), 8) * (kTraceBlock / 32) * DPRT_POOLCAP * sizeof(uint32_t);
 }
 
 void launch_path_gen(const DevParams& p, int n, cudaStream_t s) {
