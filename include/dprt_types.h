@@ -141,9 +141,10 @@ typedef struct dprt_bvh8_node {
     float    p[3];
     uint8_t  e[3];
     uint8_t  imask;
-    uint32_t childBase;
-    uint32_t triBase;
-    uint8_t  meta[8];
+    uint32_t childBase;       /* first internal child; child in slot s is childBase + popcount(imask & ((1 << s) - 1)) */
+    uint32_t triBase;         /* first leaf triangle; the triangle behind tmask bit b is triBase + popcount(tmask & ((1 << b) - 1)) */
+    uint32_t tmask;           /* bit 3 s + k: the leaf child in slot s has a k-th triangle (leaves hold <= 3) */
+    uint32_t reserved_;
     uint8_t  qlox[8], qloy[8], qloz[8];
     uint8_t  qhix[8], qhiy[8], qhiz[8];
 } dprt_bvh8_node;

@@ -937,6 +937,7 @@ bool bvh8_walk(const dprt_bvh8_node* nodes, const dprt_bvh8_tri* tris, V3 o, V3 
     struct Grp { uint32_t base, bits; };
     Grp stack[64]; int sp = 0;
     Grp ng{0u, 0x80000000u};
+    uint32_t tmask = 0u;
     for (;;) {
         Grp tg{0u, 0u};
         if (ng.bits & 0xff000000u) {
@@ -961,16 +962,17 @@ bool bvh8_walk(const dprt_bvh8_node* nodes, const dprt_bvh8_tri* tris, V3 o, V3 
                     tn = fmaxf(tn, fmaf(lo, adj[a], org[a])); tf = fminf(tf, fmaf(hi, adj[a], org[a]));
                 }
                 if (tn <= tf) {
-                    const uint32_t meta = n.meta[c];
-                    const uint32_t inner = ((meta & 0x18u) == 0x18u) ? octinv : 0u;
-                    hitmask |= (meta >> 5) << ((meta ^ inner) & 31u);
+                    if ((n.imask >> c) & 1u) hitmask |= 1u << (24u + ((uint32_t)c ^ octinv));   // internal child: octant-ordered slot
+                    else hitmask |= (7u << (3 * c)) & n.tmask;                                  // leaf child: its (<= 3) triangles
                 }
             }
             ng = Grp{n.childBase, (hitmask & 0xff000000u) | n.imask};
             tg = Grp{n.triBase, hitmask & 0x00ffffffu};
+            tmask = n.tmask;
         }
         while (tg.bits) {
-            uint32_t k = (uint32_t)__builtin_ctz(tg.bits); tg.bits &= tg.bits - 1u;
+            uint32_t b = (uint32_t)__builtin_ctz(tg.bits); tg.bits &= tg.bits - 1u;
+            const uint32_t k = (uint32_t)__builtin_popcount(tmask & ((1u << b) - 1u));
             const dprt_bvh8_tri& t = tris[tg.base + k];
             cnt.tris++;
             float tv[9] = {t.v0[0], t.v0[1], t.v0[2], t.v1[0], t.v1[1], t.v1[2], t.v2[0], t.v2[1], t.v2[2]};

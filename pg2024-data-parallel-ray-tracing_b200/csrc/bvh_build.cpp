@@ -250,7 +250,6 @@ int bvh8_build(const float* verts, const int32_t* mat_ids, int64_t ntris64, floa
         for (int s = 0; s < 8; s++) {
             int c = child_in_slot[s];
             if (c < 0) {
-                node.meta[s] = 0;
                 node.qlox[s] = node.qloy[s] = node.qloz[s] = 255;
                 node.qhix[s] = node.qhiy[s] = node.qhiz[s] = 0;
                 continue;
@@ -258,12 +257,11 @@ int bvh8_build(const float* verts, const int32_t* mat_ids, int64_t ntris64, floa
             const Node2& cn = n2[c];
             if (cn.count == 0) {
                 node.imask |= (uint8_t)(1u << s);
-                node.meta[s] = (uint8_t)((1u << 5) | (24 + s));
                 queue.push_back({c, (int)node.childBase + irank, it.depth + 1});
                 irank++;
             } else {
                 uint8_t unary = cn.count == 1 ? 1 : (cn.count == 2 ? 3 : 7);
-                node.meta[s] = (uint8_t)((unary << 5) | toff);
+                node.tmask |= (uint32_t)unary << (3 * s);
                 for (int k = 0; k < cn.count; k++) {
                     int p = idx[cn.first + k];
                     dprt_bvh8_tri t;

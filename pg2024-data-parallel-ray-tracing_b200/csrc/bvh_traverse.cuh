@@ -69,8 +69,21 @@ DPRT_D void trav_enter_object(Trav& s, const uint4* nodes, const float4* tris) {
 // tests its own leaf. tbest of a lane lags by the queueing delay, which only makes node culling conservative.
 // Slab test of the 8 children of node `ni` against one ray: returns the node's child base / triangle base and the
 // hit bits of its internal children (bits 24..31, octant order: higher bit = nearer) and of its leaf triangles (0..23).
+// bit s -> bit s ^ o of an 8-bit mask (o = 7 - octant): three conditional swaps
+DPRT_D uint32_t xor_permute8(uint32_t m, uint32_t o) {
+    if (o & 1u) m = ((m & 0x55u) << 1) | ((m >> 1) & 0x55u);
+    if (o & 2u) m = ((m & 0x33u) << 2) | ((m >> 2) & 0x33u);
+    if (o & 4u) m = ((m & 0x0fu) << 4) | (m >> 4);
+    return m;
+}
+
+// Slab test of the 8 children of node `ni` against one ray. Every child slot s owns a fixed pattern of bits -- 3 s .. 3 s + 2
+// for its (at most three) leaf triangles, 24 + s for "internal child" -- so the per-child work after the slab test is one
+// select of an immediate; the node's tmask / imask then keep the bits that exist, and the internal bits are moved to
+// octant order (higher bit = nearer) for the whole node at once. Returns the child base / triangle base with those bits,
+// and tmask: the triangle behind bit b is triBase + popc(tmask & ((1 << b) - 1)).
 DPRT_D void expand_node(const uint4* __restrict__ nodes, uint32_t ni, float ox, float oy, float oz, float idx, float idy, float idz,
-                        uint32_t octinv, float tmin, float tbest, uint32_t magic, uint2& ng, uint2& tg) {
+                        uint32_t octinv, float tmin, float tbest, uint32_t magic, uint2& ng, uint2& tg, uint32_t& tmask) {
     const uint4* np = nodes + 5 * (size_t)ni;
     const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
     const bool nx = !(octinv & 1u), ny = !(octinv & 2u), nz = !(octinv & 4u);
@@ -87,10 +100,9 @@ DPRT_D void expand_node(const uint4* __restrict__ nodes, uint32_t ni, float ox, 
     const float orgy = fmaf(-32768.0f, adjy, (__uint_as_float(n0.y) - oy) * idy);
     const float orgz = fmaf(-32768.0f, adjz, (__uint_as_float(n0.z) - oz) * idz);
 
-    uint32_t hitmask = 0;
+    uint32_t acc = 0;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        const uint32_t meta4 = h ? n1.w : n1.z;
         const uint32_t lox = h ? (nx ? n3.w : n2.y) : (nx ? n3.z : n2.x);
         const uint32_t hix = h ? (nx ? n2.y : n3.w) : (nx ? n2.x : n3.z);
         const uint32_t loy = h ? (ny ? n4.y : n2.w) : (ny ? n4.x : n2.z);
@@ -107,18 +119,17 @@ DPRT_D void expand_node(const uint4* __restrict__ nodes, uint32_t ni, float ox, 
             const float tfz = fmaf(qbias<J>(hiz, magic), adjz, orgz);                                   \
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                  \
             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));                                 \
-            /* branch-free: child bits are computed for every slot and masked by the slab test */      \
-            const uint32_t meta = (meta4 >> (8 * J)) & 0xffu;                                           \
-            const uint32_t inner = ((meta & 0x18u) == 0x18u) ? octinv : 0u;                             \
-            const uint32_t bidx = (meta ^ inner) & 31u;                                                 \
-            const uint32_t bits = (meta >> 5) << bidx;                                                  \
-            hitmask |= (tn <= tf) ? bits : 0u;                                                          \
+            constexpr uint32_t kSlot = 4u * h_ + J;                                                     \
+            acc |= (tn <= tf) ? ((7u << (3u * kSlot)) | (1u << (24u + kSlot))) : 0u;                     \
         }
-        DPRT_CHILD(0) DPRT_CHILD(1) DPRT_CHILD(2) DPRT_CHILD(3)
+        if (h == 0) { constexpr uint32_t h_ = 0; DPRT_CHILD(0) DPRT_CHILD(1) DPRT_CHILD(2) DPRT_CHILD(3) }
+        else        { constexpr uint32_t h_ = 1; DPRT_CHILD(0) DPRT_CHILD(1) DPRT_CHILD(2) DPRT_CHILD(3) }
 #undef DPRT_CHILD
     }
-    ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
-    tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
+    const uint32_t imask = n0.w >> 24;
+    tmask = n1.z;
+    ng = make_uint2(n1.x, (xor_permute8((acc >> 24) & imask, octinv) << 24) | imask);
+    tg = make_uint2(n1.y, acc & tmask);
 }
 
 // index of the node that bit `bit` (24..31) of node group g stands for
@@ -127,14 +138,18 @@ DPRT_D uint32_t group_node(uint2 g, uint32_t bit, uint32_t octinv) {
     return g.x + __popc(g.y & 0xffu & ((1u << slot) - 1u));
 }
 
+// expands the nearest pending node of the lane; returns the node's tmask (the caller parks it in WarpQueue::tmask while
+// the lane's triangle group s.tg is pending)
 template <bool COUNT>
-DPRT_D void trav_node(Trav& s, uint2* stack, TraceCount& cnt, const uint32_t magic) {
+DPRT_D uint32_t trav_node(Trav& s, uint2* stack, TraceCount& cnt, const uint32_t magic) {
     const uint32_t bit = 31u - __clz(s.ng.y);
     const uint32_t ni = group_node(s.ng, bit, s.octinv);
     s.ng.y &= ~(1u << bit);
     if (s.ng.y & 0xff000000u) { if (s.sp < DPRT_STACK) stack[s.sp++] = s.ng; }
     if (COUNT) cnt.nodes++;
-    expand_node(s.nodes, ni, s.o.x, s.o.y, s.o.z, s.idx, s.idy, s.idz, s.octinv, s.tmin, s.tbest, magic, s.ng, s.tg);
+    uint32_t tmask;
+    expand_node(s.nodes, ni, s.o.x, s.o.y, s.o.z, s.idx, s.idy, s.idz, s.octinv, s.tmin, s.tbest, magic, s.ng, s.tg, tmask);
+    return tmask;
 }
 
 // ---- warp-wide triangle queue -----------------------------------------------------------------------
@@ -152,6 +167,7 @@ struct WarpQueue {
     const float4* tris[32];                // triangle array of the owner's current object
     float  tlimit[32];                     // strict upper bound for the owner's current object
     int    cnt[32];                        // pairs of this owner tested in the round
+    uint32_t tmask[32];                    // tmask of the node whose leaf triangles the lane's s.tg refers to
     uint32_t q[DPRT_QCAP];
     int    plen;                           // cooperative tail mode: pool length hand-over
 };
@@ -174,10 +190,11 @@ DPRT_D void wq_append(WarpQueue& w, int& qlen, int lane, bool busy, Trav& s, int
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
     const int total = __shfl_sync(FULL, incl, 31);
     int pos = qlen + incl - c;
+    const uint32_t tm = w.tmask[lane];
     while (s.tg.y != 0u && busy && pos < DPRT_QCAP) {
         const uint32_t k = __ffs(s.tg.y) - 1u;
         s.tg.y &= s.tg.y - 1u;
-        w.q[pos++] = ((uint32_t)lane << DPRT_TRI_BITS) | (s.tg.x + k);
+        w.q[pos++] = ((uint32_t)lane << DPRT_TRI_BITS) | (s.tg.x + __popc(tm & ((1u << k) - 1u)));
         pend++;
     }
     qlen = min(DPRT_QCAP, qlen + total);
@@ -241,7 +258,7 @@ DPRT_D void tri_round(WarpQueue& w, int& qlen, int lane, Trav& s, int obj, int& 
 
 // appends the pending triangles of all lanes (tg) to the queue on behalf of `owner`, as far as they fit; returns the
 // number appended (warp-uniform)
-DPRT_D int coop_append(WarpQueue& w, int& qlen, int lane, int owner, uint2& tg) {
+DPRT_D int coop_append(WarpQueue& w, int& qlen, int lane, int owner, uint2& tg, uint32_t tm) {
     const unsigned FULL = 0xffffffffu;
     const int c = __popc(tg.y);
     if (__ballot_sync(FULL, c > 0) == 0u) return 0;
@@ -253,7 +270,7 @@ DPRT_D int coop_append(WarpQueue& w, int& qlen, int lane, int owner, uint2& tg) 
     while (tg.y != 0u && pos < DPRT_QCAP) {
         const uint32_t k = __ffs(tg.y) - 1u;
         tg.y &= tg.y - 1u;
-        w.q[pos++] = ((uint32_t)owner << DPRT_TRI_BITS) | (tg.x + k);
+        w.q[pos++] = ((uint32_t)owner << DPRT_TRI_BITS) | (tg.x + __popc(tm & ((1u << k) - 1u)));
     }
     const int before = qlen;
     qlen = min(DPRT_QCAP, qlen + total);
@@ -273,6 +290,7 @@ DPRT_D void coop_run(WarpQueue& w, uint32_t* __restrict__ pool, int& qlen, int l
     const uint4* nodes = (const uint4*)(uintptr_t)__shfl_sync(FULL, (unsigned long long)(uintptr_t)s.nodes, L);
     float ct = __shfl_sync(FULL, s.tbest, L);
     uint2 ctg = make_uint2(0u, 0u);
+    uint32_t ctm = 0u;                  // tmask of the node behind this lane's ctg
     if (lane == L) {
         int n = 0;
         for (int i = 0; i <= s.sp; i++) {                 // bottom of the stack first, the current group last (on top)
@@ -281,13 +299,13 @@ DPRT_D void coop_run(WarpQueue& w, uint32_t* __restrict__ pool, int& qlen, int l
             while (m) { const uint32_t bit = __ffs(m) - 1u; m &= m - 1u; pool[n++] = group_node(g, bit, octinv); }   // far first
         }
         w.plen = n;
-        ctg = s.tg;
+        ctg = s.tg; ctm = w.tmask[lane];
         s.ng = make_uint2(0u, 0u); s.tg = make_uint2(0u, 0u); s.sp = 0;
     }
     __syncwarp();
     int plen = w.plen;
     for (;;) {
-        const int added = coop_append(w, qlen, lane, L, ctg);
+        const int added = coop_append(w, qlen, lane, L, ctg, ctm);
         if (lane == L) pend += added;
         const bool more = __ballot_sync(FULL, ctg.y != 0u) != 0u;
         if (qlen > 0 && (qlen >= 32 || more || plen == 0)) {
@@ -307,7 +325,7 @@ DPRT_D void coop_run(WarpQueue& w, uint32_t* __restrict__ pool, int& qlen, int l
         if (lane < np) {
             const uint32_t ni = pool[plen - 1 - lane];
             if (COUNT) cnt.nodes++;
-            expand_node(nodes, ni, ox, oy, oz, idx, idy, idz, octinv, tmin, ct, magic, cg, ctg);
+            expand_node(nodes, ni, ox, oy, oz, idx, idy, idz, octinv, tmin, ct, magic, cg, ctg, ctm);
         }
         plen -= np;
         __syncwarp();

@@ -323,8 +323,9 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
                 int left = a.nodesPerStep;
 #pragma unroll 1
                 for (;;) {
-                    trav_node<COUNT>(s, stack, cnt, a.prmtMagic);
-                    if (--left == 0 || s.tg.y != 0u) break;
+                    const uint32_t tm = trav_node<COUNT>(s, stack, cnt, a.prmtMagic);
+                    if (s.tg.y != 0u) { w.tmask[lane] = tm; break; }
+                    if (--left == 0) break;
                     if ((s.ng.y & 0xff000000u) == 0u) { if (s.sp == 0) break; s.ng = stack[--s.sp]; }
                 }
             }

@@ -49,7 +49,7 @@ HIT_DTYPE = np.dtype([("t", "<f4"), ("primID", "<i4")])
 MATERIAL_DTYPE = np.dtype([("baseColor", "<f4", 3), ("bsdfType", "<i4")])
 LIGHT_DTYPE = np.dtype([("p0", "<f4", 3), ("p1", "<f4", 3), ("p2", "<f4", 3), ("Le", "<f4", 3)])
 NODE_DTYPE = np.dtype([("p", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("childBase", "<u4"), ("triBase", "<u4"),
-                       ("meta", "u1", 8), ("qlox", "u1", 8), ("qloy", "u1", 8), ("qloz", "u1", 8),
+                       ("tmask", "<u4"), ("reserved_", "<u4"), ("qlox", "u1", 8), ("qloy", "u1", 8), ("qloz", "u1", 8),
                        ("qhix", "u1", 8), ("qhiy", "u1", 8), ("qhiz", "u1", 8)])
 TRI_DTYPE = np.dtype([("v0", "<f4", 3), ("primID", "<i4"), ("v1", "<f4", 3), ("matID", "<i4"), ("v2", "<f4", 3), ("pad_", "<i4")])
 

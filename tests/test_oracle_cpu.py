@@ -246,11 +246,16 @@ def test_bvh8_build_host_only_properties():
     chunks, _, _ = dprt.scene.make_scene(1, 5000)
     nodes, tris, depth = dprt.build_bvh8(chunks[0].verts, chunks[0].mats)
     assert nodes.dtype.itemsize == 80 and tris.dtype.itemsize == 48
-    # every internal child slot has meta 001xxxxx with index 24+slot, leaves have unary counts
+    # leaf children own tmask bits 3s..3s+2 (a unary count 1/3/7), internal children (imask) own none; triangles are
+    # stored in tmask-bit order, so every node's triangle count is popcount(tmask) and the ranges tile the triangle array
     for s in range(8):
-        m = nodes["meta"][:, s]
+        bits = (nodes["tmask"] >> (3 * s)) & 7
         inner = (nodes["imask"] >> s) & 1
-        assert np.all((m[inner == 1] >> 5) == 1) and np.all((m[inner == 1] & 31) == 24 + s)
-        leaf = (inner == 0) & (m != 0)
-        assert np.all(np.isin(m[leaf] >> 5, [1, 3, 7]))
+        assert np.all(bits[inner == 1] == 0)
+        assert np.all(np.isin(bits, [0, 1, 3, 7]))
+    assert np.all(nodes["tmask"] < (1 << 24)) and np.all(nodes["reserved_"] == 0)
+    per_node = np.array([bin(int(t)).count("1") for t in nodes["tmask"]])
+    assert per_node.sum() == tris.shape[0]
+    order = np.argsort(nodes["triBase"], kind="stable")
+    assert np.array_equal(np.cumsum(per_node[order])[:-1][per_node[order][1:] > 0], nodes["triBase"][order][1:][per_node[order][1:] > 0])
     assert depth >= 2
