@@ -17,10 +17,10 @@ namespace dprt {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kItems = 4;
-constexpr int kTile = kThreads * kItems;      // 1024 records per tile
 constexpr int kWarps = kThreads / 32;
-constexpr int kSteps = kWarps * kItems;       // 32 (warp, item) steps per tile, in index order
+// ITEMS records per thread: a tile is kThreads * ITEMS records and kWarps * ITEMS (warp, item) steps in index order.
+// 4 for the 64-byte path records; 16 for NN queries, where the key is one byte, nearly all slots are empty and the cost
+// is the length of the tile chain, not the bytes.
 
 constexpr uint32_t ST_AGG = 1u << 30, ST_INC = 2u << 30, ST_MASK = 3u << 30, VAL_MASK = ~ST_MASK;
 
@@ -62,10 +62,11 @@ struct QueryOps {
     }
 };
 
-template <class Ops>
+template <class Ops, int kItems>
 __global__ void __launch_bounds__(kThreads) partition_kernel(Ops ops, int n, const int32_t* __restrict__ hist,
                                                               int32_t* __restrict__ offsets, uint32_t* tileState,
                                                               int32_t* tileCounter) {
+    constexpr int kTile = kThreads * kItems, kSteps = kWarps * kItems;
     __shared__ int s_tile;
     __shared__ int s_cnt[kSteps][32];
     __shared__ int s_base[32];
@@ -175,13 +176,14 @@ __global__ void empty_offsets_kernel(int32_t* offsets, int B) {
     if (threadIdx.x <= B) offsets[threadIdx.x] = 0;
 }
 
-template <class Ops>
+template <class Ops, int kItems>
 void run_partition(Ops ops, int n, const int32_t* hist, int32_t* offsets, const PartitionScratch& s, cudaStream_t stream) {
     if (n <= 0) { empty_offsets_kernel<<<1, 64, 0, stream>>>(offsets, ops.B); return; }
-    const int tiles = (n + kTile - 1) / kTile;
+    constexpr int kTile = kThreads * kItems;
+    const int tiles = (n + kTile - 1) / kTile;                 // <= PartitionScratch::maxTiles, which is sized for 1024-record tiles
     cudaMemsetAsync(s.tileState, 0, (size_t)tiles * 32 * sizeof(uint32_t), stream);
     cudaMemsetAsync(s.tileCounter, 0, sizeof(int32_t), stream);
-    partition_kernel<Ops><<<tiles, kThreads, 0, stream>>>(ops, n, hist, offsets, s.tileState, s.tileCounter);
+    partition_kernel<Ops, kItems><<<tiles, kThreads, 0, stream>>>(ops, n, hist, offsets, s.tileState, s.tileCounter);
 }
 
 }  // namespace
@@ -194,7 +196,7 @@ void launch_path_histogram(const dprt_path_record* paths, int n, int W, int32_t*
 void launch_partition_paths(const dprt_path_record* paths, int n, int W, int B, int me, int splitL, const int32_t* hist,
                             dprt_path_record* out, int32_t* offsets, const PartitionScratch& s, cudaStream_t stream) {
     PathOps ops{paths, out, B, W, B > W ? me : -1, splitL};
-    run_partition(ops, n, hist, offsets, s, stream);
+    run_partition<PathOps, 4>(ops, n, hist, offsets, s, stream);
 }
 
 void launch_query_histogram(const dprt_nn_query* q, int n, int S, int insideOnly, int32_t* hist, cudaStream_t stream) {
@@ -206,7 +208,8 @@ void launch_partition_queries(const dprt_nn_query* q, const uint8_t* keys, const
                               const int32_t* hist, dprt_nn_query* outQ, dprt_half* outIn, int32_t* offsets,
                               const PartitionScratch& s, cudaStream_t stream) {
     QueryOps ops{q, keys, in, outQ, outIn, S, insideOnly};
-    run_partition(ops, n, hist, offsets, s, stream);
+    if (keys) run_partition<QueryOps, 16>(ops, n, hist, offsets, s, stream);
+    else run_partition<QueryOps, 4>(ops, n, hist, offsets, s, stream);
 }
 
 }  // namespace dprt

@@ -38,11 +38,16 @@ for r in range(W):
 G = dprt.RankGroup(rs)
 for R in rs:
     R.reset_frame()
+for R in rs:
+    R.stage_profile(True)
 for s in range(2):
     G.run_sample(s)
 for R in rs:
     R.synchronize()
 print("stats", rs[0].stats())
+print("stage ms (rank 0, 2 samples):", {k: (round(t, 3), n) for k, (t, n) in rs[0].stage_times().items() if n})
+for R in rs:
+    R.stage_profile(False)
 P = rs[0]
 n = 1 << 20
 x = np.random.default_rng(0).random((n, 5)).astype(np.float16).view(np.uint16)
