@@ -81,7 +81,11 @@ int  dprt_proxy_infer(dprt_ctx* ctx, int kind, int pred_offset);
 int  dprt_frame_buffer_update(dprt_ctx* ctx);         /* Frame_Buffer_Update   frame_buffer_update.cu:129 */
 int  dprt_depth_buffer_update(dprt_ctx* ctx);         /* Depth_Buffer_Update   frame_buffer_update.cu:194 */
 int  dprt_target_node_update(dprt_ctx* ctx);          /* Target_Node_Update    frame_buffer_update.cu:326 */
-/* composite modules, same order as the reference helpers */
+/* composite modules, same order as the reference helpers. The composites may schedule differently from a plain
+ * sequence of the stage calls above -- the migrate loop keeps settled paths out of the per-iteration work
+ * (cfg.referenceMigrate), dprt_render_sample runs the ShadowRay module beside the next TraRay loop on a second stream
+ * (cfg.serialStages), MainRay reuses TraRay's hit (cfg.mainRayRetrace) -- but every buffer the reference defines holds the
+ * same bytes when they return. */
 int  dprt_primary_ray_module(dprt_ctx* ctx);          /* primaryRayModule          renderer.cpp:1212-1318 */
 int  dprt_shadow_ray_module(dprt_ctx* ctx);           /* shadowRayModuleBasedNN    renderer.cpp:1349-1405 */
 int  dprt_secondary_ray_module(dprt_ctx* ctx);        /* secondaryRayModuleBasedNN renderer.cpp:1407-1452 */
