@@ -109,8 +109,8 @@ constexpr int kTraceBlock = 128;
 #define DPRT_TRACE_MINBLOCKS 6
 #endif
 constexpr int kTraceBlocksPerSM = DPRT_TRACE_MINBLOCKS;
-constexpr int kNodesPerStepDefault = 1;
-constexpr int kRefillDefault = 8;
+constexpr int kNodesPerStepDefault = 2;
+constexpr int kRefillDefault = 12;
 constexpr int kTriVoteDefault = 8;
 constexpr int kCoopDefault = 8;
 constexpr int kRaysPerLaneDefault = 1;
