@@ -1103,6 +1103,19 @@ int deque_finish(dprt_ctx* ctx) {
 
 }  // namespace
 
+int dprt_plan_exchange_deque(const int32_t* rows, int W, int me, int32_t* send_count, int32_t* recv_count, int32_t* piece,
+                             int32_t* new_nl, int32_t* new_active, int* all_local) {
+    if (!rows || W < 1 || W >= DPRT_MAX_WORLD || me < 0 || me >= W) return DPRT_ERR_INVALID;
+    DequePlan p;
+    if (deque_plan(rows, W, me, p)) return DPRT_ERR_INVALID;
+    for (int k = 0; k < W; k++) { if (send_count) send_count[k] = p.sendCnt[k]; if (recv_count) recv_count[k] = p.recvCnt[k]; }
+    if (piece) { piece[0] = p.offL; piece[1] = p.cL; piece[2] = p.offR; piece[3] = p.cR; }
+    if (new_nl) *new_nl = p.newNL;
+    if (new_active) *new_active = p.newActive;
+    if (all_local) *all_local = p.allLocal ? 1 : 0;
+    return 0;
+}
+
 // ---- composite modules ---------------------------------------------------------------------------
 int dprt_primary_ray_module(dprt_ctx* ctx) {
     if (!ctx) return DPRT_ERR_INVALID;

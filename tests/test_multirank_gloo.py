@@ -64,3 +64,86 @@ def test_bench_reference_arm_under_torchrun_prints_one_line():
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["n_gpus"] == 2 and j["unit"] == "Mrays/s" and j["value"] > 0
     assert j["cpu_baseline"]["kind"] == "port" and j["e2e"]["h2d_bytes_per_step"] == 0
+
+
+# ---- settled deque: the host-side model of the migrate loop ---------------------------------------------------------
+def _simulate_migrate(W, itineraries, start_rank, deque):
+    """Paths with fixed itineraries (the ranks a path asks for after each trace; the last one is where it settles and is
+    traced once more as a rider, like a path returning to the rank of its closest hit). Returns the final buffer of every
+    rank (path ids in order) and the number of exchange iterations. deque=False: every iteration partitions every path
+    (Work_Efficient_Scan + MPI_Alltoallv, renderer.cpp:1212-1318); deque=True: only travelling paths, planned by
+    dprt_plan_exchange_deque."""
+    step = {p: 0 for p in range(len(itineraries))}
+
+    def target(p, here):
+        it = itineraries[p]
+        if step[p] < len(it):
+            t = it[step[p]]
+            step[p] += 1
+            return t
+        return here                                           # settled (or a rider): stays
+
+    bufs = [[p for p in range(len(itineraries)) if start_rank[p] == r] for r in range(W)]
+    settled = [[] for _ in range(W)]
+    nl = [0] * W
+    iters = 0
+    while True:
+        iters += 1
+        if not deque:
+            seg = [[[] for _ in range(W)] for _ in range(W)]      # seg[s][d]
+            for s in range(W):
+                for p in bufs[s]:
+                    seg[s][target(p, s)].append(p)
+            off = sum(len(seg[s][d]) for s in range(W) for d in range(W) if s != d)
+            bufs = [[p for s in range(W) for p in seg[s][d]] for d in range(W)]
+            if off == 0:
+                return bufs, iters
+        else:
+            rows = np.zeros((W, W + 2), np.int32)
+            buckets = [[[] for _ in range(W + 1)] for _ in range(W)]
+            for s in range(W):
+                for i, p in enumerate(bufs[s]):
+                    t = target(p, s)
+                    buckets[s][W if (t == s and i >= nl[s]) else t].append(p)
+                rows[s, 1:] = np.cumsum([len(b) for b in buckets[s]])
+            new_bufs = []
+            done = None
+            for d in range(W):
+                plan = dprt.plan_exchange_deque(rows, d)
+                flat = [p for b in buckets[d] for p in b]
+                oL, cL, oR, cR = plan["piece"]
+                settled[d] = flat[oL:oL + cL] + settled[d] + flat[oR:oR + cR]
+                recv = []
+                for s in range(W):
+                    if s != d:
+                        assert plan["recv_count"][s] == len(buckets[s][d])
+                        recv += buckets[s][d]
+                assert plan["new_active"] == len(recv) and plan["new_nl"] == sum(len(buckets[s][d]) for s in range(d))
+                new_bufs.append(recv)
+                nl[d] = plan["new_nl"]
+                done = plan["all_local"] if done is None else (done and plan["all_local"])
+            bufs = new_bufs
+            if done:
+                assert all(len(b) == 0 for b in bufs)
+                return settled, iters
+
+
+@pytest.mark.parametrize("W,npaths,seed", [(2, 200, 0), (3, 500, 1), (8, 3000, 2), (16, 2000, 3), (31, 1500, 4)])
+def test_settled_deque_reproduces_the_reference_buffers(W, npaths, seed):
+    """Property behind cfg.referenceMigrate = 0: for arbitrary itineraries the deque schedule leaves every
+    rank with exactly the records, in exactly the order, of the reference's iterate-over-everything schedule."""
+    rng = np.random.default_rng(seed)
+    its, start = [], []
+    for _ in range(npaths):
+        hops = int(rng.integers(0, min(W, 6)))
+        order = rng.permutation(W)[:hops + 1]
+        start.append(int(order[0]))
+        it = [int(x) for x in order[1:]]
+        if hops and rng.random() < 0.5:
+            it.append(int(order[rng.integers(0, hops + 1)]))   # return to an earlier rank (the one that owns the closest hit)
+        its.append(it)
+    ref, it_ref = _simulate_migrate(W, its, start, deque=False)
+    fast, it_fast = _simulate_migrate(W, its, start, deque=True)
+    assert it_ref == it_fast
+    assert ref == fast
+    assert sum(len(b) for b in ref) == npaths
