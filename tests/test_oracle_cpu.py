@@ -213,6 +213,30 @@ def test_library_exports_every_declared_symbol():
     assert set(declared) == set(dprt.host.EXPORTED_SYMBOLS)
 
 
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing in the package imports, includes, links or dlopens it."""
+    import subprocess
+    pkg = os.path.dirname(dprt.host.LIB_PATH)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            path = os.path.join(dirpath, f)
+            if f.endswith(".py"):
+                src = open(path).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{path} imports the oracle"
+                assert "liboracle" not in src, f"{path} mentions liboracle"
+            elif f.endswith((".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                src = open(path).read()
+                assert not re.search(r"#include\s+[\"<][^\">]*oracle", src), f"{path} includes oracle sources"
+                assert "liboracle" not in src and "../../oracle" not in src, f"{path} links against the oracle"
+    for binary in (dprt.host.LIB_PATH, os.path.join(pkg, "dprt_render")):
+        needed = subprocess.run(["readelf", "-d", binary], capture_output=True, text=True).stdout
+        assert "oracle" not in needed and "libdprt" in (needed if binary.endswith("dprt_render") else "libdprt"), binary
+    for root_file in ("bench.py",):
+        src = open(os.path.join(os.path.dirname(pkg), root_file)).read()
+        uses = [m.start() for m in re.finditer(r"from oracle import", src)]
+        assert len(uses) == 2          # run_reference (the --impl reference arm) and cpu_baseline: the two allowed places
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
