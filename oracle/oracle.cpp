@@ -575,7 +575,7 @@ void shade(World& w, Rank& r) {
         if (!path.isValid) continue;
         walked += has_local_work(w, r.id, 0u, false);     // the oracle always re-traces (kernel.cu:382-413)
         const V3 o = v3(path.origin[0], path.origin[1], path.origin[2]), d = v3(path.direction[0], path.direction[1], path.direction[2]);
-        Hit h; int hobj = -1; float tMax = FLT_MAX;
+        Hit h{}; int hobj = -1; float tMax = FLT_MAX;
         const bool isHit = trace_local(w, r.id, o, d, DPRT_EPSILON, tMax, 0u, false, h, hobj);
         if (!r.hitPrim.empty()) r.hitPrim[i] = isHit ? h.prim : -1;
         if (!isHit) {
