@@ -188,7 +188,7 @@ def workload_config(args, W, fw, fh):
     return {"workload": f"configs[1] scene per GPU: synthetic {args.tris}-triangle chunk x {W} chunk(s), {fw}x{fh} frame "
                         f"(1920x1080 pixels per GPU), 1 spp per step, full per-sample loop with bounces={args.bounces}, spc=4, mc=3",
             "chunks": W, "tris_per_chunk": args.tris, "chunk_layout": "single chunk" if W == 1 else
-            ("load-balanced x-slabs (k/W quantiles of the primary-ray footprint)" if args.layout == "slabs" else "2x1x1 / 2x2x1 / 2x2x2 cells"), "width": fw, "height": fh, "bounces": args.bounces,
+            ("one continuous terrain in load-balanced x-slabs (k/W quantiles of where the primary rays land)" if args.layout == "slabs" else "2x1x1 / 2x2x1 / 2x2x2 cells"), "width": fw, "height": fh, "bounces": args.bounces,
             "proxy": bool(args.proxy and W > 1), "main_ray": "re-trace" if args.retrace else "hit cache",
             "stage_overlap": bool(not args.serial and not (args.proxy and W > 1)), "path_gen": "rank0" if (args.path_gen_mode == 0 or W == 1) else "striped",
             "l2": "inputs larger than L2: 5 x 64 B path records per pixel (663 MB at 1080p) are rewritten every bounce",

@@ -44,29 +44,42 @@ def cell_layout(W):
     return cells
 
 
-def balanced_slab_layout(W, cam, plane_z=0.45):
+def terrain_height(x, y, ts):
+    """The height function of make_heightfield_chunk (before vertex jitter), as a fraction of the cell's z range."""
+    return np.clip(0.45 + 0.22 * np.sin(7.0 * x + 0.6 * ts) * np.cos(6.0 * y - 0.3 * ts) + 0.08 * np.sin(23.0 * x * y + ts), 0.02, 0.98)
+
+
+def balanced_slab_layout(W, cam, terrain_seed=0):
     """Load-balanced k-d partition of the unit cube along x: W slabs whose boundaries are the k/W quantiles of where the
-    camera's primary rays meet the mean terrain plane z = plane_z (the usual way a data-parallel renderer places its
-    cuts: by expected load, not by volume). Every slab still gets the same number of triangles."""
-    n = 512
-    a = (np.arange(n) + 0.5) / n * 2.0 - 1.0
-    A, B = np.meshgrid(a, a, indexing="xy")
+    camera's primary rays land on the landscape (ray-marched against the analytic height function; the usual way a
+    data-parallel renderer places its cuts: by expected load, not by volume). Shadow rays start where primary rays land,
+    so this balances most of the work; every slab still gets the same number of triangles."""
+    nx, ny = 384, 216
+    a = (np.arange(nx) + 0.5) / nx * 2.0 - 1.0
+    b = 1.0 - (np.arange(ny) + 0.5) / ny * 2.0
+    A, B = np.meshgrid(a, b, indexing="xy")
     U, V, Wv, O = (np.array(list(v), np.float64) for v in (cam.U, cam.V, cam.W, cam.origin))
     d = A[..., None] * U + B[..., None] * V + Wv
-    with np.errstate(divide="ignore", invalid="ignore"):
-        t = (plane_z - O[2]) / d[..., 2]
-    hx, hy = O[0] + t * d[..., 0], O[1] + t * d[..., 1]
-    ok = (t > 0) & (hx >= 0) & (hx <= 1) & (hy >= 0) & (hy <= 1)
-    xs = np.sort(hx[ok])
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    hx = np.full(A.shape, np.nan)
+    alive = np.ones(A.shape, bool)
+    for t in np.arange(0.0, 4.0, 0.004):
+        p = O + t * d
+        x, y, z = p[..., 0], p[..., 1], p[..., 2]
+        inside = (x >= 0) & (x <= 1) & (y >= 0) & (y <= 1)
+        hit = alive & inside & (z <= terrain_height(x, y, terrain_seed))
+        hx[hit] = x[hit]
+        alive &= ~hit
+    xs = np.sort(hx[~np.isnan(hx)])
     cuts = [0.0] + [float(xs[int(len(xs) * k / W)]) for k in range(1, W)] + [1.0]
-    cells = []
-    for k in range(W):
-        cells.append((np.array([cuts[k], 0.0, 0.0]), np.array([cuts[k + 1], 1.0, 1.0]), 0, 1))
-    return cells
+    return [(np.array([cuts[k], 0.0, 0.0]), np.array([cuts[k + 1], 1.0, 1.0]), 0, 1) for k in range(W)]
 
 
-def make_heightfield_chunk(cell_min, cell_max, nx, ny, seed, hole_frac=0.0, n_materials=16, water_frac=0.0):
-    """nx*ny quads -> 2*nx*ny triangles (minus holes). Returns verts9, normals9, mat_ids (float32/int32)."""
+def make_heightfield_chunk(cell_min, cell_max, nx, ny, seed, hole_frac=0.0, n_materials=16, water_frac=0.0, terrain_seed=None):
+    """nx*ny quads -> 2*nx*ny triangles (minus holes). Returns verts9, normals9, mat_ids (float32/int32).
+    terrain_seed: phase of the height function (default: the chunk's own seed, i.e. every chunk its own landscape; the same
+    value for all chunks gives ONE landscape cut into chunks, continuous across the cuts up to the vertex jitter)."""
+    ts = seed if terrain_seed is None else terrain_seed
     gx, gy = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="ij")
     x = cell_min[0] + (cell_max[0] - cell_min[0]) * gx / nx
     y = cell_min[1] + (cell_max[1] - cell_min[1]) * gy / ny
@@ -74,7 +87,7 @@ def make_heightfield_chunk(cell_min, cell_max, nx, ny, seed, hole_frac=0.0, n_ma
     s = tea4_np(vid, np.uint32(0xC0FFEE + seed))
     j, s = rnd_np(s)
     zr = cell_max[2] - cell_min[2]
-    h = 0.45 + 0.22 * np.sin(7.0 * x + 0.6 * seed) * np.cos(6.0 * y - 0.3 * seed) + 0.08 * np.sin(23.0 * x * y + seed)
+    h = 0.45 + 0.22 * np.sin(7.0 * x + 0.6 * ts) * np.cos(6.0 * y - 0.3 * ts) + 0.08 * np.sin(23.0 * x * y + ts)   # == terrain_height before the clip
     amp = 0.25 * min((cell_max[0] - cell_min[0]) / nx, (cell_max[1] - cell_min[1]) / ny) / max(zr, 1e-9)
     z = cell_min[2] + zr * np.clip(h + amp * (j.astype(np.float64) - 0.5), 0.02, 0.98)
     P = np.stack([x, y, z], -1)                                   # [nx+1, ny+1, 3]
@@ -152,10 +165,10 @@ class Chunk:
         return self.verts.shape[0]
 
 
-def make_scene(W, tris_per_chunk, water_frac=0.0, seed=0, layout="cells", camera=None):
+def make_scene(W, tris_per_chunk, water_frac=0.0, seed=0, layout="cells", camera=None, continuous=False):
     """W chunks (one per rank); ~tris_per_chunk triangles each. Returns (chunks, materials, lights).
     layout "cells": 2x1x1 / 2x2x1 / 2x2x2 spatial cells (upper cells perforated); "slabs": load-balanced x-slabs for `camera`."""
-    cells = balanced_slab_layout(W, camera) if (layout == "slabs" and W > 1) else cell_layout(W)
+    cells = balanced_slab_layout(W, camera, seed) if (layout == "slabs" and W > 1) else cell_layout(W)
     chunks = []
     for k, (mn, mx, iz, nz) in enumerate(cells):
         hole = 0.35 if (nz > 1 and iz == nz - 1) else 0.0           # upper sheets let rays through to the lower cells
@@ -163,7 +176,8 @@ def make_scene(W, tris_per_chunk, water_frac=0.0, seed=0, layout="cells", camera
         ax, ay = mx[0] - mn[0], mx[1] - mn[1]
         nx = max(2, int(round(np.sqrt(quads * ax / ay))))
         ny = max(2, int(round(quads / nx)))
-        v, n, m = make_heightfield_chunk(mn, mx, nx, ny, seed + k, hole_frac=hole, water_frac=water_frac)
+        v, n, m = make_heightfield_chunk(mn, mx, nx, ny, seed + k, hole_frac=hole, water_frac=water_frac,
+                                         terrain_seed=seed if continuous else None)
         chunks.append(Chunk(k, k, v, n, m))
     return chunks, make_materials(16, water_last=water_frac > 0), make_lights()
 
