@@ -150,9 +150,13 @@ def run_reference(args):
     dprt = importlib.import_module("pg2024-data-parallel-ray-tracing_b200")
     from oracle import oracle as O
     O.lib()
+    O.use_all_host_threads()          # rank 0 runs alone (the other ranks exited): torchrun's OMP_NUM_THREADS=1 does not apply
     W = args.gpus
     fw, fh = frame_for(W)
-    w, h = max(16, fw // args.ref_scale), max(9, fh // args.ref_scale)
+    # bounded sample: the reference's migrate loop handles every path of a rank in every iteration (~9 per bounce at 8
+    # chunks), so a sample costs more per pixel as W grows; the frame shrinks with it to keep a step around a second
+    scale = args.ref_scale * (1 if W == 1 else (2 if W <= 4 else 3))
+    w, h = max(16, fw // scale), max(9, fh // scale)
     chunks, mats, lights = build_world_scene(dprt, W, args.tris, args.layout)
     cfg = dprt.make_config(w, h, spp=1, bounces=args.bounces, scene_size=W, proxy_mode=1 if (args.proxy and W > 1) else 0,
                            path_gen_mode=args.path_gen_mode if W > 1 else 0, mlp_dtype=1)
@@ -176,7 +180,7 @@ def run_reference(args):
     rays = rays_total() - r0
     val = rays / dt / 1e6
     cores = O.num_threads()
-    sample = f"{args.steps} x runSample over a {w}x{h} frame (1/{args.ref_scale} per side of {fw}x{fh}) of the same {W}-chunk scene"
+    sample = f"{args.steps} x runSample over a {w}x{h} frame (1/{scale} per side of {fw}x{fh}) of the same {W}-chunk scene"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": W, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -205,6 +209,7 @@ def cpu_baseline(dprt, args, seconds_target=15.0):
     """The oracle on this box's host cores over a bounded sample of the N=1 workload (reduced frame, same scene)."""
     from oracle import oracle as O
     O.lib()
+    O.use_all_host_threads()
     fw, fh = frame_for(1)
     w, h = fw // args.ref_scale, fh // args.ref_scale
     chunks, mats, lights = build_world_scene(dprt, 1, args.tris)

@@ -1210,6 +1210,14 @@ int orc_mlp_forward(const void* blob, size_t bytes, const uint16_t* x, int64_t n
     return 0;
 }
 
+// all host threads for the timed CPU arms, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
+int orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+    return 0;
+}
+
 int orc_num_threads(void) {
     int n = 1;
 #ifdef _OPENMP

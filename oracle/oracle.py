@@ -60,6 +60,7 @@ def lib():
         L.orc_atan2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_f2h.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -80,6 +81,13 @@ def rnd_sequence(seed, n):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def use_all_host_threads():
+    """The timed CPU arms use every hardware thread the process may run on, whatever OMP_NUM_THREADS says."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
 
 
 def mlp_forward(blob, x_half):
