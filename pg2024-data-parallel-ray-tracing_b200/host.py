@@ -211,6 +211,50 @@ def exchange_host_records(transfer, offsets, rank, world, dist):
     return out, all_local
 
 
+def partition_host_records_deque(paths, rank, world, n_lower):
+    """The W+1-bucket stable partition of the settled-deque migrate loop on HOST records (what partition_kernel<PathOps>
+    does on the device with B = W + 1): bucket = targetNode, except that records which stay on this rank and sit at index
+    >= n_lower (they came from higher ranks) go to bucket W. Returns (bucket-major records, offsets row [W+2])."""
+    p = np.ascontiguousarray(paths, D.PATH_DTYPE)
+    t = p["targetNode"].astype(np.int64)
+    valid = (p["isValid"] != 0) & (t >= 0) & (t < world)
+    key = np.where((t == rank) & (np.arange(p.size) >= n_lower), world, t)
+    idx = np.nonzero(valid)[0]
+    order = idx[np.argsort(key[idx], kind="stable")]
+    row = np.zeros(world + 2, np.int32)
+    row[1:] = np.cumsum(np.bincount(key[idx], minlength=world + 1)[: world + 1])
+    return p[order], row
+
+
+def exchange_host_records_deque(buckets, row, rank, world, dist):
+    """The settled-deque exchange of dprt_primary_ray_module on HOST record arrays over a torch.distributed process group
+    (gloo on CPU-only machines; the product moves device buffers with NCCL): all-gather of the W+2 offsets, plan from
+    dprt_plan_exchange_deque, send/recv of the travelling buckets. Returns (new active records: arrivals from lower ranks,
+    then from higher ranks; n_lower; first self piece; second self piece; done)."""
+    import torch
+    rows = [torch.zeros(world + 2, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(rows, torch.from_numpy(np.ascontiguousarray(row, np.int32).copy()))
+    plan = plan_exchange_deque(torch.stack(rows).numpy(), rank)
+    sc, rc = plan["send_count"], plan["recv_count"]
+    R = D.PATH_DTYPE.itemsize
+    reqs, keep, got = [], [], {}
+    for peer in range(world):
+        if peer == rank:
+            continue
+        if sc[peer] > 0:
+            t = torch.from_numpy(np.ascontiguousarray(buckets[row[peer]:row[peer] + sc[peer]]).view(np.uint8).copy()); keep.append(t)
+            reqs.append(dist.isend(t, peer))
+        if rc[peer] > 0:
+            t = torch.zeros(int(rc[peer]) * R, dtype=torch.uint8); got[peer] = t
+            reqs.append(dist.irecv(t, peer))
+    for q in reqs:
+        q.wait()
+    parts = [got[peer].numpy().view(D.PATH_DTYPE) for peer in range(world) if peer in got]     # source-rank order: lower ranks first
+    active = np.concatenate(parts) if parts else np.zeros(0, D.PATH_DTYPE)
+    oL, cL, oR, cR = plan["piece"]
+    return active, plan["new_nl"], buckets[oL:oL + cL], buckets[oR:oR + cR], plan["all_local"]
+
+
 class Renderer:
     """One rank of the data-parallel renderer (one GPU, one scene-chunk owner)."""
 

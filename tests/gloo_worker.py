@@ -21,6 +21,7 @@ def main():
     import torch.distributed as dist
     rank, W = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     path_gen_mode = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    deque = len(sys.argv) > 2 and sys.argv[2] == "deque"       # the settled-deque migrate loop instead of the reference one
     dist.init_process_group("gloo")
     dprt = importlib.import_module("pg2024-data-parallel-ray-tracing_b200")
     D = dprt.ctypes_defs
@@ -48,6 +49,25 @@ def main():
     mine.path_gen(rank)
     iters = sent = 0
     for bounce in range(bounces + 1):
+        if deque:
+            # only the travelling paths are traced / partitioned / sent; the settled block grows at both ends
+            settled, n_lower = np.zeros(0, D.PATH_DTYPE), 0
+            while True:
+                mine.traverse(rank)                                        # the oracle's TraRay over the ACTIVE records only
+                act = mine.download(rank, D.BUF_PATHS, mine.path_size(rank))
+                buckets, row = dprt.host.partition_host_records_deque(act, rank, W, n_lower)
+                active, n_lower, first, second, done = dprt.host.exchange_host_records_deque(buckets, row, rank, W, dist)
+                settled = np.concatenate([first, settled, second])
+                sent += int(row[W + 1] - (row[rank + 1] - row[rank]) - (row[W + 1] - row[W]))
+                mine.upload(rank, D.BUF_PATHS, active)
+                mine.set_path_size(rank, active.size)
+                iters += 1
+                if done:
+                    break
+            mine.upload(rank, D.BUF_PATHS, settled)
+            mine.set_path_size(rank, settled.size)
+            mine.shade(rank); mine.reset_nn(rank); mine.shadow_trace(rank); mine.frame_buffer_update(rank)
+            continue
         while True:
             mine.traverse(rank)
             mine.partition(rank)

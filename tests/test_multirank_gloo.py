@@ -32,6 +32,14 @@ def test_exchange_protocol_over_gloo_matches_single_process_oracle(W, path_gen_m
     assert p.returncode == 0 and "GLOO_WORKER_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
 
 
+@pytest.mark.parametrize("W,path_gen_mode", [(2, 1), (4, 0)])
+def test_settled_deque_protocol_over_gloo_matches_single_process_oracle(W, path_gen_mode):
+    """The migrate loop of cfg.referenceMigrate = 0 (W+1-bucket partition, dprt_plan_exchange_deque, settled block growing
+    at both ends) with one process per rank over gloo: same final buffers as the oracle's iterate-over-everything loop."""
+    p = _torchrun(W, [os.path.join(ROOT, "tests", "gloo_worker.py"), str(path_gen_mode), "deque"])
+    assert p.returncode == 0 and "GLOO_WORKER_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
+
+
 def test_plan_exchange_known_answers():
     # rank s row = exclusive offsets of its segments per destination
     M = np.array([[0, 5, 7, 7], [0, 0, 3, 4], [0, 2, 2, 9]], np.int32)
