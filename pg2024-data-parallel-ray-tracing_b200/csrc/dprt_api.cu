@@ -20,6 +20,7 @@
 #include "dprt_internal.cuh"
 #include "bvh_build.h"
 #include "mlp.cuh"
+#include "p2p_exchange.cuh"
 
 using namespace dprt;
 
@@ -106,6 +107,16 @@ struct dprt_ctx {
     dprt_path_record* d_settled = nullptr;   // 2N records; the block [front, back) grows at both ends from the middle
     int front = 0, back = 0;
     int nL = 0;                         // active records [0, nL) came from lower ranks, [nL, pathSize) from higher ones
+    // EXPERIMENTAL peer-memory exchange (DPRT_P2P=1; p2p_exchange.cuh)
+    bool p2p = false;                   // tables connected: the deque exchange runs over peer memory
+    P2PMailbox* d_mailbox = nullptr;
+    dprt_path_record* d_active[2] = {nullptr, nullptr};    // arrivals land here (never in `paths`)
+    P2PPeers* d_peers = nullptr;
+    P2PPlan* d_plan = nullptr;
+    P2PPlan* h_plan = nullptr;          // mapped pinned copy the host polls
+    P2PPlan* d_hplan = nullptr;         // device address of h_plan
+    uint32_t p2pSeq = 0;                // one per migrate iteration, never reset
+    std::vector<void*> ipcOpened;       // peer mappings to close
     int32_t* d_secLive = nullptr;       // pixels whose tMax scratch the last Target_Node_Update used
     int secDirty = 0;                   // entries of d_secLive to clear at the next resetNNBuffers
     bool nnScratchDirty = false;        // occlusion / contribution may hold non-zero data
@@ -165,6 +176,13 @@ namespace {
     } while (0)
 
 int fail(dprt_ctx* ctx, int code, const std::string& msg) { ctx->err = msg; return code; }
+
+// experimental peer-memory exchange, defined further down (inside the extern "C" part of this file)
+extern "C" {
+bool p2p_requested();
+int p2p_connect_nccl(dprt_ctx* ctx);
+void p2p_free(dprt_ctx* ctx);
+}
 
 // makes `stream` wait for the ShadowRay module that dprt_render_sample left running on the aux stream
 int join_aux(dprt_ctx* ctx) {
@@ -382,6 +400,7 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
             ncclUniqueId id; std::memcpy(&id, nccl_unique_id, 128);
             if (!g_nccl.load()) { ctx->err = g_nccl.error; return DPRT_ERR_NCCL; }
             NK(g_nccl.CommInitRank(&ctx->comm, world, id, rank));
+            if (p2p_requested()) { int pr = p2p_connect_nccl(ctx); if (pr) return pr; }
         }
         CK(cudaStreamSynchronize(ctx->stream));
         return 0;
@@ -416,6 +435,7 @@ void dprt_destroy(dprt_ctx* ctx) {
     if (ctx->d_nnKey) cudaFree(ctx->d_nnKey);
     for (int k = 0; k < 2; k++) if (ctx->d_live[k]) cudaFree(ctx->d_live[k]);
     if (ctx->d_secLive) cudaFree(ctx->d_secLive);
+    p2p_free(ctx);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->evShade) cudaEventDestroy(ctx->evShade);
     if (ctx->evAux) cudaEventDestroy(ctx->evAux);
@@ -1093,6 +1113,7 @@ int deque_exchange_group(dprt_ctx** ctxs, int W, int* done) {
 // the active set is empty: the settled block is the path buffer
 int deque_finish(dprt_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
+    ctx->hp.paths = (dprt_path_record*)ctx->buf_ptr[DPRT_BUF_PATHS];      // the peer-memory exchange reads arrivals from its own buffers
     const int n = ctx->back - ctx->front;
     if (ctx->auxPending && n > ctx->auxGuardBase) { int jr = join_aux(ctx); if (jr) return jr; }
     StageScope sc_(ctx, DPRT_STAGE_EXCHANGE);
@@ -1116,6 +1137,139 @@ int dprt_plan_exchange_deque(const int32_t* rows, int W, int me, int32_t* send_c
     return 0;
 }
 
+// ---- EXPERIMENTAL: the deque exchange over peer memory (DPRT_P2P=1; p2p_exchange.cuh) -------------
+namespace {
+
+bool p2p_requested() { const char* v = getenv("DPRT_P2P"); return v && v[0] == '1'; }
+
+int p2p_alloc(dprt_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMalloc(&ctx->d_mailbox, sizeof(P2PMailbox)));
+    CK(cudaMemset(ctx->d_mailbox, 0, sizeof(P2PMailbox)));
+    for (int k = 0; k < 2; k++) CK(cudaMalloc(&ctx->d_active[k], (size_t)ctx->N * sizeof(dprt_path_record)));
+    CK(cudaMalloc(&ctx->d_peers, sizeof(P2PPeers)));
+    CK(cudaMalloc(&ctx->d_plan, sizeof(P2PPlan)));
+    CK(cudaHostAlloc(&ctx->h_plan, sizeof(P2PPlan), cudaHostAllocMapped));
+    std::memset(ctx->h_plan, 0, sizeof(P2PPlan));
+    CK(cudaHostGetDevicePointer((void**)&ctx->d_hplan, ctx->h_plan, 0));
+    return 0;
+}
+
+void p2p_free(dprt_ctx* ctx) {
+    for (void* q : ctx->ipcOpened) cudaIpcCloseMemHandle(q);
+    ctx->ipcOpened.clear();
+    if (ctx->d_mailbox) cudaFree(ctx->d_mailbox);
+    for (int k = 0; k < 2; k++) if (ctx->d_active[k]) cudaFree(ctx->d_active[k]);
+    if (ctx->d_peers) cudaFree(ctx->d_peers);
+    if (ctx->d_plan) cudaFree(ctx->d_plan);
+    if (ctx->h_plan) cudaFreeHost(ctx->h_plan);
+    ctx->d_mailbox = nullptr; ctx->d_active[0] = ctx->d_active[1] = nullptr; ctx->d_peers = nullptr; ctx->d_plan = nullptr; ctx->h_plan = nullptr;
+    ctx->p2p = false;
+}
+
+// one process per GPU: cudaIpc handles of the mailbox and the two active buffers, all-gathered over the communicator
+int p2p_connect_nccl(dprt_ctx* ctx) {
+    const int W = ctx->world, me = ctx->rank;
+    if (!ctx->comm || !ctx->d_settled || W > kP2PMaxWorld) return 0;
+    int r = p2p_alloc(ctx); if (r) return r;
+    struct Handles { cudaIpcMemHandle_t h[3]; };
+    Handles mine;
+    CK(cudaIpcGetMemHandle(&mine.h[0], ctx->d_mailbox));
+    CK(cudaIpcGetMemHandle(&mine.h[1], ctx->d_active[0]));
+    CK(cudaIpcGetMemHandle(&mine.h[2], ctx->d_active[1]));
+    Handles* d_all = nullptr;
+    CK(cudaMalloc(&d_all, sizeof(Handles) * (size_t)(W + 1)));
+    CK(cudaMemcpyAsync(d_all + W, &mine, sizeof(Handles), cudaMemcpyHostToDevice, ctx->stream));
+    NK(g_nccl.AllGather(d_all + W, d_all, sizeof(Handles), ncclUint8, ctx->comm, ctx->stream));
+    std::vector<Handles> all(W);
+    CK(cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(d_all));
+    P2PPeers tbl; std::memset(&tbl, 0, sizeof(tbl));
+    for (int s = 0; s < W; s++) {
+        void* ptr[3] = {ctx->d_mailbox, ctx->d_active[0], ctx->d_active[1]};
+        if (s != me)
+            for (int k = 0; k < 3; k++) {
+                CK(cudaIpcOpenMemHandle(&ptr[k], all[s].h[k], cudaIpcMemLazyEnablePeerAccess));
+                ctx->ipcOpened.push_back(ptr[k]);
+            }
+        tbl.mailbox[s] = (P2PMailbox*)ptr[0]; tbl.active[s][0] = (dprt_path_record*)ptr[1]; tbl.active[s][1] = (dprt_path_record*)ptr[2];
+    }
+    CK(cudaMemcpy(ctx->d_peers, &tbl, sizeof(tbl), cudaMemcpyHostToDevice));
+    ctx->p2p = true;
+    return 0;
+}
+
+// in-process rank group: the other contexts' pointers are valid as they are (peer access enabled across devices)
+int p2p_connect_group(dprt_ctx** ctxs, int W) {
+    if (W > kP2PMaxWorld) return 0;
+    for (int k = 0; k < W; k++) {
+        if (!ctxs[k]->d_settled) return 0;
+        if (!ctxs[k]->d_mailbox) { int r = p2p_alloc(ctxs[k]); if (r) return r; }
+    }
+    for (int k = 0; k < W; k++) {
+        dprt_ctx* ctx = ctxs[k];
+        CK(cudaSetDevice(ctx->device));
+        P2PPeers tbl; std::memset(&tbl, 0, sizeof(tbl));
+        for (int s = 0; s < W; s++) {
+            if (ctxs[s]->device != ctx->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[s]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, DPRT_ERR_CUDA, "no peer access between the group's devices");
+                cudaGetLastError();
+            }
+            tbl.mailbox[s] = ctxs[s]->d_mailbox; tbl.active[s][0] = ctxs[s]->d_active[0]; tbl.active[s][1] = ctxs[s]->d_active[1];
+        }
+        CK(cudaMemcpy(ctx->d_peers, &tbl, sizeof(tbl), cudaMemcpyHostToDevice));
+        ctx->p2p = true;
+    }
+    return 0;
+}
+
+// after deque_partition: counts -> scatter -> barrier, all on the rank's stream; nothing here waits on the host
+int p2p_exchange_enqueue(dprt_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    const int W = ctx->world, me = ctx->rank;
+    const uint32_t seq = ++ctx->p2pSeq;
+    const int parity = (int)((seq - 1u) & 1u);
+    StageScope sc_(ctx, DPRT_STAGE_EXCHANGE);
+    launch_p2p_counts(ctx->d_peers, ctx->d_mailbox, ctx->hp.transferOffset, W, me, parity, seq, ctx->d_plan, ctx->d_hplan, ctx->stream);
+    launch_p2p_scatter(ctx->d_peers, ctx->hp.transfer, ctx->d_plan, W, me, parity, ctx->pathSize, ctx->stream);
+    launch_p2p_barrier(ctx->d_peers, ctx->d_mailbox, W, me, parity, seq, ctx->stream);
+    ctx->stats.kernel_launches += 3;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// the host learns the plan from the mapped copy the counts kernel wrote (while scatter and barrier are still running),
+// then absorbs the two self pieces and switches to the buffer the arrivals are landing in
+int p2p_exchange_finish(dprt_ctx* ctx, int* done) {
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t seq = ctx->p2pSeq;
+    const int parity = (int)((seq - 1u) & 1u);
+    const volatile P2PPlan* hp = ctx->h_plan;
+    for (long spins = 0; hp->seq != seq; spins++) {
+        if ((spins & 0x3fff) == 0x3fff) {
+            cudaError_t e = cudaStreamQuery(ctx->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) return fail(ctx, DPRT_ERR_CUDA, std::string("peer-memory exchange: ") + cudaGetErrorString(e));
+            if (e == cudaSuccess && hp->seq != seq) return fail(ctx, DPRT_ERR_STATE, "peer-memory exchange: the stream drained without a plan");
+        }
+    }
+    P2PPlan plan;
+    std::memcpy(&plan, (const void*)ctx->h_plan, sizeof(plan));
+    if (plan.newActive > ctx->N) return fail(ctx, DPRT_ERR_CAPACITY, "received more paths than the frame holds");
+    const size_t R = sizeof(dprt_path_record);
+    for (int d = 0; d < ctx->world; d++) { ctx->stats.paths_sent_offrank += plan.sendCnt[d]; ctx->stats.bytes_alltoall += (int64_t)plan.sendCnt[d] * R; }
+    DequePlan dp; dp.cL = plan.cL; dp.cR = plan.cR; dp.offL = plan.offL; dp.offR = plan.offR;
+    int r = deque_absorb(ctx, dp); if (r) return r;
+    ctx->pathSize = plan.newActive; ctx->nL = plan.newNL;
+    ctx->hp.paths = ctx->d_active[parity ^ 1];             // restored by deque_finish
+    if (done) *done = plan.allLocal;
+    ctx->stats.exchange_iters++;
+    return 0;
+}
+
+}  // namespace
+
 // ---- composite modules ---------------------------------------------------------------------------
 int dprt_primary_ray_module(dprt_ctx* ctx) {
     if (!ctx) return DPRT_ERR_INVALID;
@@ -1125,7 +1279,9 @@ int dprt_primary_ray_module(dprt_ctx* ctx) {
             int done = 0;
             if ((r = deque_traverse(ctx))) return r;
             if ((r = deque_partition(ctx))) return r;
-            if ((r = deque_exchange(ctx, &done))) return r;
+            if (ctx->p2p) { if ((r = p2p_exchange_enqueue(ctx))) return r; r = p2p_exchange_finish(ctx, &done); }
+            else r = deque_exchange(ctx, &done);
+            if (r) return r;
             if (done) break;
         }
         return deque_finish(ctx);
@@ -1225,6 +1381,9 @@ int dprt_render_sample_group(dprt_ctx** ctxs, int W, int sample) {
     const int bounces = ctxs[0]->cfg.bounces;
     bool deque = true;
     for (int k = 0; k < W; k++) deque = deque && ctxs[k] && deque_enabled(ctxs[k]) && ctxs[k]->world == W && ctxs[k]->rank == k;
+    bool p2p = deque && W > 1 && p2p_requested();
+    if (p2p && !ctxs[0]->p2p) { if ((r = p2p_connect_group(ctxs, W))) return r; }
+    for (int k = 0; k < W; k++) p2p = p2p && ctxs[k]->p2p;
     for (int bounce = 0; bounce <= bounces; bounce++) {
         for (int k = 0; k < W; k++) if ((r = bounce_pre(ctxs[k], bounce))) return r;
         if (deque) for (int k = 0; k < W; k++) deque_begin(ctxs[k]);
@@ -1234,7 +1393,10 @@ int dprt_render_sample_group(dprt_ctx** ctxs, int W, int sample) {
                 if ((r = deque ? deque_traverse(ctxs[k]) : dprt_traverse(ctxs[k]))) return r;
                 if ((r = deque ? deque_partition(ctxs[k]) : dprt_partition(ctxs[k]))) return r;
             }
-            if ((r = deque ? deque_exchange_group(ctxs, W, &done) : dprt_exchange_group(ctxs, W, &done))) return r;
+            if (p2p) {
+                for (int k = 0; k < W; k++) if ((r = p2p_exchange_enqueue(ctxs[k]))) return r;      // every rank's kernels are in flight ...
+                for (int k = 0; k < W; k++) { int dk = 0; if ((r = p2p_exchange_finish(ctxs[k], &dk))) return r; done = dk; }   // ... before any is waited for
+            } else if ((r = deque ? deque_exchange_group(ctxs, W, &done) : dprt_exchange_group(ctxs, W, &done))) return r;
             if (done) break;
         }
         if (deque) for (int k = 0; k < W; k++) if ((r = deque_finish(ctxs[k]))) return r;
