@@ -72,11 +72,12 @@ int  dprt_plan_exchange(const int32_t* gathered_offsets, int world, int rank, in
  * partition of the travelling paths has W + 1 buckets: 0..W-1 by destination, W = the second piece of the self segment
  * (records that stay on the rank and came from HIGHER ranks; bucket `rank` holds the ones that came from lower ranks).
  * rows: W rows of W + 2 offsets. Outputs for rank `rank`: send_count[W] / recv_count[W] (the self entries are 0),
+ * dst_offset[W] = where this rank's bucket d starts among the arrivals of rank d (arrivals are ordered by source rank),
  * piece[4] = {offset, count of the first self piece, offset, count of the second}, new_nl = records arriving from lower
  * ranks (they precede the ones from higher ranks in the new active set), new_active = all arrivals, all_local =
  * termination flag of renderer.cpp:1292-1298. Output pointers may be NULL. */
 int  dprt_plan_exchange_deque(const int32_t* rows, int world, int rank, int32_t* send_count, int32_t* recv_count,
-                              int32_t* piece, int32_t* new_nl, int32_t* new_active, int* all_local);
+                              int32_t* dst_offset, int32_t* piece, int32_t* new_nl, int32_t* new_active, int* all_local);
 int  dprt_shade(dprt_ctx* ctx);                       /* optixLaunch(MainRay)         renderer.cpp:1320-1347 */
 int  dprt_reset_nn(dprt_ctx* ctx);                    /* resetNNBuffers               renderer.cpp:367-414 */
 int  dprt_shadow_trace(dprt_ctx* ctx);                /* optixLaunch(ShadowRay)       renderer.cpp:1366-1379 */

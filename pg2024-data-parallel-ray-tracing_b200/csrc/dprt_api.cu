@@ -1008,9 +1008,13 @@ int deque_partition(dprt_ctx* ctx) {
 }
 
 // rows: W rows of W + 2 offsets (row s = transferOffset of rank s: buckets 0..W-1 by destination, bucket W = second self piece)
-struct DequePlan { std::vector<int> sendCnt, recvCnt; int cL = 0, cR = 0, offL = 0, offR = 0, newNL = 0, newActive = 0; bool allLocal = true; };
+struct DequePlan {
+    std::vector<int> sendCnt, recvCnt;
+    std::vector<int> dstOffset;      // where this rank's bucket d starts among the arrivals of rank d (source-rank order)
+    int cL = 0, cR = 0, offL = 0, offR = 0, newNL = 0, newActive = 0; bool allLocal = true;
+};
 int deque_plan(const int32_t* rows, int W, int me, DequePlan& p) {
-    p.sendCnt.assign(W, 0); p.recvCnt.assign(W, 0);
+    p.sendCnt.assign(W, 0); p.recvCnt.assign(W, 0); p.dstOffset.assign(W, 0);
     for (int s = 0; s < W; s++) {
         const int32_t* r = rows + (size_t)s * (W + 2);
         if (r[0] != 0) return DPRT_ERR_INVALID;
@@ -1020,6 +1024,7 @@ int deque_plan(const int32_t* rows, int W, int me, DequePlan& p) {
             if (s != d && c > 0) p.allLocal = false;
             if (s == me && d != me) p.sendCnt[d] = c;
             if (d == me && s != me) { p.recvCnt[s] = c; p.newActive += c; if (s < me) p.newNL += c; }
+            if (s < me && s != d) p.dstOffset[d] += c;               // lower ranks' records precede mine at every destination
         }
         if (s == me) { p.offL = r[me]; p.cL = r[me + 1] - r[me]; p.offR = r[W]; p.cR = r[W + 1] - r[W]; }
     }
@@ -1124,12 +1129,16 @@ int deque_finish(dprt_ctx* ctx) {
 
 }  // namespace
 
-int dprt_plan_exchange_deque(const int32_t* rows, int W, int me, int32_t* send_count, int32_t* recv_count, int32_t* piece,
-                             int32_t* new_nl, int32_t* new_active, int* all_local) {
+int dprt_plan_exchange_deque(const int32_t* rows, int W, int me, int32_t* send_count, int32_t* recv_count, int32_t* dst_offset,
+                             int32_t* piece, int32_t* new_nl, int32_t* new_active, int* all_local) {
     if (!rows || W < 1 || W >= DPRT_MAX_WORLD || me < 0 || me >= W) return DPRT_ERR_INVALID;
     DequePlan p;
     if (deque_plan(rows, W, me, p)) return DPRT_ERR_INVALID;
-    for (int k = 0; k < W; k++) { if (send_count) send_count[k] = p.sendCnt[k]; if (recv_count) recv_count[k] = p.recvCnt[k]; }
+    for (int k = 0; k < W; k++) {
+        if (send_count) send_count[k] = p.sendCnt[k];
+        if (recv_count) recv_count[k] = p.recvCnt[k];
+        if (dst_offset) dst_offset[k] = p.dstOffset[k];
+    }
     if (piece) { piece[0] = p.offL; piece[1] = p.cL; piece[2] = p.offR; piece[3] = p.cR; }
     if (new_nl) *new_nl = p.newNL;
     if (new_active) *new_active = p.newActive;
@@ -1381,7 +1390,9 @@ int dprt_render_sample_group(dprt_ctx** ctxs, int W, int sample) {
     const int bounces = ctxs[0]->cfg.bounces;
     bool deque = true;
     for (int k = 0; k < W; k++) deque = deque && ctxs[k] && deque_enabled(ctxs[k]) && ctxs[k]->world == W && ctxs[k]->rank == k;
-    bool p2p = deque && W > 1 && p2p_requested();
+    // one thread driving W ranks on shared devices: the spinning kernels of all ranks must be able to run side by side, which
+    // needs a hardware queue per stream (8 by default); keep the experiment to small groups
+    bool p2p = deque && W > 1 && W <= 4 && p2p_requested();
     if (p2p && !ctxs[0]->p2p) { if ((r = p2p_connect_group(ctxs, W))) return r; }
     for (int k = 0; k < W; k++) p2p = p2p && ctxs[k]->p2p;
     for (int bounce = 0; bounce <= bounces; bounce++) {

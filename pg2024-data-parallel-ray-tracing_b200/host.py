@@ -43,7 +43,7 @@ _PROTOTYPES = {
     "dprt_exchange": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "dprt_plan_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64),
                                     C.POINTER(C.c_int)]),
-    "dprt_plan_exchange_deque": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32),
+    "dprt_plan_exchange_deque": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32),
                                            C.POINTER(C.c_int32), C.POINTER(C.c_int)]),
     "dprt_shade": (C.c_int, [C.c_void_p]),
     "dprt_reset_nn": (C.c_int, [C.c_void_p]),
@@ -162,17 +162,17 @@ def plan_exchange(gathered_offsets, rank):
 
 def plan_exchange_deque(rows, rank):
     """dprt_plan_exchange_deque: rows [W, W+2] int32 (W+1-bucket partition offsets of every rank's travelling paths) ->
-    dict(send_count, recv_count, piece=(offL, cL, offR, cR), new_nl, new_active, all_local). Host only."""
+    dict(send_count, recv_count, dst_offset, piece=(offL, cL, offR, cR), new_nl, new_active, all_local). Host only."""
     M = np.ascontiguousarray(rows, np.int32)
     W = M.shape[0]
     if M.shape != (W, W + 2):
         raise DprtError(f"offset rows must be [W, W+2], got {M.shape}")
-    sc, rc, piece = np.zeros(W, np.int32), np.zeros(W, np.int32), np.zeros(4, np.int32)
+    sc, rc, do, piece = np.zeros(W, np.int32), np.zeros(W, np.int32), np.zeros(W, np.int32), np.zeros(4, np.int32)
     nl, na, loc = C.c_int32(0), C.c_int32(0), C.c_int(0)
-    r = load_library().dprt_plan_exchange_deque(_ptr(M), W, int(rank), _ptr(sc), _ptr(rc), _ptr(piece), C.byref(nl), C.byref(na), C.byref(loc))
+    r = load_library().dprt_plan_exchange_deque(_ptr(M), W, int(rank), _ptr(sc), _ptr(rc), _ptr(do), _ptr(piece), C.byref(nl), C.byref(na), C.byref(loc))
     if r:
         raise DprtError(f"dprt_plan_exchange_deque failed ({r})")
-    return {"send_count": sc, "recv_count": rc, "piece": tuple(int(x) for x in piece), "new_nl": int(nl.value),
+    return {"send_count": sc, "recv_count": rc, "dst_offset": do, "piece": tuple(int(x) for x in piece), "new_nl": int(nl.value),
             "new_active": int(na.value), "all_local": bool(loc.value)}
 
 

@@ -116,8 +116,9 @@ def _simulate_migrate(W, itineraries, start_rank, deque):
                 rows[s, 1:] = np.cumsum([len(b) for b in buckets[s]])
             new_bufs = []
             done = None
+            plans = [dprt.plan_exchange_deque(rows, r) for r in range(W)]
             for d in range(W):
-                plan = dprt.plan_exchange_deque(rows, d)
+                plan = plans[d]
                 flat = [p for b in buckets[d] for p in b]
                 oL, cL, oR, cR = plan["piece"]
                 settled[d] = flat[oL:oL + cL] + settled[d] + flat[oR:oR + cR]
@@ -127,6 +128,13 @@ def _simulate_migrate(W, itineraries, start_rank, deque):
                         assert plan["recv_count"][s] == len(buckets[s][d])
                         recv += buckets[s][d]
                 assert plan["new_active"] == len(recv) and plan["new_nl"] == sum(len(buckets[s][d]) for s in range(d))
+                # one-sided placement (what the peer-memory exchange does): every sender writes its bucket at its dst_offset
+                placed = [None] * len(recv)
+                for s in range(W):
+                    if s != d:
+                        o = int(plans[s]["dst_offset"][d])
+                        placed[o:o + len(buckets[s][d])] = buckets[s][d]
+                assert placed == recv
                 new_bufs.append(recv)
                 nl[d] = plan["new_nl"]
                 done = plan["all_local"] if done is None else (done and plan["all_local"])
