@@ -283,3 +283,52 @@ def test_bvh8_build_host_only_properties():
     order = np.argsort(nodes["triBase"], kind="stable")
     assert np.array_equal(np.cumsum(per_node[order])[:-1][per_node[order][1:] > 0], nodes["triBase"][order][1:][per_node[order][1:] > 0])
     assert depth >= 2
+
+
+def test_balanced_slab_layout_cuts_equal_primary_load():
+    """bench.py's N > 1 workload: x-slabs cut at the k/W quantiles of where the primary rays land on the (continuous)
+    landscape. The cuts are increasing, span [0, 1], and an independent ray-march at another resolution finds the same
+    share of primary hits in every slab."""
+    cam = dprt.scene.default_camera(1920, 1080)
+    for W in (2, 4, 8):
+        cells = dprt.scene.balanced_slab_layout(W, cam, terrain_seed=0)
+        cuts = [float(c[0][0]) for c in cells] + [float(cells[-1][1][0])]
+        assert cuts[0] == 0.0 and cuts[-1] == 1.0 and all(b > a for a, b in zip(cuts, cuts[1:]))
+        assert all(float(c[0][1]) == 0.0 and float(c[1][1]) == 1.0 and float(c[0][2]) == 0.0 and float(c[1][2]) == 1.0 for c in cells)
+        # independent check: coarser image, finer march
+        nx, ny = 160, 90
+        a = (np.arange(nx) + 0.5) / nx * 2.0 - 1.0
+        b = 1.0 - (np.arange(ny) + 0.5) / ny * 2.0
+        A, B = np.meshgrid(a, b, indexing="xy")
+        U, V, Wv, O = (np.array(list(v), np.float64) for v in (cam.U, cam.V, cam.W, cam.origin))
+        d = A[..., None] * U + B[..., None] * V + Wv
+        d /= np.linalg.norm(d, axis=-1, keepdims=True)
+        hx = np.full(A.shape, np.nan)
+        alive = np.ones(A.shape, bool)
+        for t in np.arange(0.0, 4.0, 0.002):
+            p = O + t * d
+            inside = (p[..., 0] >= 0) & (p[..., 0] <= 1) & (p[..., 1] >= 0) & (p[..., 1] <= 1)
+            hit = alive & inside & (p[..., 2] <= dprt.scene.terrain_height(p[..., 0], p[..., 1], 0))
+            hx[hit] = p[..., 0][hit]
+            alive &= ~hit
+        xs = hx[~np.isnan(hx)]
+        share = np.histogram(xs, bins=cuts)[0] / xs.size
+        assert np.abs(share - 1.0 / W).max() < 0.03, (W, share)
+
+
+def test_scene_file_and_pfm_round_trip(tmp_path):
+    """scene.save_scene writes what csrc/dprt_render.cpp documents; load_pfm reads what it writes."""
+    chunks, mats, lights = dprt.scene.make_scene(2, 400)
+    cam = dprt.scene.default_camera(32, 18)
+    path = str(tmp_path / "s.dprt")
+    dprt.scene.save_scene(path, chunks, mats, lights, cam, models={1: (b"abc", None)})
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"DPRTSCN1" and np.frombuffer(raw, np.int32, 3, 8).tolist() == [2, len(mats), len(lights)]
+    expect = 8 + 12 + 56 + 16 * len(mats) + 48 * len(lights) + sum(84 + 8 + c.ntris * (36 + 36 + 4) + 16 for c in chunks) + 3
+    assert len(raw) == expect
+    img = np.random.default_rng(0).random((18, 32, 3)).astype(np.float32)
+    pfm = str(tmp_path / "i.pfm")
+    with open(pfm, "wb") as f:                       # the writer of dprt_render.cpp: header, rows bottom-up
+        f.write(b"PF\n32 18\n-1.0\n")
+        f.write(img[::-1].tobytes())
+    assert np.array_equal(dprt.scene.load_pfm(pfm), img)
