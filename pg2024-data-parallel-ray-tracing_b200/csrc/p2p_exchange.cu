@@ -17,7 +17,6 @@ __device__ __forceinline__ void spin_until(const volatile uint32_t* flag, uint32
 __global__ void __launch_bounds__(64) p2p_counts_kernel(const P2PPeers* __restrict__ peers, P2PMailbox* mine, const int32_t* __restrict__ row,
                                                         int W, int me, int parity, uint32_t seq, P2PPlan* plan, P2PPlan* hostPlan) {
     __shared__ int32_t s_rows[kP2PMaxWorld][kP2PRow];
-    __shared__ int s_allLocal, s_newActive, s_newNL;
     const int t = threadIdx.x;
     // (1) my offsets row into every mailbox (my own included)
     if (t < W + 2) {
@@ -30,34 +29,14 @@ __global__ void __launch_bounds__(64) p2p_counts_kernel(const P2PPeers* __restri
     // (2) everybody's row
     if (t < W) spin_until(&mine->rowFlag[parity][t], seq);
     __threadfence_system();
-    if (t == 0) { s_allLocal = 1; s_newActive = 0; s_newNL = 0; }
     __syncthreads();
     for (int k = t; k < W * (W + 2); k += blockDim.x) {
         const int s = k / (W + 2), c = k - s * (W + 2);
         s_rows[s][c] = ((const volatile int32_t*)mine->rows[parity][s])[c];
     }
     __syncthreads();
-    // (3) the plan: arrivals at a rank are ordered by source rank, so my bucket d starts after what lower ranks send to d
-    if (t < W) {
-        int off = 0;
-        for (int s = 0; s < me; s++) if (s != t) off += s_rows[s][t + 1] - s_rows[s][t];
-        plan->dstOffset[t] = off;
-        plan->sendCnt[t] = t != me ? s_rows[me][t + 1] - s_rows[me][t] : 0;
-        const int rc = t != me ? s_rows[t][me + 1] - s_rows[t][me] : 0;
-        plan->recvCnt[t] = rc;
-        if (rc) { atomicAdd(&s_newActive, rc); if (t < me) atomicAdd(&s_newNL, rc); }
-        int offDiag = 0;
-        for (int d = 0; d < W; d++) if (d != t) offDiag += s_rows[t][d + 1] - s_rows[t][d];
-        if (offDiag) atomicAnd(&s_allLocal, 0);                       // renderer.cpp:1292-1298: any rank sent anything off-rank
-    }
-    if (t < W + 2) plan->row[t] = s_rows[me][t];
-    __syncthreads();
-    if (t == 0) {
-        plan->offL = s_rows[me][me]; plan->cL = s_rows[me][me + 1] - s_rows[me][me];
-        plan->offR = s_rows[me][W];  plan->cR = s_rows[me][W + 1] - s_rows[me][W];
-        plan->newNL = s_newNL; plan->newActive = s_newActive; plan->allLocal = s_allLocal;
-        plan->seq = seq;
-    }
+    // (3) the plan (p2p_exchange.cuh: one serial pass, shared with the host-side check)
+    if (t == 0) { p2p_plan_from_rows(&s_rows[0][0], kP2PRow, W, me, plan); plan->seq = seq; }
     __threadfence();
     __syncthreads();
     // (4) the same plan for the host (mapped pinned memory), sequence number last

@@ -39,6 +39,28 @@ struct P2PPeers {                                 // device-side pointer table o
     dprt_path_record* active[kP2PMaxWorld][2];
 };
 
+// The plan of rank `me` from the W gathered offsets rows (row s = rows + s * stride): one serial pass, a few hundred
+// operations; shared by the counts kernel (thread 0) and the host-side unit test (tests/p2p_plan_check.cpp). Same content
+// as deque_plan() in dprt_api.cu, which the NCCL path uses and the CPU model test checks for W up to 31.
+__host__ __device__ inline void p2p_plan_from_rows(const int32_t* rows, int stride, int W, int me, P2PPlan* plan) {
+    int newActive = 0, newNL = 0, allLocal = 1;
+    for (int d = 0; d < W; d++) {
+        int off = 0;
+        for (int s = 0; s < me; s++) if (s != d) off += rows[s * stride + d + 1] - rows[s * stride + d];
+        plan->dstOffset[d] = off;                                     // arrivals at d are ordered by source rank
+        plan->sendCnt[d] = d != me ? rows[me * stride + d + 1] - rows[me * stride + d] : 0;
+        const int rc = d != me ? rows[d * stride + me + 1] - rows[d * stride + me] : 0;      // what rank d sends to me
+        plan->recvCnt[d] = rc;
+        newActive += rc;
+        if (d < me) newNL += rc;
+        for (int k = 0; k < W; k++) if (k != d && rows[d * stride + k + 1] - rows[d * stride + k] != 0) allLocal = 0;
+    }
+    for (int k = 0; k < W + 2; k++) plan->row[k] = rows[me * stride + k];
+    plan->offL = rows[me * stride + me]; plan->cL = rows[me * stride + me + 1] - rows[me * stride + me];
+    plan->offR = rows[me * stride + W];  plan->cR = rows[me * stride + W + 1] - rows[me * stride + W];
+    plan->newNL = newNL; plan->newActive = newActive; plan->allLocal = allLocal;
+}
+
 // all asynchronous on `stream`; `row` = the W + 2 offsets the partition kernel wrote (transferOffset)
 void launch_p2p_counts(const P2PPeers* peers, P2PMailbox* mine, const int32_t* row, int W, int me, int parity, uint32_t seq,
                        P2PPlan* plan, P2PPlan* hostPlan, cudaStream_t stream);

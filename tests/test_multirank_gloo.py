@@ -163,3 +163,34 @@ def test_settled_deque_reproduces_the_reference_buffers(W, npaths, seed):
     assert it_ref == it_fast
     assert ref == fast
     assert sum(len(b) for b in ref) == npaths
+
+
+def test_p2p_plan_matches_deque_plan(tmp_path):
+    """The plan the experimental peer-memory exchange computes on the device (p2p_plan_from_rows, compiled here for the
+    host) equals dprt_plan_exchange_deque, which the verified NCCL path executes, on random offset matrices."""
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    exe = str(tmp_path / "p2p_plan_check")
+    csrc = os.path.join(ROOT, "pg2024-data-parallel-ray-tracing_b200", "csrc")
+    cc = subprocess.run(["g++", "-O1", "-std=c++17", "-I", cuda_inc, "-I", csrc, "-I", os.path.join(ROOT, "include"),
+                         os.path.join(ROOT, "tests", "p2p_plan_check.cpp"), "-o", exe], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr[-3000:]
+    rng = np.random.default_rng(5)
+    for W in (2, 3, 8, 31):
+        counts = rng.integers(0, 50, (W, W + 1)) * (rng.random((W, W + 1)) < 0.6)
+        if W == 3:
+            counts[~np.eye(W, W + 1, dtype=bool)] = 0            # nothing crosses ranks: termination
+            counts[:, W] = 7
+        rows = np.zeros((W, W + 2), np.int32)
+        rows[:, 1:] = np.cumsum(counts, axis=1)
+        for me in {0, W // 2, W - 1}:
+            inp = f"{W} {me}\n" + " ".join(str(int(v)) for v in rows.reshape(-1)) + "\n"
+            out = subprocess.run([exe], input=inp, capture_output=True, text=True)
+            assert out.returncode == 0
+            v = [int(x) for x in out.stdout.split()]
+            ref = dprt.plan_exchange_deque(rows, me)
+            assert v[0:3 * W:3] == ref["send_count"].tolist() and v[1:3 * W:3] == ref["recv_count"].tolist()
+            assert v[2:3 * W:3] == ref["dst_offset"].tolist()
+            assert tuple(v[3 * W:3 * W + 4]) == ref["piece"]
+            assert v[3 * W + 4] == ref["new_nl"] and v[3 * W + 5] == ref["new_active"] and bool(v[3 * W + 6]) == ref["all_local"]
