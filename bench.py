@@ -77,7 +77,7 @@ class ClockSampler:
         try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu)], stdout=f, stderr=subprocess.DEVNULL)
             f.close()
         except Exception:
@@ -389,7 +389,6 @@ def run_dprt(args):
         R.run_sample(args.warmup + s)
     ms = R.timer_stop()
     barrier()
-    clk = clocks.stop() if rank == 0 else None
     st = R.stats()
     my_rays_walked = st["rays_walked"]
     ms = allreduce(ms, dist.ReduceOp.MAX if W > 1 else None)
@@ -402,6 +401,7 @@ def run_dprt(args):
         R.run_sample(args.warmup + s)
     ms_serial = R.timer_stop()
     barrier()
+    clk = clocks.stop() if rank == 0 else None          # sampled through the timed region and the serial pass right after it
     stage = R.stage_times()
     R.stage_profile(False)
     # per-rank view of the serial pass: time inside the exchange stage is mostly waiting for the slowest chunk owner
