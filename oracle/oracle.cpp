@@ -16,6 +16,7 @@
 //   src/cuda/frame_buffer_update.cu:31-127,172-192,222-324                     -> frame/depth/target updates
 //   src/render/renderer.cpp:1212-1318,1320-1452,1457-1574,2031-2052            -> World::render_sample, image
 //   trainingcode/module.py:36-45,755-837        4Res256/6Res256 proxy MLP      -> mlp_forward_row (fp32)
+//   optix/vis_ray_kernel.cu:98-161              Vis pipeline (training samples) -> orc_gen_train_data
 //
 // PARITY PINNING. The reference ships no tests or golden vectors and cannot be built (README.md:5). What is
 // pinned against reference code executed in the build container: tea<4>/lcg/rnd against optix/random.hpp
