@@ -347,7 +347,7 @@ def run_dprt(args):
     N = fw * fh
     proxy = 1 if (args.proxy and W > 1) else 0
     cfg = dprt.make_config(fw, fh, spp=1, bounces=args.bounces, scene_size=W, proxy_mode=proxy,
-                           path_gen_mode=args.path_gen_mode if W > 1 else 0, mlp_dtype=0, main_ray_retrace=args.retrace,
+                           path_gen_mode=args.path_gen_mode if W > 1 else 0, mlp_dtype=args.mlp_dtype, main_ray_retrace=args.retrace,
                            serial_stages=args.serial)
     chunks, mats, lights = build_world_scene(dprt, W, args.tris, args.layout)
     blobs = proxy_blobs(dprt, W, proxy)
@@ -521,6 +521,7 @@ def main():
     ap.add_argument("--retrace", type=int, default=0, help="1 = MainRay always re-traces (no hit cache), for A/B")
     ap.add_argument("--layout", choices=("slabs", "cells"), default="slabs", help="N>1: how the unit cube is cut into chunks")
     ap.add_argument("--serial", type=int, default=0, help="1 = no shadow/traverse stream overlap inside dprt_render_sample, for A/B")
+    ap.add_argument("--mlp-dtype", type=int, default=1, help="proxy MLP operands: 1 = fp16 (reference's NN_Float, meets 1e-3), 0 = bf16 (out of tolerance)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")
     args = ap.parse_args()

@@ -27,6 +27,10 @@ typedef struct dprt_bvh8 dprt_bvh8;
  * context that is only driven single-rank or through dprt_*_group(). */
 int  dprt_get_unique_id(void* out128);
 int  dprt_create(const dprt_config* cfg, int rank, int world, int device, const void* nccl_unique_id, dprt_ctx** out);
+/* A second context of the same rank (other frame size / scene) that BORROWS the parent's NCCL communicator instead of
+ * creating one (several frames in one MPI job share MPI_COMM_WORLD the same way). Collective like dprt_create; the parent
+ * must outlive it, and the two contexts' collectives must not interleave across ranks. */
+int  dprt_create_shared(const dprt_config* cfg, dprt_ctx* parent, dprt_ctx** out);
 void dprt_destroy(dprt_ctx* ctx);
 const char* dprt_last_error(const dprt_ctx* ctx);   /* ctx may be NULL: last create-time error */
 int  dprt_synchronize(dprt_ctx* ctx);
@@ -103,6 +107,17 @@ int  dprt_render_sample(dprt_ctx* ctx, int sample);   /* runSample              
 /* (direct+env)/spp on device, ncclReduce(sum) to root, copy to out_host (3*N floats, root only; may be NULL
  * elsewhere): renderer.cpp:2031-2052. */
 int  dprt_reduce_image(dprt_ctx* ctx, int root, float* out_host);
+
+/* ---- peer-memory exchange (the data plane of dprt_primary_ray_module when every rank's buffers are reachable over
+ * NVLink: MPI_Alltoall + MPI_Alltoallv + MPI_Allreduce of renderer.cpp:1254-1298 without a host round trip).
+ * A context created with an NCCL id wires itself up inside dprt_create (and falls back to ncclSend/ncclRecv on all ranks
+ * when any rank cannot; DPRT_P2P=0 forces the fallback). A host with its own bootstrap and no NCCL does it by hand:
+ * every rank exports DPRT_P2P_HANDLE_BYTES, the host all-gathers them, every rank connects, the host agrees on
+ * min(*connected) and tells every rank the verdict. All three calls are collective over the job. */
+int  dprt_p2p_export(dprt_ctx* ctx, void* handle_out);
+int  dprt_p2p_connect(dprt_ctx* ctx, const void* all_handles, int* connected);
+int  dprt_p2p_enable(dprt_ctx* ctx, int enable);
+int  dprt_p2p_enabled(const dprt_ctx* ctx);
 
 /* ---- in-process rank group: W contexts driven by one thread (tests on fewer GPUs than ranks) --- */
 int  dprt_exchange_group(dprt_ctx** ctxs, int world, int* done);

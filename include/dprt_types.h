@@ -110,7 +110,7 @@ typedef struct dprt_config {
     int32_t sceneSize;        /* number of scene objects (local + proxy) */
     int32_t proxyMode;        /* 1 = reference behaviour (neural proxies), 0 = sequential visiting only */
     int32_t pathGenMode;      /* 0 = rank 0 generates all camera paths (renderer.cpp:1514), 1 = striped */
-    int32_t mlpDtype;         /* 0 = bf16 operands, 1 = fp16 operands (fp32 accumulate either way) */
+    int32_t mlpDtype;         /* 1 = fp16 operands (the reference's NN_Float; meets the 1e-3 proxy tolerance; what every host here defaults to), 0 = bf16 operands (opt-in, ~3e-3); fp32 accumulate either way */
     float   envColor[3];      /* analytic environment: Le = envColor * (0.5 + 0.5*dir.z) */
     int32_t mainRayRetrace;   /* 0 = MainRay reuses the closest hit TraRay / SecondaryRay found for the same ray on this rank
                                  (identical result, see DESIGN.md "hit cache"); 1 = always re-trace like kernel.cu:382-413 */
@@ -171,7 +171,11 @@ typedef struct dprt_stats {
     int64_t rays_walked;       /* rays of all four stages that actually walked a local BVH: live record, at least one local
                                   object not yet visited, not answered from the hit cache (rays_* count launch sizes, like
                                   the reference's optixLaunch dimensions) */
-    int64_t reserved_[5];
+    int64_t walked_traverse;   /* rays_walked split by stage (TraRay / MainRay / ShadowRay / SecondaryRay): the rays whose records */
+    int64_t walked_shade;      /* a launch actually traced -- what bench.py bills record bytes for (riders of a TraRay launch  */
+    int64_t walked_shadow;     /* and cache-answered MainRay queries are in rays_* but not here)                               */
+    int64_t walked_secondary;
+    int64_t paths_partitioned; /* records written by the path partition (Work_Efficient_Scan): the reorder roofline's unit */
 } dprt_stats;
 
 /* Buffer identifiers for dprt_download/dprt_upload (parity harness access to Params buffers). */
@@ -211,6 +215,9 @@ enum dprt_stage_id {
     DPRT_STAGE_TRACE_CLOSEST = 13,
     DPRT_STAGE_COUNT = 14
 };
+
+/* bytes one rank exports for the peer-memory exchange (dprt_p2p_export): three CUDA IPC handles + a status word */
+#define DPRT_P2P_HANDLE_BYTES 208
 
 enum dprt_error {
     DPRT_OK = 0,

@@ -365,12 +365,17 @@ struct Mlp {
     }
 };
 
+struct World;
+struct Rank;
 // ---- world: all scene objects + W simulated ranks ----
 struct Object {
     dprt_object_desc desc{};
     bool present = false;
     Mesh mesh;
     Mlp vis, depth; bool hasVis = false, hasDepth = false;
+    // optional copy of the PRODUCT's BVH8 blob (orc_world_set_bvh8): never used for results, only walked a second time by a
+    // scalar exact-tbest walker to count the nodes / triangles the algorithm has to touch per ray (bench.py roofline)
+    std::vector<dprt_bvh8_node> nodes8; std::vector<dprt_bvh8_tri> tris8;
 };
 
 struct World;
@@ -385,6 +390,8 @@ struct Rank {
     int pathSize = 0, shadowPathSize = 0, queryTotal = 0;
     dprt_stats stats{};
     int64_t bvhNodes = 0, bvhTris = 0;
+    // per dprt_stage_id: BVH8 nodes fetched / triangles tested / rays walked by the counting walker
+    int64_t cntNodes[DPRT_STAGE_COUNT] = {0}, cntTris[DPRT_STAGE_COUNT] = {0}, cntRays[DPRT_STAGE_COUNT] = {0};
 };
 
 struct World {
@@ -394,6 +401,7 @@ struct World {
     std::vector<dprt_light_tri> lights;
     dprt_camera cam{};
     std::vector<Rank> ranks;
+    bool countBvh8 = false;          // orc_count_bvh8: walk the product's BVH8 beside every trace, for the counters only
 
     bool is_proxy(int rank, int i) const { return objects[i].desc.nodeID != rank; }
     V3 env_radiance(V3 d) const {
@@ -408,6 +416,77 @@ void add_env(World& w, Rank& r, dprt_path_record& p) {
     const int px = p.pixelIndex * 3;
     r.env[px + 0] += p.throughput[0]; r.env[px + 1] += p.throughput[1]; r.env[px + 2] += p.throughput[2];
 }
+
+// ---- scalar walker over the PRODUCT's BVH8 blob: per-ray node/triangle counters for the roofline ----
+struct Bvh8Count { int64_t nodes, tris; };
+// any = true: any-hit semantics, the walk stops at the first accepted triangle (near-first depth-first order)
+bool bvh8_walk(const dprt_bvh8_node* nodes, const dprt_bvh8_tri* tris, V3 o, V3 d, float tmin, float tmax, Hit& hit, Bvh8Count& cnt, bool any = false) {
+    Shear rs = make_shear(d);
+    const float dxs = fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x);
+    const float dys = fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y);
+    const float dzs = fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z);
+    const float idir[3] = {1.0f / dxs, 1.0f / dys, 1.0f / dzs};
+    const bool negd[3] = {dxs < 0.f, dys < 0.f, dzs < 0.f};
+    const uint32_t octinv = 7u - ((negd[0] ? 1u : 0u) | (negd[1] ? 2u : 0u) | (negd[2] ? 4u : 0u));
+    const float oo[3] = {o.x, o.y, o.z};
+    float tbest = tmax; int bestPrim = 0x7fffffff; bool found = false; float ba = 0, bb = 0;
+    struct Grp { uint32_t base, bits; };
+    Grp stack[64]; int sp = 0;
+    Grp ng{0u, 0x80000000u};
+    uint32_t tmask = 0u;
+    for (;;) {
+        Grp tg{0u, 0u};
+        if (ng.bits & 0xff000000u) {
+            uint32_t bit = 31u - (uint32_t)__builtin_clz(ng.bits);
+            uint32_t slot = (bit - 24u) ^ octinv;
+            uint32_t rel = (uint32_t)__builtin_popcount(ng.bits & 0xffu & ((1u << slot) - 1u));
+            ng.bits &= ~(1u << bit);
+            const dprt_bvh8_node& n = nodes[ng.base + rel];
+            if (ng.bits & 0xff000000u) stack[sp++] = ng;
+            cnt.nodes++;
+            float adj[3], org[3];
+            for (int a = 0; a < 3; a++) {
+                uint32_t eb = (uint32_t)n.e[a] << 23; float sc; std::memcpy(&sc, &eb, 4);
+                adj[a] = sc * idir[a]; org[a] = (n.p[a] - oo[a]) * idir[a];
+            }
+            uint32_t hitmask = 0;
+            const uint8_t* qlo[3] = {n.qlox, n.qloy, n.qloz}; const uint8_t* qhi[3] = {n.qhix, n.qhiy, n.qhiz};
+            for (int c = 0; c < 8; c++) {
+                float tn = tmin, tf = tbest;
+                for (int a = 0; a < 3; a++) {
+                    const float lo = (float)(negd[a] ? qhi[a][c] : qlo[a][c]), hi = (float)(negd[a] ? qlo[a][c] : qhi[a][c]);
+                    tn = fmaxf(tn, fmaf(lo, adj[a], org[a])); tf = fminf(tf, fmaf(hi, adj[a], org[a]));
+                }
+                if (tn <= tf) {
+                    if ((n.imask >> c) & 1u) hitmask |= 1u << (24u + ((uint32_t)c ^ octinv));   // internal child: octant-ordered slot
+                    else hitmask |= (7u << (3 * c)) & n.tmask;                                  // leaf child: its (<= 3) triangles
+                }
+            }
+            ng = Grp{n.childBase, (hitmask & 0xff000000u) | n.imask};
+            tg = Grp{n.triBase, hitmask & 0x00ffffffu};
+            tmask = n.tmask;
+        }
+        while (tg.bits) {
+            uint32_t b = (uint32_t)__builtin_ctz(tg.bits); tg.bits &= tg.bits - 1u;
+            const uint32_t k = (uint32_t)__builtin_popcount(tmask & ((1u << b) - 1u));
+            const dprt_bvh8_tri& t = tris[tg.base + k];
+            cnt.tris++;
+            float tv[9] = {t.v0[0], t.v0[1], t.v0[2], t.v1[0], t.v1[1], t.v1[2], t.v2[0], t.v2[1], t.v2[2]};
+            float tt, al, be;
+            if (tri_hit(rs, o, tv, tmin, tmax, &tt, &al, &be)) {
+                if (any) { hit.t = tt; hit.prim = t.primID; hit.alpha = al; hit.beta = be; return true; }
+                if (tt < tbest || (tt == tbest && t.primID < bestPrim)) { tbest = tt; bestPrim = t.primID; ba = al; bb = be; found = true; }
+            }
+        }
+        if ((ng.bits & 0xff000000u) == 0u) { if (sp == 0) break; ng = stack[--sp]; }
+    }
+    hit.t = tbest; hit.prim = found ? bestPrim : -1; hit.alpha = ba; hit.beta = bb;
+    return found;
+}
+
+// Counting walk of one ray over the rank's local objects (same object order, same shrinking tMax as trace_local): what a
+// scalar walker with an exact tbest fetches from the product's BVH8. Results are discarded; objects without a blob are skipped.
+void count_local(const World& w, Rank& r, int stage, V3 o, V3 d, float tmin, float tMax, uint32_t visited, bool skipVisited, bool any);
 
 // does a ray with this visited set walk any local BVH on this rank? (dprt_stats.rays_walked)
 bool has_local_work(const World& w, int rank, uint32_t visited, bool skipVisited) {
@@ -432,6 +511,24 @@ bool trace_local(const World& w, int rank, V3 o, V3 d, float tmin, float& tMax, 
         if (ob.mesh.trace(o, d, tmin, tMax, false, h)) { tMax = h.t; best = h; bestObj = i; any = true; }
     }
     return any;
+}
+
+void count_local(const World& w, Rank& r, int stage, V3 o, V3 d, float tmin, float tMax, uint32_t visited, bool skipVisited, bool any) {
+    if (!w.countBvh8) return;
+    Bvh8Count c{0, 0}; bool walkedAny = false;
+    for (int i = 0; i < (int)w.objects.size(); i++) {
+        const Object& ob = w.objects[i];
+        if (!ob.present || w.is_proxy(r.id, i) || ob.nodes8.empty()) continue;
+        if (skipVisited && ((visited >> ob.desc.nodeID) & 1u)) continue;
+        walkedAny = true;
+        Hit h;
+        const bool hit = bvh8_walk(ob.nodes8.data(), ob.tris8.data(), o, d, tmin, tMax, h, c, any);
+        if (hit) { if (any) break; tMax = h.t; }
+    }
+    if (!walkedAny) return;
+    __atomic_fetch_add(&r.cntNodes[stage], c.nodes, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&r.cntTris[stage], c.tris, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&r.cntRays[stage], (int64_t)1, __ATOMIC_RELAXED);
 }
 
 void path_gen(World& w, Rank& r) {
@@ -470,6 +567,7 @@ void traverse(World& w, Rank& r) {
         walked += has_local_work(w, r.id, p.visitedMask, true);
         const V3 o = v3(p.origin[0], p.origin[1], p.origin[2]), d = v3(p.direction[0], p.direction[1], p.direction[2]);
         Hit h; h.prim = -1; int hobj = -1; float tMax = p.tMax;
+        count_local(w, r, DPRT_STAGE_TRAVERSE, o, d, DPRT_EPSILON, p.tMax, p.visitedMask, true, false);
         if (trace_local(w, r.id, o, d, DPRT_EPSILON, tMax, p.visitedMask, true, h, hobj)) {
             p.tMax = tMax; p.isHit = 1; p.currentNode = r.id;
         }
@@ -490,7 +588,7 @@ void traverse(World& w, Rank& r) {
         if (!proxyHit && !p.isHit) { add_env(w, r, p); p.isValid = 0; }
         r.paths[i] = p;
     }
-    r.stats.rays_traverse += n; r.stats.rays_walked += walked;
+    r.stats.rays_traverse += n; r.stats.rays_walked += walked; r.stats.walked_traverse += walked;
 }
 
 // Work_Efficient_Scan: stable partition of valid paths by targetNode (bucket-major, index order inside)
@@ -577,6 +675,13 @@ void shade(World& w, Rank& r) {
         walked += has_local_work(w, r.id, 0u, false);     // the oracle always re-traces (kernel.cu:382-413)
         const V3 o = v3(path.origin[0], path.origin[1], path.origin[2]), d = v3(path.direction[0], path.direction[1], path.direction[2]);
         Hit h{}; int hobj = -1; float tMax = FLT_MAX;
+        {   // counted with the bound a walker may use without changing the result: "hit on this rank at tMax" -> next float up
+            float tc = FLT_MAX;
+            if (path.isHit && path.currentNode == r.id && path.tMax > 0.0f && path.tMax < FLT_MAX) {
+                uint32_t b; std::memcpy(&b, &path.tMax, 4); b += 1u; std::memcpy(&tc, &b, 4);
+            }
+            count_local(w, r, DPRT_STAGE_SHADE, o, d, DPRT_EPSILON, tc, 0u, false, false);
+        }
         const bool isHit = trace_local(w, r.id, o, d, DPRT_EPSILON, tMax, 0u, false, h, hobj);
         if (!r.hitPrim.empty()) r.hitPrim[i] = isHit ? h.prim : -1;
         if (!isHit) {
@@ -650,7 +755,7 @@ void shade(World& w, Rank& r) {
             slot = sh;
         }
     }
-    r.stats.rays_shade += n; r.stats.rays_walked += walked;
+    r.stats.rays_shade += n; r.stats.rays_walked += walked; r.stats.walked_shade += walked;
 }
 
 // proxy-AABB march shared by ShadowRay / SecondaryRay; returns -1 when nothing was in the way
@@ -730,6 +835,7 @@ void shadow_trace(World& w, Rank& r) {
         walked += has_local_work(w, r.id, 0u, false);
         const V3 o = v3(path.origin[0], path.origin[1], path.origin[2]), d = v3(path.direction[0], path.direction[1], path.direction[2]);
         bool occluded = false;
+        count_local(w, r, DPRT_STAGE_SHADOW_TRACE, o, d, DPRT_EPSILON, path.tMax, 0u, false, true);
         for (int k = 0; k < (int)w.objects.size() && !occluded; k++) {
             const Object& ob = w.objects[k];
             if (!ob.present || w.is_proxy(r.id, k)) continue;
@@ -748,7 +854,7 @@ void shadow_trace(World& w, Rank& r) {
             r.direct[px + 2] += path.throughput[2] / inv;
         }
     }
-    r.stats.rays_shadow += n; r.stats.rays_walked += walked;
+    r.stats.rays_shadow += n; r.stats.rays_walked += walked; r.stats.walked_shadow += walked;
 }
 
 void secondary_trace(World& w, Rank& r) {
@@ -763,13 +869,14 @@ void secondary_trace(World& w, Rank& r) {
         for (size_t k = 0; k < w.objects.size(); k++) if (w.objects[k].present) path.visitedMask |= (1u << w.objects[k].desc.nodeID);
         const V3 o = v3(path.origin[0], path.origin[1], path.origin[2]), d = v3(path.direction[0], path.direction[1], path.direction[2]);
         Hit h; int hobj = -1; float tMax = path.tMax;
+        count_local(w, r, DPRT_STAGE_SECONDARY_TRACE, o, d, DPRT_EPSILON, path.tMax, 0u, false, false);
         if (trace_local(w, r.id, o, d, DPRT_EPSILON, tMax, 0u, false, h, hobj)) { path.tMax = tMax; path.isHit = 1; path.currentNode = r.id; }
         if (!r.hitPrim.empty()) r.hitPrim[i] = hobj >= 0 ? h.prim : -1;
         const int res = proxy_march(w, r, path, i, path.tMax, true);
         if (res < 0 && !path.isHit) { add_env(w, r, path); path.isValid = 0; }
         r.paths[i] = path;
     }
-    r.stats.rays_secondary += n; r.stats.rays_walked += walked;
+    r.stats.rays_secondary += n; r.stats.rays_walked += walked; r.stats.walked_secondary += walked;
 }
 
 // Work_Efficient_Scan_For_NN(_HIT_INSIDE): stable bucket of queries by hitAABBID
@@ -923,70 +1030,6 @@ void render_sample(World& w, int sample) {
     }
 }
 
-// ---- scalar walker over the PRODUCT's BVH8 blob: per-ray node/triangle counters for the roofline ----
-struct Bvh8Count { int64_t nodes, tris; };
-bool bvh8_walk(const dprt_bvh8_node* nodes, const dprt_bvh8_tri* tris, V3 o, V3 d, float tmin, float tmax, Hit& hit, Bvh8Count& cnt) {
-    Shear rs = make_shear(d);
-    const float dxs = fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x);
-    const float dys = fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y);
-    const float dzs = fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z);
-    const float idir[3] = {1.0f / dxs, 1.0f / dys, 1.0f / dzs};
-    const bool negd[3] = {dxs < 0.f, dys < 0.f, dzs < 0.f};
-    const uint32_t octinv = 7u - ((negd[0] ? 1u : 0u) | (negd[1] ? 2u : 0u) | (negd[2] ? 4u : 0u));
-    const float oo[3] = {o.x, o.y, o.z};
-    float tbest = tmax; int bestPrim = 0x7fffffff; bool found = false; float ba = 0, bb = 0;
-    struct Grp { uint32_t base, bits; };
-    Grp stack[64]; int sp = 0;
-    Grp ng{0u, 0x80000000u};
-    uint32_t tmask = 0u;
-    for (;;) {
-        Grp tg{0u, 0u};
-        if (ng.bits & 0xff000000u) {
-            uint32_t bit = 31u - (uint32_t)__builtin_clz(ng.bits);
-            uint32_t slot = (bit - 24u) ^ octinv;
-            uint32_t rel = (uint32_t)__builtin_popcount(ng.bits & 0xffu & ((1u << slot) - 1u));
-            ng.bits &= ~(1u << bit);
-            const dprt_bvh8_node& n = nodes[ng.base + rel];
-            if (ng.bits & 0xff000000u) stack[sp++] = ng;
-            cnt.nodes++;
-            float adj[3], org[3];
-            for (int a = 0; a < 3; a++) {
-                uint32_t eb = (uint32_t)n.e[a] << 23; float sc; std::memcpy(&sc, &eb, 4);
-                adj[a] = sc * idir[a]; org[a] = (n.p[a] - oo[a]) * idir[a];
-            }
-            uint32_t hitmask = 0;
-            const uint8_t* qlo[3] = {n.qlox, n.qloy, n.qloz}; const uint8_t* qhi[3] = {n.qhix, n.qhiy, n.qhiz};
-            for (int c = 0; c < 8; c++) {
-                float tn = tmin, tf = tbest;
-                for (int a = 0; a < 3; a++) {
-                    const float lo = (float)(negd[a] ? qhi[a][c] : qlo[a][c]), hi = (float)(negd[a] ? qlo[a][c] : qhi[a][c]);
-                    tn = fmaxf(tn, fmaf(lo, adj[a], org[a])); tf = fminf(tf, fmaf(hi, adj[a], org[a]));
-                }
-                if (tn <= tf) {
-                    if ((n.imask >> c) & 1u) hitmask |= 1u << (24u + ((uint32_t)c ^ octinv));   // internal child: octant-ordered slot
-                    else hitmask |= (7u << (3 * c)) & n.tmask;                                  // leaf child: its (<= 3) triangles
-                }
-            }
-            ng = Grp{n.childBase, (hitmask & 0xff000000u) | n.imask};
-            tg = Grp{n.triBase, hitmask & 0x00ffffffu};
-            tmask = n.tmask;
-        }
-        while (tg.bits) {
-            uint32_t b = (uint32_t)__builtin_ctz(tg.bits); tg.bits &= tg.bits - 1u;
-            const uint32_t k = (uint32_t)__builtin_popcount(tmask & ((1u << b) - 1u));
-            const dprt_bvh8_tri& t = tris[tg.base + k];
-            cnt.tris++;
-            float tv[9] = {t.v0[0], t.v0[1], t.v0[2], t.v1[0], t.v1[1], t.v1[2], t.v2[0], t.v2[1], t.v2[2]};
-            float tt, al, be;
-            if (tri_hit(rs, o, tv, tmin, tmax, &tt, &al, &be))
-                if (tt < tbest || (tt == tbest && t.primID < bestPrim)) { tbest = tt; bestPrim = t.primID; ba = al; bb = be; found = true; }
-        }
-        if ((ng.bits & 0xff000000u) == 0u) { if (sp == 0) break; ng = stack[--sp]; }
-    }
-    hit.t = tbest; hit.prim = found ? bestPrim : -1; hit.alpha = ba; hit.beta = bb;
-    return found;
-}
-
 Rank* get_rank(World* w, int rank) { return (w && rank >= 0 && rank < w->W) ? &w->ranks[rank] : nullptr; }
 
 }  // namespace
@@ -1015,7 +1058,7 @@ void* orc_world_create(const dprt_config* cfg, int W) {
         r.paths.assign((1 + spc) * N, dprt_path_record{}); r.transfer.assign(N, dprt_path_record{});
         r.transferOffset.assign(64, 0); r.sceneOffset.assign(64, 0);
         r.direct.assign(spc * 3 * N, 0.f); r.env.assign(3 * N, 0.f);
-        r.contribution.assign(3 * N * spc, 0.f); r.occlusion.assign(N * mc * spc, 0.f);
+        r.contribution.assign(3 * N * spc, 0.f); r.occlusion.assign(N * mc * std::max<size_t>(spc, 2), 0.f);
         r.nnInput.assign(Q * 5, 0); r.nnPackedInput.assign(Q * 5, 0); r.pred.assign(Q * 4, 0);
         r.nnQuery.assign(Q, dprt_nn_query{}); r.nnPackedQuery.assign(Q, dprt_nn_query{});
     }
@@ -1042,6 +1085,23 @@ int orc_world_set_model(void* wp, int si, int kind, const void* blob, size_t byt
     Object& ob = w->objects[si];
     if (kind == 0) { ob.hasVis = ob.vis.load(blob, bytes); return ob.hasVis ? 0 : -1; }
     ob.hasDepth = ob.depth.load(blob, bytes); return ob.hasDepth ? 0 : -1;
+}
+// a copy of the product's BVH8 blob of scene object si (dprt_bvh8_copy): only the counting walker reads it
+int orc_world_set_bvh8(void* wp, int si, const dprt_bvh8_node* nodes, int64_t nnodes, const dprt_bvh8_tri* tris, int64_t ntris) {
+    World* w = (World*)wp;
+    if (!w || si < 0 || si >= (int)w->objects.size() || !nodes || !tris || nnodes < 1 || ntris < 0) return -1;
+    w->objects[si].nodes8.assign(nodes, nodes + nnodes); w->objects[si].tris8.assign(tris, tris + ntris);
+    return 0;
+}
+int orc_count_bvh8(void* wp, int enable) { World* w = (World*)wp; if (!w) return -1; w->countBvh8 = enable != 0; return 0; }
+// out: DPRT_STAGE_COUNT x {nodes, tris, rays} of rank `rank` since the last reset
+int orc_get_bvh8_counters(void* wp, int rank, int64_t* out, int reset) {
+    Rank* r = get_rank((World*)wp, rank); if (!r || !out) return -1;
+    for (int s = 0; s < DPRT_STAGE_COUNT; s++) {
+        out[3 * s] = r->cntNodes[s]; out[3 * s + 1] = r->cntTris[s]; out[3 * s + 2] = r->cntRays[s];
+        if (reset) r->cntNodes[s] = r->cntTris[s] = r->cntRays[s] = 0;
+    }
+    return 0;
 }
 int orc_world_set_materials(void* wp, const dprt_material* m, int n) { World* w = (World*)wp; w->materials.assign(m, m + n); return 0; }
 int orc_world_set_lights(void* wp, const dprt_light_tri* l, int n) { World* w = (World*)wp; w->lights.assign(l, l + n); return 0; }

@@ -50,6 +50,9 @@ def lib():
         L.orc_upload.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]
         L.orc_trace_closest.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
         L.orc_gen_train_data.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.orc_world_set_bvh8.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        L.orc_count_bvh8.argtypes = [C.c_void_p, C.c_int]
+        L.orc_get_bvh8_counters.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.orc_bvh8_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.orc_mlp_forward.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_tea4.restype = C.c_uint32
@@ -234,6 +237,20 @@ class World:
 
     def set_query_total(self, rank, n):
         self.L.orc_set_query_total(self.h, rank, int(n))
+
+    def set_bvh8(self, scene_index, nodes, tris):
+        """A copy of the PRODUCT's BVH8 blob (dprt.build_bvh8 / dprt_bvh8_copy): walked by the counting walker only."""
+        nodes = np.ascontiguousarray(nodes, D.NODE_DTYPE); tris = np.ascontiguousarray(tris, D.TRI_DTYPE)
+        assert self.L.orc_world_set_bvh8(self.h, scene_index, _p(nodes), nodes.size, _p(tris), tris.size) == 0
+
+    def count_bvh8(self, enable=True):
+        self.L.orc_count_bvh8(self.h, 1 if enable else 0)
+
+    def bvh8_counters(self, rank=0, reset=False):
+        """{stage: (nodes fetched, triangles tested, rays walked)} of the scalar exact-tbest walk over the product's BVH8."""
+        out = np.zeros(3 * D.STAGE_COUNT, np.int64)
+        assert self.L.orc_get_bvh8_counters(self.h, rank, _p(out), 1 if reset else 0) == 0
+        return {D.STAGE_NAMES[s]: (int(out[3 * s]), int(out[3 * s + 1]), int(out[3 * s + 2])) for s in range(D.STAGE_COUNT)}
 
     def stats(self, rank=0):
         s = D.Stats()

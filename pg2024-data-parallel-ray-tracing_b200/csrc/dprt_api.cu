@@ -11,6 +11,7 @@
 #include <nccl.h>   // types only: the library is bound at run time (see NcclApi)
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -25,6 +26,8 @@
 using namespace dprt;
 
 struct dprt_bvh8 { Bvh8 b; };
+
+constexpr int kDevStats = 2 + DPRT_STAGE_COUNT;     // words of dprt_ctx::d_cacheHits
 
 namespace {
 
@@ -96,7 +99,7 @@ struct dprt_ctx {
     uint8_t* d_nnKey = nullptr;         // one key byte per NN query slot
     HitRec* d_hits = nullptr;           // N closest-hit records (MainRay)
     HitRec* d_hitCache = nullptr;       // N per-pixel closest hits of the current epoch (null when cfg.mainRayRetrace)
-    unsigned long long* d_cacheHits = nullptr;   // [0] MainRay queries answered from the cache, [1] rays that walked a BVH (since reset_stats)
+    unsigned long long* d_cacheHits = nullptr;   // kDevStats words: [0] MainRay queries answered from the cache, [1] rays that walked a BVH, [2 + stage] per stage (since reset_stats)
     // "reset by count" of the shadow planes of directLightingBuffer: MainRay records which pixels get shadow paths
     // (two lists, ping-pong: one describes the planes that are dirty now, the other is free for the next MainRay)
     int32_t* d_live[2] = {nullptr, nullptr};
@@ -107,14 +110,16 @@ struct dprt_ctx {
     dprt_path_record* d_settled = nullptr;   // 2N records; the block [front, back) grows at both ends from the middle
     int front = 0, back = 0;
     int nL = 0;                         // active records [0, nL) came from lower ranks, [nL, pathSize) from higher ones
-    // EXPERIMENTAL peer-memory exchange (DPRT_P2P=1; p2p_exchange.cuh)
+    // peer-memory exchange (p2p_exchange.cuh; DPRT_P2P=0 forces the NCCL fallback)
     bool p2p = false;                   // tables connected: the deque exchange runs over peer memory
+    bool p2pGroup = false;              // connected as an in-process group (dprt_*_group only)
+    bool ownsComm = true;               // false: communicator borrowed from the parent context (dprt_create_shared)
     P2PMailbox* d_mailbox = nullptr;
     dprt_path_record* d_active[2] = {nullptr, nullptr};    // arrivals land here (never in `paths`)
     P2PPeers* d_peers = nullptr;
     P2PPlan* d_plan = nullptr;
-    P2PPlan* h_plan = nullptr;          // mapped pinned copy the host polls
-    P2PPlan* d_hplan = nullptr;         // device address of h_plan
+    P2PHostPlan* h_plan = nullptr;      // mapped pinned memory the host polls
+    P2PHostPlan* d_hplan = nullptr;     // device address of h_plan
     uint32_t p2pSeq = 0;                // one per migrate iteration, never reset
     std::vector<void*> ipcOpened;       // peer mappings to close
     int32_t* d_secLive = nullptr;       // pixels whose tMax scratch the last Target_Node_Update used
@@ -177,7 +182,7 @@ namespace {
 
 int fail(dprt_ctx* ctx, int code, const std::string& msg) { ctx->err = msg; return code; }
 
-// experimental peer-memory exchange, defined further down (inside the extern "C" part of this file)
+// peer-memory exchange, defined further down (inside the extern "C" part of this file)
 extern "C" {
 bool p2p_requested();
 int p2p_connect_nccl(dprt_ctx* ctx);
@@ -300,12 +305,12 @@ int dprt_get_unique_id(void* out128) {
 
 const char* dprt_last_error(const dprt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-int dprt_create(const dprt_config* cfg, int rank, int world, int device, const void* nccl_unique_id, dprt_ctx** out) {
+static int create_impl(const dprt_config* cfg, int rank, int world, int device, const void* nccl_unique_id, dprt_ctx* parent, dprt_ctx** out) {
     if (!cfg || !out) { g_create_error = "null argument"; return DPRT_ERR_INVALID; }
     *out = nullptr;
     if (world < 1 || world > DPRT_MAX_WORLD || rank < 0 || rank >= world || cfg->width <= 0 || cfg->height <= 0 ||
         cfg->sceneSize < 1 || cfg->sceneSize > 32 || cfg->shadowPathCount < 1 || cfg->maxCount < 1 || cfg->maxCount > 8 ||
-        cfg->shadowPathCount > 16) {
+        cfg->shadowPathCount > 16 || cfg->spp < 1 || cfg->bounces < 0 || (int64_t)cfg->width * cfg->height > (int64_t)0x7fffffff / 64) {
         g_create_error = "invalid configuration"; return DPRT_ERR_INVALID;
     }
     int ndev = 0;
@@ -336,7 +341,9 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
         if ((r = alloc_buf(ctx, DPRT_BUF_DIRECT, spc * 3 * N * sizeof(float)))) return r;
         if ((r = alloc_buf(ctx, DPRT_BUF_ENV, 3 * N * sizeof(float)))) return r;
         if ((r = alloc_buf(ctx, DPRT_BUF_SCENE_OFFSET, 64 * sizeof(int32_t)))) return r;
-        if ((r = alloc_buf(ctx, DPRT_BUF_OCCLUSION, N * mc * spc * sizeof(float)))) return r;
+        // N*mc*spc floats (renderer.cpp:709-711); Target_Node_Update reuses the buffer as a [pixel][mc][2] scratch
+        // (frame_buffer_update.cu:239-248 -- the reference hard-codes spc = 4), so never fewer than 2 floats per (pixel, mc)
+        if ((r = alloc_buf(ctx, DPRT_BUF_OCCLUSION, N * mc * std::max<size_t>(spc, 2) * sizeof(float)))) return r;
         if ((r = alloc_buf(ctx, DPRT_BUF_CONTRIBUTION, 3 * N * spc * sizeof(float)))) return r;
         const size_t Q = cfg->proxyMode ? N * mc * spc : 1;
         if ((r = alloc_buf(ctx, DPRT_BUF_NN_INPUT, Q * 5 * sizeof(dprt_half)))) return r;
@@ -356,8 +363,8 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
             CK(cudaMalloc(&ctx->d_hitCache, N * sizeof(HitRec)));
             CK(cudaMemsetAsync(ctx->d_hitCache, 0, N * sizeof(HitRec), ctx->stream));      // epoch 0 = never written
         }
-        CK(cudaMalloc(&ctx->d_cacheHits, 2 * sizeof(unsigned long long)));
-        CK(cudaMemsetAsync(ctx->d_cacheHits, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        CK(cudaMalloc(&ctx->d_cacheHits, kDevStats * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(ctx->d_cacheHits, 0, kDevStats * sizeof(unsigned long long), ctx->stream));
         CK(cudaMalloc(&ctx->d_queue, trace_scratch_bytes()));
         if (!cfg->serialStages && !cfg->proxyMode) {
             int lo = 0, hi = 0;
@@ -396,12 +403,15 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
         ctx->h_offsets.assign(world + 1, 0);
         for (int i = 0; i < cfg->sceneSize; i++) { ctx->objects[i].desc.nodeID = 0; ctx->objects[i].desc.isProxy = 1; }
         if ((r = upload_objects(ctx))) return r;
-        if (nccl_unique_id && world > 1) {
+        if (parent && parent->comm && world > 1) {
+            ctx->comm = parent->comm; ctx->ownsComm = false;              // collectives of the two contexts must not interleave
+        } else if (nccl_unique_id && world > 1) {
             ncclUniqueId id; std::memcpy(&id, nccl_unique_id, 128);
             if (!g_nccl.load()) { ctx->err = g_nccl.error; return DPRT_ERR_NCCL; }
             NK(g_nccl.CommInitRank(&ctx->comm, world, id, rank));
-            if (p2p_requested()) { int pr = p2p_connect_nccl(ctx); if (pr) return pr; }
         }
+        // peer-memory exchange: a collective decision over the communicator (all ranks or none, p2p_connect_nccl)
+        if (ctx->comm) { int pr = p2p_connect_nccl(ctx); if (pr) return pr; }
         CK(cudaStreamSynchronize(ctx->stream));
         return 0;
     };
@@ -411,11 +421,20 @@ int dprt_create(const dprt_config* cfg, int rank, int world, int device, const v
     return 0;
 }
 
+int dprt_create(const dprt_config* cfg, int rank, int world, int device, const void* nccl_unique_id, dprt_ctx** out) {
+    return create_impl(cfg, rank, world, device, nccl_unique_id, nullptr, out);
+}
+
+int dprt_create_shared(const dprt_config* cfg, dprt_ctx* parent, dprt_ctx** out) {
+    if (!parent) { g_create_error = "null parent"; return DPRT_ERR_INVALID; }
+    return create_impl(cfg, parent->rank, parent->world, parent->device, nullptr, parent, out);
+}
+
 void dprt_destroy(dprt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
+    if (ctx->comm && ctx->ownsComm) g_nccl.CommDestroy(ctx->comm);
     for (auto& o : ctx->objects) {
         if (o.d_nodes) cudaFree(o.d_nodes);
         if (o.d_tris) cudaFree(o.d_tris);
@@ -470,10 +489,12 @@ int dprt_get_stats(const dprt_ctx* ctx, dprt_stats* out) {
     if (!ctx || !out) return DPRT_ERR_INVALID;
     *out = ctx->stats;
     if (ctx->d_cacheHits) {            // the one statistic that is only known on the device
-        unsigned long long v[2] = {0, 0};
+        unsigned long long v[kDevStats] = {0};
         if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
             cudaMemcpy(v, ctx->d_cacheHits, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return DPRT_ERR_CUDA;
         out->rays_shade_cached = (int64_t)v[0]; out->rays_walked = (int64_t)v[1];
+        out->walked_traverse = (int64_t)v[2 + DPRT_STAGE_TRAVERSE]; out->walked_shade = (int64_t)v[2 + DPRT_STAGE_SHADE];
+        out->walked_shadow = (int64_t)v[2 + DPRT_STAGE_SHADOW_TRACE]; out->walked_secondary = (int64_t)v[2 + DPRT_STAGE_SECONDARY_TRACE];
     }
     return 0;
 }
@@ -484,7 +505,7 @@ int dprt_reset_stats(dprt_ctx* ctx) {
     resolve_pending(ctx);
     for (int i = 0; i < DPRT_STAGE_COUNT; i++) { ctx->stageMs[i] = 0.0; ctx->stageLaunches[i] = 0; }
     if (ctx->d_counters) CK(cudaMemsetAsync(ctx->d_counters, 0, 2 * DPRT_STAGE_COUNT * sizeof(unsigned long long), ctx->stream));
-    if (ctx->d_cacheHits) CK(cudaMemsetAsync(ctx->d_cacheHits, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (ctx->d_cacheHits) CK(cudaMemsetAsync(ctx->d_cacheHits, 0, kDevStats * sizeof(unsigned long long), ctx->stream));
     return 0;
 }
 
@@ -714,7 +735,7 @@ int dprt_exchange(dprt_ctx* ctx, int* done) {
         int r = read_offsets(ctx); if (r) return r;
         const int cnt = ctx->h_offsets[1];
         if (cnt > 0) CK(cudaMemcpyAsync(ctx->hp.paths, ctx->hp.transfer, cnt * R, cudaMemcpyDeviceToDevice, ctx->stream));
-        ctx->pathSize = cnt;
+        ctx->pathSize = cnt; ctx->stats.paths_partitioned += cnt;
         if (done) *done = 1;
         ctx->stats.exchange_iters++;
         return 0;
@@ -726,6 +747,7 @@ int dprt_exchange(dprt_ctx* ctx, int* done) {
     CK(cudaStreamSynchronize(ctx->stream));
     const int32_t* M = ctx->h_pinned;     // M[s*(W+1)+d] = offset of rank s's segment for destination d
     ctx->h_offsets.assign(M + me * (W + 1), M + (me + 1) * (W + 1));
+    ctx->stats.paths_partitioned += ctx->h_offsets[W];
     std::vector<int32_t> sendCnt(W), recvOff(W + 1, 0), recvCnt(W);
     int64_t recvTotal64 = 0; int allLocal = 0;
     if (dprt_plan_exchange(M, W, me, sendCnt.data(), recvOff.data(), recvCnt.data(), &recvTotal64, &allLocal))
@@ -763,6 +785,7 @@ int dprt_exchange_group(dprt_ctx** ctxs, int W, int* done) {
         dprt_ctx* ctx = ctxs[s];
         CK(cudaSetDevice(ctx->device));
         int r = read_offsets(ctx); if (r) return r;
+        ctx->stats.paths_partitioned += ctx->h_offsets[W];
     }
     long offdiag = 0;
     for (int d = 0; d < W; d++) {
@@ -1056,6 +1079,7 @@ int deque_exchange(dprt_ctx* ctx, int* done) {
     if (p.newActive > ctx->N) return fail(ctx, DPRT_ERR_CAPACITY, "received more paths than the frame holds");
     if (ctx->auxPending && p.newActive > ctx->auxGuardBase) { int jr = join_aux(ctx); if (jr) return jr; }
     const int32_t* row = ctx->h_pinned + (size_t)me * (W + 2);
+    ctx->stats.paths_partitioned += row[W + 1];
     NK(g_nccl.GroupStart());
     int roff = 0;
     for (int peer = 0; peer < W; peer++) {
@@ -1083,6 +1107,7 @@ int deque_exchange_group(dprt_ctx** ctxs, int W, int* done) {
         CK(cudaMemcpyAsync(ctx->h_pinned, ctx->hp.transferOffset, (W + 2) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         std::copy(ctx->h_pinned, ctx->h_pinned + W + 2, rows.begin() + (size_t)s * (W + 2));
+        ctx->stats.paths_partitioned += ctx->h_pinned[W + 1];
     }
     bool allLocal = true;
     for (int d = 0; d < W; d++) {
@@ -1146,21 +1171,31 @@ int dprt_plan_exchange_deque(const int32_t* rows, int W, int me, int32_t* send_c
     return 0;
 }
 
-// ---- EXPERIMENTAL: the deque exchange over peer memory (DPRT_P2P=1; p2p_exchange.cuh) -------------
+// ---- the deque exchange over peer memory (p2p_exchange.cuh) ------------------------------------------
 namespace {
 
-bool p2p_requested() { const char* v = getenv("DPRT_P2P"); return v && v[0] == '1'; }
+bool p2p_requested() { const char* v = getenv("DPRT_P2P"); return !(v && v[0] == '0'); }     // default on; DPRT_P2P=0 forces NCCL
+
+unsigned long long p2p_timeout_ns() {
+    static unsigned long long v = [] { const char* e = getenv("DPRT_P2P_TIMEOUT_MS"); long ms = e ? atol(e) : 20000; return (unsigned long long)(ms < 1 ? 1 : ms) * 1000000ull; }();
+    return v;
+}
 
 int p2p_alloc(dprt_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
+    if (ctx->d_mailbox) return 0;
     CK(cudaMalloc(&ctx->d_mailbox, sizeof(P2PMailbox)));
     CK(cudaMemset(ctx->d_mailbox, 0, sizeof(P2PMailbox)));
     for (int k = 0; k < 2; k++) CK(cudaMalloc(&ctx->d_active[k], (size_t)ctx->N * sizeof(dprt_path_record)));
     CK(cudaMalloc(&ctx->d_peers, sizeof(P2PPeers)));
     CK(cudaMalloc(&ctx->d_plan, sizeof(P2PPlan)));
-    CK(cudaHostAlloc(&ctx->h_plan, sizeof(P2PPlan), cudaHostAllocMapped));
-    std::memset(ctx->h_plan, 0, sizeof(P2PPlan));
+    CK(cudaMemset(ctx->d_plan, 0, sizeof(P2PPlan)));
+    CK(cudaHostAlloc(&ctx->h_plan, sizeof(P2PHostPlan), cudaHostAllocMapped));
+    std::memset(ctx->h_plan, 0, sizeof(P2PHostPlan));
     CK(cudaHostGetDevicePointer((void**)&ctx->d_hplan, ctx->h_plan, 0));
+    // every kernel of the migrate loop is loaded NOW: with lazy module loading a first launch may synchronise the context,
+    // which deadlocks when it happens beside another rank's waiting kernel (one thread driving several ranks)
+    CK(p2p_preload_kernels()); CK(partition_preload_kernels()); CK(trace_preload_kernels());
     return 0;
 }
 
@@ -1176,36 +1211,61 @@ void p2p_free(dprt_ctx* ctx) {
     ctx->p2p = false;
 }
 
-// one process per GPU: cudaIpc handles of the mailbox and the two active buffers, all-gathered over the communicator
-int p2p_connect_nccl(dprt_ctx* ctx) {
+struct P2PHandles { cudaIpcMemHandle_t h[3]; int32_t ok; int32_t pad_[3]; };     // mailbox, active[0], active[1]
+static_assert(sizeof(P2PHandles) == DPRT_P2P_HANDLE_BYTES, "dprt_p2p_export size");
+
+bool p2p_eligible(const dprt_ctx* ctx) { return ctx->d_settled && ctx->world > 1 && ctx->world <= kP2PMaxWorld; }
+
+// my three IPC handles (ok = 0 when this rank cannot take part: the peers then fall back together)
+int p2p_export(dprt_ctx* ctx, P2PHandles* out) {
+    std::memset(out, 0, sizeof(*out));
+    if (!p2p_eligible(ctx) || !p2p_requested()) return 0;
+    if (p2p_alloc(ctx)) return 0;
+    if (cudaIpcGetMemHandle(&out->h[0], ctx->d_mailbox) != cudaSuccess || cudaIpcGetMemHandle(&out->h[1], ctx->d_active[0]) != cudaSuccess ||
+        cudaIpcGetMemHandle(&out->h[2], ctx->d_active[1]) != cudaSuccess) { cudaGetLastError(); return 0; }
+    out->ok = 1;
+    return 0;
+}
+
+// opens every peer's handles; returns 1 when this rank now holds a complete pointer table (not yet enabled)
+int p2p_open(dprt_ctx* ctx, const P2PHandles* all) {
     const int W = ctx->world, me = ctx->rank;
-    if (!ctx->comm || !ctx->d_settled || W > kP2PMaxWorld) return 0;
-    int r = p2p_alloc(ctx); if (r) return r;
-    struct Handles { cudaIpcMemHandle_t h[3]; };
-    Handles mine;
-    CK(cudaIpcGetMemHandle(&mine.h[0], ctx->d_mailbox));
-    CK(cudaIpcGetMemHandle(&mine.h[1], ctx->d_active[0]));
-    CK(cudaIpcGetMemHandle(&mine.h[2], ctx->d_active[1]));
-    Handles* d_all = nullptr;
-    CK(cudaMalloc(&d_all, sizeof(Handles) * (size_t)(W + 1)));
-    CK(cudaMemcpyAsync(d_all + W, &mine, sizeof(Handles), cudaMemcpyHostToDevice, ctx->stream));
-    NK(g_nccl.AllGather(d_all + W, d_all, sizeof(Handles), ncclUint8, ctx->comm, ctx->stream));
-    std::vector<Handles> all(W);
-    CK(cudaMemcpyAsync(all.data(), d_all, sizeof(Handles) * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaFree(d_all));
+    for (int s = 0; s < W; s++) if (!all[s].ok) return 0;
     P2PPeers tbl; std::memset(&tbl, 0, sizeof(tbl));
     for (int s = 0; s < W; s++) {
         void* ptr[3] = {ctx->d_mailbox, ctx->d_active[0], ctx->d_active[1]};
         if (s != me)
             for (int k = 0; k < 3; k++) {
-                CK(cudaIpcOpenMemHandle(&ptr[k], all[s].h[k], cudaIpcMemLazyEnablePeerAccess));
+                if (cudaIpcOpenMemHandle(&ptr[k], all[s].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return 0; }
                 ctx->ipcOpened.push_back(ptr[k]);
             }
         tbl.mailbox[s] = (P2PMailbox*)ptr[0]; tbl.active[s][0] = (dprt_path_record*)ptr[1]; tbl.active[s][1] = (dprt_path_record*)ptr[2];
     }
-    CK(cudaMemcpy(ctx->d_peers, &tbl, sizeof(tbl), cudaMemcpyHostToDevice));
-    ctx->p2p = true;
+    if (cudaMemcpy(ctx->d_peers, &tbl, sizeof(tbl), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return 1;
+}
+
+// one process per GPU: handles all-gathered over the communicator, then a second all-gather agrees on "every rank opened
+// every handle" -- either all ranks use peer memory or all use the NCCL exchange (a split decision would deadlock)
+int p2p_connect_nccl(dprt_ctx* ctx) {
+    const int W = ctx->world;
+    if (!ctx->comm || W > kP2PMaxWorld) return 0;
+    P2PHandles mine;
+    p2p_export(ctx, &mine);
+    char* d_all = nullptr;
+    CK(cudaMalloc(&d_all, sizeof(P2PHandles) * (size_t)(W + 1)));
+    std::vector<P2PHandles> all(W);
+    for (int round = 0; round < 2; round++) {
+        CK(cudaMemcpyAsync(d_all + sizeof(P2PHandles) * W, &mine, sizeof(P2PHandles), cudaMemcpyHostToDevice, ctx->stream));
+        NK(g_nccl.AllGather(d_all + sizeof(P2PHandles) * W, d_all, sizeof(P2PHandles), ncclUint8, ctx->comm, ctx->stream));
+        CK(cudaMemcpyAsync(all.data(), d_all, sizeof(P2PHandles) * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (round == 0) mine.ok = p2p_open(ctx, all.data());         // second round carries "opened everything"
+    }
+    CK(cudaFree(d_all));
+    bool ok = true;
+    for (int s = 0; s < W; s++) ok = ok && all[s].ok;
+    if (ok) ctx->p2p = true; else p2p_free(ctx);
     return 0;
 }
 
@@ -1214,7 +1274,7 @@ int p2p_connect_group(dprt_ctx** ctxs, int W) {
     if (W > kP2PMaxWorld) return 0;
     for (int k = 0; k < W; k++) {
         if (!ctxs[k]->d_settled) return 0;
-        if (!ctxs[k]->d_mailbox) { int r = p2p_alloc(ctxs[k]); if (r) return r; }
+        int r = p2p_alloc(ctxs[k]); if (r) return r;
     }
     for (int k = 0; k < W; k++) {
         dprt_ctx* ctx = ctxs[k];
@@ -1229,47 +1289,66 @@ int p2p_connect_group(dprt_ctx** ctxs, int W) {
             tbl.mailbox[s] = ctxs[s]->d_mailbox; tbl.active[s][0] = ctxs[s]->d_active[0]; tbl.active[s][1] = ctxs[s]->d_active[1];
         }
         CK(cudaMemcpy(ctx->d_peers, &tbl, sizeof(tbl), cudaMemcpyHostToDevice));
-        ctx->p2p = true;
+        ctx->p2p = true; ctx->p2pGroup = true;
     }
     return 0;
 }
 
-// after deque_partition: counts -> scatter -> barrier, all on the rank's stream; nothing here waits on the host
+// after deque_traverse: counts -> partition (scattering straight into the owners' buffers) -> barrier, all on the rank's
+// stream; nothing here waits on the host
 int p2p_exchange_enqueue(dprt_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     const int W = ctx->world, me = ctx->rank;
     const uint32_t seq = ++ctx->p2pSeq;
     const int parity = (int)((seq - 1u) & 1u);
-    StageScope sc_(ctx, DPRT_STAGE_EXCHANGE);
-    launch_p2p_counts(ctx->d_peers, ctx->d_mailbox, ctx->hp.transferOffset, W, me, parity, seq, ctx->d_plan, ctx->d_hplan, ctx->stream);
-    launch_p2p_scatter(ctx->d_peers, ctx->hp.transfer, ctx->d_plan, W, me, parity, ctx->pathSize, ctx->stream);
-    launch_p2p_barrier(ctx->d_peers, ctx->d_mailbox, W, me, parity, seq, ctx->stream);
-    ctx->stats.kernel_launches += 3;
+    {
+        StageScope sc_(ctx, DPRT_STAGE_EXCHANGE);
+        P2PCountsArgs a;
+        a.peers = ctx->d_peers; a.mine = ctx->d_mailbox; a.hist = ctx->hp.pathHist; a.W = W; a.me = me; a.parity = parity; a.seq = seq;
+        a.settled = ctx->d_settled; a.front = ctx->front; a.back = ctx->back; a.capacity = ctx->N;
+        a.plan = ctx->d_plan; a.hostPlan = ctx->d_hplan; a.timeoutNs = p2p_timeout_ns();
+        launch_p2p_counts(a, ctx->stream);
+    }
+    {
+        StageScope sc_(ctx, DPRT_STAGE_PARTITION, ctx->pathSize > 0);
+        launch_partition_paths_peer(ctx->hp.paths, ctx->pathSize, W, me, ctx->nL, ctx->d_plan, ctx->scratch, ctx->stream);
+    }
+    {
+        StageScope sc_(ctx, DPRT_STAGE_EXCHANGE);
+        launch_p2p_barrier(ctx->d_peers, ctx->d_mailbox, ctx->d_plan, ctx->d_hplan, W, me, parity, seq, p2p_timeout_ns(), ctx->stream);
+    }
+    ctx->stats.kernel_launches += 2 + (ctx->pathSize > 0);
+    ctx->histFresh = false;
     CK(cudaGetLastError());
     return 0;
 }
 
-// the host learns the plan from the mapped copy the counts kernel wrote (while scatter and barrier are still running),
-// then absorbs the two self pieces and switches to the buffer the arrivals are landing in
+// the host learns the plan from the mapped copy the counts kernel wrote (while partition and barrier are still running),
+// extends the settled block by the two self pieces and switches to the buffer the arrivals are landing in
 int p2p_exchange_finish(dprt_ctx* ctx, int* done) {
     CK(cudaSetDevice(ctx->device));
     const uint32_t seq = ctx->p2pSeq;
     const int parity = (int)((seq - 1u) & 1u);
-    const volatile P2PPlan* hp = ctx->h_plan;
+    volatile P2PHostPlan* hp = ctx->h_plan;
     for (long spins = 0; hp->seq != seq; spins++) {
-        if ((spins & 0x3fff) == 0x3fff) {
+        if ((spins & 0xfff) == 0xfff) {
             cudaError_t e = cudaStreamQuery(ctx->stream);
             if (e != cudaSuccess && e != cudaErrorNotReady) return fail(ctx, DPRT_ERR_CUDA, std::string("peer-memory exchange: ") + cudaGetErrorString(e));
             if (e == cudaSuccess && hp->seq != seq) return fail(ctx, DPRT_ERR_STATE, "peer-memory exchange: the stream drained without a plan");
         }
     }
-    P2PPlan plan;
+    std::atomic_thread_fence(std::memory_order_acquire);
+    P2PHostPlan plan;
     std::memcpy(&plan, (const void*)ctx->h_plan, sizeof(plan));
-    if (plan.newActive > ctx->N) return fail(ctx, DPRT_ERR_CAPACITY, "received more paths than the frame holds");
-    const size_t R = sizeof(dprt_path_record);
-    for (int d = 0; d < ctx->world; d++) { ctx->stats.paths_sent_offrank += plan.sendCnt[d]; ctx->stats.bytes_alltoall += (int64_t)plan.sendCnt[d] * R; }
-    DequePlan dp; dp.cL = plan.cL; dp.cR = plan.cR; dp.offL = plan.offL; dp.offR = plan.offR;
-    int r = deque_absorb(ctx, dp); if (r) return r;
+    if (plan.error) {
+        hp->abort = 1u;
+        static const char* what[] = {"", "a peer did not arrive in time", "aborted by a peer", "more paths than a receive buffer or the settled block holds", "inconsistent histogram rows"};
+        return fail(ctx, plan.error == P2P_ERR_CAPACITY ? DPRT_ERR_CAPACITY : DPRT_ERR_STATE,
+                    std::string("peer-memory exchange: ") + what[plan.error >= 0 && plan.error <= 4 ? plan.error : 0]);
+    }
+    ctx->stats.paths_sent_offrank += plan.sent; ctx->stats.bytes_alltoall += (int64_t)plan.sent * (int64_t)sizeof(dprt_path_record);
+    ctx->stats.paths_partitioned += plan.total;
+    ctx->front -= plan.cL; ctx->back += plan.cR;
     ctx->pathSize = plan.newActive; ctx->nL = plan.newNL;
     ctx->hp.paths = ctx->d_active[parity ^ 1];             // restored by deque_finish
     if (done) *done = plan.allLocal;
@@ -1279,6 +1358,31 @@ int p2p_exchange_finish(dprt_ctx* ctx, int* done) {
 
 }  // namespace
 
+// Peer-memory wiring for hosts that bring their own bootstrap (no NCCL communicator in the context): every rank exports
+// DPRT_P2P_HANDLE_BYTES, the host all-gathers them by whatever means it has (MPI, a socket, torch.distributed), every rank
+// connects. Collective: call on all ranks or on none. *enabled = 0 when any rank could not take part (the context then
+// needs an NCCL communicator for dprt_primary_ray_module).
+int dprt_p2p_export(dprt_ctx* ctx, void* handle_out) {
+    if (!ctx || !handle_out) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    return p2p_export(ctx, (P2PHandles*)handle_out);
+}
+int dprt_p2p_connect(dprt_ctx* ctx, const void* all_handles, int* enabled) {
+    if (!ctx || !all_handles) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int ok = ctx->d_mailbox ? p2p_open(ctx, (const P2PHandles*)all_handles) : 0;
+    if (enabled) *enabled = ok;
+    return 0;
+}
+// second half: the host has agreed (all-reduce of *enabled) on whether every rank connected
+int dprt_p2p_enable(dprt_ctx* ctx, int enable) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (enable && ctx->d_mailbox) ctx->p2p = true; else p2p_free(ctx);
+    return 0;
+}
+int dprt_p2p_enabled(const dprt_ctx* ctx) { return ctx && ctx->p2p ? 1 : 0; }
+
 // ---- composite modules ---------------------------------------------------------------------------
 int dprt_primary_ray_module(dprt_ctx* ctx) {
     if (!ctx) return DPRT_ERR_INVALID;
@@ -1287,9 +1391,8 @@ int dprt_primary_ray_module(dprt_ctx* ctx) {
         for (;;) {
             int done = 0;
             if ((r = deque_traverse(ctx))) return r;
-            if ((r = deque_partition(ctx))) return r;
-            if (ctx->p2p) { if ((r = p2p_exchange_enqueue(ctx))) return r; r = p2p_exchange_finish(ctx, &done); }
-            else r = deque_exchange(ctx, &done);
+            if (ctx->p2p && !ctx->p2pGroup) { if ((r = p2p_exchange_enqueue(ctx))) return r; r = p2p_exchange_finish(ctx, &done); }
+            else { if ((r = deque_partition(ctx))) return r; r = deque_exchange(ctx, &done); }
             if (r) return r;
             if (done) break;
         }
@@ -1390,11 +1493,13 @@ int dprt_render_sample_group(dprt_ctx** ctxs, int W, int sample) {
     const int bounces = ctxs[0]->cfg.bounces;
     bool deque = true;
     for (int k = 0; k < W; k++) deque = deque && ctxs[k] && deque_enabled(ctxs[k]) && ctxs[k]->world == W && ctxs[k]->rank == k;
-    // one thread driving W ranks on shared devices: the spinning kernels of all ranks must be able to run side by side, which
-    // needs a hardware queue per stream (8 by default); keep the experiment to small groups
-    bool p2p = deque && W > 1 && W <= 4 && p2p_requested();
-    if (p2p && !ctxs[0]->p2p) { if ((r = p2p_connect_group(ctxs, W))) return r; }
-    for (int k = 0; k < W; k++) p2p = p2p && ctxs[k]->p2p;
+    // one thread driving W ranks on shared devices: the waiting kernels of all ranks must be able to run side by side, which
+    // needs a hardware queue per stream (8 by default, CUDA_DEVICE_MAX_CONNECTIONS); small groups only, opt-in (the
+    // group's default exchange is plain peer copies driven by the host)
+    const char* pg = getenv("DPRT_P2P_GROUP");
+    bool p2p = deque && W > 1 && W <= 8 && pg && pg[0] == '1';
+    if (p2p && !ctxs[0]->p2pGroup) { if ((r = p2p_connect_group(ctxs, W))) return r; }
+    for (int k = 0; k < W; k++) p2p = p2p && ctxs[k]->p2p && ctxs[k]->p2pGroup;
     for (int bounce = 0; bounce <= bounces; bounce++) {
         for (int k = 0; k < W; k++) if ((r = bounce_pre(ctxs[k], bounce))) return r;
         if (deque) for (int k = 0; k < W; k++) deque_begin(ctxs[k]);
@@ -1402,7 +1507,7 @@ int dprt_render_sample_group(dprt_ctx** ctxs, int W, int sample) {
             int done = 0;
             for (int k = 0; k < W; k++) {
                 if ((r = deque ? deque_traverse(ctxs[k]) : dprt_traverse(ctxs[k]))) return r;
-                if ((r = deque ? deque_partition(ctxs[k]) : dprt_partition(ctxs[k]))) return r;
+                if (!p2p && (r = deque ? deque_partition(ctxs[k]) : dprt_partition(ctxs[k]))) return r;
             }
             if (p2p) {
                 for (int k = 0; k < W; k++) if ((r = p2p_exchange_enqueue(ctxs[k]))) return r;      // every rank's kernels are in flight ...
@@ -1420,16 +1525,17 @@ int dprt_reduce_image(dprt_ctx* ctx, int root, float* out_host) {
     if (!ctx) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     const int n3 = ctx->N * 3;
-    StageScope* sc_ = new StageScope(ctx, DPRT_STAGE_IMAGE);
-    launch_image_average(ctx->hp.direct, ctx->hp.env, ctx->d_image, n3, (float)ctx->cfg.spp, ctx->stream);
-    ctx->stats.kernel_launches += 1;
     const float* src = ctx->d_image;
-    if (ctx->world > 1) {
-        if (!ctx->comm) return fail(ctx, DPRT_ERR_STATE, "dprt_reduce_image on a multi-rank context without an NCCL communicator");
-        NK(g_nccl.Reduce(ctx->d_image, ctx->d_image_sum, n3, ncclFloat32, ncclSum, root, ctx->comm, ctx->stream));
-        src = ctx->d_image_sum;
+    {
+        StageScope sc_(ctx, DPRT_STAGE_IMAGE);
+        launch_image_average(ctx->hp.direct, ctx->hp.env, ctx->d_image, n3, (float)ctx->cfg.spp, ctx->stream);
+        ctx->stats.kernel_launches += 1;
+        if (ctx->world > 1) {
+            if (!ctx->comm) return fail(ctx, DPRT_ERR_STATE, "dprt_reduce_image on a multi-rank context without an NCCL communicator");
+            NK(g_nccl.Reduce(ctx->d_image, ctx->d_image_sum, n3, ncclFloat32, ncclSum, root, ctx->comm, ctx->stream));
+            src = ctx->d_image_sum;
+        }
     }
-    delete sc_;
     if (ctx->rank == root && out_host)
         CK(cudaMemcpyAsync(out_host, src, sizeof(float) * n3, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1504,8 +1610,12 @@ int dprt_enable_hit_prim(dprt_ctx* ctx, int enable) {
 }
 
 // ---- standalone operators ----------------------------------------------------------------------------
+// the ray queue head of the persistent trace kernel is a 32-bit counter that every resident warp may bump by 32 past n
+static const int64_t kMaxTraceRays = (int64_t)0x7fffffff - (int64_t)(1 << 20);
+
 int dprt_trace_closest_device(dprt_ctx* ctx, const void* rays_dev, int64_t n, void* hits_dev) {
     if (!ctx || !rays_dev || !hits_dev || n < 0) return DPRT_ERR_INVALID;
+    if (n > kMaxTraceRays) return fail(ctx, DPRT_ERR_INVALID, "more rays than one launch can index (split the batch)");
     CK(cudaSetDevice(ctx->device));
     StageScope sc_(ctx, DPRT_STAGE_TRACE_CLOSEST, n > 0);
     launch_trace_closest(ctx->d_objects, ctx->cfg.sceneSize, (const dprt_ray*)rays_dev, (dprt_hit*)hits_dev, n, ctx->d_queue,
@@ -1518,6 +1628,7 @@ int dprt_trace_closest_device(dprt_ctx* ctx, const void* rays_dev, int64_t n, vo
 
 int dprt_trace_closest(dprt_ctx* ctx, const dprt_ray* rays_host, int64_t n, dprt_hit* hits_host) {
     if (!ctx || !rays_host || !hits_host || n < 0) return DPRT_ERR_INVALID;
+    if (n > kMaxTraceRays) return fail(ctx, DPRT_ERR_INVALID, "more rays than one launch can index (split the batch)");
     if (n == 0) return 0;
     CK(cudaSetDevice(ctx->device));
     const size_t rb = (size_t)n * sizeof(dprt_ray), hb = (size_t)n * sizeof(dprt_hit);
@@ -1534,6 +1645,7 @@ int dprt_gen_train_data(dprt_ctx* ctx, int si, const dprt_ray* rays_host, int64_
     if (!ctx || !rays_host || !features_host || !labels_host || n < 0) return DPRT_ERR_INVALID;
     if (si < 0 || si >= ctx->cfg.sceneSize || !ctx->objects[si].present || ctx->objects[si].desc.isProxy || !ctx->objects[si].d_nodes)
         return fail(ctx, DPRT_ERR_STATE, "training data can only be generated for an object whose geometry is on this rank");
+    if (n > kMaxTraceRays) return fail(ctx, DPRT_ERR_INVALID, "more rays than one launch can index (split the batch)");
     if (n == 0) return 0;
     CK(cudaSetDevice(ctx->device));
     const size_t rb = (size_t)n * sizeof(dprt_ray), hb = (size_t)n * sizeof(dprt_hit), fb = (size_t)n * 5 * sizeof(float), lb = (size_t)n * sizeof(float);

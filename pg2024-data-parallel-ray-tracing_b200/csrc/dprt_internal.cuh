@@ -104,6 +104,12 @@ void launch_path_histogram(const dprt_path_record* paths, int n, int W, int32_t*
 // sit at index >= splitL go to bucket W, so that the self segment comes out in two pieces (before / after the old own block).
 void launch_partition_paths(const dprt_path_record* paths, int n, int W, int B, int me, int splitL, const int32_t* hist,
                             dprt_path_record* out, int32_t* offsets, const PartitionScratch& s, cudaStream_t stream);
+// peer-memory exchange: W + 1 buckets, bucket b's records go to plan->dst[b] + (index inside the bucket); no offsets output
+struct P2PPlan;
+void launch_partition_paths_peer(const dprt_path_record* paths, int n, int W, int me, int splitL, const P2PPlan* plan,
+                                 const PartitionScratch& s, cudaStream_t stream);
+cudaError_t partition_preload_kernels();
+cudaError_t trace_preload_kernels();
 void launch_query_histogram(const dprt_nn_query* q, int n, int S, int insideOnly, int32_t* hist, cudaStream_t stream);
 // keys: DevParams::nnKey when it is known to mirror q (written by the same launch that wrote q), else null
 void launch_partition_queries(const dprt_nn_query* q, const uint8_t* keys, const dprt_half* in, int n, int S, int insideOnly,

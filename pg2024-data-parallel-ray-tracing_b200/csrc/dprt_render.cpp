@@ -140,7 +140,7 @@ int main(int argc, char** argv) {
     cfg.sceneSize = (int)sc.objects.size();
     cfg.proxyMode = std::atoi(arg(argc, argv, "--proxy", "0"));
     cfg.pathGenMode = std::atoi(arg(argc, argv, "--path-gen", world > 1 ? "1" : "0"));
-    cfg.mlpDtype = std::atoi(arg(argc, argv, "--mlp-dtype", "0"));
+    cfg.mlpDtype = std::atoi(arg(argc, argv, "--mlp-dtype", "1"));
     cfg.envColor[0] = 0.6f; cfg.envColor[1] = 0.7f; cfg.envColor[2] = 0.9f;
     const size_t N = (size_t)cfg.width * cfg.height;
     std::vector<float> image(3 * N);

@@ -331,13 +331,13 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
             }
         } while (__popc(__ballot_sync(FULL, idx >= 0)) >= minBusy);
     }
-    if (a.cacheHits) {               // device-side statistics: [0] MainRay queries answered from the cache, [1] rays that walked a BVH
+    if (a.cacheHits) {               // device-side statistics: [0] MainRay queries answered from the cache, [1] rays that walked a BVH, [2 + stage] the same per stage
         if (MODE == TM_SHADE) {
             cached = __reduce_add_sync(FULL, cached);
             if (lane == 0 && cached) atomicAdd(a.cacheHits, (unsigned long long)cached);
         }
         walked = __reduce_add_sync(FULL, walked);
-        if (lane == 0 && walked) atomicAdd(a.cacheHits + 1, (unsigned long long)walked);
+        if (lane == 0 && walked) { atomicAdd(a.cacheHits + 1, (unsigned long long)walked); atomicAdd(a.cacheHits + 2 + StageOf<MODE>::id, (unsigned long long)walked); }
     }
     if (COUNT) {
         if (cnt.nodes) atomicAdd(a.counters + 2 * StageOf<MODE>::id, (unsigned long long)cnt.nodes);
@@ -736,6 +736,15 @@ TraceArgs trace_args(const DevParams& p, dprt_path_record* recs) {
 size_t trace_scratch_bytes() {
     // 64 B for the ray-queue head + one cooperative-mode node pool per warp that can be resident
     return 64 + (size_t)num_sms() * std::max(tune_blocks(), 8) * (kTraceBlock / 32) * DPRT_POOLCAP * sizeof(uint32_t);
+}
+
+// forces the module load of the kernels of the migrate loop (p2p_exchange.cuh: never a first launch beside a spinning kernel)
+cudaError_t trace_preload_kernels() {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, trace_kernel<TM_TRAVERSE, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_kernel<TM_TRAVERSE, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, traverse_post_kernel);
+    return e;
 }
 
 void launch_path_gen(const DevParams& p, int n, cudaStream_t s) {

@@ -11,6 +11,7 @@
 // Output order is the reference's: bucket-major, original index order inside a bucket, dead entries dropped.
 #include <algorithm>
 #include "dprt_internal.cuh"
+#include "p2p_exchange.cuh"
 
 namespace dprt {
 
@@ -25,7 +26,9 @@ constexpr int kWarps = kThreads / 32;
 constexpr uint32_t ST_AGG = 1u << 30, ST_INC = 2u << 30, ST_MASK = 3u << 30, VAL_MASK = ~ST_MASK;
 
 struct PathOps {
+    static constexpr bool kDirect = false;
     const dprt_path_record* in; dprt_path_record* out; int B; int W; int me; int splitL;
+    __device__ __forceinline__ bool skip() const { return false; }
     __device__ __forceinline__ int key(int i) const {
         const uint4 w = reinterpret_cast<const uint4*>(in + i)[3];   // visitedMask, currentNode, targetNode, flags
         const int target = (int)w.z;
@@ -33,7 +36,7 @@ struct PathOps {
         if (!(valid && target >= 0 && target < W)) return -1;
         return (target == me && i >= splitL) ? W : target;           // bucket W only exists in settled-deque mode (B == W + 1)
     }
-    __device__ __forceinline__ void copy(int src, int dst) const {
+    __device__ __forceinline__ void copy(int src, int /*bucket*/, int dst) const {
         const float4* s = reinterpret_cast<const float4*>(in + src);
         float4* d = reinterpret_cast<float4*>(out + dst);
         const float4 a = s[0], b = s[1], c = s[2], e = s[3];
@@ -41,7 +44,31 @@ struct PathOps {
     }
 };
 
+// Peer-memory exchange (p2p_exchange.cuh): same keys as PathOps in settled-deque mode, but every bucket has its own
+// destination pointer, taken from the plan the counts kernel left in device memory -- a peer's receive buffer behind
+// NVLink for the travelling buckets, the local settled block for the two self pieces. `dst` is the index inside the bucket.
+struct PeerPathOps {
+    static constexpr bool kDirect = true;
+    const dprt_path_record* in; const P2PPlan* plan; int B; int W; int me; int splitL;
+    __device__ __forceinline__ bool skip() const { return *(const volatile int32_t*)&plan->error != 0; }
+    __device__ __forceinline__ int key(int i) const {
+        const uint4 w = reinterpret_cast<const uint4*>(in + i)[3];
+        const int target = (int)w.z;
+        const bool valid = (w.w >> 16) & 0xffu;
+        if (!(valid && target >= 0 && target < W)) return -1;
+        return (target == me && i >= splitL) ? W : target;
+    }
+    __device__ __forceinline__ void copy(int src, int bucket, int dst) const {
+        const float4* s = reinterpret_cast<const float4*>(in + src);
+        float4* d = reinterpret_cast<float4*>(plan->dst[bucket] + dst);
+        const float4 a = s[0], b = s[1], c = s[2], e = s[3];
+        d[0] = a; d[1] = b; d[2] = c; d[3] = e;
+    }
+};
+
 struct QueryOps {
+    static constexpr bool kDirect = false;
+    __device__ __forceinline__ bool skip() const { return false; }
     const dprt_nn_query* in; const uint8_t* keys; const dprt_half* fin; dprt_nn_query* out; dprt_half* fout; int B; int insideOnly;
     __device__ __forceinline__ int key(int i) const {
         int id; bool inside;
@@ -51,7 +78,7 @@ struct QueryOps {
         if (insideOnly && !inside) return -1;           // preKernelNN_HIT_INSIDE
         return id - 1;
     }
-    __device__ __forceinline__ void copy(int src, int dst) const {
+    __device__ __forceinline__ void copy(int src, int /*bucket*/, int dst) const {
         const float4* s = reinterpret_cast<const float4*>(in + src);
         float4* d = reinterpret_cast<float4*>(out + dst);
         const float4 a = s[0], b = s[1], c = s[2];
@@ -72,6 +99,7 @@ __global__ void __launch_bounds__(kThreads) partition_kernel(Ops ops, int n, con
     __shared__ int s_base[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int B = ops.B;
+    if (ops.skip()) return;                                      // block-uniform (peer exchange: the plan carries an error)
 
     if (threadIdx.x == 0) s_tile = atomicAdd(tileCounter, 1);   // launch-order tile ids: predecessors are always running
     for (int k = threadIdx.x; k < kSteps * 32; k += kThreads) (&s_cnt[0][0])[k] = 0;
@@ -103,15 +131,18 @@ __global__ void __launch_bounds__(kThreads) partition_kernel(Ops ops, int n, con
         int run = 0;
 #pragma unroll 8
         for (int s = 0; s < kSteps; s++) { const int c = s_cnt[s][lane]; s_cnt[s][lane] = run; run += c; }
-        // bucket bases = exclusive prefix of the histogram
-        const int h = lane < B ? hist[lane] : 0;
-        int incl = h;
+        // bucket bases = exclusive prefix of the histogram (direct mode: every bucket has its own destination, base 0)
+        int bucketBase = 0;
+        if (!Ops::kDirect) {
+            const int h = lane < B ? hist[lane] : 0;
+            int incl = h;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        const int bucketBase = incl - h;
-        if (tile == 0) {
-            if (lane < B) offsets[lane] = bucketBase;
-            if (lane == B - 1) offsets[B] = incl;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            bucketBase = incl - h;
+            if (tile == 0) {
+                if (lane < B) offsets[lane] = bucketBase;
+                if (lane == B - 1) offsets[B] = incl;
+            }
         }
         // decoupled look-back, one chain per bucket
         int excl = 0;
@@ -142,7 +173,7 @@ __global__ void __launch_bounds__(kThreads) partition_kernel(Ops ops, int n, con
         if (key[j] >= 0) {
             const int idx = base + j * 32 + lane;
             const int dst = s_base[key[j]] + s_cnt[warp * kItems + j][key[j]] + rank[j];
-            ops.copy(idx, dst);
+            ops.copy(idx, key[j], dst);
         }
     }
 }
@@ -178,7 +209,7 @@ __global__ void empty_offsets_kernel(int32_t* offsets, int B) {
 
 template <class Ops, int kItems>
 void run_partition(Ops ops, int n, const int32_t* hist, int32_t* offsets, const PartitionScratch& s, cudaStream_t stream) {
-    if (n <= 0) { empty_offsets_kernel<<<1, 64, 0, stream>>>(offsets, ops.B); return; }
+    if (n <= 0) { if (!Ops::kDirect) empty_offsets_kernel<<<1, 64, 0, stream>>>(offsets, ops.B); return; }
     constexpr int kTile = kThreads * kItems;
     const int tiles = (n + kTile - 1) / kTile;                 // <= PartitionScratch::maxTiles, which is sized for 1024-record tiles
     cudaMemsetAsync(s.tileState, 0, (size_t)tiles * 32 * sizeof(uint32_t), stream);
@@ -197,6 +228,19 @@ void launch_partition_paths(const dprt_path_record* paths, int n, int W, int B, 
                             dprt_path_record* out, int32_t* offsets, const PartitionScratch& s, cudaStream_t stream) {
     PathOps ops{paths, out, B, W, B > W ? me : -1, splitL};
     run_partition<PathOps, 4>(ops, n, hist, offsets, s, stream);
+}
+
+void launch_partition_paths_peer(const dprt_path_record* paths, int n, int W, int me, int splitL, const P2PPlan* plan,
+                                 const PartitionScratch& s, cudaStream_t stream) {
+    PeerPathOps ops{paths, plan, W + 1, W, me, splitL};
+    run_partition<PeerPathOps, 4>(ops, n, nullptr, nullptr, s, stream);
+}
+
+cudaError_t partition_preload_kernels() {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, partition_kernel<PeerPathOps, 4>);
+    if (e != cudaSuccess) return e;
+    return cudaFuncGetAttributes(&fa, partition_kernel<PathOps, 4>);
 }
 
 void launch_query_histogram(const dprt_nn_query* q, int n, int S, int insideOnly, int32_t* hist, cudaStream_t stream) {

@@ -32,7 +32,8 @@ class Stats(C.Structure):
     _fields_ = [("rays_traverse", C.c_int64), ("rays_shade", C.c_int64), ("rays_shadow", C.c_int64),
                 ("rays_secondary", C.c_int64), ("nn_queries", C.c_int64), ("paths_sent_offrank", C.c_int64),
                 ("exchange_iters", C.c_int64), ("kernel_launches", C.c_int64), ("bytes_alltoall", C.c_int64),
-                ("rays_shade_cached", C.c_int64), ("rays_walked", C.c_int64), ("reserved_", C.c_int64 * 5)]
+                ("rays_shade_cached", C.c_int64), ("rays_walked", C.c_int64), ("walked_traverse", C.c_int64),
+                ("walked_shade", C.c_int64), ("walked_shadow", C.c_int64), ("walked_secondary", C.c_int64), ("paths_partitioned", C.c_int64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "reserved_"}
@@ -57,6 +58,8 @@ assert PATH_DTYPE.itemsize == 64 and QUERY_DTYPE.itemsize == 48 and RAY_DTYPE.it
 assert NODE_DTYPE.itemsize == 80 and TRI_DTYPE.itemsize == 48 and MATERIAL_DTYPE.itemsize == 16 and LIGHT_DTYPE.itemsize == 48
 assert C.sizeof(Config) == 64 and C.sizeof(ObjectDesc) == 84 and C.sizeof(Camera) == 56 and C.sizeof(Stats) == 128
 
+P2P_HANDLE_BYTES = 208     # DPRT_P2P_HANDLE_BYTES
+
 # dprt_buffer_id
 BUF_PATHS, BUF_TRANSFER, BUF_TRANSFER_OFFSET, BUF_DIRECT, BUF_ENV, BUF_NN_INPUT, BUF_NN_QUERY, BUF_NN_PACKED_INPUT, \
     BUF_NN_PACKED_QUERY, BUF_SCENE_OFFSET, BUF_PRED, BUF_OCCLUSION, BUF_CONTRIBUTION, BUF_HIT_PRIM = range(14)
@@ -75,7 +78,7 @@ BUFFER_DTYPES = {
 
 
 def make_config(width, height, spp=1, bounces=4, spc=4, mc=3, scene_size=1, proxy_mode=0, path_gen_mode=0,
-                mlp_dtype=0, env_color=(0.6, 0.7, 0.9), main_ray_retrace=0, serial_stages=0, reference_migrate=0):
+                mlp_dtype=1, env_color=(0.6, 0.7, 0.9), main_ray_retrace=0, serial_stages=0, reference_migrate=0):
     cfg = Config()
     cfg.mainRayRetrace, cfg.serialStages, cfg.referenceMigrate = int(main_ray_retrace), int(serial_stages), int(reference_migrate)
     cfg.width, cfg.height, cfg.spp, cfg.bounces = width, height, spp, bounces

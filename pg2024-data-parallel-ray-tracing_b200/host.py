@@ -21,6 +21,7 @@ _PROTOTYPES = {
     # name: (restype, argtypes)
     "dprt_get_unique_id": (C.c_int, [C.c_void_p]),
     "dprt_create": (C.c_int, [C.POINTER(D.Config), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dprt_create_shared": (C.c_int, [C.POINTER(D.Config), C.c_void_p, C.POINTER(C.c_void_p)]),
     "dprt_destroy": (None, [C.c_void_p]),
     "dprt_last_error": (C.c_char_p, [C.c_void_p]),
     "dprt_synchronize": (C.c_int, [C.c_void_p]),
@@ -59,6 +60,10 @@ _PROTOTYPES = {
     "dprt_secondary_ray_module": (C.c_int, [C.c_void_p]),
     "dprt_render_sample": (C.c_int, [C.c_void_p, C.c_int]),
     "dprt_reduce_image": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "dprt_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dprt_p2p_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "dprt_p2p_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "dprt_p2p_enabled": (C.c_int, [C.c_void_p]),
     "dprt_exchange_group": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int)]),
     "dprt_render_sample_group": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "dprt_reduce_image_group": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]),
@@ -258,19 +263,43 @@ def exchange_host_records_deque(buckets, row, rank, world, dist):
 class Renderer:
     """One rank of the data-parallel renderer (one GPU, one scene-chunk owner)."""
 
-    def __init__(self, cfg, rank=0, world=1, device=0, nccl_unique_id=None):
+    def __init__(self, cfg, rank=0, world=1, device=0, nccl_unique_id=None, parent=None):
+        """parent: another Renderer of the same rank whose NCCL communicator this one borrows (dprt_create_shared)."""
         self.lib = load_library()
         self.cfg = cfg
-        self.rank, self.world = rank, world
         self.N = cfg.width * cfg.height
         h = C.c_void_p()
-        idbuf = None
-        if nccl_unique_id is not None:
-            idbuf = C.create_string_buffer(bytes(nccl_unique_id), 128)
-        rc = self.lib.dprt_create(C.byref(cfg), rank, world, device, idbuf, C.byref(h))
+        if parent is not None:
+            rank, world = parent.rank, parent.world
+            rc = self.lib.dprt_create_shared(C.byref(cfg), parent.h, C.byref(h))
+        else:
+            idbuf = None
+            if nccl_unique_id is not None:
+                idbuf = C.create_string_buffer(bytes(nccl_unique_id), 128)
+            rc = self.lib.dprt_create(C.byref(cfg), rank, world, device, idbuf, C.byref(h))
+        self.rank, self.world = rank, world
         if rc:
             raise DprtError(f"dprt_create failed ({rc}): {self.lib.dprt_last_error(None).decode()}")
         self.h = h
+
+    # -- peer-memory exchange wiring for hosts without NCCL (dprt.h: export -> all-gather -> connect -> agree -> enable)
+    @property
+    def p2p_enabled(self):
+        return bool(self.lib.dprt_p2p_enabled(self.h))
+
+    def p2p_export(self):
+        buf = C.create_string_buffer(D.P2P_HANDLE_BYTES)
+        self._ck(self.lib.dprt_p2p_export(self.h, buf), "dprt_p2p_export")
+        return bytes(buf.raw)
+
+    def p2p_connect(self, all_handles):
+        blob = b"".join(all_handles)
+        ok = C.c_int(0)
+        self._ck(self.lib.dprt_p2p_connect(self.h, blob, C.byref(ok)), "dprt_p2p_connect")
+        return bool(ok.value)
+
+    def p2p_enable(self, enable):
+        self._ck(self.lib.dprt_p2p_enable(self.h, 1 if enable else 0), "dprt_p2p_enable")
 
     # -- plumbing ---------------------------------------------------------------------------------
     def _ck(self, rc, what):

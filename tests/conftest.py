@@ -5,6 +5,11 @@ import sys
 import numpy as np
 import pytest
 
+# before CUDA initialises: one hardware queue per stream for the in-process rank groups (W contexts x 2 streams on one device),
+# and a short leash on the peer-memory exchange's device-side waits (a lost peer becomes an error, never a hang)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("DPRT_P2P_TIMEOUT_MS", "8000")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -79,7 +79,7 @@ def main():
         assert err <= 1e-6, f"reduced image differs: {err}"
         if W == 2:
             assert_bits_equal(img, img_o, "2-rank reduced image (a two-term fp32 sum is order-independent)")
-        print(f"MGPU_CHECK_OK world={W} migrated_paths={int(sent.item())} image_rel_err={err:.2e}", flush=True)
+        print(f"MGPU_CHECK_OK world={W} migrated_paths={int(sent.item())} image_rel_err={err:.2e} peer_memory_exchange={R.p2p_enabled}", flush=True)
     R.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -121,7 +121,7 @@ def test_all_rays_miss_empty_wavefronts(gpu_required, oracle):
             R.close()
 
 
-@pytest.mark.parametrize("spc,mc,W,proxy", [(1, 1, 1, 0), (7, 2, 2, 0), (2, 5, 2, 1)])
+@pytest.mark.parametrize("spc,mc,W,proxy", [(1, 1, 1, 0), (7, 2, 2, 0), (2, 5, 2, 1), (1, 3, 2, 1)])
 def test_shadow_path_and_march_counts_other_than_default(gpu_required, oracle, spc, mc, W, proxy):
     """renderer.cpp:1602-1603 fixes shadowPathCount = 4 and maxCount = 3; the buffers and kernels are sized by them."""
     import torch

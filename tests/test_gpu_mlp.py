@@ -30,7 +30,10 @@ def _model(nres, spread=False):
     return m
 
 
-@pytest.mark.parametrize("nres,mlp_dtype,tol", [(4, 1, 1e-3), (6, 1, 1e-3), (4, 0, 4e-3)])
+# north_star fixes proxy parity at 1e-3 abs: fp16 operands (the reference's NN_Float, and the default mlpDtype) meet it.
+# bf16 operands (mlpDtype = 0, opt-in) do NOT: 8 mantissa bits give ~3e-3 on this chain. That row is an informational bound
+# on the opt-in mode, not a parity claim -- every parity statement in DESIGN.md refers to fp16.
+@pytest.mark.parametrize("nres,mlp_dtype,tol", [(4, 1, 1e-3), (6, 1, 1e-3), pytest.param(4, 0, 4e-3, id="4-bf16-out-of-tolerance-mode-4e-3")])
 def test_mlp_matches_reference_module_golden(gpu_required, oracle, golden_dir, nres, mlp_dtype, tol):
     g = np.load(os.path.join(golden_dir, "mlp_golden.npz"))
     m = _model(nres)

@@ -1,5 +1,7 @@
-"""Real multi-GPU parity (-m gpu, needs >= 2 devices; skipped on a 1-GPU box): one process per GPU over NCCL,
-launched through torch.distributed.run exactly like bench.py, checked inside tests/mgpu_check.py."""
+"""Multi-process parity (-m gpu). test_nccl_*: one process per GPU over NCCL + peer memory, launched through
+torch.distributed.run exactly like bench.py, checked inside tests/mgpu_check.py (needs >= 2 devices; skipped on a 1-GPU
+box -- bench.py's own `parity` gate covers the driver's N > 1 runs). test_peer_memory_exchange_between_processes_*: W
+processes sharing ONE device, wired with CUDA IPC over gloo (tests/p2p_ipc_check.py) -- runs on any GPU box."""
 import os
 import socket
 import subprocess
@@ -30,3 +32,11 @@ def test_nccl_exchange_and_reduce_match_oracle(gpu_required, W, path_gen_mode):
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_check.py"), "--path-gen-mode", str(path_gen_mode)]
     p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "MGPU_CHECK_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
+
+
+@pytest.mark.parametrize("W", [2, 3])
+def test_peer_memory_exchange_between_processes_on_one_device(gpu_required, W):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={W}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "p2p_ipc_check.py")]
+    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=420)
+    assert p.returncode == 0 and "P2P_IPC_CHECK_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]

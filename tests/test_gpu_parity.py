@@ -136,6 +136,31 @@ def test_multi_rank_group_migration_bit_exact(gpu_required, oracle, W, refmig):
     assert_bits_equal(G.reduce_image(0), world.image(), "reduced image")
 
 
+@pytest.mark.parametrize("W,spp,pgm", [(2, 1, 0), (3, 2, 1), (4, 2, 0)])
+def test_multi_rank_group_peer_memory_exchange_bit_exact(gpu_required, oracle, monkeypatch, W, spp, pgm):
+    """The peer-memory exchange (p2p_exchange.cuh: counts kernel -> partition scattering straight into the owners' receive
+    buffers -> flag barrier, no host round trip) driven for W contexts on one device: same kernels and protocol as one
+    process per GPU, with plain device pointers where those use CUDA IPC mappings. Every buffer bit-exact against the oracle."""
+    monkeypatch.setenv("DPRT_P2P_GROUP", "1")
+    rs, world, _ = build_pair(oracle, W, 6000, 128, 72, spp=spp, bounces=3, proxy_mode=0, path_gen_mode=pgm, serial_stages=1)
+    G = dprt.RankGroup(rs)
+    img_g, img_o = G.launch(), world.launch()
+    assert all(R.p2p_enabled for R in rs), "the group did not switch to the peer-memory exchange"
+    N, spc = 128 * 72, rs[0].cfg.shadowPathCount
+    sent = 0
+    for r, R in enumerate(rs):
+        n = R.path_size
+        assert n == world.path_size(r), f"rank {r} pathSize"
+        assert_records_equal(R.download(D.BUF_PATHS, n * (1 + spc)), world.download(r, D.BUF_PATHS, n * (1 + spc)), f"rank {r} paths")
+        assert_bits_equal(R.download(D.BUF_ENV), world.download(r, D.BUF_ENV, 3 * N), f"rank {r} env")
+        assert_bits_equal(R.download(D.BUF_DIRECT), world.download(r, D.BUF_DIRECT, 3 * N * spc), f"rank {r} direct")
+        sg, so = R.stats(), world.stats(r)
+        assert sg["paths_sent_offrank"] == so["paths_sent_offrank"] and sg["exchange_iters"] == so["exchange_iters"]
+        sent += sg["paths_sent_offrank"]
+    assert sent > 0
+    assert_bits_equal(img_g, img_o, "reduced image")
+
+
 def test_striped_path_generation_same_image(gpu_required, oracle):
     rs, world, _ = build_pair(oracle, 2, 6000, 96, 54, bounces=1, proxy_mode=0, path_gen_mode=1)
     img_g = dprt.RankGroup(rs).launch()
@@ -204,3 +229,31 @@ def test_trace_closest_full_size_properties(gpu_required, oracle):
     ho = world.trace_closest(0, sub)
     assert_bits_equal(hg[::16]["primID"], ho["primID"], "sampled primitive ids at full size")
     assert_bits_equal(hg[::16]["t"], ho["t"], "sampled t at full size")
+
+
+def test_traversal_counters_against_oracle_bvh8_walker(gpu_required, oracle):
+    """bench.py's roofline bills BVH bytes from the ORACLE's scalar exact-tbest walk over the uploaded BVH8,
+    not from the kernel's own counters. Here both are taken on the same rays: the kernel culls with a lagging tbest and expands
+    nodes ahead of its triangle tests, so in the closest-hit stages it can only fetch MORE than the scalar walker -- and it
+    must stay within a small factor of it; rays walked per stage must agree exactly."""
+    W, w, h = 2, 160, 90
+    rs, world, chunks = build_pair(oracle, W, 20000, w, h, spp=1, bounces=2, proxy_mode=0, main_ray_retrace=1)
+    for c in chunks:
+        nodes, tris, _ = dprt.build_bvh8(c.verts, c.mats)
+        world.set_bvh8(c.index, nodes, tris)
+    world.count_bvh8(True)
+    for R in rs:
+        R.enable_counters(True); R.reset_stats()
+    G = dprt.RankGroup(rs)
+    img_g, img_o = G.launch(), world.launch()
+    assert_bits_equal(img_g, img_o, "image with counters on")
+    for r, R in enumerate(rs):
+        cg, co, sg, so = R.counters(), world.bvh8_counters(r), R.stats(), world.stats(r)
+        for stage, key in (("traverse", "walked_traverse"), ("shade", "walked_shade"), ("shadow_trace", "walked_shadow")):
+            assert sg[key] == so[key] == co[stage][2], (r, stage, sg[key], so[key], co[stage][2])
+            gn, gt = cg[stage]; on, ot, _ = co[stage]
+            print(f"rank {r} {stage}: nodes gpu/oracle = {gn}/{on} = {gn / max(on, 1):.3f}, tris {gt}/{ot} = {gt / max(ot, 1):.3f}")
+            if stage != "shadow_trace":       # any-hit: whichever occluder is found first ends the walk, no ordering between the two
+                assert gn >= on and gt >= ot, (r, stage)
+            assert gn <= 2.0 * on + 64 and gt <= 2.5 * ot + 64, (r, stage)
+        R.close()

@@ -332,3 +332,34 @@ def test_scene_file_and_pfm_round_trip(tmp_path):
         f.write(b"PF\n32 18\n-1.0\n")
         f.write(img[::-1].tobytes())
     assert np.array_equal(dprt.scene.load_pfm(pfm), img)
+
+
+def test_bvh8_counting_walker_per_stage(oracle):
+    """The roofline's algorithmic node / triangle counts: a scalar exact-tbest walk over the PRODUCT's BVH8 beside every
+    oracle trace. It must not change any result, count exactly the rays that walk a BVH, and fetch at least the root."""
+    W, w, h = 2, 64, 36
+    chunks, mats, lights = dprt.scene.make_scene(W, 3000)
+    cfg = dprt.make_config(w, h, spp=1, bounces=2, scene_size=W, proxy_mode=0)
+    cam = dprt.scene.default_camera(w, h)
+    imgs, stats = [], []
+    for count in (False, True):
+        world = oracle.World(cfg, W)
+        for c in chunks:
+            world.add_object(c.index, c.desc(False), c.verts, c.normals, c.mats)
+            if count:
+                nodes, tris, _ = dprt.build_bvh8(c.verts, c.mats)
+                world.set_bvh8(c.index, nodes, tris)
+        world.set_materials(mats); world.set_lights(lights); world.set_camera(cam)
+        world.count_bvh8(count)
+        imgs.append(world.launch())
+        stats.append([(world.stats(r), world.bvh8_counters(r)) for r in range(W)])
+    assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32))
+    for r in range(W):
+        st, cnt = stats[1][r]
+        assert stats[0][r][0] == st                                      # counting changes no statistic
+        assert all(v == (0, 0, 0) for v in stats[0][r][1].values())      # and nothing is counted when it is off
+        for stage, key in (("traverse", "walked_traverse"), ("shade", "walked_shade"), ("shadow_trace", "walked_shadow")):
+            nodes, tris, rays = cnt[stage]
+            assert rays == st[key], (r, stage, rays, st[key])
+            assert nodes >= rays                                          # every walk fetches the root
+        assert st["walked_traverse"] + st["walked_shade"] + st["walked_shadow"] + st["walked_secondary"] == st["rays_walked"]

@@ -93,7 +93,7 @@ def test_gpu_trained_proxies_beat_untrained_ones(gpu_required):
     cam = dprt.scene.default_camera(w, h)
 
     def render(proxy_mode, blobs):
-        cfg = dprt.make_config(w, h, spp=4, bounces=2, scene_size=W, proxy_mode=proxy_mode, path_gen_mode=1, mlp_dtype=0)
+        cfg = dprt.make_config(w, h, spp=4, bounces=2, scene_size=W, proxy_mode=proxy_mode, path_gen_mode=1, mlp_dtype=1)
         rs = []
         for r in range(W):
             R = dprt.Renderer(cfg, rank=r, world=W, device=0)
