@@ -155,13 +155,15 @@ def run_reference(args):
     fw, fh = frame_for(W)
     # bounded sample: the reference's migrate loop handles every path of a rank in every iteration (~9 per bounce at 8
     # chunks), so a sample costs more per pixel as W grows; the frame shrinks with it to keep a step around a second
-    scale = args.ref_scale * (1 if W == 1 else (2 if W <= 4 else 3))
+    scale = 1 if W == 1 else args.ref_scale * (2 if W <= 4 else 3)      # N = 1: the whole 1920x1080 frame (~2 s per step)
     w, h = max(16, fw // scale), max(9, fh // scale)
     chunks, mats, lights = build_world_scene(dprt, W, args.tris, args.layout)
     cfg = dprt.make_config(w, h, spp=1, bounces=args.bounces, scene_size=W, proxy_mode=1 if (args.proxy and W > 1) else 0,
                            path_gen_mode=args.path_gen_mode if W > 1 else 0, mlp_dtype=1)
     world = O.World(cfg, W)
     blobs = proxy_blobs(dprt, W, args.proxy)
+    if W == 1 and args.warmup > 1:
+        args.warmup = 1                 # a CPU pass has nothing to warm beyond the first touch; keeps the full-frame arm inside the budget
     for c in chunks:
         world.add_object(c.index, c.desc(False), c.verts, c.normals, c.mats)
         if c.index in blobs:
@@ -180,12 +182,17 @@ def run_reference(args):
     rays = rays_total() - r0
     val = rays / dt / 1e6
     cores = O.num_threads()
-    sample = f"{args.steps} x runSample over a {w}x{h} frame (1/{scale} per side of {fw}x{fh}) of the same {W}-chunk scene"
+    sample = (f"{args.steps} x runSample over the full {w}x{h} frame of the same 1-chunk scene" if scale == 1 else
+              f"{args.steps} x runSample over a {w}x{h} frame (1/{scale} per side of {fw}x{fh}) of the same {W}-chunk scene")
+    cfg_out = workload_config(args, W, fw, fh)
+    cfg_out["reference_arm_frame"] = f"{w}x{h}"
+    if scale != 1:
+        cfg_out["workload"] += f" -- the CPU arm renders a {w}x{h} sub-sampled frame of it (rate metric, same scene and camera)"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": W, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "samples_per_s": w * h * args.steps / dt,
-        "config": workload_config(args, W, fw, fh),
+        "config": cfg_out,
         "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -317,6 +324,102 @@ def bench_mlp(dprt, args, pk, device):
             "bound": "tensor", **out}
 
 
+def oracle_bvh8_counts(dprt, args, W, proxy, chunks, mats, lights, blobs):
+    """the BVH bytes of the roofline come from the ORACLE -- a scalar walker with an exact tbest over the very
+    BVH8 blob the product uploads (dprt_bvh8_build is deterministic) -- not from the kernel's own counters. One sample of the
+    same scene, camera and loop over a sub-sampled frame; per stage: nodes fetched and triangles tested per ray that walked."""
+    from oracle import oracle as O
+    O.lib(); O.use_all_host_threads()
+    fw, fh = frame_for(W)
+    w, h = max(16, fw // args.count_scale), max(9, fh // args.count_scale)
+    cfg = dprt.make_config(w, h, spp=1, bounces=args.bounces, scene_size=W, proxy_mode=proxy, path_gen_mode=args.path_gen_mode if W > 1 else 0, mlp_dtype=1)
+    world = O.World(cfg, W)
+    for c in chunks:
+        world.add_object(c.index, c.desc(False), c.verts, c.normals, c.mats)
+        nodes, tris, _ = dprt.build_bvh8(c.verts, c.mats)
+        world.set_bvh8(c.index, nodes, tris)
+        if c.index in blobs:
+            world.set_model(c.index, 0, blobs[c.index][0]); world.set_model(c.index, 1, blobs[c.index][1])
+    world.set_materials(mats); world.set_lights(lights); world.set_camera(dprt.scene.default_camera(w, h))
+    world.count_bvh8(True)
+    world.reset_frame()
+    world.render_sample(args.warmup)
+    out = {}
+    for name in TRAVERSAL_STAGES:
+        n = t = r = 0
+        for k in range(W):
+            cn, ct, cr = world.bvh8_counters(k)[name]
+            n += cn; t += ct; r += cr
+        if r:
+            out[name] = {"nodes_per_ray": n / r, "tris_per_ray": t / r, "rays_sampled": r}
+    world.close()
+    return out, f"{w}x{h}"
+
+
+def parity_gate(dprt, R, args, rank, W, dist, torch):
+    """N > 1, before anything is timed: a small frame rendered through the SAME data plane the timed runs use -- a second
+    context of this rank on the parent's NCCL communicator, peer-memory exchange wired the same way -- and compared with the
+    oracle's W-rank world exactly as tests/mgpu_check.py does: every rank its own path / env / direct buffers bit for bit,
+    rank 0 the ncclReduce'd image (NCCL chooses the summation order: 1e-6 relative). Proxies off: with them on the GPU and
+    the oracle may legitimately disagree at a threshold, which tests/test_gpu_proxy.py bounds separately."""
+    from oracle import oracle as O
+    O.lib()
+    O.lib().orc_set_num_threads(max(1, (os.cpu_count() or 1) // W))
+    D = dprt.ctypes_defs
+    w, h, spp, bounces, tris = 256, 144, 2, 4, 20000
+    cam = dprt.scene.default_camera(w, h)
+    chunks, mats, lights = dprt.scene.make_scene(W, tris, layout=args.layout, camera=cam)
+    cfg = dprt.make_config(w, h, spp=spp, bounces=bounces, scene_size=W, proxy_mode=0, path_gen_mode=args.path_gen_mode,
+                           main_ray_retrace=args.retrace, serial_stages=args.serial)
+    P = dprt.Renderer(cfg, parent=R)
+    world = O.World(cfg, W)
+    for c in chunks:
+        world.add_object(c.index, c.desc(False), c.verts, c.normals, c.mats)
+        if c.node_id == rank:
+            P.upload_chunk(c.index, c.desc(False), c.verts, c.normals, c.mats)
+        else:
+            P.upload_proxy(c.index, c.desc(True), None, None)
+    for X in (P, world):
+        X.set_materials(mats); X.set_lights(lights); X.set_camera(cam)
+    img = P.launch()
+    img_o = world.launch()
+    N, spc = w * h, cfg.shadowPathCount
+    problems = []
+
+    def same(a, b, what):
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        if a.shape != b.shape or not np.array_equal(a.view(np.uint8), b.view(np.uint8)):
+            problems.append(f"rank {rank}: {what} differs from the oracle")
+    n = P.path_size
+    if n != world.path_size(rank):
+        problems.append(f"rank {rank}: pathSize {n} vs oracle {world.path_size(rank)}")
+    else:
+        same(P.download(D.BUF_PATHS, n * (1 + spc)), world.download(rank, D.BUF_PATHS, n * (1 + spc)), "path records")
+    same(P.download(D.BUF_ENV), world.download(rank, D.BUF_ENV, 3 * N), "envLightingBuffer")
+    same(P.download(D.BUF_DIRECT), world.download(rank, D.BUF_DIRECT, 3 * N * spc), "directLightingBuffer")
+    sg, so = P.stats(), world.stats(rank)
+    for k in ("rays_traverse", "rays_shade", "rays_shadow", "paths_sent_offrank", "exchange_iters"):
+        if sg[k] != so[k]:
+            problems.append(f"rank {rank}: {k} {sg[k]} vs oracle {so[k]}")
+    err = 0.0
+    if rank == 0:
+        err = float(np.abs(img - img_o).max() / max(1e-30, float(np.abs(img_o).max())))
+        if not (np.isfinite(img).all() and err <= 1e-6):
+            problems.append(f"reduced image differs from the oracle: rel err {err:.3e}")
+    p2p = P.p2p_enabled
+    P.close(); world.close()
+    t = torch.tensor([len(problems), sg["paths_sent_offrank"]], dtype=torch.int64, device="cuda")
+    dist.all_reduce(t)
+    every = [None] * W
+    dist.all_gather_object(every, problems)
+    return {"ok": int(t[0].item()) == 0, "world": W, "migrated_paths": int(t[1].item()), "image_rel_err": err,
+            "data_plane": "peer memory over NVLink (CUDA IPC) + ncclReduce" if p2p else "ncclAllGather + ncclSend/ncclRecv + ncclReduce",
+            "frame": f"{w}x{h}, {spp} spp, bounces={bounces}, {tris} triangles per chunk, proxies off",
+            "checked": "per rank: pathSize, path records, envLightingBuffer, directLightingBuffer, launch sizes, exchange statistics "
+                       "bit-exact vs the oracle's W-rank world; rank 0: reduced image <= 1e-6 rel",
+            "problems": [q for ps in every for q in ps][:8]}
+
+
 def run_dprt(args):
     import torch
     import torch.distributed as dist
@@ -360,7 +463,8 @@ def run_dprt(args):
             vb, db = blobs.get(c.index, (None, None))
             R.upload_proxy(c.index, c.desc(True), vb, db)
     R.set_materials(mats); R.set_lights(lights); R.set_camera(cam)
-    del chunks
+    if rank != 0 or args.skip_oracle_counts:
+        del chunks                      # rank 0 keeps the scene for the oracle's counting pass (after the timed region)
 
     def barrier():
         torch.cuda.synchronize()
@@ -374,6 +478,16 @@ def run_dprt(args):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=op)
         return float(t.item())
+
+    # ---- N > 1: parity gate on the same communicator / peer-memory wiring, before anything is timed ---------
+    parity = None
+    if W > 1 and not args.skip_parity:
+        parity = parity_gate(dprt, R, args, rank, W, dist, torch)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "value": None, "n_gpus": W, "parity": parity, "error": "parity gate failed: nothing was timed"}), flush=True)
+            dist.barrier()
+            raise SystemExit(3)
 
     # ---- device-resident timing: W warm-up samples, then exactly K samples between two events ----------------
     R.reset_frame()
@@ -402,12 +516,23 @@ def run_dprt(args):
     ms_serial = R.timer_stop()
     barrier()
     clk = clocks.stop() if rank == 0 else None          # sampled through the timed region and the serial pass right after it
+    # the per-frame image average + ncclReduce (renderer.cpp:2031-2052), profiled like a stage: 3 times, device events
+    keep_r, himg_r = pinned_array((fh, fw, 3), np.float32)
+    for _ in range(3):
+        R._ck(R.lib.dprt_reduce_image(R.h, 0, himg_r.ctypes.data if rank == 0 else None), "dprt_reduce_image")
+    barrier()
     stage = R.stage_times()
+    sst = R.stats()
     R.stage_profile(False)
+    reduce_ms = allreduce(stage["image"][0] / max(1, stage["image"][1]), dist.ReduceOp.MAX if W > 1 else None)
+    stage.pop("image")
     # per-rank view of the serial pass: time inside the exchange stage is mostly waiting for the slowest chunk owner
     mine = {"rank": rank, "rays_walked_per_step": my_rays_walked / args.steps,
             "busy_ms_per_step": sum(t for k, (t, _) in stage.items() if k != "exchange") / args.steps,
-            "exchange_ms_per_step": stage["exchange"][0] / args.steps}
+            "exchange_ms_per_step": stage["exchange"][0] / args.steps,
+            "sent_bytes_per_step": sst["bytes_alltoall"] / args.steps,
+            # the records leave inside the partition launch when the peer-memory exchange is on, inside ncclSend/ncclRecv otherwise
+            "alltoall_GBps": sst["bytes_alltoall"] / max(1e-9, (stage["exchange"][0] + (stage["partition"][0] if R.p2p_enabled else 0.0)) * 1e-3) / 1e9}
     per_rank = [mine]
     if W > 1:
         per_rank = [None] * W
@@ -422,40 +547,71 @@ def run_dprt(args):
     sent = allreduce(float(st["bytes_alltoall"]), dist.ReduceOp.SUM if W > 1 else None)
     value = rays / (ms * 1e-3) / 1e6
 
-    # ---- instrumented pass over the same sample indices: algorithmic bytes of the traversal kernels ---------
+    # ---- algorithmic bytes of the traversal kernels -------------------------------------------------
+    # rays: the records each launch actually traced (dprt_stats.walked_*: riders of a TraRay launch and cache-answered
+    # MainRay queries are not billed); nodes / triangles per ray: the ORACLE's scalar exact-tbest walk over the uploaded BVH8.
+    # The kernel's own counters (instrumented variant, never timed) are reported beside them as gpu_*_per_ray.
     R.reset_stats(); R.enable_counters(True)
     for s in range(args.steps):
         R.run_sample(args.warmup + s)
     R.synchronize()
     cnt = R.counters(); cst = R.stats()
     R.enable_counters(False)
-    nrays = {"traverse": cst["rays_traverse"], "shade": cst["rays_shade"] - cst["rays_shade_cached"], "shadow_trace": cst["rays_shadow"], "secondary_trace": cst["rays_secondary"]}
+    oc, oc_frame = ({}, None)
+    if rank == 0 and not args.skip_oracle_counts:
+        oc, oc_frame = oracle_bvh8_counts(dprt, args, W, proxy, chunks, mats, lights, blobs)
+        del chunks
+    if W > 1:
+        box = [oc, oc_frame]
+        dist.broadcast_object_list(box, 0)
+        oc, oc_frame = box
+    walked = {"traverse": sst["walked_traverse"], "shade": sst["walked_shade"], "shadow_trace": sst["walked_shadow"], "secondary_trace": sst["walked_secondary"]}
+    gwalked = {"traverse": cst["walked_traverse"], "shade": cst["walked_shade"], "shadow_trace": cst["walked_shadow"], "secondary_trace": cst["walked_secondary"]}
     stages_out = {}
     for name in TRAVERSAL_STAGES:
         t_ms, ln = stage[name]
-        if ln == 0 or nrays[name] == 0:
+        if ln == 0 or walked[name] == 0:
             continue
-        nodes, tris = cnt[name]
-        alg = nrays[name] * RECORD_BYTES[name] + nodes * NODE_BYTES + tris * TRI_BYTES
-        stages_out[name] = {"ms": t_ms, "launches": ln, "rays": nrays[name], "Mrays_per_s": nrays[name] / t_ms / 1e3,
-                            "alg_bytes": alg, "GBps": alg / (t_ms * 1e-3) / 1e9, "bytes_per_ray": alg / nrays[name],
-                            "nodes_per_ray": nodes / nrays[name], "tris_per_ray": tris / nrays[name]}
+        gn, gt = cnt[name]
+        g_npr, g_tpr = gn / max(1, gwalked[name]), gt / max(1, gwalked[name])
+        if name in oc:
+            npr, tpr, src = oc[name]["nodes_per_ray"], oc[name]["tris_per_ray"], "oracle"
+        else:
+            npr, tpr, src = g_npr, g_tpr, "kernel counters (no oracle sample)"
+        alg = walked[name] * (RECORD_BYTES[name] + npr * NODE_BYTES + tpr * TRI_BYTES)
+        stages_out[name] = {"ms": t_ms, "launches": ln, "rays": walked[name], "Mrays_per_s": walked[name] / t_ms / 1e3,
+                            "alg_bytes": alg, "GBps": alg / (t_ms * 1e-3) / 1e9, "bytes_per_ray": alg / walked[name],
+                            "nodes_per_ray": npr, "tris_per_ray": tpr, "counts_from": src,
+                            "gpu_nodes_per_ray": g_npr, "gpu_tris_per_ray": g_tpr}
     for name, (t_ms, ln) in stage.items():
         if name not in stages_out and ln:
             stages_out[name] = {"ms": t_ms, "launches": ln}
     dom = max((k for k in TRAVERSAL_STAGES if k in stages_out and "GBps" in stages_out[k]), key=lambda k: stages_out[k]["ms"])
     d = stages_out[dom]
-    traffic = None
+    ncu = {}
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
-        if tj.get("n_gpus") == W and args.tris == 1000000 and dom in tj.get("kernels", {}):     # captured on the default workload
-            traffic = tj["kernels"][dom]["dram_bytes_per_launch"]
+        if tj.get("n_gpus") == W and args.tris == tj.get("tris_per_chunk", 1000000) and dom in tj.get("kernels", {}):     # captured on this workload
+            ncu = tj["kernels"][dom]
     roofline = {"bound": "hbm", "kernel": dom + "_kernel", "achieved": d["GBps"], "peak": pk["hbm"], "unit": "GB/s",
-                "frac": d["GBps"] / pk["hbm"], "traffic": traffic, "alg_bytes_per_launch": d["alg_bytes"] / d["launches"],
+                "frac": d["GBps"] / pk["hbm"], "traffic": ncu.get("dram_bytes_per_launch"), "alg_bytes_per_launch": d["alg_bytes"] / d["launches"],
                 "avg_launch_ms": d["ms"] / d["launches"], "share_of_step": d["ms"] / ms_serial, "serial_pass_ms_per_step": ms_serial / args.steps, "peak_source": pk["source"],
-                "note": "working set of a 1 M-triangle chunk (48 MB triangles + 12 MB BVH8) is L2-resident: achieved counts bytes the kernel "
-                        "must touch per ray, served mostly by L2/L1; see profiles/ for the ncu DRAM figure"}
+                "counts_from": d["counts_from"], "oracle_counting_frame": oc_frame,
+                # what actually bounds the kernel (ncu --set full of the same command, profiles/): L2 throughput, issue slots, lanes
+                "l2_gbs": ncu.get("l2_gbs"), "issue_active_pct": ncu.get("issue_active_pct"), "lanes_per_inst": ncu.get("lanes_per_inst"),
+                "ncu_source": ncu.get("source"),
+                "note": "a 1 M-triangle chunk (48 MB triangles + 15 MB BVH8) is L2-resident: `achieved` is bytes the algorithm must touch per "
+                        "ray over the launch time, served mostly by L2/L1 -- `traffic` is what reached DRAM; the kernel is issue-bound "
+                        "(issue_active_pct x lanes_per_inst / 32), see DESIGN.md 3.1"}
+    # reorder (Work_Efficient_Scan): 64 B read + 64 B written per record the partition emits, over the partition launches
+    p_ms, p_ln = stage.get("partition", (0.0, 0))
+    reorder = None
+    if p_ln and sst["paths_partitioned"]:
+        rb = 128.0 * sst["paths_partitioned"]
+        reorder = {"bound": "hbm", "kernel": "partition_kernel", "records_per_step": sst["paths_partitioned"] / args.steps, "alg_bytes_per_step": rb / args.steps,
+                   "ms_per_step": p_ms / args.steps, "launches_per_step": p_ln / args.steps, "achieved": rb / (p_ms * 1e-3) / 1e9, "peak": pk["hbm"],
+                   "unit": "GB/s", "frac": rb / (p_ms * 1e-3) / 1e9 / pk["hbm"], "share_of_step": p_ms / ms_serial}
 
     # ---- end to end: Renderer::launch() call sequence with host buffers -------------------------------------
     keep, himg = pinned_array((fh, fw, 3), np.float32)
@@ -489,8 +645,13 @@ def run_dprt(args):
                 "data": "synthetic", "samples_per_s": N * args.steps / (ms * 1e-3), "rays_per_step": rays / args.steps,
                 "main_ray_queries_from_hit_cache_per_step": cached / args.steps,
                 "config": workload_config(args, W, fw, fh), "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clk, "stages": stages_out, "ranks": per_rank,
-                "alltoall": {"bytes_per_step": sent / args.steps, "exchange_iters_per_step": st["exchange_iters"] / args.steps}}
+                "clocks": clk, "stages": stages_out, "ranks": per_rank, "reorder": reorder, "parity": parity,
+                "exchange_data_plane": ("peer memory over NVLink (CUDA IPC), no host round trip" if R.p2p_enabled else "ncclAllGather + pinned read + ncclSend/ncclRecv") if W > 1 else "single rank",
+                "alltoall": {"bytes_per_step": sent / args.steps, "exchange_iters_per_step": st["exchange_iters"] / args.steps,
+                             "GBps_per_gpu_max": max(r["alltoall_GBps"] for r in per_rank), "nvlink_peak_GBps_per_direction": 900.0,
+                             "exchange_wait_ms_per_step_max": max(r["exchange_ms_per_step"] for r in per_rank)},
+                "image_reduce": {"ms": reduce_ms, "bytes": int(N * 12), "what": "image_average_kernel + ncclReduce(fp32 sum, root 0), device events, max over ranks"},
+                "load_balance": {"rays_walked_max_over_mean": max(r["rays_walked_per_step"] for r in per_rank) / max(1e-9, sum(r["rays_walked_per_step"] for r in per_rank) / W)}}
     if W == 1:
         if not args.skip_extras:
             line["primary_closest_hit"] = bench_primary(dprt, R, args, pk)
@@ -522,6 +683,9 @@ def main():
     ap.add_argument("--layout", choices=("slabs", "cells"), default="slabs", help="N>1: how the unit cube is cut into chunks")
     ap.add_argument("--serial", type=int, default=0, help="1 = no shadow/traverse stream overlap inside dprt_render_sample, for A/B")
     ap.add_argument("--mlp-dtype", type=int, default=1, help="proxy MLP operands: 1 = fp16 (reference's NN_Float, meets 1e-3), 0 = bf16 (out of tolerance)")
+    ap.add_argument("--count-scale", type=int, default=8, help="oracle BVH8 counting pass: frame reduced by this factor per side")
+    ap.add_argument("--skip-oracle-counts", action="store_true", help="roofline bytes from the kernel's own counters (A/B runs only)")
+    ap.add_argument("--skip-parity", action="store_true", help="N>1: skip the parity gate (A/B runs only)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extras", action="store_true")
     args = ap.parse_args()

@@ -94,6 +94,7 @@ struct dprt_ctx {
     dprt_light_tri* d_lights = nullptr;
     size_t buf_bytes[DPRT_BUF_COUNT] = {0};
     void* buf_ptr[DPRT_BUF_COUNT] = {nullptr};
+    MlpGroupEntry* d_mlpTable = nullptr; // [2][32]: per kind (vis, depth) the proxy network of every scene object (grouped MLP launch)
     int32_t* d_hist = nullptr;          // 32 path + 64 query counters
     PartitionScratch scratch{};
     uint8_t* d_nnKey = nullptr;         // one key byte per NN query slot
@@ -351,6 +352,8 @@ static int create_impl(const dprt_config* cfg, int rank, int world, int device, 
         if ((r = alloc_buf(ctx, DPRT_BUF_NN_QUERY, Q * sizeof(dprt_nn_query)))) return r;
         if ((r = alloc_buf(ctx, DPRT_BUF_NN_PACKED_QUERY, Q * sizeof(dprt_nn_query)))) return r;
         if ((r = alloc_buf(ctx, DPRT_BUF_PRED, Q * 4 * sizeof(dprt_half)))) return r;
+        CK(cudaMalloc(&ctx->d_mlpTable, 2 * 32 * sizeof(MlpGroupEntry)));
+        CK(cudaMemsetAsync(ctx->d_mlpTable, 0, 2 * 32 * sizeof(MlpGroupEntry), ctx->stream));
         CK(cudaMalloc(&ctx->d_hist, 128 * sizeof(int32_t)));
         CK(cudaMemsetAsync(ctx->d_hist, 0, 128 * sizeof(int32_t), ctx->stream));
         ctx->scratch.maxTiles = (int)((std::max(Q, N) + 1023) / 1024) + 1;
@@ -448,6 +451,7 @@ void dprt_destroy(dprt_ctx* ctx) {
     if (ctx->d_materials) cudaFree(ctx->d_materials);
     if (ctx->d_lights) cudaFree(ctx->d_lights);
     if (ctx->d_hist) cudaFree(ctx->d_hist);
+    if (ctx->d_mlpTable) cudaFree(ctx->d_mlpTable);
     if (ctx->scratch.tileState) cudaFree(ctx->scratch.tileState);
     if (ctx->scratch.tileCounter) cudaFree(ctx->scratch.tileCounter);
     if (ctx->d_hits) cudaFree(ctx->d_hits);
@@ -604,6 +608,10 @@ int dprt_upload_proxy(dprt_ctx* ctx, int si, const dprt_object_desc* desc, const
     if (o.depth) { mlp_destroy(o.depth); o.depth = nullptr; }
     if (vis_blob && mlp_create(vis_blob, vis_bytes, ctx->cfg.mlpDtype, &o.vis, ctx->err)) return DPRT_ERR_INVALID;
     if (depth_blob && mlp_create(depth_blob, depth_bytes, ctx->cfg.mlpDtype, &o.depth, ctx->err)) return DPRT_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));            // a launch in flight may still read the old table rows
+    const MlpGroupEntry ev = mlp_group_entry(o.vis), ed = mlp_group_entry(o.depth);
+    CK(cudaMemcpy(ctx->d_mlpTable + si, &ev, sizeof(ev), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_mlpTable + 32 + si, &ed, sizeof(ed), cudaMemcpyHostToDevice));
     return upload_objects(ctx);
 }
 
@@ -934,15 +942,20 @@ int dprt_proxy_infer(dprt_ctx* ctx, int kind, int pred_offset) {
     StageScope sc_(ctx, DPRT_STAGE_PROXY_MLP, ctx->queryTotal > 0);
     if (ctx->queryTotal > 0)
         CK(cudaMemsetAsync(ctx->hp.pred + pred_offset, 0, (size_t)ctx->queryTotal * sizeof(dprt_half), ctx->stream));
+    // ONE launch for every proxy (the per-object forward loops of renderer.cpp:879-969, 1040-1120): object i owns rows
+    // [sceneOffset[i], sceneOffset[i+1]) of the packed queries; the kernel reads the offsets and the model table on the device
+    int64_t pairs = 0, rows = 0;
     for (int i = 0; i < S; i++) {
-        const int start = ctx->h_sceneOffset[i], cnt = ctx->h_sceneOffset[i + 1] - start;
-        if (cnt <= 0) continue;
+        const int cnt = ctx->h_sceneOffset[i + 1] - ctx->h_sceneOffset[i];
         const MlpModel* m = kind == 0 ? ctx->objects[i].vis : ctx->objects[i].depth;
-        if (!m) continue;                                    // "padding" model slot (renderer.cpp:791)
-        if (mlp_forward(m, ctx->hp.nnPackedInput + (size_t)start * 5, ctx->hp.pred + pred_offset + start, cnt, ctx->stream, ctx->err))
-            return DPRT_ERR_CUDA;
+        if (cnt <= 0 || !m) continue;                        // "padding" model slot (renderer.cpp:791): predictions stay 0
+        pairs += ((cnt + 127) / 128 + 1) / 2; rows += cnt;
+    }
+    if (pairs > 0) {
+        if (mlp_forward_group(ctx->d_mlpTable + (kind ? 32 : 0), ctx->hp.sceneOffset, S, pairs, ctx->cfg.mlpDtype, ctx->hp.nnPackedInput,
+                              ctx->hp.pred + pred_offset, ctx->stream, ctx->err)) return DPRT_ERR_CUDA;
         ctx->stats.kernel_launches += 1;
-        ctx->stats.nn_queries += cnt;
+        ctx->stats.nn_queries += rows;
     }
     CK(cudaGetLastError());
     return 0;

@@ -41,10 +41,11 @@ constexpr uint32_t kBlobMagic = 0x50524d4cu;
 constexpr int kE3W0 = 0, kE3B0 = 96, kE2W0 = 128, kE2B0 = 192, kBEnc = 224, kBRes = 480;
 __host__ __device__ constexpr int small_floats(int nres) { return kBRes + nres * kWidth + 64 + 64 + 1; }
 constexpr int kSmallMax = small_floats(kMaxRes);   // 2145 floats
-// The fp32 side parameters (input layers, all biases, the 64->1 output layer: 8.6 KB) travel as a
-// __grid_constant__ kernel parameter: every access is warp-uniform, which is what the constant bank is for,
-// and shared memory is left to the two A tiles and the weight ring.
+// The fp32 side parameters (input layers, all biases, the 64->1 output layer: 8.6 KB) live in global memory next to the
+// weight stages and are read with warp-uniform 16-byte loads (they stay in the SM's L1): one launch serves every proxy of
+// a stage, so they cannot be a kernel parameter, and shared memory is full with the two A tiles and the weight ring.
 struct SmallParams { float v[kSmallMax + 3]; };
+static_assert((kBEnc % 4) == 0 && (kBRes % 4) == 0 && (kE3B0 % 4) == 0 && (kE2W0 % 4) == 0 && (kE2B0 % 4) == 0, "float4 loads of the side parameters");
 
 // shared memory map (bytes from the 1024-aligned base)
 constexpr int kSmemA = 0;                                    // 2 slots x (128 x 256 x 16 bit = 4 K-blocks of 16 KiB)
@@ -52,7 +53,8 @@ constexpr int kSmemStages = kSlots * 65536;                  // 131072
 constexpr int kSmemBars = kSmemStages + kStages * kStageBytes;            // 229376: full[3], empty[3], mmaDone[2], aReady[2]
 constexpr int kNumBars = 2 * kStages + 2 * kSlots;
 constexpr int kSmemTmemPtr = kSmemBars + kNumBars * 8;
-constexpr int kSmemTotal = kSmemTmemPtr + 16 + 1024;                      // + alignment slack
+constexpr int kSmemTable = kSmemTmemPtr + 16;                             // grouped launch: pair prefix [33] + row offsets [33]
+constexpr int kSmemTotal = kSmemTable + 2 * 33 * 4 + 8 + 1024;            // + alignment slack
 static_assert(kSmemTotal <= 232448, "shared memory budget");
 
 // ---- PTX helpers ------------------------------------------------------------------------------------
@@ -183,10 +185,15 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // accumulate on top). The outer skip (out1) is kept by the row's own thread as 128 packed 16-bit pairs in
 // registers (the very words it wrote into the A tile), which is what the 208-register epilogue budget
 // (setmaxnreg) is for.
+// One launch evaluates every proxy of a stage (castSecondaryRaysNN / castShadowRaysNN / castShadowRaysDepthNN loop over the
+// scene objects, renderer.cpp:768-1159): the packed queries are bucket-major, object i owns rows [offsets[i], offsets[i+1]);
+// a work unit is a PAIR of 128-row tiles of one object (the two slots share that object's weight stream); unit -> object
+// comes from a prefix table every CTA derives from the offsets itself (device memory: no host round trip is needed for it).
+// offsets == nullptr: one batch, entry 0, rows [0, n).
 template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1)
-mlp_kernel(const uint8_t* __restrict__ wstages, const __grid_constant__ SmallParams sp, int nres, const uint16_t* __restrict__ x,
-           uint16_t* __restrict__ y, int n) {
+mlp_kernel(const MlpGroupEntry* __restrict__ table, const int32_t* __restrict__ offsets, int S, int n, const uint16_t* __restrict__ x,
+           uint16_t* __restrict__ y) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t aBase0 = smem_u32(smem + kSmemA);
@@ -197,11 +204,21 @@ mlp_kernel(const uint8_t* __restrict__ wstages, const __grid_constant__ SmallPar
     auto mmaDoneBar = [&](int slot) { return barBase + 8u * (uint32_t)(2 * kStages + slot); };
     auto aReadyBar = [&](int slot) { return barBase + 8u * (uint32_t)(2 * kStages + kSlots + slot); };
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem + kSmemTmemPtr);
+    int32_t* sPair = reinterpret_cast<int32_t*>(smem + kSmemTable);       // [S + 1] exclusive prefix of tile pairs per object
+    int32_t* sOff = sPair + 33;                                           // [S + 1] row offsets
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ntiles = (n + kRows - 1) / kRows;
 
     if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < S; i++) {
+            const int a = offsets ? offsets[i] : 0, b = offsets ? offsets[i + 1] : n;
+            sOff[i] = a; sPair[i] = run;
+            const int tiles = table[i].wstages ? (max(b - a, 0) + kRows - 1) / kRows : 0;     // no model: "padding" slot, rows keep 0
+            run += (tiles + kSlots - 1) / kSlots;
+            if (i == S - 1) sOff[S] = b;
+        }
+        sPair[S] = run;
         for (int s = 0; s < kStages; s++) { mbar_init(fullBar(s), 1); mbar_init(emptyBar(s), 1); }
         for (int s = 0; s < kSlots; s++) { mbar_init(mmaDoneBar(s), 1); mbar_init(aReadyBar(s), kRows); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -215,26 +232,36 @@ mlp_kernel(const uint8_t* __restrict__ wstages, const __grid_constant__ SmallPar
     tc_fence_after();
     const uint32_t tmem = *sTmem;
     const int fmt = BF16 ? 1 : 0;
+    const int totalPairs = sPair[S];
+    // unit u -> (object, first local tile, tiles in flight); every role walks the same unit sequence
+    auto unit = [&](int u, int& obj, int& lt0, int& nact) {
+        int i = 0;
+        while (u >= sPair[i + 1]) i++;
+        obj = i; lt0 = (u - sPair[i]) * kSlots;
+        const int tiles = (sOff[i + 1] - sOff[i] + kRows - 1) / kRows;
+        nact = lt0 + 1 < tiles ? 2 : 1;
+    };
 
     if (warp >= 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         if (warp == 9 && lane == 0) {
             // ---------------- weight loader: the stage sequence the MMA thread consumes, through a 3-deep ring ----------------
             uint32_t it = 0;
-            auto load = [&](int chunk) {
+            auto load = [&](const uint8_t* wstages, int chunk) {
                 const int s = it % kStages;
                 if (it >= kStages) mbar_wait(emptyBar(s), ((it / kStages) - 1) & 1);
                 mbar_expect_tx(fullBar(s), kStageBytes);
                 bulk_g2s(stageBase + s * kStageBytes, wstages + (size_t)chunk * kStageBytes, kStageBytes, fullBar(s));
                 it++;
             };
-            for (int t0 = blockIdx.x * kSlots; t0 < ntiles; t0 += gridDim.x * kSlots) {
-                const int nact = t0 + 1 < ntiles ? 2 : 1;
-                for (int s = 0; s < nact; s++) load(0);
+            for (int u = blockIdx.x; u < totalPairs; u += gridDim.x) {
+                int obj, lt0, nact; unit(u, obj, lt0, nact);
+                const uint8_t* wstages = table[obj].wstages; const int nres = table[obj].nres;
+                for (int s = 0; s < nact; s++) load(wstages, 0);
                 for (int l = 0; l < nres; l++)
                     for (int s = 0; s < nact; s++)
-                        for (int kc = 0; kc < 4; kc++) load(1 + l * 4 + kc);
-                for (int s = 0; s < nact; s++) load(1 + 4 * nres);
+                        for (int kc = 0; kc < 4; kc++) load(wstages, 1 + l * 4 + kc);
+                for (int s = 0; s < nact; s++) load(wstages, 1 + 4 * nres);
             }
         } else if (warp == 8 && lane == 0) {
             // ---------------- MMA issuer ----------------
@@ -247,8 +274,9 @@ mlp_kernel(const uint8_t* __restrict__ wstages, const __grid_constant__ SmallPar
                 tc_fence_after();
                 return s;
             };
-            for (int t0 = blockIdx.x * kSlots; t0 < ntiles; t0 += gridDim.x * kSlots) {
-                const int nact = t0 + 1 < ntiles ? 2 : 1;
+            for (int u = blockIdx.x; u < totalPairs; u += gridDim.x) {
+                int obj, lt0, nact; unit(u, obj, lt0, nact);
+                const int nres = table[obj].nres;
                 // encoder second layers as one block-diagonal 64 -> 256 GEMM
                 for (int sl = 0; sl < nact; sl++) {
                     mbar_wait(aReadyBar(sl), rdy[sl]); rdy[sl] ^= 1u;
@@ -303,18 +331,23 @@ mlp_kernel(const uint8_t* __restrict__ wstages, const __grid_constant__ SmallPar
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(slot * 256);
         const uint32_t doneBar = mmaDoneBar(slot), readyBar = aReadyBar(slot);
         uint32_t phase = 0;
-        const float* P = sp.v;
-        const float* bRes = P + kBRes;
-        const float* bP0 = P + kBRes + nres * kWidth;
-        const float* wP1 = bP0 + 64;
-        const float bP1 = wP1[64];
+        auto ld4 = [](const float* p, float* o) { const float4 v = __ldg(reinterpret_cast<const float4*>(p)); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; };
         auto publish = [&]() {           // operand (and residual) of this slot are in place: hand over to the MMA thread
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(readyBar);
         };
-        for (int tile = blockIdx.x * kSlots + slot; tile < ntiles; tile += gridDim.x * kSlots) {
-            const int g = tile * kRows + row;
+        for (int u = blockIdx.x; u < totalPairs; u += gridDim.x) {
+            int obj, lt0, nact; unit(u, obj, lt0, nact);
+            if (slot >= nact) continue;
+            const int nres = table[obj].nres;
+            const float* P = table[obj].small;
+            const float* bRes = P + kBRes;
+            const float* bP0 = P + kBRes + nres * kWidth;
+            const float* wP1 = bP0 + 64;
+            const int rowEnd = sOff[obj + 1];
+            const int g = sOff[obj] + (lt0 + slot) * kRows + row;
+            const int n = rowEnd;
             // input layers on CUDA cores: h = [LReLU(W3 x[0:3] + b3) | LReLU(W2 x[3:5] + b2)], 64 values -> K-block 0
             float xin[5];
 #pragma unroll
@@ -322,13 +355,20 @@ mlp_kernel(const uint8_t* __restrict__ wstages, const __grid_constant__ SmallPar
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 float h[8];
+                if (j < 4) {          // outputs 8 j .. 8 j + 7 of Lin(3, 32): 24 weights + 8 biases
+                    float w[24], b[8];
 #pragma unroll
-                for (int e = 0; e < 8; e++) {
-                    const int o = j * 8 + e;
-                    float s;
-                    if (o < 32) s = fmaf(P[kE3W0 + o * 3 + 2], xin[2], fmaf(P[kE3W0 + o * 3 + 1], xin[1], fmaf(P[kE3W0 + o * 3], xin[0], P[kE3B0 + o])));
-                    else s = fmaf(P[kE2W0 + (o - 32) * 2 + 1], xin[4], fmaf(P[kE2W0 + (o - 32) * 2], xin[3], P[kE2B0 + o - 32]));
-                    h[e] = lrelu(s);
+                    for (int q = 0; q < 6; q++) ld4(P + kE3W0 + j * 24 + q * 4, w + q * 4);
+                    ld4(P + kE3B0 + j * 8, b); ld4(P + kE3B0 + j * 8 + 4, b + 4);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) h[e] = lrelu(fmaf(w[e * 3 + 2], xin[2], fmaf(w[e * 3 + 1], xin[1], fmaf(w[e * 3], xin[0], b[e]))));
+                } else {              // outputs of Lin(2, 32): 16 weights + 8 biases
+                    float w[16], b[8];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) ld4(P + kE2W0 + (j - 4) * 16 + q * 4, w + q * 4);
+                    ld4(P + kE2B0 + (j - 4) * 8, b); ld4(P + kE2B0 + (j - 4) * 8 + 4, b + 4);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) h[e] = lrelu(fmaf(w[e * 2 + 1], xin[4], fmaf(w[e * 2], xin[3], b[e])));
                 }
                 uint4 w;
                 w.x = pack2<BF16>(h[0], h[1]); w.y = pack2<BF16>(h[2], h[3]); w.z = pack2<BF16>(h[4], h[5]); w.w = pack2<BF16>(h[6], h[7]);
@@ -345,8 +385,13 @@ mlp_kernel(const uint8_t* __restrict__ wstages, const __grid_constant__ SmallPar
                 uint32_t v[32];
                 TMEM_LD32(tlane + c * 32, v);
                 tc_wait_ld();
+                {
+                    float bb[32];
 #pragma unroll
-                for (int i = 0; i < 32; i++) v[i] = __float_as_uint(lrelu(__uint_as_float(v[i]) + P[kBEnc + c * 32 + i]));
+                    for (int q = 0; q < 8; q++) ld4(P + kBEnc + c * 32 + q * 4, bb + q * 4);
+#pragma unroll
+                    for (int i = 0; i < 32; i++) v[i] = __float_as_uint(lrelu(__uint_as_float(v[i]) + bb[i]));
+                }
                 TMEM_ST32(tlane + c * 32, v);
 #pragma unroll
                 for (int i = 0; i < 16; i++) skip[c * 16 + i] = pack2<BF16>(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
@@ -368,9 +413,11 @@ mlp_kernel(const uint8_t* __restrict__ wstages, const __grid_constant__ SmallPar
                     uint32_t v[32];
                     TMEM_LD32(tlane + c * 32, v);
                     tc_wait_ld();
-                    float yv[32];
+                    float yv[32], bb[32];
 #pragma unroll
-                    for (int i = 0; i < 32; i++) { yv[i] = lrelu(__uint_as_float(v[i]) + b[c * 32 + i]); v[i] = __float_as_uint(yv[i]); }
+                    for (int q = 0; q < 8; q++) ld4(b + c * 32 + q * 4, bb + q * 4);
+#pragma unroll
+                    for (int i = 0; i < 32; i++) { yv[i] = lrelu(__uint_as_float(v[i]) + bb[i]); v[i] = __float_as_uint(yv[i]); }
                     TMEM_ST32(tlane + c * 32, v);
                     store_a32<BF16>(sA, row, c, yv);
                 }
@@ -386,13 +433,15 @@ mlp_kernel(const uint8_t* __restrict__ wstages, const __grid_constant__ SmallPar
                     uint32_t v[32];
                     TMEM_LD32(tlane + c * 32, v);
                     tc_wait_ld();
-                    float yv[32];
+                    float yv[32], bb[32];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) ld4(b + c * 32 + q * 4, bb + q * 4);
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
                         float s0, s1;
                         unpack2<BF16>(skip[c * 16 + i], s0, s1);
-                        yv[2 * i] = lrelu(__uint_as_float(v[2 * i]) + b[c * 32 + 2 * i]) + s0;
-                        yv[2 * i + 1] = lrelu(__uint_as_float(v[2 * i + 1]) + b[c * 32 + 2 * i + 1]) + s1;
+                        yv[2 * i] = lrelu(__uint_as_float(v[2 * i]) + bb[2 * i]) + s0;
+                        yv[2 * i + 1] = lrelu(__uint_as_float(v[2 * i + 1]) + bb[2 * i + 1]) + s1;
                     }
                     store_a32<BF16>(sA, row, c, yv);
                 }
@@ -402,14 +451,17 @@ mlp_kernel(const uint8_t* __restrict__ wstages, const __grid_constant__ SmallPar
             // post epilogue: z = LReLU(acc[:,0:64] + b0); out = LReLU(w1 . z + b1) on CUDA cores
             mbar_wait(doneBar, phase); phase ^= 1;
             tc_fence_after();
-            float acc = bP1;
+            float acc = __ldg(wP1 + 64);
 #pragma unroll
             for (int c = 0; c < 2; c++) {
                 uint32_t v[32];
                 TMEM_LD32(tlane + c * 32, v);
                 tc_wait_ld();
+                float bb[32], ww[32];
 #pragma unroll
-                for (int i = 0; i < 32; i++) acc = fmaf(lrelu(__uint_as_float(v[i]) + bP0[c * 32 + i]), wP1[c * 32 + i], acc);
+                for (int q = 0; q < 8; q++) { ld4(bP0 + c * 32 + q * 4, bb + q * 4); ld4(wP1 + c * 32 + q * 4, ww + q * 4); }
+#pragma unroll
+                for (int i = 0; i < 32; i++) acc = fmaf(lrelu(__uint_as_float(v[i]) + bb[i]), ww[i], acc);
             }
             if (g < n) y[g] = __half_as_ushort(__float2half_rn(lrelu(acc)));
             tc_fence_before();
@@ -436,7 +488,8 @@ inline size_t tile_off(int nrow, int kk) { return (size_t)(nrow / 8) * 1024 + (n
 struct MlpModel {
     int width = 0, nres = 0, dtype = 0;
     uint8_t* d_stages = nullptr;
-    SmallParams small;                     // fp32 side parameters, passed by value at every launch
+    float* d_small = nullptr;              // fp32 side parameters (SmallParams)
+    MlpGroupEntry* d_entry = nullptr;      // one-entry table for the single-model launch
     int num_sms = 148;
 };
 
@@ -486,10 +539,16 @@ int mlp_create(const void* blob, size_t bytes, int dtype, MlpModel** out, std::s
     MlpModel* m = new MlpModel();
     m->width = width; m->nres = nres; m->dtype = dtype;
     cudaError_t e;
-    std::memset(&m->small, 0, sizeof(SmallParams));
-    std::memcpy(m->small.v, sm.data(), sm.size() * 4);
+    SmallParams small;
+    std::memset(&small, 0, sizeof(SmallParams));
+    std::memcpy(small.v, sm.data(), sm.size() * 4);
+    MlpGroupEntry ent{};
     if ((e = cudaMalloc(&m->d_stages, stages.size())) != cudaSuccess ||
-        (e = cudaMemcpy(m->d_stages, stages.data(), stages.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        (e = cudaMemcpy(m->d_stages, stages.data(), stages.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMalloc(&m->d_small, sizeof(SmallParams))) != cudaSuccess ||
+        (e = cudaMemcpy(m->d_small, &small, sizeof(SmallParams), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMalloc(&m->d_entry, sizeof(MlpGroupEntry))) != cudaSuccess ||
+        (ent = mlp_group_entry(m), e = cudaMemcpy(m->d_entry, &ent, sizeof(ent), cudaMemcpyHostToDevice)) != cudaSuccess) {
         err = std::string("mlp_create: ") + cudaGetErrorString(e);
         mlp_destroy(m);
         return -1;
@@ -505,7 +564,15 @@ int mlp_create(const void* blob, size_t bytes, int dtype, MlpModel** out, std::s
 void mlp_destroy(MlpModel* m) {
     if (!m) return;
     if (m->d_stages) cudaFree(m->d_stages);
+    if (m->d_small) cudaFree(m->d_small);
+    if (m->d_entry) cudaFree(m->d_entry);
     delete m;
+}
+
+MlpGroupEntry mlp_group_entry(const MlpModel* m) {
+    MlpGroupEntry e{};
+    if (m) { e.wstages = m->d_stages; e.small = m->d_small; e.nres = m->nres; }
+    return e;
 }
 
 int mlp_forward(const MlpModel* m, const dprt_half* x_dev, dprt_half* y_dev, int64_t n, cudaStream_t stream, std::string& err) {
@@ -515,8 +582,21 @@ int mlp_forward(const MlpModel* m, const dprt_half* x_dev, dprt_half* y_dev, int
     const int ntiles = (int)((n + kRows - 1) / kRows);
     const int npairs = (ntiles + kSlots - 1) / kSlots;
     const int grid = npairs < m->num_sms ? npairs : m->num_sms;
-    if (m->dtype == 0) mlp_kernel<true><<<grid, kThreads, kSmemTotal, stream>>>(m->d_stages, m->small, m->nres, x_dev, y_dev, (int)n);
-    else mlp_kernel<false><<<grid, kThreads, kSmemTotal, stream>>>(m->d_stages, m->small, m->nres, x_dev, y_dev, (int)n);
+    if (m->dtype == 0) mlp_kernel<true><<<grid, kThreads, kSmemTotal, stream>>>(m->d_entry, nullptr, 1, (int)n, x_dev, y_dev);
+    else mlp_kernel<false><<<grid, kThreads, kSmemTotal, stream>>>(m->d_entry, nullptr, 1, (int)n, x_dev, y_dev);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("mlp_kernel launch: ") + cudaGetErrorString(e); return -1; }
+    return 0;
+}
+
+int mlp_forward_group(const MlpGroupEntry* table_dev, const int32_t* offsets_dev, int S, int64_t pairs_upper, int dtype, const dprt_half* x_dev,
+                      dprt_half* y_dev, cudaStream_t stream, std::string& err) {
+    if (!table_dev || !offsets_dev || S < 1 || S > 32) { err = "mlp_forward_group: bad table"; return -1; }
+    if (pairs_upper <= 0) return 0;
+    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)(pairs_upper < sms ? pairs_upper : sms);
+    if (dtype == 0) mlp_kernel<true><<<grid, kThreads, kSmemTotal, stream>>>(table_dev, offsets_dev, S, 0, x_dev, y_dev);
+    else mlp_kernel<false><<<grid, kThreads, kSmemTotal, stream>>>(table_dev, offsets_dev, S, 0, x_dev, y_dev);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("mlp_kernel launch: ") + cudaGetErrorString(e); return -1; }
     return 0;

@@ -257,3 +257,31 @@ def test_traversal_counters_against_oracle_bvh8_walker(gpu_required, oracle):
                 assert gn >= on and gt >= ot, (r, stage)
             assert gn <= 2.0 * on + 64 and gt <= 2.5 * ot + 64, (r, stage)
         R.close()
+
+
+def test_config3_full_size_two_chunks_1080p_four_bounces(gpu_required, oracle):
+    """BASELINE configs[2] at full size: 2 chunk owners x 1 M triangles, 1920x1080, bounces = 4 (5 loop iterations), ray
+    migration through the exchange -- every pixel of the frame, every record of both ranks, bit-exact against the oracle
+    (which needs a few seconds for it on the box's host cores). Two contexts on one device stand in for the two GPUs; the
+    NCCL / peer-memory data planes are covered by test_gpu_multi.py and by bench.py's parity gate."""
+    oracle.use_all_host_threads()
+    W, w, h = 2, 1920, 1080
+    rs, world, _ = build_pair(oracle, W, 1000000, w, h, spp=1, bounces=4, proxy_mode=0)
+    G = dprt.RankGroup(rs)
+    img_g, img_o = G.launch(), world.launch()
+    N, spc = w * h, rs[0].cfg.shadowPathCount
+    sent = 0
+    for r, R in enumerate(rs):
+        n = R.path_size
+        assert n == world.path_size(r), f"rank {r} pathSize"
+        assert_records_equal(R.download(D.BUF_PATHS, n * (1 + spc)), world.download(r, D.BUF_PATHS, n * (1 + spc)), f"rank {r} paths")
+        assert_bits_equal(R.download(D.BUF_ENV), world.download(r, D.BUF_ENV, 3 * N), f"rank {r} env")
+        assert_bits_equal(R.download(D.BUF_DIRECT), world.download(r, D.BUF_DIRECT, 3 * N * spc), f"rank {r} direct")
+        sg, so = R.stats(), world.stats(r)
+        for k in ("rays_traverse", "rays_shade", "rays_shadow", "paths_sent_offrank", "exchange_iters"):
+            assert sg[k] == so[k], (r, k, sg[k], so[k])
+        sent += sg["paths_sent_offrank"]
+        R.close()
+    assert sent > 100000, "config 3 is about migration: expected many paths to cross ranks"
+    assert_bits_equal(img_g, img_o, "1080p image")
+    assert np.isfinite(img_g).all() and img_g.max() > 0
