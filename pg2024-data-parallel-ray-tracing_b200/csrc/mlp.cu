@@ -54,7 +54,10 @@ constexpr int kSmemBars = kSmemStages + kStages * kStageBytes;            // 229
 constexpr int kNumBars = 2 * kStages + 2 * kSlots;
 constexpr int kSmemTmemPtr = kSmemBars + kNumBars * 8;
 constexpr int kSmemTable = kSmemTmemPtr + 16;                             // grouped launch: pair prefix [33] + row offsets [33]
-constexpr int kSmemTotal = kSmemTable + 2 * 33 * 4 + 8 + 1024;            // + alignment slack
+constexpr int kSmemParams = kSmemTable + 272;                             // 2 slots x 1 KiB: fp32 side parameters of the current phase
+// The kernel has no static shared memory, so the dynamic window starts at the CTA's shared base (1 KiB-aligned); the
+// kernel checks that and traps otherwise instead of carrying 1 KiB of alignment slack it has no room for.
+constexpr int kSmemTotal = kSmemParams + 2 * 1024;
 static_assert(kSmemTotal <= 232448, "shared memory budget");
 
 // ---- PTX helpers ------------------------------------------------------------------------------------
@@ -194,8 +197,9 @@ template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_kernel(const MlpGroupEntry* __restrict__ table, const int32_t* __restrict__ offsets, int S, int n, const uint16_t* __restrict__ x,
            uint16_t* __restrict__ y) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if (smem_u32(smem) & 1023u) __trap();                     // swizzled operand tiles need a 1 KiB-aligned base
     const uint32_t aBase0 = smem_u32(smem + kSmemA);
     const uint32_t stageBase = smem_u32(smem + kSmemStages);
     const uint32_t barBase = smem_u32(smem + kSmemBars);
@@ -331,42 +335,55 @@ mlp_kernel(const MlpGroupEntry* __restrict__ table, const int32_t* __restrict__ 
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(slot * 256);
         const uint32_t doneBar = mmaDoneBar(slot), readyBar = aReadyBar(slot);
         uint32_t phase = 0;
-        auto ld4 = [](const float* p, float* o) { const float4 v = __ldg(reinterpret_cast<const float4*>(p)); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; };
+        // fp32 side parameters of the current phase (input layers / one bias vector / output layer), staged per slot: every
+        // thread fetches 2 floats from global memory one phase ahead (latency hidden behind the MMA wait), the 128 threads
+        // of the slot publish them to a 1 KiB shared buffer and read them back as warp-uniform 16-byte LDS
+        float* sPar = reinterpret_cast<float*>(smem + kSmemParams + slot * 1024);
+        float2 pre = make_float2(0.f, 0.f);
+        auto prefetch = [&](const float* src, int count) {       // count even, <= 256; src 8-byte aligned
+            pre = 2 * row < count ? __ldg(reinterpret_cast<const float2*>(src) + row) : make_float2(0.f, 0.f);
+        };
+        auto commit = [&]() { reinterpret_cast<float2*>(sPar)[row] = pre; named_bar_sync(1 + slot, kRows); };
+        auto par4 = [&](int i4, float* o) { const float4 v = reinterpret_cast<const float4*>(sPar)[i4]; o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; };
         auto publish = [&]() {           // operand (and residual) of this slot are in place: hand over to the MMA thread
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(readyBar);
         };
+        bool havePre = false;            // `pre` already holds the input-layer parameters of this unit (fetched during the last one)
         for (int u = blockIdx.x; u < totalPairs; u += gridDim.x) {
             int obj, lt0, nact; unit(u, obj, lt0, nact);
-            if (slot >= nact) continue;
+            if (slot >= nact) { havePre = false; continue; }
             const int nres = table[obj].nres;
             const float* P = table[obj].small;
             const float* bRes = P + kBRes;
             const float* bP0 = P + kBRes + nres * kWidth;
-            const float* wP1 = bP0 + 64;
             const int rowEnd = sOff[obj + 1];
             const int g = sOff[obj] + (lt0 + slot) * kRows + row;
             const int n = rowEnd;
+            if (!havePre) prefetch(P, kBEnc);
             // input layers on CUDA cores: h = [LReLU(W3 x[0:3] + b3) | LReLU(W2 x[3:5] + b2)], 64 values -> K-block 0
             float xin[5];
 #pragma unroll
             for (int k = 0; k < 5; k++) xin[k] = g < n ? __half2float(__ushort_as_half(x[(size_t)g * 5 + k])) : 0.0f;
+            named_bar_sync(1 + slot, kRows);     // the slot's threads are done with the previous unit's output-layer parameters
+            commit();
+            prefetch(P + kBEnc, kWidth);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 float h[8];
                 if (j < 4) {          // outputs 8 j .. 8 j + 7 of Lin(3, 32): 24 weights + 8 biases
                     float w[24], b[8];
 #pragma unroll
-                    for (int q = 0; q < 6; q++) ld4(P + kE3W0 + j * 24 + q * 4, w + q * 4);
-                    ld4(P + kE3B0 + j * 8, b); ld4(P + kE3B0 + j * 8 + 4, b + 4);
+                    for (int q = 0; q < 6; q++) par4((kE3W0 + j * 24) / 4 + q, w + q * 4);
+                    par4((kE3B0 + j * 8) / 4, b); par4((kE3B0 + j * 8) / 4 + 1, b + 4);
 #pragma unroll
                     for (int e = 0; e < 8; e++) h[e] = lrelu(fmaf(w[e * 3 + 2], xin[2], fmaf(w[e * 3 + 1], xin[1], fmaf(w[e * 3], xin[0], b[e]))));
                 } else {              // outputs of Lin(2, 32): 16 weights + 8 biases
                     float w[16], b[8];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) ld4(P + kE2W0 + (j - 4) * 16 + q * 4, w + q * 4);
-                    ld4(P + kE2B0 + (j - 4) * 8, b); ld4(P + kE2B0 + (j - 4) * 8 + 4, b + 4);
+                    for (int q = 0; q < 4; q++) par4((kE2W0 + (j - 4) * 16) / 4 + q, w + q * 4);
+                    par4((kE2B0 + (j - 4) * 8) / 4, b); par4((kE2B0 + (j - 4) * 8) / 4 + 1, b + 4);
 #pragma unroll
                     for (int e = 0; e < 8; e++) h[e] = lrelu(fmaf(w[e * 2 + 1], xin[4], fmaf(w[e * 2], xin[3], b[e])));
                 }
@@ -380,17 +397,18 @@ mlp_kernel(const MlpGroupEntry* __restrict__ table, const int32_t* __restrict__ 
             uint32_t skip[128];
             mbar_wait(doneBar, phase); phase ^= 1;
             tc_fence_after();
+            commit();
+            prefetch(bRes, kWidth);
 #pragma unroll
             for (int c = 0; c < 8; c++) {
                 uint32_t v[32];
                 TMEM_LD32(tlane + c * 32, v);
                 tc_wait_ld();
-                {
-                    float bb[32];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) ld4(P + kBEnc + c * 32 + q * 4, bb + q * 4);
+                for (int q = 0; q < 8; q++) {
+                    float bb[4]; par4(c * 8 + q, bb);
 #pragma unroll
-                    for (int i = 0; i < 32; i++) v[i] = __float_as_uint(lrelu(__uint_as_float(v[i]) + bb[i]));
+                    for (int i = 0; i < 4; i++) v[q * 4 + i] = __float_as_uint(lrelu(__uint_as_float(v[q * 4 + i]) + bb[i]));
                 }
                 TMEM_ST32(tlane + c * 32, v);
 #pragma unroll
@@ -407,17 +425,20 @@ mlp_kernel(const MlpGroupEntry* __restrict__ table, const int32_t* __restrict__ 
             for (int l = 0; l < nres - 1; l++) {
                 mbar_wait(doneBar, phase); phase ^= 1;
                 tc_fence_after();
-                const float* b = bRes + l * kWidth;
+                commit();
+                prefetch(bRes + (l + 1) * kWidth, kWidth);
 #pragma unroll 2
                 for (int c = 0; c < 8; c++) {
                     uint32_t v[32];
                     TMEM_LD32(tlane + c * 32, v);
                     tc_wait_ld();
-                    float yv[32], bb[32];
+                    float yv[32];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) ld4(b + c * 32 + q * 4, bb + q * 4);
+                    for (int q = 0; q < 8; q++) {
+                        float bb[4]; par4(c * 8 + q, bb);
 #pragma unroll
-                    for (int i = 0; i < 32; i++) { yv[i] = lrelu(__uint_as_float(v[i]) + bb[i]); v[i] = __float_as_uint(yv[i]); }
+                        for (int i = 0; i < 4; i++) { yv[q * 4 + i] = lrelu(__uint_as_float(v[q * 4 + i]) + bb[i]); v[q * 4 + i] = __float_as_uint(yv[q * 4 + i]); }
+                    }
                     TMEM_ST32(tlane + c * 32, v);
                     store_a32<BF16>(sA, row, c, yv);
                 }
@@ -427,21 +448,24 @@ mlp_kernel(const MlpGroupEntry* __restrict__ table, const int32_t* __restrict__ 
             {   // last residual layer: add the outer skip (out1 + out2), no residual write-back
                 mbar_wait(doneBar, phase); phase ^= 1;
                 tc_fence_after();
-                const float* b = bRes + (nres - 1) * kWidth;
+                commit();
+                prefetch(bP0, 130);              // b0[64], w1[64], b1, one float of padding
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     uint32_t v[32];
                     TMEM_LD32(tlane + c * 32, v);
                     tc_wait_ld();
-                    float yv[32], bb[32];
+                    float yv[32];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) ld4(b + c * 32 + q * 4, bb + q * 4);
+                    for (int q = 0; q < 8; q++) {
+                        float bb[4]; par4(c * 8 + q, bb);
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        float s0, s1;
-                        unpack2<BF16>(skip[c * 16 + i], s0, s1);
-                        yv[2 * i] = lrelu(__uint_as_float(v[2 * i]) + bb[2 * i]) + s0;
-                        yv[2 * i + 1] = lrelu(__uint_as_float(v[2 * i + 1]) + bb[2 * i + 1]) + s1;
+                        for (int i = 0; i < 2; i++) {
+                            float s0, s1;
+                            unpack2<BF16>(skip[c * 16 + q * 2 + i], s0, s1);
+                            yv[q * 4 + 2 * i] = lrelu(__uint_as_float(v[q * 4 + 2 * i]) + bb[2 * i]) + s0;
+                            yv[q * 4 + 2 * i + 1] = lrelu(__uint_as_float(v[q * 4 + 2 * i + 1]) + bb[2 * i + 1]) + s1;
+                        }
                     }
                     store_a32<BF16>(sA, row, c, yv);
                 }
@@ -451,17 +475,27 @@ mlp_kernel(const MlpGroupEntry* __restrict__ table, const int32_t* __restrict__ 
             // post epilogue: z = LReLU(acc[:,0:64] + b0); out = LReLU(w1 . z + b1) on CUDA cores
             mbar_wait(doneBar, phase); phase ^= 1;
             tc_fence_after();
-            float acc = __ldg(wP1 + 64);
+            commit();
+            {   // input-layer parameters of this slot's next unit, if it has one
+                const int un = u + gridDim.x;
+                havePre = false;
+                if (un < totalPairs) {
+                    int o2, l2, n2; unit(un, o2, l2, n2);
+                    if (slot < n2) { prefetch(table[o2].small, kBEnc); havePre = true; }
+                }
+            }
+            float acc = sPar[128];
 #pragma unroll
             for (int c = 0; c < 2; c++) {
                 uint32_t v[32];
                 TMEM_LD32(tlane + c * 32, v);
                 tc_wait_ld();
-                float bb[32], ww[32];
 #pragma unroll
-                for (int q = 0; q < 8; q++) { ld4(bP0 + c * 32 + q * 4, bb + q * 4); ld4(wP1 + c * 32 + q * 4, ww + q * 4); }
+                for (int q = 0; q < 8; q++) {
+                    float bb[4], ww[4]; par4(c * 8 + q, bb); par4(16 + c * 8 + q, ww);
 #pragma unroll
-                for (int i = 0; i < 32; i++) acc = fmaf(lrelu(__uint_as_float(v[i]) + bb[i]), ww[i], acc);
+                    for (int i = 0; i < 4; i++) acc = fmaf(lrelu(__uint_as_float(v[q * 4 + i]) + bb[i]), ww[i], acc);
+                }
             }
             if (g < n) y[g] = __half_as_ushort(__float2half_rn(lrelu(acc)));
             tc_fence_before();
