@@ -151,6 +151,16 @@ int  dprt_mlp_infer_device(dprt_ctx* ctx, int scene_index, int kind, const void*
 int  dprt_gen_train_data(dprt_ctx* ctx, int scene_index, const dprt_ray* rays_host, int64_t n, float* features_host,
                          float* labels_host);
 
+/* The Precom pipeline, optix/precom_ray_kernel.cu:193-299 (+ copyOutputBuffersForTrainData renderer.cpp:264-285): the other
+ * training-set generator. Each ray (a camera path: tMin 1e-2, tMax = path.tMax in the record) is intersected with the proxied
+ * object's AABB -- front face, or back face with the direction reversed when the origin is inside -- and the MLP input is taken
+ * AT THE AABB HIT: features_host[5n] = ((p_aabb - aabbMin) / (aabbMax - aabbMin), phi / 2pi, theta / pi) in object space; then
+ * the object's original geometry is traced with tMax = inf and labels_host[n] = (t_geo - t_aabb) / maxLength. A ray that hits
+ * the AABB but not the geometry gets the loaders' miss value 1.0 (the reference leaves the buffer's reset value there);
+ * valid_host[n] = 0 for rays that miss the AABB (features 0: the reference writes nothing for them). */
+int  dprt_gen_precom_data(dprt_ctx* ctx, int scene_index, const dprt_ray* rays_host, int64_t n, float* features_host,
+                          float* labels_host, uint8_t* valid_host);
+
 int  dprt_device_alloc(dprt_ctx* ctx, size_t bytes, void** dev_ptr);
 int  dprt_device_free(dprt_ctx* ctx, void* dev_ptr);
 int  dprt_memcpy_h2d(dprt_ctx* ctx, void* dev, const void* host, size_t bytes);

@@ -17,6 +17,7 @@
 //   src/render/renderer.cpp:1212-1318,1320-1452,1457-1574,2031-2052            -> World::render_sample, image
 //   trainingcode/module.py:36-45,755-837        4Res256/6Res256 proxy MLP      -> mlp_forward_row (fp32)
 //   optix/vis_ray_kernel.cu:98-161              Vis pipeline (training samples) -> orc_gen_train_data
+//   optix/precom_ray_kernel.cu:193-299          Precom pipeline (training samples) -> orc_gen_precom_data
 //
 // PARITY PINNING. The reference ships no tests or golden vectors and cannot be built (README.md:5). What is
 // pinned against reference code executed in the build container: tea<4>/lcg/rnd against optix/random.hpp
@@ -1234,6 +1235,41 @@ int orc_gen_train_data(void* wp, int si, const dprt_ray* rays, int64_t n, float*
         f[3] = phi / 6.28318530717958647692f;
         f[4] = theta / 3.14159265358979323846f;
         label[i] = hit ? h.t / ob.desc.maxLength : 1.0f;
+    }
+    return 0;
+}
+
+// Precom pipeline (optix/precom_ray_kernel.cu:193-299): features at the proxy-AABB hit of each ray, label = depth of the
+// original geometry behind the AABB surface / maxLength (1.0: AABB hit, geometry missed; valid 0: AABB missed).
+int orc_gen_precom_data(void* wp, int si, const dprt_ray* rays, int64_t n, float* feat, float* label, uint8_t* valid) {
+    World* w = (World*)wp;
+    if (!w || si < 0 || si >= (int)w->objects.size() || !w->objects[si].present) return -1;
+    const Object& ob = w->objects[si];
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; i++) {
+        const dprt_ray& ry = rays[i];
+        const V3 o = v3(ry.origin[0], ry.origin[1], ry.origin[2]), d = v3(ry.direction[0], ry.direction[1], ry.direction[2]);
+        const V3 ol = xform_point(ob.desc.worldToObject, o), dl = xform_vector(ob.desc.worldToObject, d);
+        float* f = feat + 5 * i;
+        float ta; bool inside;
+        const bool aabb = aabb_hit(ol, dl, ob.desc.aabbMin, ob.desc.aabbMax, ry.tMin, ry.tMax, &ta, &inside);
+        if (aabb) {
+            const V3 pl = xform_point(ob.desc.worldToObject, at(o, d, ta));
+            const V3 dirL = inside ? neg(dl) : dl;
+            float phi, theta;
+            cartesian_to_spherical(normalized(dirL), &phi, &theta);
+            f[0] = (pl.x - ob.desc.aabbMin[0]) / (ob.desc.aabbMax[0] - ob.desc.aabbMin[0]);
+            f[1] = (pl.y - ob.desc.aabbMin[1]) / (ob.desc.aabbMax[1] - ob.desc.aabbMin[1]);
+            f[2] = (pl.z - ob.desc.aabbMin[2]) / (ob.desc.aabbMax[2] - ob.desc.aabbMin[2]);
+            f[3] = phi / 6.28318530717958647692f;
+            f[4] = theta / 3.14159265358979323846f;
+        } else {
+            f[0] = f[1] = f[2] = f[3] = f[4] = 0.0f;
+        }
+        Hit h;
+        const bool geo = ob.mesh.trace(o, d, ry.tMin, FLT_MAX, false, h);
+        label[i] = aabb ? (geo ? (h.t - ta) / ob.desc.maxLength : 1.0f) : 1.0f;
+        valid[i] = aabb ? 1 : 0;
     }
     return 0;
 }

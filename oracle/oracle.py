@@ -53,6 +53,7 @@ def lib():
         L.orc_world_set_bvh8.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
         L.orc_count_bvh8.argtypes = [C.c_void_p, C.c_int]
         L.orc_get_bvh8_counters.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_gen_precom_data.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_bvh8_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.orc_mlp_forward.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_tea4.restype = C.c_uint32
@@ -275,6 +276,12 @@ class World:
         feat, lab = np.zeros((r.size, 5), np.float32), np.zeros(r.size, np.float32)
         assert self.L.orc_gen_train_data(self.h, scene_index, _p(r), r.size, _p(feat), _p(lab)) == 0
         return feat, lab
+
+    def gen_precom_data(self, scene_index, rays):
+        r = np.ascontiguousarray(rays, D.RAY_DTYPE)
+        feat, lab, valid = np.zeros((r.size, 5), np.float32), np.zeros(r.size, np.float32), np.zeros(r.size, np.uint8)
+        assert self.L.orc_gen_precom_data(self.h, scene_index, _p(r), r.size, _p(feat), _p(lab), _p(valid)) == 0
+        return feat, lab, valid
 
     def trace_closest(self, rank, rays, brute=False):
         r = np.ascontiguousarray(rays, D.RAY_DTYPE)

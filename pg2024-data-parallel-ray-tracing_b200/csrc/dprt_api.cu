@@ -1678,6 +1678,36 @@ int dprt_gen_train_data(dprt_ctx* ctx, int si, const dprt_ray* rays_host, int64_
     return 0;
 }
 
+int dprt_gen_precom_data(dprt_ctx* ctx, int si, const dprt_ray* rays_host, int64_t n, float* features_host, float* labels_host,
+                         uint8_t* valid_host) {
+    if (!ctx || !rays_host || !features_host || !labels_host || !valid_host || n < 0) return DPRT_ERR_INVALID;
+    if (si < 0 || si >= ctx->cfg.sceneSize || !ctx->objects[si].present || ctx->objects[si].desc.isProxy || !ctx->objects[si].d_nodes)
+        return fail(ctx, DPRT_ERR_STATE, "training data can only be generated for an object whose geometry is on this rank");
+    if (n > kMaxTraceRays) return fail(ctx, DPRT_ERR_INVALID, "more rays than one launch can index (split the batch)");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const size_t rb = (size_t)n * sizeof(dprt_ray), hb = (size_t)n * sizeof(dprt_hit), fb = (size_t)n * 5 * sizeof(float), lb = (size_t)n * sizeof(float);
+    int r = ensure_io(ctx, rb + hb + fb + 2 * lb + (size_t)n + 256); if (r) return r;
+    char* d = (char*)ctx->d_io;
+    dprt_ray* d_rays = (dprt_ray*)d; dprt_hit* d_hits = (dprt_hit*)(d + rb);
+    float* d_feat = (float*)(d + rb + hb); float* d_label = (float*)(d + rb + hb + fb); float* d_ta = (float*)(d + rb + hb + fb + lb);
+    uint8_t* d_valid = (uint8_t*)(d + rb + hb + fb + 2 * lb);
+    CK(cudaMemcpyAsync(d_rays, rays_host, rb, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        StageScope sc_(ctx, DPRT_STAGE_TRACE_CLOSEST);
+        launch_precom_features(ctx->d_objects + si, d_rays, n, d_feat, d_ta, ctx->stream);                 // proxy AABB (aabbHandle)
+        launch_trace_closest(ctx->d_objects + si, 1, d_rays, d_hits, n, ctx->d_queue, ctx->hp.counters, ctx->stream);   // originHandle, tMax = inf
+        launch_precom_labels(ctx->d_objects + si, d_hits, d_ta, n, d_label, d_valid, ctx->stream);
+    }
+    ctx->stats.kernel_launches += 3;
+    CK(cudaMemcpyAsync(features_host, d_feat, fb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(labels_host, d_label, lb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(valid_host, d_valid, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int dprt_mlp_infer_device(dprt_ctx* ctx, int si, int kind, const void* x_dev, int64_t n, void* y_dev) {
     if (!ctx || si < 0 || si >= ctx->cfg.sceneSize || !x_dev || !y_dev || n < 0) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));

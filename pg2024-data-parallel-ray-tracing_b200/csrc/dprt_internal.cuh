@@ -93,6 +93,12 @@ void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ra
 void launch_train_features(const DevObject* obj, const dprt_ray* rays, const dprt_hit* hits, int64_t n, float* features,
                            float* labels, cudaStream_t stream);
 
+// Precom pipeline (precom_ray_kernel.cu:193-299): AABB stage (features, t_aabb; rewrites the staged rays' tMax to inf for the
+// geometry trace that follows), then the label from the geometry hit
+void launch_precom_features(const DevObject* obj, dprt_ray* rays, int64_t n, float* features, float* t_aabb, cudaStream_t stream);
+void launch_precom_labels(const DevObject* obj, const dprt_hit* hits, const float* t_aabb, int64_t n, float* labels, uint8_t* valid,
+                          cudaStream_t stream);
+
 // partition / bucketing (partition.cu)
 struct PartitionScratch {
     uint32_t* tileState;           // tiles * 32 words

@@ -685,6 +685,51 @@ __global__ void __launch_bounds__(kBlock) train_features_kernel(const DevObject*
     label[i] = __float_as_int(h.y) >= 0 ? h.x / ob.maxLength : 1.0f;
 }
 
+// Precom pipeline (precom_ray_kernel.cu:193-299): a camera path meets the proxied object's AABB (front face, or back face when
+// the origin is inside) -> the MLP input encoding at the AABB hit; the object's ORIGINAL geometry is then traced with
+// tMax = inf and the label is the depth behind the AABB surface, (t_geo - t_aabb) / maxLength. This kernel does the AABB
+// stage and rewrites the staged ray for the geometry stage (tMax = inf); precom_label_kernel finishes after the trace.
+__global__ void __launch_bounds__(kBlock) precom_features_kernel(const DevObject* __restrict__ obj, dprt_ray* __restrict__ rays, int64_t n,
+                                                                  float* __restrict__ feat, float* __restrict__ tAabb) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevObject& ob = *obj;
+    float4* rp = reinterpret_cast<float4*>(rays) + 2 * i;
+    const float4 r0 = rp[0], r1 = rp[1];
+    const V3 o = v3(r0.x, r0.y, r0.z), d = v3(r1.x, r1.y, r1.z);
+    const V3 ol = xform_point(ob.w2o, o), dl = xform_vector(ob.w2o, d);
+    float* f = feat + 5 * i;
+    float t; bool inside;
+    if (aabb_intersect(ol, dl, ob.aabbMin, ob.aabbMax, r0.w, r1.w, &t, &inside)) {
+        const V3 pl = xform_point(ob.w2o, v3at(o, d, t));
+        const V3 dirL = inside ? v3neg(dl) : dl;
+        float phi, theta;
+        det_cartesian_to_spherical(v3normalized(dirL), &phi, &theta);
+        f[0] = (pl.x - ob.aabbMin[0]) / (ob.aabbMax[0] - ob.aabbMin[0]);
+        f[1] = (pl.y - ob.aabbMin[1]) / (ob.aabbMax[1] - ob.aabbMin[1]);
+        f[2] = (pl.z - ob.aabbMin[2]) / (ob.aabbMax[2] - ob.aabbMin[2]);
+        f[3] = phi / 6.28318530717958647692f;
+        f[4] = theta / 3.14159265358979323846f;
+        tAabb[i] = t;
+    } else {
+        f[0] = f[1] = f[2] = f[3] = f[4] = 0.0f;     // the reference leaves its (zeroed) buffers untouched
+        tAabb[i] = -1.0f;
+    }
+    rp[1] = make_float4(r1.x, r1.y, r1.z, FLT_MAX);  // geometry stage: path.tMax = __FLT_MAX__ (precom_ray_kernel.cu:262)
+}
+// label: (t_geo - t_aabb) / maxLength when AABB and geometry are both hit; 1.0 -- the loaders' "miss" value
+// (trainingcode/datasets.py:166-170) -- when the AABB is hit and the geometry is not; valid = 0 when the AABB is missed
+__global__ void __launch_bounds__(kBlock) precom_label_kernel(const DevObject* __restrict__ obj, const dprt_hit* __restrict__ hits, const float* __restrict__ tAabb,
+                                                               int64_t n, float* __restrict__ label, uint8_t* __restrict__ valid) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float ta = tAabb[i];
+    const float2 h = reinterpret_cast<const float2*>(hits)[i];
+    const bool aabb = ta >= 0.0f, geo = __float_as_int(h.y) >= 0;
+    label[i] = aabb ? (geo ? (h.x - ta) / obj->maxLength : 1.0f) : 1.0f;
+    valid[i] = aabb ? 1 : 0;
+}
+
 inline int blocks_for(int64_t n) { return (int)((n + kBlock - 1) / kBlock); }
 
 int num_sms() {
@@ -773,6 +818,12 @@ void launch_secondary_trace(const DevParams& p, int n, cudaStream_t s) {
 void launch_train_features(const DevObject* obj, const dprt_ray* rays, const dprt_hit* hits, int64_t n, float* features,
                            float* labels, cudaStream_t s) {
     if (n > 0) train_features_kernel<<<blocks_for(n), kBlock, 0, s>>>(obj, rays, hits, n, features, labels);
+}
+void launch_precom_features(const DevObject* obj, dprt_ray* rays, int64_t n, float* features, float* t_aabb, cudaStream_t s) {
+    if (n > 0) precom_features_kernel<<<blocks_for(n), kBlock, 0, s>>>(obj, rays, n, features, t_aabb);
+}
+void launch_precom_labels(const DevObject* obj, const dprt_hit* hits, const float* t_aabb, int64_t n, float* labels, uint8_t* valid, cudaStream_t s) {
+    if (n > 0) precom_label_kernel<<<blocks_for(n), kBlock, 0, s>>>(obj, hits, t_aabb, n, labels, valid);
 }
 void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ray* rays, dprt_hit* hits, int64_t n,
                           int32_t* queue, unsigned long long* counters, cudaStream_t s) {

@@ -76,6 +76,7 @@ _PROTOTYPES = {
     "dprt_trace_closest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "dprt_trace_closest_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "dprt_gen_train_data": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "dprt_gen_precom_data": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dprt_mlp_infer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "dprt_mlp_infer_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "dprt_device_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -476,6 +477,14 @@ class Renderer:
         feat, lab = np.zeros((r.size, 5), np.float32), np.zeros(r.size, np.float32)
         self._ck(self.lib.dprt_gen_train_data(self.h, scene_index, _ptr(r), r.size, _ptr(feat), _ptr(lab)), "dprt_gen_train_data")
         return feat, lab
+
+    def gen_precom_data(self, scene_index, rays):
+        """Precom pipeline (precom_ray_kernel.cu:193-299): (features [n,5] at the proxy-AABB hit, labels [n] = depth of the
+        geometry behind the AABB surface / maxLength, 1.0 = geometry missed; valid [n] u8 = the ray met the AABB)."""
+        r = np.ascontiguousarray(rays, D.RAY_DTYPE)
+        feat, lab, valid = np.zeros((r.size, 5), np.float32), np.zeros(r.size, np.float32), np.zeros(r.size, np.uint8)
+        self._ck(self.lib.dprt_gen_precom_data(self.h, scene_index, _ptr(r), r.size, _ptr(feat), _ptr(lab), _ptr(valid)), "dprt_gen_precom_data")
+        return feat, lab, valid
 
     def mlp_infer(self, scene_index, kind, x_half):
         x = np.ascontiguousarray(x_half, np.uint16).reshape(-1, 5)

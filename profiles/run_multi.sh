@@ -13,7 +13,7 @@ python - <<PY
 import json
 for f in ("${TAG}_bench_n${N}", "${TAG}_bench_n${N}_nccl", "${TAG}_bench_n${N}_proxy"):
     try:
-        l = json.load(open(f"$O/{f}.json"))
+        l = [json.loads(x) for x in open(f"$O/{f}.json") if x.startswith("{")][-1]
         print(f, "value", round(l["value"]), "ms/step", round(l["ms_per_step"], 2), "e2e", round(l["e2e"]["value"]), "parity", (l.get("parity") or {}).get("ok"),
               "plane", l.get("exchange_data_plane"), "iters", l["alltoall"]["exchange_iters_per_step"], "wait", round(l["alltoall"]["exchange_wait_ms_per_step_max"], 2),
               "GBps", round(l["alltoall"]["GBps_per_gpu_max"], 1), "reduce_ms", round(l["image_reduce"]["ms"], 3), "lb", round(l["load_balance"]["rays_walked_max_over_mean"], 3))

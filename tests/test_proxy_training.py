@@ -50,6 +50,40 @@ def test_oracle_train_data_encoding(oracle):
     assert yd.size == nh and (yd < 1.0).all() and (yd > 0).all()
 
 
+def _precom_rays(c, n_side=160):
+    """Camera paths as the Precom pipeline receives them (precom_ray_kernel.cu:205-212): tMin 1e-2, tMax = path.tMax = FLT_MAX;
+    the benchmark camera (outside every chunk's AABB) plus a camera INSIDE the AABB, so both AABB faces occur."""
+    cam = dprt.scene.default_camera(n_side, n_side * 9 // 16)
+    a = dprt.scene.camera_rays(cam)
+    b = a.copy()
+    b["origin"] = (0.5 * (np.asarray(c.aabb_min) + np.asarray(c.aabb_max)) + np.float32([0.0, 0.0, 0.2 * (c.aabb_max[2] - c.aabb_min[2])])).astype(np.float32)
+    rays = np.concatenate([a, b])
+    rays["tMin"] = np.float32(1e-2)
+    rays["tMax"] = np.finfo(np.float32).max
+    return rays
+
+
+def test_oracle_precom_data_encoding(oracle):
+    """Precom pipeline (optix/precom_ray_kernel.cu:193-299): features at the proxy-AABB hit, label = geometry depth behind it."""
+    world, c = _world(oracle)
+    rays = _precom_rays(c)
+    feat, lab, valid = world.gen_precom_data(0, rays)
+    v = valid.astype(bool)
+    assert 0.2 < v.mean() <= 1.0 and np.isfinite(feat).all() and np.isfinite(lab).all()
+    assert (feat[~v] == 0).all() and (lab[~v] == 1.0).all()
+    # the AABB hit point lies ON the box: one normalised coordinate is 0 or 1 (fp32 rounding of the transform aside)
+    on_face = (np.abs(feat[v, :3]) < 1e-4) | (np.abs(feat[v, :3] - 1.0) < 1e-4)
+    assert on_face.any(axis=1).all()
+    assert feat[v, 3:].min() >= -1e-6 and feat[v, 3:].max() <= 1.0 + 1e-6
+    # label: geometry hit -> (t_geo - t_aabb) / maxLength, never negative for a ray that enters from outside
+    hits = world.trace_closest(0, rays)
+    geo = hits["primID"] >= 0
+    assert (lab[v & ~geo] == 1.0).all()
+    n_out = rays.size // 2                                              # first half: camera outside the box
+    assert (lab[:n_out][v[:n_out] & geo[:n_out]] >= 0).all() and (lab[v & geo] < 1.0).all()
+    assert (v[n_out:]).all()                                            # a camera inside the box always meets its back face
+
+
 def test_training_loop_learns_visibility(oracle):
     """A small trunk on 60 k oracle samples: the test loss must fall well below the constant predictor's."""
     import torch
@@ -63,6 +97,24 @@ def test_training_loop_learns_visibility(oracle):
     assert hist[-1] < 0.6 * base, (hist, base)
     blob = dprt.proxy.pack_module(model)
     assert len(blob) > 16 and dprt.proxy.unpack_blob(blob) is not None
+
+
+@pytest.mark.gpu
+def test_gpu_precom_data_matches_oracle(gpu_required, oracle):
+    rs, world, chunks = build_pair(oracle, 2, 20000, 32, 18, proxy_mode=0)
+    for r, R in enumerate(rs):
+        c = chunks[r]
+        rays = _precom_rays(c, 320)
+        fg, lg, vg = R.gen_precom_data(c.index, rays)
+        fo, lo, vo = world.gen_precom_data(c.index, rays)
+        assert_bits_equal(vg, vo, f"valid flags of chunk {r}")
+        assert_bits_equal(fg, fo, f"Precom features of chunk {r}")
+        assert_bits_equal(lg, lo, f"Precom labels of chunk {r}")
+        assert vg.mean() > 0.2 and ((lg != 1.0) & (vg == 1)).mean() > 0.05
+        with pytest.raises(dprt.DprtError):
+            R.gen_precom_data(chunks[1 - r].index, rays[:8])
+        f0, l0, v0 = R.gen_precom_data(c.index, rays[:0])
+        assert f0.shape == (0, 5) and l0.shape == (0,) and v0.shape == (0,)
 
 
 @pytest.mark.gpu
