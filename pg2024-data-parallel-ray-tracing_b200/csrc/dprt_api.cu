@@ -114,6 +114,7 @@ struct dprt_ctx {
     // peer-memory exchange (p2p_exchange.cuh; DPRT_P2P=0 forces the NCCL fallback)
     bool p2p = false;                   // tables connected: the deque exchange runs over peer memory
     bool p2pGroup = false;              // connected as an in-process group (dprt_*_group only)
+    bool p2pGroupActive = false;        // the group driver is running the peer-memory exchange right now
     bool ownsComm = true;               // false: communicator borrowed from the parent context (dprt_create_shared)
     P2PMailbox* d_mailbox = nullptr;
     dprt_path_record* d_active[2] = {nullptr, nullptr};    // arrivals land here (never in `paths`)
@@ -140,6 +141,7 @@ struct dprt_ctx {
     int32_t* h_pinned = nullptr;        // pinned staging for counts/offsets
     void* d_flush = nullptr; size_t flush_bytes = 0;
     void* d_io = nullptr; size_t io_bytes = 0;   // staging for the standalone host-buffer operators
+    HitRec* d_rayPark = nullptr; size_t rayParkCount = 0;     // tail-parking scratch of the standalone closest-hit operator
     int pathSize = 0, shadowPathSize = 0;
     int sample = 0;
     int queryTotal = 0;                 // rows of the last bucketing
@@ -271,6 +273,16 @@ int upload_objects(dprt_ctx* ctx) {
     return 0;
 }
 
+// n HitRec for the parked tail of a standalone closest-hit launch (the stage launches use the stage's own hits[] array)
+int ensure_ray_park(dprt_ctx* ctx, size_t n) {
+    if (ctx->rayParkCount >= n) return 0;
+    if (ctx->d_rayPark) cudaFree(ctx->d_rayPark);
+    ctx->d_rayPark = nullptr; ctx->rayParkCount = 0;
+    CK(cudaMalloc(&ctx->d_rayPark, n * sizeof(HitRec)));
+    ctx->rayParkCount = n;
+    return 0;
+}
+
 int ensure_io(dprt_ctx* ctx, size_t bytes) {
     if (ctx->io_bytes >= bytes) return 0;
     if (ctx->d_io) cudaFree(ctx->d_io);
@@ -357,8 +369,11 @@ static int create_impl(const dprt_config* cfg, int rank, int world, int device, 
         CK(cudaMalloc(&ctx->d_hist, 128 * sizeof(int32_t)));
         CK(cudaMemsetAsync(ctx->d_hist, 0, 128 * sizeof(int32_t), ctx->stream));
         ctx->scratch.maxTiles = (int)((std::max(Q, N) + 1023) / 1024) + 1;
-        CK(cudaMalloc(&ctx->scratch.tileState, (size_t)ctx->scratch.maxTiles * 32 * sizeof(uint32_t)));
-        CK(cudaMalloc(&ctx->scratch.tileCounter, sizeof(int32_t)));
+        CK(cudaMalloc(&ctx->scratch.tileState, (size_t)ctx->scratch.maxTiles * 32 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(ctx->scratch.tileState, 0, (size_t)ctx->scratch.maxTiles * 32 * sizeof(unsigned long long), ctx->stream));
+        CK(cudaMalloc(&ctx->scratch.tileCounter, sizeof(uint32_t)));
+        CK(cudaMemsetAsync(ctx->scratch.tileCounter, 0, sizeof(uint32_t), ctx->stream));
+        ctx->scratch.tickets = 0u; ctx->scratch.generation = 0u;
         CK(cudaMalloc(&ctx->d_hits, N * sizeof(HitRec)));
         for (int k = 0; k < 2; k++) CK(cudaMalloc(&ctx->d_live[k], N * sizeof(int32_t)));
         if (cfg->proxyMode) CK(cudaMalloc(&ctx->d_secLive, N * sizeof(int32_t)));
@@ -369,6 +384,7 @@ static int create_impl(const dprt_config* cfg, int rank, int world, int device, 
         CK(cudaMalloc(&ctx->d_cacheHits, kDevStats * sizeof(unsigned long long)));
         CK(cudaMemsetAsync(ctx->d_cacheHits, 0, kDevStats * sizeof(unsigned long long), ctx->stream));
         CK(cudaMalloc(&ctx->d_queue, trace_scratch_bytes()));
+        CK(cudaMemsetAsync(ctx->d_queue, 0, 64, ctx->stream));
         if (!cfg->serialStages && !cfg->proxyMode) {
             int lo = 0, hi = 0;
             CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // the main stream carries the critical path: aux gets the lowest priority
@@ -376,6 +392,7 @@ static int create_impl(const dprt_config* cfg, int rank, int world, int device, 
             CK(cudaEventCreateWithFlags(&ctx->evShade, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ctx->evAux, cudaEventDisableTiming));
             CK(cudaMalloc(&ctx->d_queue_aux, trace_scratch_bytes()));
+            CK(cudaMemsetAsync(ctx->d_queue_aux, 0, 64, ctx->stream));
         }
         CK(cudaMalloc(&ctx->d_image, 3 * N * sizeof(float)));
         CK(cudaMalloc(&ctx->d_image_sum, 3 * N * sizeof(float)));
@@ -476,6 +493,7 @@ void dprt_destroy(dprt_ctx* ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_flush) cudaFree(ctx->d_flush);
     if (ctx->d_io) cudaFree(ctx->d_io);
+    if (ctx->d_rayPark) cudaFree(ctx->d_rayPark);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -684,7 +702,7 @@ int dprt_traverse(dprt_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->hp.pathHist, 0, 32 * sizeof(int32_t), ctx->stream));
     StageScope sc_(ctx, DPRT_STAGE_TRAVERSE, ctx->pathSize > 0);
     launch_traverse(ctx->hp, ctx->pathSize, ctx->stream);
-    ctx->stats.kernel_launches += 2 * (ctx->pathSize > 0);
+    ctx->stats.kernel_launches += trace_kernels_per_stage() * (ctx->pathSize > 0);
     ctx->stats.rays_traverse += ctx->pathSize;
     ctx->histFresh = true;
     CK(cudaGetLastError());
@@ -832,7 +850,7 @@ int dprt_shade(dprt_ctx* ctx) {
     sync_params(ctx);
     StageScope sc_(ctx, DPRT_STAGE_SHADE, ctx->pathSize > 0);
     launch_shade(ctx->hp, ctx->pathSize, ctx->stream);
-    ctx->stats.kernel_launches += 2 * (ctx->pathSize > 0);
+    ctx->stats.kernel_launches += trace_kernels_per_stage() * (ctx->pathSize > 0);
     ctx->stats.rays_shade += ctx->pathSize;
     ctx->epoch++;                       // the records now hold the next bounce's rays: cached hits are stale
     ctx->histFresh = false;
@@ -880,7 +898,7 @@ int dprt_shadow_trace(dprt_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->hp.queryHist, 0, 64 * sizeof(int32_t), ctx->stream));
     StageScope sc_(ctx, DPRT_STAGE_SHADOW_TRACE, ctx->shadowPathSize > 0);
     launch_shadow_trace(ctx->hp, ctx->shadowPathSize, ctx->stream);
-    ctx->stats.kernel_launches += 2 * (ctx->shadowPathSize > 0);
+    ctx->stats.kernel_launches += trace_kernels_per_stage() * (ctx->shadowPathSize > 0);
     ctx->stats.rays_shadow += ctx->shadowPathSize;
     // planes now hold this bounce's terms: covered by the MainRay list if nothing else was dirty, else unknown
     if (ctx->shadowPathSize > 0)
@@ -898,7 +916,7 @@ int dprt_secondary_trace(dprt_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->hp.queryHist, 0, 64 * sizeof(int32_t), ctx->stream));
     StageScope sc_(ctx, DPRT_STAGE_SECONDARY_TRACE, ctx->pathSize > 0);
     launch_secondary_trace(ctx->hp, ctx->pathSize, ctx->stream);
-    ctx->stats.kernel_launches += 2 * (ctx->pathSize > 0);
+    ctx->stats.kernel_launches += trace_kernels_per_stage() * (ctx->pathSize > 0);
     ctx->stats.rays_secondary += ctx->pathSize;
     ctx->qhistFresh = true; ctx->queryWhich = 1;
     ctx->histFresh = false;
@@ -1015,19 +1033,28 @@ namespace {
 
 bool deque_enabled(const dprt_ctx* ctx) { return ctx->d_settled && !ctx->hp.hitPrim; }
 
-int deque_begin(dprt_ctx* ctx) { ctx->front = ctx->back = ctx->N; ctx->nL = 0; return 0; }
+bool deque_p2p(const dprt_ctx* ctx) { return ctx->p2p && (ctx->p2pGroup ? ctx->p2pGroupActive : true); }
+
+int deque_begin(dprt_ctx* ctx) {
+    ctx->front = ctx->back = ctx->N; ctx->nL = 0;
+    if (deque_p2p(ctx)) {          // inside the loop the counts kernel leaves the histogram zeroed for the next TraRay launch
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaMemsetAsync(ctx->hp.pathHist, 0, 32 * sizeof(int32_t), ctx->stream));
+    }
+    return 0;
+}
 
 int deque_traverse(dprt_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     sync_params(ctx);
     ctx->hp.splitL = ctx->nL;
-    CK(cudaMemsetAsync(ctx->hp.pathHist, 0, 32 * sizeof(int32_t), ctx->stream));   // W + 1 <= 32 buckets
+    if (!deque_p2p(ctx)) CK(cudaMemsetAsync(ctx->hp.pathHist, 0, 32 * sizeof(int32_t), ctx->stream));   // W + 1 <= 32 buckets
     {
         StageScope sc_(ctx, DPRT_STAGE_TRAVERSE, ctx->pathSize > 0);
         launch_traverse(ctx->hp, ctx->pathSize, ctx->stream);
     }
     ctx->hp.splitL = 0x7fffffff;
-    ctx->stats.kernel_launches += 2 * (ctx->pathSize > 0);
+    ctx->stats.kernel_launches += trace_kernels_per_stage() * (ctx->pathSize > 0);
     ctx->stats.rays_traverse += ctx->pathSize + (ctx->back - ctx->front);          // the reference launches over the riders too
     CK(cudaGetLastError());
     return 0;
@@ -1404,7 +1431,7 @@ int dprt_primary_ray_module(dprt_ctx* ctx) {
         for (;;) {
             int done = 0;
             if ((r = deque_traverse(ctx))) return r;
-            if (ctx->p2p && !ctx->p2pGroup) { if ((r = p2p_exchange_enqueue(ctx))) return r; r = p2p_exchange_finish(ctx, &done); }
+            if (deque_p2p(ctx) && !ctx->p2pGroup) { if ((r = p2p_exchange_enqueue(ctx))) return r; r = p2p_exchange_finish(ctx, &done); }
             else { if ((r = deque_partition(ctx))) return r; r = deque_exchange(ctx, &done); }
             if (r) return r;
             if (done) break;
@@ -1513,6 +1540,7 @@ int dprt_render_sample_group(dprt_ctx** ctxs, int W, int sample) {
     bool p2p = deque && W > 1 && W <= 8 && pg && pg[0] == '1';
     if (p2p && !ctxs[0]->p2pGroup) { if ((r = p2p_connect_group(ctxs, W))) return r; }
     for (int k = 0; k < W; k++) p2p = p2p && ctxs[k]->p2p && ctxs[k]->p2pGroup;
+    for (int k = 0; k < W; k++) ctxs[k]->p2pGroupActive = p2p;
     for (int bounce = 0; bounce <= bounces; bounce++) {
         for (int k = 0; k < W; k++) if ((r = bounce_pre(ctxs[k], bounce))) return r;
         if (deque) for (int k = 0; k < W; k++) deque_begin(ctxs[k]);
@@ -1630,9 +1658,10 @@ int dprt_trace_closest_device(dprt_ctx* ctx, const void* rays_dev, int64_t n, vo
     if (!ctx || !rays_dev || !hits_dev || n < 0) return DPRT_ERR_INVALID;
     if (n > kMaxTraceRays) return fail(ctx, DPRT_ERR_INVALID, "more rays than one launch can index (split the batch)");
     CK(cudaSetDevice(ctx->device));
+    { int r = ensure_ray_park(ctx, (size_t)n); if (r) return r; }
     StageScope sc_(ctx, DPRT_STAGE_TRACE_CLOSEST, n > 0);
     launch_trace_closest(ctx->d_objects, ctx->cfg.sceneSize, (const dprt_ray*)rays_dev, (dprt_hit*)hits_dev, n, ctx->d_queue,
-                         ctx->hp.counters, ctx->stream);
+                         ctx->hp.counters, ctx->d_rayPark, ctx->stream);
     ctx->stats.kernel_launches += n > 0;
     ctx->stats.rays_traverse += n;
     CK(cudaGetLastError());
@@ -1667,7 +1696,7 @@ int dprt_gen_train_data(dprt_ctx* ctx, int si, const dprt_ray* rays_host, int64_
     CK(cudaMemcpyAsync(d, rays_host, rb, cudaMemcpyHostToDevice, ctx->stream));
     {
         StageScope sc_(ctx, DPRT_STAGE_TRACE_CLOSEST);
-        launch_trace_closest(ctx->d_objects + si, 1, (const dprt_ray*)d, (dprt_hit*)(d + rb), n, ctx->d_queue, ctx->hp.counters, ctx->stream);   // startObj only
+        launch_trace_closest(ctx->d_objects + si, 1, (const dprt_ray*)d, (dprt_hit*)(d + rb), n, ctx->d_queue, ctx->hp.counters, nullptr, ctx->stream);   // startObj only
         launch_train_features(ctx->d_objects + si, (const dprt_ray*)d, (const dprt_hit*)(d + rb), n, (float*)(d + rb + hb), (float*)(d + rb + hb + fb), ctx->stream);
     }
     ctx->stats.kernel_launches += 2;
@@ -1696,7 +1725,7 @@ int dprt_gen_precom_data(dprt_ctx* ctx, int si, const dprt_ray* rays_host, int64
     {
         StageScope sc_(ctx, DPRT_STAGE_TRACE_CLOSEST);
         launch_precom_features(ctx->d_objects + si, d_rays, n, d_feat, d_ta, ctx->stream);                 // proxy AABB (aabbHandle)
-        launch_trace_closest(ctx->d_objects + si, 1, d_rays, d_hits, n, ctx->d_queue, ctx->hp.counters, ctx->stream);   // originHandle, tMax = inf
+        launch_trace_closest(ctx->d_objects + si, 1, d_rays, d_hits, n, ctx->d_queue, ctx->hp.counters, nullptr, ctx->stream);   // originHandle, tMax = inf
         launch_precom_labels(ctx->d_objects + si, d_hits, d_ta, n, d_label, d_valid, ctx->stream);
     }
     ctx->stats.kernel_launches += 3;

@@ -85,9 +85,11 @@ void launch_traverse(const DevParams& p, int n, cudaStream_t stream);
 void launch_shade(const DevParams& p, int n, cudaStream_t stream);
 void launch_shadow_trace(const DevParams& p, int nShadow, cudaStream_t stream);
 void launch_secondary_trace(const DevParams& p, int n, cudaStream_t stream);
+int trace_kernels_per_stage();  // kernels one traversal stage launches (trace, the parked tail's finish kernel, post)
 size_t trace_scratch_bytes();   // per-context scratch of the persistent trace kernel (queue head + cooperative-mode pools)
+// park: n HitRec of scratch for the tail of the launch (kernels.cu "tail parking"), or null
 void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ray* rays, dprt_hit* hits, int64_t n,
-                          int32_t* queue, unsigned long long* counters, cudaStream_t stream);
+                          int32_t* queue, unsigned long long* counters, HitRec* park, cudaStream_t stream);
 
 // Vis pipeline epilogue (vis_ray_kernel.cu:145-160): features and label of every traced training ray of object `obj`
 void launch_train_features(const DevObject* obj, const dprt_ray* rays, const dprt_hit* hits, int64_t n, float* features,
@@ -101,26 +103,28 @@ void launch_precom_labels(const DevObject* obj, const dprt_hit* hits, const floa
 
 // partition / bucketing (partition.cu)
 struct PartitionScratch {
-    uint32_t* tileState;           // tiles * 32 words
-    int32_t*  tileCounter;         // dynamic tile id
+    unsigned long long* tileState; // tiles * 32 words {generation, status | value}; zeroed once at allocation, never cleared
+    uint32_t* tileCounter;         // running ticket counter (dynamic tile ids); zeroed once, never cleared
     int32_t   maxTiles;
+    uint32_t  tickets;             // host mirror: tickets taken by all earlier launches on this scratch
+    uint32_t  generation;          // host mirror: launches so far (0 = the zeroed state array matches no launch)
 };
 void launch_path_histogram(const dprt_path_record* paths, int n, int W, int32_t* hist, cudaStream_t stream);
 // B buckets. B == W: bucket = targetNode (reference). B == W + 1 (settled-deque mode): records that stay on rank `me` and
 // sit at index >= splitL go to bucket W, so that the self segment comes out in two pieces (before / after the old own block).
 void launch_partition_paths(const dprt_path_record* paths, int n, int W, int B, int me, int splitL, const int32_t* hist,
-                            dprt_path_record* out, int32_t* offsets, const PartitionScratch& s, cudaStream_t stream);
+                            dprt_path_record* out, int32_t* offsets, PartitionScratch& s, cudaStream_t stream);
 // peer-memory exchange: W + 1 buckets, bucket b's records go to plan->dst[b] + (index inside the bucket); no offsets output
 struct P2PPlan;
 void launch_partition_paths_peer(const dprt_path_record* paths, int n, int W, int me, int splitL, const P2PPlan* plan,
-                                 const PartitionScratch& s, cudaStream_t stream);
+                                 PartitionScratch& s, cudaStream_t stream);
 cudaError_t partition_preload_kernels();
 cudaError_t trace_preload_kernels();
 void launch_query_histogram(const dprt_nn_query* q, int n, int S, int insideOnly, int32_t* hist, cudaStream_t stream);
 // keys: DevParams::nnKey when it is known to mirror q (written by the same launch that wrote q), else null
 void launch_partition_queries(const dprt_nn_query* q, const uint8_t* keys, const dprt_half* in, int n, int S, int insideOnly,
                               const int32_t* hist, dprt_nn_query* outQ, dprt_half* outIn, int32_t* offsets,
-                              const PartitionScratch& s, cudaStream_t stream);
+                              PartitionScratch& s, cudaStream_t stream);
 
 // NN epilogues (epilogue.cu): frame_buffer_update.cu equivalents
 void launch_shadow_occlusion(const DevParams& p, int size, cudaStream_t stream);

@@ -114,6 +114,7 @@ constexpr int kRefillDefault = 12;
 constexpr int kTriVoteDefault = 8;
 constexpr int kCoopDefault = 8;
 constexpr int kRaysPerLaneDefault = 1;
+constexpr int kTailDefault = 16;          // steps a warp's leftover rays get after the queue ran dry before they are parked (0 = off)
 
 template <int MODE> struct StageOf;
 template <> struct StageOf<TM_TRAVERSE> { static constexpr int id = DPRT_STAGE_TRAVERSE; };
@@ -137,7 +138,15 @@ struct TraceArgs {
     int coop;                        // tail: a warp left with at most this many rays finishes them one at a time, 32 lanes per ray
     int nodesPerStep;                // a lane expands up to this many nodes per warp step while it finds no leaf triangles
     HitRec* hitCache; uint32_t epoch; unsigned long long* cacheHits;   // DevParams::hitCache (null = off)
+    // tail parking (launch_trace): once the ray queue is exhausted a warp gives its remaining rays `tailBudget` more steps, then
+    // parks them -- index into parkList (queue[1] counts them), best hit so far into park[idx] -- and trace_finish_kernel
+    // gives every parked ray a whole warp. 0 = off (the in-kernel cooperative tail, `coop`, finishes them instead).
+    int tailBudget;
+    int32_t* parkList;               // capacity: one entry per lane of the trace grid (a lane holds one ray when it parks)
+    HitRec* park;                    // closest-hit modes: resume state per ray index (the stage's hits[] array, or scratch for TM_RAYS)
 };
+
+constexpr int kParkCapacity = 148 * 8 * 128 + 4096;       // >= lanes of the largest trace grid
 
 // next local object at or after `from` that the ray still has to visit; sceneSize when none
 DPRT_D int next_object(const TraceArgs& a, int from, uint32_t skipMask) {
@@ -148,6 +157,58 @@ DPRT_D int next_object(const TraceArgs& a, int from, uint32_t skipMask) {
         return k;
     }
     return a.sceneSize;
+}
+
+
+// end(idx): what the stage keeps of a finished ray
+template <int MODE>
+DPRT_D void trace_end(const TraceArgs& a, int idx, const Trav& s, uint32_t flags) {
+    const bool hit = s.hitTri >= 0;
+    if (MODE == TM_TRAVERSE || MODE == TM_SECONDARY || MODE == TM_SHADE) {
+        // TraRay / SecondaryRay: the result goes to hits[idx] (32 coalesced bytes); the post kernel, which rewrites the whole
+        // record anyway, folds it in (tMax / currentNode / isHit) and files it in the hit cache under the pixel -- no
+        // dependent record read and no scattered 4-byte stores in here. MainRay: hits[idx] is what the shading program reads.
+        float4* h = reinterpret_cast<float4*>(a.hits + idx);
+        h[0] = make_float4(s.tbest, __int_as_float(hit ? s.hitPrim : -1), __int_as_float(s.hitTri), __int_as_float(s.hitObj));
+        h[1] = make_float4(s.ha, s.hb, 0.f, 0.f);
+    } else if (MODE == TM_SHADOW) {
+        if (hit) {    // any local occluder kills the shadow path (shadow_ray_kernel.cu:169-195)
+            flags = (flags | F_HIT) & ~F_VALID;
+            reinterpret_cast<uint32_t*>(a.recs + idx)[15] = flags;
+        }
+    } else {
+        reinterpret_cast<float2*>(a.rayHits)[idx] = make_float2(s.tbest, __int_as_float(hit ? s.hitPrim : -1));
+    }
+}
+
+// begin(i) without the hit-cache lookup: the ray of record / query i. Returns false for a dead record.
+template <int MODE>
+DPRT_D bool trace_load_ray(const TraceArgs& a, int my, V3& o, V3& d, float& tmin, float& tmax, uint32_t& flags, uint32_t& skipMask, bool& retry) {
+    tmin = DPRT_EPSILON; skipMask = 0u; retry = false; flags = 0u;
+    if (MODE == TM_RAYS) {
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(a.rays) + 2 * (size_t)my);
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(a.rays) + 2 * (size_t)my + 1);
+        o = v3(r0.x, r0.y, r0.z); tmin = r0.w; d = v3(r1.x, r1.y, r1.z); tmax = r1.w;
+        return true;
+    }
+    const float4* q = reinterpret_cast<const float4*>(a.recs + my);
+    const float4 q0 = q[0], q1 = q[1], q3 = q[3];
+    o = v3(q0.x, q0.y, q0.z); d = v3(q0.w, q1.x, q1.y); tmax = q1.z;
+    flags = __float_as_uint(q3.w);
+    if (MODE == TM_TRAVERSE) skipMask = __float_as_uint(q3.x);
+    if (MODE == TM_SHADE) {
+        // The reference re-traces with tMax = infinity (kernel.cu:382-413). When the record says "hit on this rank at tMax", the
+        // closest local hit is at t <= tMax: a trace bounded by the next float above tMax returns the very same (t, prim,
+        // barycentrics) while culling part of the BVH. A bounded trace that finds nothing is repeated unbounded, so the hint
+        // never changes a result.
+        const int currentNode = __float_as_int(q3.y);
+        if ((flags & F_HIT) && currentNode == a.worldID && tmax > 0.0f && tmax < FLT_MAX) {
+            tmax = __uint_as_float(__float_as_uint(tmax) + 1u); retry = true;
+        } else {
+            tmax = FLT_MAX;
+        }
+    }
+    return (flags & F_VALID) != 0u;
 }
 
 // Resident blocks per SM = register budget. The any-hit (shadow) trace has the shortest dependency chains per ray and gains
@@ -173,6 +234,7 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
     TraceCount cnt = {0u, 0u};
     bool exhausted = false;          // warp-uniform: the ray queue has no more rays
     int qlen = 0;                    // warp-uniform: pairs waiting in the triangle queue
+    int tail = 0;                    // warp-uniform: steps taken since the queue ran dry (tail parking)
     const int kRefill = a.refill;
 
     for (;;) {
@@ -231,8 +293,6 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
                     wq_set_ray(w, lane, s);
                     obj = next_object(a, 0, skipMask);
                     if (obj < a.sceneSize) { trav_enter_object(s, a.objects[obj].nodes, a.objects[obj].tris); wq_set_object(w, lane, s); walked++; }
-                } else if ((MODE == TM_TRAVERSE || MODE == TM_SECONDARY) && a.hitPrim) {
-                    a.hitPrim[my] = -1;
                 }
             }
         }
@@ -242,8 +302,12 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
         // ---- traverse until too few lanes are busy ----
         const int minBusy = exhausted ? 1 : (32 - kRefill + 1);
         do {
+            // (0) tail parking: the queue is dry and this warp's leftovers have had their extra steps. Everything queued is
+            // tested first (pend == 0 in every lane), step (2) then completes whatever is complete, the rest is parked.
+            const bool parkNow = exhausted && a.tailBudget > 0 && ++tail > a.tailBudget;
+            if (parkNow) { while (qlen > 0) tri_round<ANY, COUNT>(w, qlen, lane, s, obj, pend, cnt); }
             // (1) leaf triangles found by the last node phase go to the warp queue
-            wq_append(w, qlen, lane, idx >= 0, s, pend);
+            if (!parkNow) wq_append(w, qlen, lane, idx >= 0, s, pend);
             // (2) pop / object switch / ray completion
             if (idx >= 0) {
                 bool done = false;
@@ -273,34 +337,31 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
                     } else done = true;
                 }
                 if (done) {
-                    // ---- end(idx) ----
-                    const bool hit = s.hitTri >= 0;
-                    if (MODE == TM_TRAVERSE || MODE == TM_SECONDARY) {
-                        dprt_path_record* rec = a.recs + idx;
-                        if (hit) {
-                            rec->tMax = s.tbest; rec->currentNode = a.worldID; rec->isHit = 1;
-                            if (a.hitCache) {
-                                const int pixel = rec->pixelIndex;
-                                float4* c = reinterpret_cast<float4*>(a.hitCache + pixel);
-                                c[0] = make_float4(s.tbest, __int_as_float(s.hitPrim), __int_as_float(s.hitTri), __int_as_float(s.hitObj));
-                                c[1] = make_float4(s.ha, s.hb, __uint_as_float(a.epoch), __int_as_float(pixel));
-                            }
-                        }
-                        if (a.hitPrim) a.hitPrim[idx] = hit ? s.hitPrim : -1;
-                    } else if (MODE == TM_SHADE) {
-                        float4* h = reinterpret_cast<float4*>(a.hits + idx);
-                        h[0] = make_float4(s.tbest, __int_as_float(hit ? s.hitPrim : -1), __int_as_float(s.hitTri), __int_as_float(s.hitObj));
-                        h[1] = make_float4(s.ha, s.hb, 0.f, 0.f);
-                    } else if (MODE == TM_SHADOW) {
-                        if (hit) {    // any local occluder kills the shadow path (shadow_ray_kernel.cu:169-195)
-                            flags = (flags | F_HIT) & ~F_VALID;
-                            reinterpret_cast<uint32_t*>(a.recs + idx)[15] = flags;
-                        }
-                    } else {
-                        reinterpret_cast<float2*>(a.rayHits)[idx] = make_float2(s.tbest, __int_as_float(hit ? s.hitPrim : -1));
-                    }
+                    trace_end<MODE>(a, idx, s, flags);
                     idx = -1;
                 }
+            }
+            if (parkNow) {
+                // (2.4) park: ray index -> list; closest-hit modes also leave their best hit so far, the object they were in and its
+                // strict upper bound in park[idx], so that the finish kernel resumes that object from its root with the same
+                // candidates still to come (triangles found but not yet tested are simply found again). Any-hit rays restart.
+                const bool mine = idx >= 0;
+                const unsigned pm = __ballot_sync(FULL, mine);
+                if (pm != 0u) {
+                    int pbase = 0;
+                    if (lane == __ffs(pm) - 1) pbase = atomicAdd(a.queue + 1, __popc(pm));
+                    pbase = __shfl_sync(FULL, pbase, __ffs(pm) - 1);
+                    if (mine) {
+                        a.parkList[pbase + __popc(pm & ((1u << lane) - 1u))] = idx;
+                        if (!ANY) {
+                            float4* h = reinterpret_cast<float4*>(a.park + idx);
+                            h[0] = make_float4(s.tbest, __int_as_float(s.hitPrim), __int_as_float(s.hitTri), __int_as_float(s.hitObj));
+                            h[1] = make_float4(s.ha, s.hb, s.tlimit, __int_as_float(obj | (retry ? (1 << 30) : 0)));
+                        }
+                        idx = -1;
+                    }
+                }
+                break;
             }
             // (2.5) tail of the launch: few rays left in this warp -> all lanes work on one of them (bvh_traverse.cuh)
             if (exhausted && a.coop > 0) {
@@ -345,15 +406,107 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
     }
 }
 
+// Tail of a trace launch: every parked ray (trace_kernel step 2.4) gets a whole warp. The warp resumes the ray's current
+// object from its root with the cooperative traversal of bvh_traverse.cuh (32 nodes per step from a shared pool, triangles
+// through the warp queue), then the remaining objects, and ends the ray exactly like trace_kernel. What would be the serial
+// tail of the launch -- a few grazing rays that visit hundreds of nodes one after the other while the GPU idles -- becomes
+// parallel work for all SMs. Results do not depend on it: closest hit = minimum over all accepted triangle tests in
+// (t, primitive id) order with the same per-object bounds; any hit = a flag.
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_finish_kernel(TraceArgs a) {
+    constexpr bool ANY = MODE == TM_SHADOW;
+    const unsigned FULL = 0xffffffffu;
+    __shared__ WarpQueue s_wq[kTraceBlock / 32];
+    WarpQueue& w = s_wq[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int count = a.queue[1];
+    if (count <= 0) return;
+    w.key[lane] = ~0ull; w.cnt[lane] = 0;
+    __syncwarp();
+    uint32_t* pool = a.coopPool + (size_t)(blockIdx.x * (kTraceBlock / 32) + (threadIdx.x >> 5)) * DPRT_POOLCAP;
+    Trav s;
+    uint2 stack[DPRT_STACK];
+    TraceCount cnt = {0u, 0u};
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(a.queue + 2, 1);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= count) break;
+        const int idx = a.parkList[i];
+        V3 o, d; float tmin, tmax; uint32_t flags, skipMask; bool retry;
+        trace_load_ray<MODE>(a, idx, o, d, tmin, tmax, flags, skipMask, retry);      // warp-uniform loads
+        int obj = 0, pend = 0, qlen = 0;
+        bool exh = false;
+        trav_init_ray(s, o, d, tmin, tmax);
+        float tlimit = 0.f; bool resume = false;
+        if (!ANY) {
+            const float4 h0 = reinterpret_cast<const float4*>(a.park + idx)[0], h1 = reinterpret_cast<const float4*>(a.park + idx)[1];
+            s.tbest = h0.x; s.hitPrim = __float_as_int(h0.y); s.hitTri = __float_as_int(h0.z); s.hitObj = __float_as_int(h0.w);
+            s.ha = h1.x; s.hb = h1.y; tlimit = h1.z;
+            const int word = __float_as_int(h1.w);
+            obj = word & 0x3fffffff; retry = (word >> 30) & 1; resume = true;
+        } else {
+            obj = next_object(a, 0, skipMask);
+        }
+        if (lane == 0) wq_set_ray(w, 0, s);
+        for (;;) {
+            while (obj < a.sceneSize) {
+                if (lane == 0) {
+                    trav_enter_object(s, a.objects[obj].nodes, a.objects[obj].tris);
+                    if (resume) { s.tlimit = tlimit; s.tiePrim = (s.hitTri >= 0 && s.hitObj == obj) ? s.hitPrim : 0x7fffffff; }
+                    wq_set_object(w, 0, s);
+                }
+                resume = false;
+                __syncwarp();
+                coop_run<ANY, COUNT>(w, pool, qlen, lane, 0, s, stack, obj, pend, exh, cnt, a.prmtMagic);
+                if (ANY && __shfl_sync(FULL, (int)(s.hitTri >= 0), 0)) break;
+                obj = next_object(a, obj + 1, skipMask);
+            }
+            // MainRay: the bounded trace found nothing -> unbounded, from the first object (trace_kernel does the same)
+            const bool again = MODE == TM_SHADE && retry && !__shfl_sync(FULL, (int)(s.hitTri >= 0), 0);
+            if (!again) break;
+            retry = false;
+            if (lane == 0) s.tbest = FLT_MAX;
+            obj = next_object(a, 0, 0u);
+        }
+        if (lane == 0) trace_end<MODE>(a, idx, s, flags);
+        __syncwarp();
+    }
+    if (COUNT) {
+        if (cnt.nodes) atomicAdd(a.counters + 2 * StageOf<MODE>::id, (unsigned long long)cnt.nodes);
+        if (cnt.tris) atomicAdd(a.counters + 2 * StageOf<MODE>::id + 1, (unsigned long long)cnt.tris);
+    }
+}
+
+// What the closest-hit trace of TraRay / SecondaryRay found for record i (hits[i], written by trace_kernel for every valid
+// record of the launch): distributed_traversal_kernel.cu:256-263 / secondary_ray_kernel.cu:211-218, plus the hit cache entry
+// MainRay will look up under the path's pixel.
+DPRT_D void merge_trace_result(const DevParams& p, int i, PathRegs& path) {
+    const float4 h0 = reinterpret_cast<const float4*>(p.hits + i)[0];
+    const int prim = __float_as_int(h0.y);
+    if (prim < 0) return;
+    path.tMax = h0.x; path.currentNode = p.worldID; path.flags |= F_HIT;
+    if (p.hitPrim) p.hitPrim[i] = prim;
+    if (p.hitCache) {
+        const float4 h1 = reinterpret_cast<const float4*>(p.hits + i)[1];
+        float4* c = reinterpret_cast<float4*>(p.hitCache + path.pixelIndex);
+        c[0] = h0;
+        c[1] = make_float4(h1.x, h1.y, __uint_as_float(p.hitEpoch), __int_as_float(path.pixelIndex));
+    }
+}
+
 // ================================================================================================
 // TraRay program after the trace (distributed_traversal_kernel.cu:266-339): own bit, nearest unvisited proxy AABB
 // within tMax decides the next owner, environment light on a total miss; histogram by-product for the partition.
 __global__ void __launch_bounds__(kBlock) traverse_post_kernel(DevParams p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { p.traceQueue[0] = 0; p.traceQueue[1] = 0; p.traceQueue[2] = 0; }   // ray-queue head + park counters for the next trace launch on this stream (launch_trace)
     bool outValid = false; int target = -1;
     if (i < n) {
         PathRegs path = load_path(p.paths + i);
+        if (p.hitPrim) p.hitPrim[i] = -1;
         if (path.flags & F_VALID) {
+            merge_trace_result(p, i, path);
             const V3 o = path.origin, d = path.direction;
             path.visitedMask |= (1u << p.worldID);
             float tProxy = path.tMax; bool proxyHit = false;
@@ -433,6 +586,7 @@ DPRT_D BsdfSample sample_water(float xi1, V3 normal, V3 woWorld, bool isInside) 
 // generateNextNewPath (:134-162), generateShadowPath x spc (:66-132, :442-465).
 __global__ void __launch_bounds__(kBlock) shade_post_kernel(DevParams p, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { p.traceQueue[0] = 0; p.traceQueue[1] = 0; p.traceQueue[2] = 0; }
     if (i >= n) return;
     PathRegs path = load_path(p.paths + i);
     if (!(path.flags & F_VALID)) { if (p.livePixel) p.livePixel[i] = -1; return; }
@@ -618,6 +772,7 @@ __global__ void __launch_bounds__(kBlock) shadow_post_kernel(DevParams p, int nS
     if (threadIdx.x < 64) shHist[threadIdx.x] = 0;
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { p.traceQueue[0] = 0; p.traceQueue[1] = 0; p.traceQueue[2] = 0; }
     if (i < nShadow) {
         const PathRegs path = load_path(p.paths + (size_t)p.pathSize + i);
         if (!(path.flags & F_VALID)) {
@@ -645,11 +800,14 @@ __global__ void __launch_bounds__(kBlock) secondary_post_kernel(DevParams p, int
     if (threadIdx.x < 64) shHist[threadIdx.x] = 0;
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { p.traceQueue[0] = 0; p.traceQueue[1] = 0; p.traceQueue[2] = 0; }
     if (i < n) {
         PathRegs path = load_path(p.paths + i);
+        if (p.hitPrim) p.hitPrim[i] = -1;
         if (!(path.flags & F_VALID)) {
             clear_query_slots(p, i, 0);
         } else {
+            merge_trace_result(p, i, path);
             for (int k = 0; k < p.sceneSize; k++) if (p.objects[k].isProxy != 2) path.visitedMask |= (1u << p.objects[k].nodeID);
             const int r = proxy_march<true>(p, path, i, path.tMax, shHist);
             if (r < 0 && !(path.flags & F_HIT)) {
@@ -752,12 +910,17 @@ int tune_trivote() { static int v = env_int("DPRT_TRACE_TRIVOTE", kTriVoteDefaul
 int tune_coop() { static int v = env_int("DPRT_TRACE_COOP", kCoopDefault, 0, 32); return v; }
 int tune_rpl() { static int v = env_int("DPRT_TRACE_RPL", kRaysPerLaneDefault, 1, 64); return v; }
 int tune_nodes() { static int v = env_int("DPRT_TRACE_NODES", kNodesPerStepDefault, 1, 16); return v; }
+int tune_tail() { static int v = env_int("DPRT_TRACE_TAIL", kTailDefault, 0, 100000); return v; }
 int tune_blocks() { static int v = env_int("DPRT_TRACE_BLOCKS_PER_SM", 0, 0, 16); return v; }     // 0 = the launch bound of the mode
 
 template <int MODE>
 void launch_trace(TraceArgs a, int64_t n, cudaStream_t s) {
-    cudaMemsetAsync(a.queue, 0, sizeof(int32_t), s);
-    a.coopPool = reinterpret_cast<uint32_t*>(a.queue + 16);      // the context's trace scratch: queue head, then the node pools
+    // the queue head is zero here: cleared at allocation and again after every launch -- by the post kernel that follows each
+    // stage's trace launch on the same stream (one cudaMemsetAsync less per launch), by a memset after the bare TM_RAYS launch
+    // the context's trace scratch: queue head + park counters, the park list, then the cooperative-mode node pools
+    a.parkList = a.queue + 16;
+    a.coopPool = reinterpret_cast<uint32_t*>(a.queue + 16 + kParkCapacity);
+    if (MODE != TM_SHADOW && !a.park) a.tailBudget = 0;          // closest-hit modes need somewhere to leave their best hit
     // Grid: never more warps than keep every lane supplied with ~tune_rpl() rays. A warp runs until its longest ray is
     // done, so with one ray per lane its efficiency is mean/max ray length; with a few rays per lane the refill evens it out.
     const int64_t want = (n + (int64_t)kTraceBlock * tune_rpl() - 1) / ((int64_t)kTraceBlock * tune_rpl());
@@ -765,6 +928,11 @@ void launch_trace(TraceArgs a, int64_t n, cudaStream_t s) {
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms() * perSM));
     if (a.counters) trace_kernel<MODE, true><<<blocks, kTraceBlock, 0, s>>>(a, (int)n);
     else trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, s>>>(a, (int)n);
+    if (a.tailBudget > 0) {          // the parked tail of the launch, one warp per ray (returns at once when nothing was parked)
+        if (a.counters) trace_finish_kernel<MODE, true><<<blocks, kTraceBlock, 0, s>>>(a);
+        else trace_finish_kernel<MODE, false><<<blocks, kTraceBlock, 0, s>>>(a);
+    }
+    if (MODE == TM_RAYS) cudaMemsetAsync(a.queue, 0, 3 * sizeof(int32_t), s);
 }
 
 TraceArgs trace_args(const DevParams& p, dprt_path_record* recs) {
@@ -773,14 +941,17 @@ TraceArgs trace_args(const DevParams& p, dprt_path_record* recs) {
     a.rays = nullptr; a.rayHits = nullptr; a.hitPrim = p.hitPrim; a.queue = p.traceQueue; a.counters = p.counters;
     a.refill = tune_refill(); a.triVote = tune_trivote(); a.prmtMagic = 0x47000000u; a.coop = tune_coop(); a.nodesPerStep = tune_nodes();
     a.hitCache = p.hitCache; a.epoch = p.hitEpoch; a.cacheHits = p.cacheHits;
+    a.tailBudget = tune_tail(); a.parkList = nullptr; a.park = p.hits;
     return a;
 }
 
 }  // namespace
 
+int trace_kernels_per_stage() { return 2 + (tune_tail() > 0 ? 1 : 0); }     // trace [+ finish] + post
+
 size_t trace_scratch_bytes() {
     // 64 B for the ray-queue head + one cooperative-mode node pool per warp that can be resident
-    return 64 + (size_t)num_sms() * std::max(tune_blocks(), 8) * (kTraceBlock / 32) * DPRT_POOLCAP * sizeof(uint32_t);
+    return 64 + (size_t)kParkCapacity * sizeof(int32_t) + (size_t)num_sms() * std::max(tune_blocks(), 8) * (kTraceBlock / 32) * DPRT_POOLCAP * sizeof(uint32_t);
 }
 
 // forces the module load of the kernels of the migrate loop (p2p_exchange.cuh: never a first launch beside a spinning kernel)
@@ -788,6 +959,8 @@ cudaError_t trace_preload_kernels() {
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, trace_kernel<TM_TRAVERSE, false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_kernel<TM_TRAVERSE, true>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_finish_kernel<TM_TRAVERSE, false>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_finish_kernel<TM_TRAVERSE, true>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, traverse_post_kernel);
     return e;
 }
@@ -826,13 +999,14 @@ void launch_precom_labels(const DevObject* obj, const dprt_hit* hits, const floa
     if (n > 0) precom_label_kernel<<<blocks_for(n), kBlock, 0, s>>>(obj, hits, t_aabb, n, labels, valid);
 }
 void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ray* rays, dprt_hit* hits, int64_t n,
-                          int32_t* queue, unsigned long long* counters, cudaStream_t s) {
+                          int32_t* queue, unsigned long long* counters, HitRec* park, cudaStream_t s) {
     if (n <= 0) return;
     TraceArgs a;
     a.objects = objects; a.sceneSize = sceneSize; a.worldID = 0; a.recs = nullptr; a.hits = nullptr;
     a.rays = rays; a.rayHits = hits; a.hitPrim = nullptr; a.queue = queue; a.counters = counters;
     a.refill = tune_refill(); a.triVote = tune_trivote(); a.prmtMagic = 0x47000000u; a.coop = tune_coop(); a.nodesPerStep = tune_nodes();
     a.hitCache = nullptr; a.epoch = 0u; a.cacheHits = nullptr;
+    a.tailBudget = tune_tail(); a.parkList = nullptr; a.park = park;       // park: n records of scratch, or null (no tail parking)
     launch_trace<TM_RAYS>(a, n, s);
 }
 

@@ -24,6 +24,9 @@ constexpr int kWarps = kThreads / 32;
 // is the length of the tile chain, not the bytes.
 
 constexpr uint32_t ST_AGG = 1u << 30, ST_INC = 2u << 30, ST_MASK = 3u << 30, VAL_MASK = ~ST_MASK;
+// Tile states are 64-bit words {launch generation, status | value}: a word only counts when its generation is this launch's,
+// and tile ids are the running ticket counter minus the tickets of all earlier launches -- so neither the state array nor
+// the counter is ever cleared (two cudaMemsetAsync per partition launch gone from the migrate loop).
 
 struct PathOps {
     static constexpr bool kDirect = false;
@@ -91,17 +94,17 @@ struct QueryOps {
 
 template <class Ops, int kItems>
 __global__ void __launch_bounds__(kThreads) partition_kernel(Ops ops, int n, const int32_t* __restrict__ hist,
-                                                              int32_t* __restrict__ offsets, uint32_t* tileState,
-                                                              int32_t* tileCounter) {
+                                                              int32_t* __restrict__ offsets, unsigned long long* tileState,
+                                                              uint32_t* tileCounter, uint32_t ticketBase, uint32_t gen) {
     constexpr int kTile = kThreads * kItems, kSteps = kWarps * kItems;
     __shared__ int s_tile;
     __shared__ int s_cnt[kSteps][32];
     __shared__ int s_base[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int B = ops.B;
-    if (ops.skip()) return;                                      // block-uniform (peer exchange: the plan carries an error)
 
-    if (threadIdx.x == 0) s_tile = atomicAdd(tileCounter, 1);   // launch-order tile ids: predecessors are always running
+    if (threadIdx.x == 0) s_tile = (int)(atomicAdd(tileCounter, 1u) - ticketBase);   // launch-order tile ids: predecessors are always running
+    if (ops.skip()) return;                                      // block-uniform (peer exchange: the plan carries an error); ticket taken
     for (int k = threadIdx.x; k < kSteps * 32; k += kThreads) (&s_cnt[0][0])[k] = 0;
     __syncthreads();
     const int tile = s_tile;
@@ -147,21 +150,22 @@ __global__ void __launch_bounds__(kThreads) partition_kernel(Ops ops, int n, con
         // decoupled look-back, one chain per bucket
         int excl = 0;
         if (lane < B) {
-            volatile uint32_t* st = tileState;
+            volatile unsigned long long* st = tileState;
+            const unsigned long long g = (unsigned long long)gen << 32;
             if (tile == 0) {
-                st[lane] = ST_INC | (uint32_t)run;
+                st[lane] = g | ST_INC | (uint32_t)run;
             } else {
-                st[(size_t)tile * 32 + lane] = ST_AGG | (uint32_t)run;
-                __threadfence();
+                st[(size_t)tile * 32 + lane] = g | ST_AGG | (uint32_t)run;
                 int t = tile - 1;
                 for (;;) {
-                    uint32_t v;
-                    do { v = st[(size_t)t * 32 + lane]; } while ((v & ST_MASK) == 0u);
+                    unsigned long long w;
+                    do { w = st[(size_t)t * 32 + lane]; } while ((w >> 32) != gen);      // older generations: not written yet
+                    const uint32_t v = (uint32_t)w;
                     excl += (int)(v & VAL_MASK);
                     if ((v & ST_MASK) == ST_INC) break;
                     t--;
                 }
-                st[(size_t)tile * 32 + lane] = ST_INC | (uint32_t)(excl + run);
+                st[(size_t)tile * 32 + lane] = g | ST_INC | (uint32_t)(excl + run);
             }
         }
         s_base[lane] = bucketBase + excl;
@@ -208,13 +212,13 @@ __global__ void empty_offsets_kernel(int32_t* offsets, int B) {
 }
 
 template <class Ops, int kItems>
-void run_partition(Ops ops, int n, const int32_t* hist, int32_t* offsets, const PartitionScratch& s, cudaStream_t stream) {
+void run_partition(Ops ops, int n, const int32_t* hist, int32_t* offsets, PartitionScratch& s, cudaStream_t stream) {
     if (n <= 0) { if (!Ops::kDirect) empty_offsets_kernel<<<1, 64, 0, stream>>>(offsets, ops.B); return; }
     constexpr int kTile = kThreads * kItems;
     const int tiles = (n + kTile - 1) / kTile;                 // <= PartitionScratch::maxTiles, which is sized for 1024-record tiles
-    cudaMemsetAsync(s.tileState, 0, (size_t)tiles * 32 * sizeof(uint32_t), stream);
-    cudaMemsetAsync(s.tileCounter, 0, sizeof(int32_t), stream);
-    partition_kernel<Ops, kItems><<<tiles, kThreads, 0, stream>>>(ops, n, hist, offsets, s.tileState, s.tileCounter);
+    s.generation++;
+    partition_kernel<Ops, kItems><<<tiles, kThreads, 0, stream>>>(ops, n, hist, offsets, s.tileState, s.tileCounter, s.tickets, s.generation);
+    s.tickets += (uint32_t)tiles;                              // every block takes exactly one ticket
 }
 
 }  // namespace
@@ -225,13 +229,13 @@ void launch_path_histogram(const dprt_path_record* paths, int n, int W, int32_t*
 }
 
 void launch_partition_paths(const dprt_path_record* paths, int n, int W, int B, int me, int splitL, const int32_t* hist,
-                            dprt_path_record* out, int32_t* offsets, const PartitionScratch& s, cudaStream_t stream) {
+                            dprt_path_record* out, int32_t* offsets, PartitionScratch& s, cudaStream_t stream) {
     PathOps ops{paths, out, B, W, B > W ? me : -1, splitL};
     run_partition<PathOps, 4>(ops, n, hist, offsets, s, stream);
 }
 
 void launch_partition_paths_peer(const dprt_path_record* paths, int n, int W, int me, int splitL, const P2PPlan* plan,
-                                 const PartitionScratch& s, cudaStream_t stream) {
+                                 PartitionScratch& s, cudaStream_t stream) {
     PeerPathOps ops{paths, plan, W + 1, W, me, splitL};
     run_partition<PeerPathOps, 4>(ops, n, nullptr, nullptr, s, stream);
 }
@@ -250,7 +254,7 @@ void launch_query_histogram(const dprt_nn_query* q, int n, int S, int insideOnly
 
 void launch_partition_queries(const dprt_nn_query* q, const uint8_t* keys, const dprt_half* in, int n, int S, int insideOnly,
                               const int32_t* hist, dprt_nn_query* outQ, dprt_half* outIn, int32_t* offsets,
-                              const PartitionScratch& s, cudaStream_t stream) {
+                              PartitionScratch& s, cudaStream_t stream) {
     QueryOps ops{q, keys, in, outQ, outIn, S, insideOnly};
     if (keys) run_partition<QueryOps, 16>(ops, n, hist, offsets, s, stream);
     else run_partition<QueryOps, 4>(ops, n, hist, offsets, s, stream);
