@@ -114,7 +114,12 @@ constexpr int kRefillDefault = 12;
 constexpr int kTriVoteDefault = 8;
 constexpr int kCoopDefault = 8;
 constexpr int kRaysPerLaneDefault = 1;
-constexpr int kTailDefault = 16;          // steps a warp's leftover rays get after the queue ran dry before they are parked (0 = off)
+// Tail parking (rejected experiment, profiles/ab_r2_tail_parking.txt; compiled only with -DDPRT_TAIL_PARK=1): steps a warp's
+// leftover rays get after the queue ran dry before they are parked for trace_finish_kernel (0 = off)
+#ifndef DPRT_TAIL_PARK
+#define DPRT_TAIL_PARK 0
+#endif
+constexpr int kTailDefault = DPRT_TAIL_PARK ? 16 : 0;
 
 template <int MODE> struct StageOf;
 template <> struct StageOf<TM_TRAVERSE> { static constexpr int id = DPRT_STAGE_TRAVERSE; };
@@ -234,7 +239,9 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
     TraceCount cnt = {0u, 0u};
     bool exhausted = false;          // warp-uniform: the ray queue has no more rays
     int qlen = 0;                    // warp-uniform: pairs waiting in the triangle queue
+#if DPRT_TAIL_PARK
     int tail = 0;                    // warp-uniform: steps taken since the queue ran dry (tail parking)
+#endif
     const int kRefill = a.refill;
 
     for (;;) {
@@ -304,8 +311,12 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
         do {
             // (0) tail parking: the queue is dry and this warp's leftovers have had their extra steps. Everything queued is
             // tested first (pend == 0 in every lane), step (2) then completes whatever is complete, the rest is parked.
+#if DPRT_TAIL_PARK
             const bool parkNow = exhausted && a.tailBudget > 0 && ++tail > a.tailBudget;
             if (parkNow) { while (qlen > 0) tri_round<ANY, COUNT>(w, qlen, lane, s, obj, pend, cnt); }
+#else
+            constexpr bool parkNow = false;
+#endif
             // (1) leaf triangles found by the last node phase go to the warp queue
             if (!parkNow) wq_append(w, qlen, lane, idx >= 0, s, pend);
             // (2) pop / object switch / ray completion
@@ -341,6 +352,7 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
                     idx = -1;
                 }
             }
+#if DPRT_TAIL_PARK
             if (parkNow) {
                 // (2.4) park: ray index -> list; closest-hit modes also leave their best hit so far, the object they were in and its
                 // strict upper bound in park[idx], so that the finish kernel resumes that object from its root with the same
@@ -363,6 +375,7 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
                 }
                 break;
             }
+#endif
             // (2.5) tail of the launch: few rays left in this warp -> all lanes work on one of them (bvh_traverse.cuh)
             if (exhausted && a.coop > 0) {
                 const unsigned workM = __ballot_sync(FULL, idx >= 0 && obj < a.sceneSize && !exh);
@@ -406,6 +419,7 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
     }
 }
 
+#if DPRT_TAIL_PARK
 // Tail of a trace launch: every parked ray (trace_kernel step 2.4) gets a whole warp. The warp resumes the ray's current
 // object from its root with the cooperative traversal of bvh_traverse.cuh (32 nodes per step from a shared pool, triangles
 // through the warp queue), then the remaining objects, and ends the ray exactly like trace_kernel. What would be the serial
@@ -477,6 +491,7 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_f
         if (cnt.tris) atomicAdd(a.counters + 2 * StageOf<MODE>::id + 1, (unsigned long long)cnt.tris);
     }
 }
+#endif   // DPRT_TAIL_PARK
 
 // What the closest-hit trace of TraRay / SecondaryRay found for record i (hits[i], written by trace_kernel for every valid
 // record of the launch): distributed_traversal_kernel.cu:256-263 / secondary_ray_kernel.cu:211-218, plus the hit cache entry
@@ -910,7 +925,7 @@ int tune_trivote() { static int v = env_int("DPRT_TRACE_TRIVOTE", kTriVoteDefaul
 int tune_coop() { static int v = env_int("DPRT_TRACE_COOP", kCoopDefault, 0, 32); return v; }
 int tune_rpl() { static int v = env_int("DPRT_TRACE_RPL", kRaysPerLaneDefault, 1, 64); return v; }
 int tune_nodes() { static int v = env_int("DPRT_TRACE_NODES", kNodesPerStepDefault, 1, 16); return v; }
-int tune_tail() { static int v = env_int("DPRT_TRACE_TAIL", kTailDefault, 0, 100000); return v; }
+int tune_tail() { static int v = DPRT_TAIL_PARK ? env_int("DPRT_TRACE_TAIL", kTailDefault, 0, 100000) : 0; return v; }
 int tune_blocks() { static int v = env_int("DPRT_TRACE_BLOCKS_PER_SM", 0, 0, 16); return v; }     // 0 = the launch bound of the mode
 
 template <int MODE>
@@ -928,10 +943,12 @@ void launch_trace(TraceArgs a, int64_t n, cudaStream_t s) {
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms() * perSM));
     if (a.counters) trace_kernel<MODE, true><<<blocks, kTraceBlock, 0, s>>>(a, (int)n);
     else trace_kernel<MODE, false><<<blocks, kTraceBlock, 0, s>>>(a, (int)n);
+#if DPRT_TAIL_PARK
     if (a.tailBudget > 0) {          // the parked tail of the launch, one warp per ray (returns at once when nothing was parked)
         if (a.counters) trace_finish_kernel<MODE, true><<<blocks, kTraceBlock, 0, s>>>(a);
         else trace_finish_kernel<MODE, false><<<blocks, kTraceBlock, 0, s>>>(a);
     }
+#endif
     if (MODE == TM_RAYS) cudaMemsetAsync(a.queue, 0, 3 * sizeof(int32_t), s);
 }
 
@@ -959,8 +976,10 @@ cudaError_t trace_preload_kernels() {
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, trace_kernel<TM_TRAVERSE, false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_kernel<TM_TRAVERSE, true>);
+#if DPRT_TAIL_PARK
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_finish_kernel<TM_TRAVERSE, false>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, trace_finish_kernel<TM_TRAVERSE, true>);
+#endif
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, traverse_post_kernel);
     return e;
 }
