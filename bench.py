@@ -206,7 +206,7 @@ def workload_config(args, W, fw, fh):
             "chunks": W, "tris_per_chunk": args.tris, "chunk_layout": "single chunk" if W == 1 else
             ("one continuous terrain in load-balanced x-slabs (k/W quantiles of where the primary rays land)" if args.layout == "slabs" else "2x1x1 / 2x2x1 / 2x2x2 cells"), "width": fw, "height": fh, "bounces": args.bounces,
             "proxy": bool(args.proxy and W > 1), "main_ray": "re-trace" if args.retrace else "hit cache",
-            "stage_overlap": bool(not args.serial and not (args.proxy and W > 1)), "path_gen": "rank0" if (args.path_gen_mode == 0 or W == 1) else "striped",
+            "stage_overlap": bool(not args.serial and not (args.proxy and W > 1)), "samples_in_flight_requested": args.inflight, "path_gen": "rank0" if (args.path_gen_mode == 0 or W == 1) else "striped",
             "l2": "inputs larger than L2: 5 x 64 B path records per pixel (663 MB at 1080p) are rewritten every bounce",
             "parallelism": f"scene-chunk x{W}"}
 
@@ -489,21 +489,29 @@ def run_dprt(args):
             dist.barrier()
             raise SystemExit(3)
 
+    # ---- samples in flight (dprt.h): K contexts of this rank share the uploaded scene and the communicator; context j renders
+    # samples j, j + K, ... from its own host thread. Each sample's work is what it is with K = 1; the launches of one sample's
+    # late bounces / late migrate iterations (10^4..10^5 rays, as long as their longest ray) overlap the other's big ones.
+    F = dprt.SamplesInFlight(R, args.inflight)
+    K_inflight = len(F.ctxs)
+
     # ---- device-resident timing: W warm-up samples, then exactly K samples between two events ----------------
-    R.reset_frame()
-    for s in range(args.warmup):
-        R.run_sample(s)
+    F.reset_frame()
+    F.run_samples(0, args.warmup * K_inflight)
+    for X in F.ctxs:
+        X.synchronize()
     barrier()
-    R.reset_stats()
+    for X in F.ctxs:
+        X.reset_stats()
     clocks = ClockSampler(local if "CUDA_VISIBLE_DEVICES" not in os.environ else os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local])
     if rank == 0:
         clocks.start()
-    R.timer_start()
-    for s in range(args.steps):
-        R.run_sample(args.warmup + s)
-    ms = R.timer_stop()
+    for X in F.ctxs:
+        X.timer_start()                 # all streams are idle here: the start events coincide
+    F.run_samples(args.warmup * K_inflight, args.steps)
+    ms = max(X.timer_stop() for X in F.ctxs)
     barrier()
-    st = R.stats()
+    st = F.stats()
     my_rays_walked = st["rays_walked"]
     ms = allreduce(ms, dist.ReduceOp.MAX if W > 1 else None)
     # ---- per-stage pass over the same samples: CUDA-event pairs around every stage launch on the stream it is launched
@@ -649,7 +657,7 @@ def run_dprt(args):
                 "data": "synthetic", "samples_per_s": N * args.steps / (ms * 1e-3), "rays_per_step": rays / args.steps,
                 "main_ray_queries_from_hit_cache_per_step": cached / args.steps,
                 "config": workload_config(args, W, fw, fh), "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clk, "stages": stages_out, "ranks": per_rank, "reorder": reorder, "parity": parity,
+                "samples_in_flight": K_inflight, "clocks": clk, "stages": stages_out, "ranks": per_rank, "reorder": reorder, "parity": parity,
                 "exchange_data_plane": ("peer memory over NVLink (CUDA IPC), no host round trip" if R.p2p_enabled else "ncclAllGather + pinned read + ncclSend/ncclRecv") if W > 1 else "single rank",
                 "alltoall": {"bytes_per_step": sent / args.steps, "exchange_iters_per_step": st["exchange_iters"] / args.steps,
                              "GBps_per_gpu_max": max(r["alltoall_GBps"] for r in per_rank), "nvlink_peak_GBps_per_direction": 900.0,
@@ -659,11 +667,13 @@ def run_dprt(args):
     if W == 1:
         if not args.skip_extras:
             line["primary_closest_hit"] = bench_primary(dprt, R, args, pk)
+            F.close()
             R.close()
             line["proxy_mlp"] = bench_mlp(dprt, args, pk, local)
         if not args.skip_cpu:
             line["cpu_baseline"] = cpu_baseline(dprt, args)
     else:
+        F.close()
         R.close()
         dist.barrier()
         dist.destroy_process_group()
@@ -687,6 +697,7 @@ def main():
     ap.add_argument("--layout", choices=("slabs", "cells"), default="slabs", help="N>1: how the unit cube is cut into chunks")
     ap.add_argument("--serial", type=int, default=0, help="1 = no shadow/traverse stream overlap inside dprt_render_sample, for A/B")
     ap.add_argument("--mlp-dtype", type=int, default=1, help="proxy MLP operands: 1 = fp16 (reference's NN_Float, meets 1e-3), 0 = bf16 (out of tolerance)")
+    ap.add_argument("--inflight", type=int, default=2, help="samples in flight per GPU in the timed region (contexts sharing one scene; 1 = strictly one sample at a time)")
     ap.add_argument("--count-scale", type=int, default=8, help="oracle BVH8 counting pass: frame reduced by this factor per side")
     ap.add_argument("--skip-oracle-counts", action="store_true", help="roofline bytes from the kernel's own counters (A/B runs only)")
     ap.add_argument("--skip-parity", action="store_true", help="N>1: skip the parity gate (A/B runs only)")

@@ -108,6 +108,18 @@ int  dprt_render_sample(dprt_ctx* ctx, int sample);   /* runSample              
  * elsewhere): renderer.cpp:2031-2052. */
 int  dprt_reduce_image(dprt_ctx* ctx, int root, float* out_host);
 
+/* ---- samples in flight ----------------------------------------------------------------------------
+ * Samples of a frame are independent (renderer.cpp:1993-2022 runs them one after the other). The late bounces and the later
+ * migrate iterations of a sample carry 10^4..10^5 rays -- launches that last as long as their longest ray and leave most of
+ * the GPU idle -- so a host may keep K samples in flight: K contexts of the same rank (dprt_create_shared), one host thread
+ * each, context j rendering samples j, j + K, ... with dprt_render_sample. dprt_adopt_scene makes a context use another
+ * one's uploaded scene (chunk geometry, proxies and their networks, materials, lights, camera) without owning it -- the owner
+ * must outlive it and must not re-upload meanwhile. dprt_accumulate_from adds another context's directLighting (plane 0) and
+ * envLighting sums into this one's, after which dprt_reduce_image averages and reduces the whole frame. Each sample's
+ * arithmetic is unchanged; only the order of the per-pixel sum over samples differs (image within 1e-6 relative). */
+int  dprt_adopt_scene(dprt_ctx* ctx, dprt_ctx* from);
+int  dprt_accumulate_from(dprt_ctx* ctx, dprt_ctx* other);
+
 /* ---- peer-memory exchange (the data plane of dprt_primary_ray_module when every rank's buffers are reachable over
  * NVLink: MPI_Alltoall + MPI_Alltoallv + MPI_Allreduce of renderer.cpp:1254-1298 without a host round trip).
  * A context created with an NCCL id wires itself up inside dprt_create (and falls back to ncclSend/ncclRecv on all ranks

@@ -12,7 +12,7 @@ weight export of the training side (``proxy.py``), and the proxy training pipeli
 """
 from . import ctypes_defs, host, proxy, proxy_train, scene  # noqa: F401
 from .ctypes_defs import make_camera, make_config, make_object_desc  # noqa: F401
-from .host import DprtError, RankGroup, Renderer, build_bvh8, get_unique_id, load_library, plan_exchange, plan_exchange_deque  # noqa: F401
+from .host import DprtError, RankGroup, Renderer, SamplesInFlight, build_bvh8, get_unique_id, load_library, plan_exchange, plan_exchange_deque  # noqa: F401
 
 __all__ = ["ctypes_defs", "host", "proxy", "proxy_train", "scene", "make_camera", "make_config", "make_object_desc", "DprtError",
-           "RankGroup", "Renderer", "build_bvh8", "get_unique_id", "load_library"]
+           "RankGroup", "Renderer", "SamplesInFlight", "build_bvh8", "get_unique_id", "load_library"]

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "dprt.h"
@@ -72,6 +73,7 @@ NcclApi g_nccl;
 
 struct ObjectHost {
     bool present = false;
+    bool owned = true;               // false: device geometry and proxy networks belong to another context (dprt_adopt_scene)
     dprt_object_desc desc{};
     void* d_nodes = nullptr; void* d_tris = nullptr; void* d_normals = nullptr;
     int64_t nnodes = 0, ntris = 0;
@@ -456,6 +458,7 @@ void dprt_destroy(dprt_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && ctx->ownsComm) g_nccl.CommDestroy(ctx->comm);
     for (auto& o : ctx->objects) {
+        if (!o.owned) continue;
         if (o.d_nodes) cudaFree(o.d_nodes);
         if (o.d_tris) cudaFree(o.d_tris);
         if (o.d_normals) cudaFree(o.d_normals);
@@ -598,9 +601,12 @@ int dprt_upload_chunk(dprt_ctx* ctx, int si, const dprt_object_desc* desc, const
     if (bvh8_build(verts9, mat_ids, ntris, -1.f, b)) return fail(ctx, DPRT_ERR_INVALID, "bvh8_build failed");
     if (b.max_depth > 36) return fail(ctx, DPRT_ERR_CAPACITY, "BVH8 deeper than the traversal stack");
     ObjectHost& o = ctx->objects[si];
-    if (o.d_nodes) cudaFree(o.d_nodes);
-    if (o.d_tris) cudaFree(o.d_tris);
-    if (o.d_normals) cudaFree(o.d_normals);
+    if (o.owned) {
+        if (o.d_nodes) cudaFree(o.d_nodes);
+        if (o.d_tris) cudaFree(o.d_tris);
+        if (o.d_normals) cudaFree(o.d_normals);
+    } else { o.vis = o.depth = nullptr; }
+    o.owned = true;
     o.d_nodes = o.d_tris = o.d_normals = nullptr;
     o.desc = *desc; o.desc.isProxy = 0; o.present = true;
     o.nnodes = (int64_t)b.nodes.size(); o.ntris = (int64_t)b.tris.size();
@@ -621,6 +627,7 @@ int dprt_upload_proxy(dprt_ctx* ctx, int si, const dprt_object_desc* desc, const
     if (desc->nodeID < 0 || desc->nodeID >= ctx->world) return fail(ctx, DPRT_ERR_INVALID, "nodeID out of range");
     CK(cudaSetDevice(ctx->device));
     ObjectHost& o = ctx->objects[si];
+    if (!o.owned) { o.vis = o.depth = nullptr; o.d_nodes = o.d_tris = o.d_normals = nullptr; o.owned = true; }
     o.desc = *desc; o.desc.isProxy = 1; o.present = true;
     if (o.vis) { mlp_destroy(o.vis); o.vis = nullptr; }
     if (o.depth) { mlp_destroy(o.depth); o.depth = nullptr; }
@@ -631,6 +638,44 @@ int dprt_upload_proxy(dprt_ctx* ctx, int si, const dprt_object_desc* desc, const
     CK(cudaMemcpy(ctx->d_mlpTable + si, &ev, sizeof(ev), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_mlpTable + 32 + si, &ed, sizeof(ed), cudaMemcpyHostToDevice));
     return upload_objects(ctx);
+}
+
+int dprt_adopt_scene(dprt_ctx* ctx, dprt_ctx* from) {
+    if (!ctx || !from || ctx == from) return DPRT_ERR_INVALID;
+    if (ctx->device != from->device || ctx->rank != from->rank || ctx->world != from->world || ctx->cfg.sceneSize != from->cfg.sceneSize ||
+        ctx->cfg.mlpDtype != from->cfg.mlpDtype)
+        return fail(ctx, DPRT_ERR_INVALID, "dprt_adopt_scene: the two contexts must be the same rank, device, scene size and proxy operand type");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(from->stream));
+    for (int i = 0; i < ctx->cfg.sceneSize; i++) {
+        ObjectHost& o = ctx->objects[i];
+        if (o.owned) {
+            if (o.d_nodes) cudaFree(o.d_nodes);
+            if (o.d_tris) cudaFree(o.d_tris);
+            if (o.d_normals) cudaFree(o.d_normals);
+            if (o.vis) mlp_destroy(o.vis);
+            if (o.depth) mlp_destroy(o.depth);
+        }
+        o = from->objects[i];
+        o.owned = false;
+    }
+    CK(cudaMemcpy(ctx->d_materials, from->d_materials, sizeof(dprt_material) * DPRT_MAX_MATERIALS, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(ctx->d_lights, from->d_lights, sizeof(dprt_light_tri) * DPRT_MAX_LIGHTS, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(ctx->d_mlpTable, from->d_mlpTable, 2 * 32 * sizeof(MlpGroupEntry), cudaMemcpyDeviceToDevice));
+    ctx->hp.lightCount = from->hp.lightCount;
+    if (from->hp.camera.width == ctx->cfg.width && from->hp.camera.height == ctx->cfg.height) ctx->hp.camera = from->hp.camera;
+    return upload_objects(ctx);
+}
+
+int dprt_accumulate_from(dprt_ctx* ctx, dprt_ctx* other) {
+    if (!ctx || !other || ctx == other) return DPRT_ERR_INVALID;
+    if (ctx->device != other->device || ctx->N != other->N) return fail(ctx, DPRT_ERR_INVALID, "dprt_accumulate_from: same device and frame size required");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(other->stream));              // other's samples are complete
+    launch_accumulate(ctx->hp.direct, ctx->hp.env, other->hp.direct, other->hp.env, ctx->N * 3, ctx->stream);
+    ctx->stats.kernel_launches += 1;
+    CK(cudaGetLastError());
+    return 0;
 }
 
 int dprt_set_materials(dprt_ctx* ctx, const dprt_material* mats, int n) {
@@ -1371,6 +1416,7 @@ int p2p_exchange_finish(dprt_ctx* ctx, int* done) {
     const int parity = (int)((seq - 1u) & 1u);
     volatile P2PHostPlan* hp = ctx->h_plan;
     for (long spins = 0; hp->seq != seq; spins++) {
+        if ((spins & 0x3f) == 0x3f) std::this_thread::yield();      // several contexts of a rank may be polling (samples in flight)
         if ((spins & 0xfff) == 0xfff) {
             cudaError_t e = cudaStreamQuery(ctx->stream);
             if (e != cudaSuccess && e != cudaErrorNotReady) return fail(ctx, DPRT_ERR_CUDA, std::string("peer-memory exchange: ") + cudaGetErrorString(e));

@@ -138,6 +138,7 @@ void launch_reset_sec(const DevParams& p, const int32_t* live, int liveCount, cu
 void launch_depth_update(const DevParams& p, int size, cudaStream_t stream);
 void launch_tmax(const DevParams& p, int size, cudaStream_t stream);
 void launch_target_node(const DevParams& p, int n, cudaStream_t stream);
+void launch_accumulate(float* direct, float* env, const float* direct2, const float* env2, int n3, cudaStream_t stream);
 void launch_image_average(const float* direct, const float* env, float* out, int n3, float invSpp, cudaStream_t stream);
 
 }  // namespace dprt

@@ -103,6 +103,28 @@ int die(const char* what, dprt_ctx* ctx, int rc) {
     return 1;
 }
 
+// Samples in flight (dprt.h): `extra` contexts adopt `ctx`'s scene; context j renders samples j, j + K, ... from its own thread,
+// then everything is accumulated into `ctx`. K = 1: the plain sample loop of Renderer::launch (renderer.cpp:1993-2022).
+int render_samples(dprt_ctx* ctx, std::vector<dprt_ctx*>& extra, int spp, const char** what, dprt_ctx** failed) {
+    const int K = 1 + (int)extra.size();
+    std::vector<dprt_ctx*> all{ctx};
+    all.insert(all.end(), extra.begin(), extra.end());
+    std::vector<int> rc(K, 0);
+    auto work = [&](int j) {
+        for (int s = j; s < spp && !rc[j]; s += K) rc[j] = dprt_render_sample(all[j], s);
+    };
+    std::vector<std::thread> th;
+    for (int j = 1; j < K; j++) th.emplace_back(work, j);
+    work(0);
+    for (auto& t : th) t.join();
+    for (int j = 0; j < K; j++) if (rc[j]) { *what = "dprt_render_sample"; *failed = all[j]; return rc[j]; }
+    for (int j = 1; j < K; j++) {
+        const int r = dprt_accumulate_from(ctx, all[j]);
+        if (r) { *what = "dprt_accumulate_from"; *failed = ctx; return r; }
+    }
+    return 0;
+}
+
 const char* arg(int argc, char** argv, const char* name, const char* dflt) {
     for (int i = 1; i + 1 < argc; i++) if (!std::strcmp(argv[i], name)) return argv[i + 1];
     return dflt;
@@ -114,7 +136,7 @@ int main(int argc, char** argv) {
     const std::string scenePath = arg(argc, argv, "--scene", ""), outPath = arg(argc, argv, "--out", "");
     if (scenePath.empty()) {
         fprintf(stderr, "usage: dprt_render --scene S.dprt [--out image.pfm] [--spp n] [--bounces n] [--proxy 0|1] [--path-gen 0|1] "
-                        "[--world W | --nccl-id-file F]\n");
+                        "[--inflight K] [--world W | --nccl-id-file F]\n");
         return 2;
     }
     Scene sc; std::string err;
@@ -144,8 +166,24 @@ int main(int argc, char** argv) {
     cfg.envColor[0] = 0.6f; cfg.envColor[1] = 0.7f; cfg.envColor[2] = 0.9f;
     const size_t N = (size_t)cfg.width * cfg.height;
     std::vector<float> image(3 * N);
-    std::vector<dprt_ctx*> ctxs;
+    std::vector<dprt_ctx*> ctxs, extra;
+    int inflight = std::atoi(arg(argc, argv, "--inflight", "1"));      // samples in flight per rank
+    if (inflight < 1) inflight = 1;
+    if (inflight > cfg.spp) inflight = cfg.spp;
     int r;
+    // K - 1 more contexts of this rank on the same communicator, sharing the uploaded scene (collective across ranks)
+    auto make_inflight = [&](dprt_ctx* ctx) -> int {
+        if (world > 1 && !dprt_p2p_enabled(ctx)) return 0;          // the NCCL fallback exchange needs the communicator to itself
+        for (int j = 1; j < inflight; j++) {
+            dprt_ctx* c = nullptr;
+            int rr = dprt_create_shared(&cfg, ctx, &c);
+            if (rr) return rr;
+            extra.push_back(c);
+            if ((rr = dprt_adopt_scene(c, ctx))) return rr;
+            if ((rr = dprt_reset_frame(c))) return rr;
+        }
+        return 0;
+    };
 
     if (idFile && world > 1) {
         // ---- one process per GPU (the reference's deployment) ----
@@ -170,10 +208,10 @@ int main(int argc, char** argv) {
         if ((r = dprt_create(&cfg, rank, world, local, id, &ctx))) return die("dprt_create", nullptr, r);
         ctxs.push_back(ctx);
         if ((r = upload_scene(ctx, sc, rank))) return die("scene upload", ctx, r);
+        if ((r = make_inflight(ctx))) return die("samples in flight", nullptr, r);
         const auto t0 = std::chrono::steady_clock::now();
         if ((r = dprt_reset_frame(ctx))) return die("dprt_reset_frame", ctx, r);
-        for (int s = 0; s < cfg.spp; s++)
-            if ((r = dprt_render_sample(ctx, s))) return die("dprt_render_sample", ctx, r);
+        { const char* what = ""; dprt_ctx* bad = ctx; if ((r = render_samples(ctx, extra, cfg.spp, &what, &bad))) return die(what, bad, r); }
         if ((r = dprt_reduce_image(ctx, 0, rank == 0 ? image.data() : nullptr))) return die("dprt_reduce_image", ctx, r);
         const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         dprt_stats st; dprt_get_stats(ctx, &st);
@@ -188,11 +226,15 @@ int main(int argc, char** argv) {
             if ((r = dprt_create(&cfg, k, world, k % ndev, nullptr, &ctxs[k]))) return die("dprt_create", nullptr, r);
             if ((r = upload_scene(ctxs[k], sc, k))) return die("scene upload", ctxs[k], r);
         }
+        if (world == 1 && (r = make_inflight(ctxs[0]))) return die("samples in flight", nullptr, r);
         const auto t0 = std::chrono::steady_clock::now();
         for (int k = 0; k < world; k++) if ((r = dprt_reset_frame(ctxs[k]))) return die("dprt_reset_frame", ctxs[k], r);
-        for (int s = 0; s < cfg.spp; s++) {
-            r = world == 1 ? dprt_render_sample(ctxs[0], s) : dprt_render_sample_group(ctxs.data(), world, s);
-            if (r) return die("dprt_render_sample", ctxs[0], r);
+        if (world == 1) {
+            const char* what = ""; dprt_ctx* bad = ctxs[0];
+            if ((r = render_samples(ctxs[0], extra, cfg.spp, &what, &bad))) return die(what, bad, r);
+        } else {
+            for (int s = 0; s < cfg.spp; s++)
+                if ((r = dprt_render_sample_group(ctxs.data(), world, s))) return die("dprt_render_sample_group", ctxs[0], r);
         }
         r = world == 1 ? dprt_reduce_image(ctxs[0], 0, image.data()) : dprt_reduce_image_group(ctxs.data(), world, 0, image.data());
         if (r) return die("dprt_reduce_image", ctxs[0], r);
@@ -205,6 +247,7 @@ int main(int argc, char** argv) {
         fprintf(stderr, "dprt_render: cannot write %s\n", outPath.c_str());
         return 1;
     }
+    for (dprt_ctx* c : extra) dprt_destroy(c);         // borrowers before the owner of the scene and the communicator
     for (dprt_ctx* c : ctxs) dprt_destroy(c);
     return 0;
 }

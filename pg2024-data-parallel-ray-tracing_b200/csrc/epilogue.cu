@@ -168,6 +168,17 @@ void launch_tmax(const DevParams& p, int size, cudaStream_t s) {
 void launch_target_node(const DevParams& p, int n, cudaStream_t s) {
     if (n > 0) target_node_kernel<<<grid_for(n), kBlock, 0, s>>>(p, n);
 }
+// samples in flight: the accumulators of a second context of the same rank are added into the first one's
+__global__ void accumulate_kernel(float* __restrict__ direct, float* __restrict__ env, const float* __restrict__ direct2,
+                                  const float* __restrict__ env2, int n3) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += gridDim.x * blockDim.x) {
+        direct[i] += direct2[i];
+        env[i] += env2[i];
+    }
+}
+void launch_accumulate(float* direct, float* env, const float* direct2, const float* env2, int n3, cudaStream_t s) {
+    if (n3 > 0) accumulate_kernel<<<std::min(grid_for(n3), 148 * 16), kBlock, 0, s>>>(direct, env, direct2, env2, n3);
+}
 void launch_image_average(const float* direct, const float* env, float* out, int n3, float spp, cudaStream_t s) {
     if (n3 > 0) image_average_kernel<<<grid_for(n3), kBlock, 0, s>>>(direct, env, out, n3, spp);
 }

@@ -60,6 +60,8 @@ _PROTOTYPES = {
     "dprt_secondary_ray_module": (C.c_int, [C.c_void_p]),
     "dprt_render_sample": (C.c_int, [C.c_void_p, C.c_int]),
     "dprt_reduce_image": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "dprt_adopt_scene": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dprt_accumulate_from": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dprt_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dprt_p2p_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "dprt_p2p_enable": (C.c_int, [C.c_void_p, C.c_int]),
@@ -542,6 +544,75 @@ class Renderer:
         c = np.zeros(2 * D.STAGE_COUNT, np.uint64)
         self._ck(self.lib.dprt_get_counters(self.h, _ptr(c)), "dprt_get_counters")
         return {D.STAGE_NAMES[i]: (int(c[2 * i]), int(c[2 * i + 1])) for i in range(D.STAGE_COUNT)}
+
+
+class SamplesInFlight:
+    """K samples of a frame in flight on one rank (dprt.h "samples in flight"): K contexts sharing one uploaded scene and
+    the NCCL communicator, one host thread each; context j renders samples j, j + K, ... The frame is the primary's."""
+
+    def __init__(self, primary, k=2):
+        self.primary = primary
+        self.ctxs = [primary]
+        if primary.world > 1 and not primary.p2p_enabled:
+            k = 1        # the NCCL fallback exchange issues collectives from the sampling thread: one context per communicator
+        for _ in range(max(1, int(k)) - 1):
+            R = Renderer(primary.cfg, parent=primary)
+            R._ck(R.lib.dprt_adopt_scene(R.h, primary.h), "dprt_adopt_scene")
+            self.ctxs.append(R)
+
+    def adopt(self):
+        """Call again after the primary's scene, lights or camera changed."""
+        for R in self.ctxs[1:]:
+            R._ck(R.lib.dprt_adopt_scene(R.h, self.primary.h), "dprt_adopt_scene")
+
+    def reset_frame(self):
+        for R in self.ctxs:
+            R.reset_frame()
+
+    def run_samples(self, first, count):
+        """Samples first .. first + count - 1, dealt round-robin to the contexts; returns when all are enqueued and the
+        host side of every migrate loop is through (device work may still be running: synchronize / accumulate next)."""
+        import threading
+        k = len(self.ctxs)
+        errs = []
+
+        def work(j):
+            try:
+                for s in range(first + j, first + count, k):
+                    self.ctxs[j].run_sample(s)
+            except Exception as e:       # noqa: BLE001 -- re-raised on the calling thread
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(j,)) for j in range(1, k)]
+        for t in th:
+            t.start()
+        work(0)
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def accumulate(self):
+        for R in self.ctxs[1:]:
+            self.primary._ck(self.primary.lib.dprt_accumulate_from(self.primary.h, R.h), "dprt_accumulate_from")
+
+    def launch(self):
+        """Renderer.launch with the samples in flight: reset, spp samples, accumulate, average + reduce."""
+        self.reset_frame()
+        self.run_samples(0, self.primary.cfg.spp)
+        self.accumulate()
+        return self.primary.reduce_image(0)
+
+    def stats(self):
+        out = None
+        for R in self.ctxs:
+            st = R.stats()
+            out = st if out is None else {k: out[k] + st[k] for k in out}
+        return out
+
+    def close(self):
+        for R in self.ctxs[1:]:
+            R.close()
+        self.ctxs = [self.primary]
 
 
 class RankGroup:

@@ -285,3 +285,22 @@ def test_config3_full_size_two_chunks_1080p_four_bounces(gpu_required, oracle):
     assert sent > 100000, "config 3 is about migration: expected many paths to cross ranks"
     assert_bits_equal(img_g, img_o, "1080p image")
     assert np.isfinite(img_g).all() and img_g.max() > 0
+
+
+@pytest.mark.parametrize("k", [2, 3])
+def test_samples_in_flight_same_image(gpu_required, oracle, k):
+    """K samples in flight (K contexts sharing one uploaded scene, one host thread each): every sample is computed exactly as
+    before, only the per-pixel sum over samples is formed in another order -- image within 1e-6 relative of the oracle's, and
+    the launch sizes / walked-ray statistics add up to the oracle's exactly."""
+    rs, world, _ = build_pair(oracle, 1, 20000, 160, 90, spp=6, bounces=3, proxy_mode=0)
+    R = rs[0]
+    F = dprt.SamplesInFlight(R, k)
+    assert len(F.ctxs) == k
+    img = F.launch()
+    img_o = world.launch()
+    err = float(np.abs(img - img_o).max() / np.abs(img_o).max())
+    assert np.isfinite(img).all() and err <= 1e-6, err
+    st, so = F.stats(), world.stats(0)
+    assert st["rays_traverse"] == so["rays_traverse"] and st["rays_shadow"] == so["rays_shadow"]
+    assert st["rays_walked"] + st["rays_shade_cached"] == so["rays_walked"]
+    F.close(); R.close()
