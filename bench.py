@@ -626,29 +626,56 @@ def run_dprt(args):
                    "unit": "GB/s", "frac": rb / (p_ms * 1e-3) / 1e9 / pk["hbm"], "share_of_step": p_ms / ms_serial}
 
     # ---- end to end: Renderer::launch() call sequence with host buffers -------------------------------------
-    keep, himg = pinned_array((fh, fw, 3), np.float32)
     h2d = mats.nbytes + lights.nbytes + 56
 
-    def e2e_step(s):
-        R.set_materials(mats); R.set_lights(lights); R.set_camera(cam)       # host -> device (launch(): :1725-1849, :1990)
-        R.reset_frame()
-        R.run_sample(s)
-        R._ck(R.lib.dprt_reduce_image(R.h, 0, himg.ctypes.data if rank == 0 else None), "dprt_reduce_image")   # device -> host
-    e2e_step(0)
+    # every context in flight renders its own frames through the same public call sequence: K frames at a time, one host
+    # thread each; the ncclReduce of the frames is issued from this thread, context by context (one communicator, one order)
+    himgs = [pinned_array((fh, fw, 3), np.float32) for _ in F.ctxs]
+
+    def e2e_front(X, s):
+        X.set_materials(mats); X.set_lights(lights); X.set_camera(cam)       # host -> device (launch(): :1725-1849, :1990)
+        X.reset_frame()
+        X.run_sample(s)
+
+    def e2e_batch(first, count):
+        import threading
+        errs = []
+
+        def work(j):
+            try:
+                e2e_front(F.ctxs[j], first + j)
+            except Exception as e:      # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(j,)) for j in range(1, count)]
+        for t in th:
+            t.start()
+        work(0)
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+        for j in range(count):                                               # device -> host, pinned
+            X = F.ctxs[j]
+            X._ck(X.lib.dprt_reduce_image(X.h, 0, himgs[j][1].ctypes.data if rank == 0 else None), "dprt_reduce_image")
+    e2e_batch(0, K_inflight)
     barrier()
-    st0 = R.stats()
+    st0 = F.stats()
     t0 = time.perf_counter()
-    for s in range(args.steps):
-        e2e_step(args.warmup + s)
+    done_steps = 0
+    while done_steps < args.steps:
+        c = min(K_inflight, args.steps - done_steps)
+        e2e_batch(args.warmup + done_steps, c)
+        done_steps += c
     barrier()
     e2e_s = time.perf_counter() - t0
-    st1 = R.stats()
+    st1 = F.stats()
     e2e_s = allreduce(e2e_s, dist.ReduceOp.MAX if W > 1 else None)
     e_rays = st1["rays_walked"] - st0["rays_walked"]
     e_rays = allreduce(float(e_rays), dist.ReduceOp.SUM if W > 1 else None)
     e2e = {"value": e_rays / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(N * 12),
            "ms_per_step": e2e_s / args.steps * 1e3, "samples_per_s": N * args.steps / e2e_s,
-           "call": "set_materials/set_lights/set_camera + reset_frame + dprt_render_sample + dprt_reduce_image -> pinned host image"}
+           "call": "set_materials/set_lights/set_camera + reset_frame + dprt_render_sample + dprt_reduce_image -> pinned host image, per step; "
+                   f"{K_inflight} such frames in flight (one context and host thread each)"}
 
     line = None
     if rank == 0:
@@ -697,7 +724,7 @@ def main():
     ap.add_argument("--layout", choices=("slabs", "cells"), default="slabs", help="N>1: how the unit cube is cut into chunks")
     ap.add_argument("--serial", type=int, default=0, help="1 = no shadow/traverse stream overlap inside dprt_render_sample, for A/B")
     ap.add_argument("--mlp-dtype", type=int, default=1, help="proxy MLP operands: 1 = fp16 (reference's NN_Float, meets 1e-3), 0 = bf16 (out of tolerance)")
-    ap.add_argument("--inflight", type=int, default=2, help="samples in flight per GPU in the timed region (contexts sharing one scene; 1 = strictly one sample at a time)")
+    ap.add_argument("--inflight", type=int, default=3, help="samples in flight per GPU in the timed region (contexts sharing one scene; 1 = strictly one sample at a time)")
     ap.add_argument("--count-scale", type=int, default=8, help="oracle BVH8 counting pass: frame reduced by this factor per side")
     ap.add_argument("--skip-oracle-counts", action="store_true", help="roofline bytes from the kernel's own counters (A/B runs only)")
     ap.add_argument("--skip-parity", action="store_true", help="N>1: skip the parity gate (A/B runs only)")

