@@ -165,11 +165,16 @@ def default_camera(width, height):
 
 
 class Chunk:
-    def __init__(self, index, node_id, verts, normals, mats):
+    def __init__(self, index, node_id, verts, normals, mats, aabb=None):
+        """aabb: (min, max) known without the vertices (make_scene(only=...): every rank must describe a chunk by the same
+        box whether or not it holds the geometry); default: the vertices' own bounds."""
         self.index, self.node_id = index, node_id
         self.verts, self.normals, self.mats = verts, normals, mats
-        mn = verts.reshape(-1, 3).min(0).astype(np.float32)
-        mx = verts.reshape(-1, 3).max(0).astype(np.float32)
+        if aabb is None:
+            mn = verts.reshape(-1, 3).min(0).astype(np.float32)
+            mx = verts.reshape(-1, 3).max(0).astype(np.float32)
+        else:
+            mn, mx = np.asarray(aabb[0], np.float32), np.asarray(aabb[1], np.float32)
         eps = np.float32(1e-4)
         self.aabb_min, self.aabb_max = mn - eps, mx + eps
 
@@ -181,12 +186,15 @@ class Chunk:
         return self.verts.shape[0]
 
 
-def make_scene(W, tris_per_chunk, water_frac=0.0, seed=0, layout="cells", camera=None, continuous=None, cuts=None):
+def make_scene(W, tris_per_chunk, water_frac=0.0, seed=0, layout="cells", camera=None, continuous=None, cuts=None, only=None):
     """W chunks (one per rank); ~tris_per_chunk triangles each. Returns (chunks, materials, lights).
     layout "cells": 2x1x1 / 2x2x1 / 2x2x2 spatial cells (upper cells perforated), every cell its own landscape;
     "slabs": ONE continuous landscape over the unit square cut into W x-slabs -- at `cuts` (W + 1 increasing x values) when
     given, else at the calibrated all-bounce cuts for the benchmark camera (CALIBRATED_SLAB_CUTS), else where the camera's
-    primary rays put equal load (balanced_slab_layout)."""
+    primary rays put equal load (balanced_slab_layout).
+    only: iterable of chunk indices whose geometry is wanted (one process per GPU with 12.5 M-triangle chunks: a rank builds
+    its own chunk only). Every chunk is then described by its analytic box (cell footprint x the height function's clip range)
+    on every rank, and the chunks outside `only` come without vertices."""
     slabs = layout == "slabs" and W > 1
     if continuous is None:
         continuous = slabs
@@ -203,9 +211,16 @@ def make_scene(W, tris_per_chunk, water_frac=0.0, seed=0, layout="cells", camera
         ax, ay = mx[0] - mn[0], mx[1] - mn[1]
         nx = max(2, int(round(np.sqrt(quads * ax / ay))))
         ny = max(2, int(round(quads / nx)))
+        box = None
+        if only is not None:
+            zr = mx[2] - mn[2]
+            box = (np.array([mn[0], mn[1], mn[2] + 0.02 * zr]), np.array([mx[0], mx[1], mn[2] + 0.98 * zr]))
+            if k not in set(only):
+                chunks.append(Chunk(k, k, None, None, None, aabb=box))
+                continue
         v, n, m = make_heightfield_chunk(mn, mx, nx, ny, seed + k, hole_frac=hole, water_frac=water_frac,
                                          terrain_seed=seed if continuous else None)
-        chunks.append(Chunk(k, k, v, n, m))
+        chunks.append(Chunk(k, k, v, n, m, aabb=box))
     return chunks, make_materials(16, water_last=water_frac > 0), make_lights()
 
 
