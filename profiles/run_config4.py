@@ -35,14 +35,18 @@ def main():
     torch.cuda.set_device(local)
     dprt = importlib.import_module("pg2024-data-parallel-ray-tracing_b200")
     import bench
-    uid = None
     if W > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+
+    def fresh_uid():
+        """One NCCL unique id per communicator (a context creates its own): rank 0 draws it, everybody gets it."""
+        if W == 1:
+            return None
         t = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             t = torch.tensor(list(dprt.get_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(t, 0)
-        uid = bytes(t.cpu().tolist())
+        return bytes(t.cpu().tolist())
     w, h = args.width, args.height
     N = w * h
     cam = dprt.scene.default_camera(w, h)
@@ -54,7 +58,7 @@ def main():
 
     def build(proxy_mode, blobs):
         cfg = dprt.make_config(w, h, spp=args.spp, bounces=args.bounces, scene_size=W, proxy_mode=proxy_mode, path_gen_mode=1 if W > 1 else 0, mlp_dtype=1)
-        R = dprt.Renderer(cfg, rank=rank, world=W, device=local, nccl_unique_id=uid)
+        R = dprt.Renderer(cfg, rank=rank, world=W, device=local, nccl_unique_id=fresh_uid())
         for c in chunks:
             if c.index == rank:
                 R.upload_chunk(c.index, c.desc(False), c.verts, c.normals, c.mats)
