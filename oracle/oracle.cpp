@@ -321,7 +321,7 @@ struct Mesh {
 
 // ---- proxy MLP, fp32: trainingcode/module.py:755-837 (NeuralVisNetworkWith{4,6}Res256SingleOutput) ----
 struct Mlp {
-    int width = 0, nres = 0, half = 0;
+    int width = 0, nres = 0, half = 0, head = 0;   // head: 0 = LeakyReLU output, 1 = Sigmoid (module.py:880-958)
     std::vector<float> w;   // packed blob body
     const float *e3w0, *e3b0, *e3w1, *e3b1, *e2w0, *e2b0, *e2w1, *e2b1, *pw0, *pb0, *pw1, *pb1;
     std::vector<const float*> rw, rb;
@@ -329,7 +329,7 @@ struct Mlp {
         if (bytes < 16) return false;
         const uint32_t* h = (const uint32_t*)blob;
         if (h[0] != 0x50524d4cu) return false;     // 'LMRP'
-        width = (int)h[1]; nres = (int)h[2]; half = width / 2;
+        width = (int)h[1]; nres = (int)h[2]; half = width / 2; head = (int)(h[3] & 1u);
         size_t need = (size_t)(32 * 3 + 32 + half * 32 + half) + (size_t)(32 * 2 + 32 + half * 32 + half) +
                       (size_t)nres * ((size_t)width * width + width) + (size_t)(64 * width + 64) + 64 + 1;
         if (bytes != 16 + need * 4) return false;
@@ -362,7 +362,7 @@ struct Mlp {
         float z[64];
         for (int j = 0; j < 64; j++) { float s = pb0[j]; const float* wr = pw0 + (size_t)j * width; for (int k = 0; k < width; k++) s += wr[k] * a[k]; z[j] = lrelu(s); }
         float s = pb1[0]; for (int k = 0; k < 64; k++) s += pw1[k] * z[k];
-        return lrelu(s);
+        return head ? 1.0f / (1.0f + expf(-s)) : lrelu(s);
     }
 };
 

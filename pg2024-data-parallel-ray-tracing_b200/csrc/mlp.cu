@@ -497,7 +497,8 @@ mlp_kernel(const MlpGroupEntry* __restrict__ table, const int32_t* __restrict__ 
                     for (int i = 0; i < 4; i++) acc = fmaf(lrelu(__uint_as_float(v[q * 4 + i]) + bb[i]), ww[i], acc);
                 }
             }
-            if (g < n) y[g] = __half_as_ushort(__float2half_rn(lrelu(acc)));
+            // output activation: LeakyReLU (module.py:790-793) or the Sigmoid heads (module.py:880-958)
+            if (g < n) y[g] = __half_as_ushort(__float2half_rn(table[obj].head ? 1.0f / (1.0f + __expf(-acc)) : lrelu(acc)));
             tc_fence_before();
         }
     }
@@ -520,7 +521,7 @@ inline size_t tile_off(int nrow, int kk) { return (size_t)(nrow / 8) * 1024 + (n
 }  // namespace
 
 struct MlpModel {
-    int width = 0, nres = 0, dtype = 0;
+    int width = 0, nres = 0, dtype = 0, head = 0;      // head: 0 = LeakyReLU output, 1 = Sigmoid
     uint8_t* d_stages = nullptr;
     float* d_small = nullptr;              // fp32 side parameters (SmallParams)
     MlpGroupEntry* d_entry = nullptr;      // one-entry table for the single-model launch
@@ -531,9 +532,13 @@ int mlp_create(const void* blob, size_t bytes, int dtype, MlpModel** out, std::s
     *out = nullptr;
     if (!blob || bytes < 16) { err = "proxy blob: too small"; return -1; }
     const uint32_t* h = (const uint32_t*)blob;
-    const int width = (int)h[1], nres = (int)h[2];
+    const int width = (int)h[1], nres = (int)h[2], head = (int)(h[3] & 1u);
     if (h[0] != kBlobMagic) { err = "proxy blob: bad magic"; return -1; }
-    if (width != kWidth || nres < 1 || nres > kMaxRes) { err = "proxy blob: only width 256 with 1..6 residual blocks is built"; return -1; }
+    // 256-wide trunks run natively; a 128-wide trunk (NeuralVisNetworkWith4Res128..., module.py:839-878) is embedded in the
+    // 256-wide kernel with zero weights (concat column j -> j for the xyz branch, 128 + (j - 64) for the direction branch:
+    // the padded units stay exactly 0 through every LReLU(x + Wx + b)), so its outputs are those of the 128-wide network.
+    // The 512-wide trunk (module.py:701-753) is not built.
+    if ((width != kWidth && width != 128) || nres < 1 || nres > kMaxRes) { err = "proxy blob: trunk width 256 or 128 with 1..6 residual blocks is built (512 is not)"; return -1; }
     const int half = width / 2;
     const size_t need = (size_t)(32 * 3 + 32 + half * 32 + half) + (size_t)(32 * 2 + 32 + half * 32 + half) +
                         (size_t)nres * ((size_t)width * width + width) + (size_t)(64 * width + 64) + 65;
@@ -548,30 +553,31 @@ int mlp_create(const void* blob, size_t bytes, int dtype, MlpModel** out, std::s
     const int nstages = 2 + 4 * nres;
     std::vector<uint8_t> stages((size_t)nstages * kStageBytes, 0);
     auto put = [&](uint8_t* base, int nrow, int kk, float v) { uint16_t u = to16(v, dtype); std::memcpy(base + tile_off(nrow, kk), &u, 2); };
+    auto col = [&](int j) { return j < half ? j : kWidth / 2 + (j - half); };      // trunk column j of the network -> column of the 256-wide kernel
     // stage 0: block-diagonal encoder second layers, [256 x 64]
-    for (int nrow = 0; nrow < half; nrow++) for (int k = 0; k < 32; k++) put(stages.data(), nrow, k, e3w1[nrow * 32 + k]);
-    for (int nrow = 0; nrow < half; nrow++) for (int k = 0; k < 32; k++) put(stages.data(), half + nrow, 32 + k, e2w1[nrow * 32 + k]);
+    for (int nrow = 0; nrow < half; nrow++) for (int k = 0; k < 32; k++) put(stages.data(), col(nrow), k, e3w1[nrow * 32 + k]);
+    for (int nrow = 0; nrow < half; nrow++) for (int k = 0; k < 32; k++) put(stages.data(), col(half + nrow), 32 + k, e2w1[nrow * 32 + k]);
     for (int l = 0; l < nres; l++)
-        for (int kc = 0; kc < 4; kc++) {
-            uint8_t* base = stages.data() + (size_t)(1 + l * 4 + kc) * kStageBytes;
-            for (int nrow = 0; nrow < width; nrow++) for (int kk = 0; kk < 64; kk++) put(base, nrow, kk, rw[l][(size_t)nrow * width + kc * 64 + kk]);
+        for (int nrow = 0; nrow < width; nrow++) for (int c = 0; c < width; c++) {
+            const int kc = col(c) / 64, kk = col(c) % 64;
+            put(stages.data() + (size_t)(1 + l * 4 + kc) * kStageBytes, col(nrow), kk, rw[l][(size_t)nrow * width + c]);
         }
     {
         uint8_t* base = stages.data() + (size_t)(1 + 4 * nres) * kStageBytes;
-        for (int kb = 0; kb < 4; kb++) for (int nrow = 0; nrow < 64; nrow++) for (int kk = 0; kk < 64; kk++)
-            put(base + kb * 8192, nrow, kk, pw0[(size_t)nrow * width + kb * 64 + kk]);
+        for (int nrow = 0; nrow < 64; nrow++) for (int c = 0; c < width; c++)
+            put(base + (col(c) / 64) * 8192, nrow, col(c) % 64, pw0[(size_t)nrow * width + c]);
     }
     std::vector<float> sm(small_floats(nres), 0.f);
     std::memcpy(&sm[kE3W0], e3w0, 96 * 4); std::memcpy(&sm[kE3B0], e3b0, 32 * 4);
     std::memcpy(&sm[kE2W0], e2w0, 64 * 4); std::memcpy(&sm[kE2B0], e2b0, 32 * 4);
-    std::memcpy(&sm[kBEnc], e3b1, half * 4); std::memcpy(&sm[kBEnc + half], e2b1, half * 4);
-    for (int l = 0; l < nres; l++) std::memcpy(&sm[kBRes + l * kWidth], rb[l], width * 4);
+    for (int j = 0; j < half; j++) { sm[kBEnc + col(j)] = e3b1[j]; sm[kBEnc + col(half + j)] = e2b1[j]; }
+    for (int l = 0; l < nres; l++) for (int j = 0; j < width; j++) sm[kBRes + l * kWidth + col(j)] = rb[l][j];
     std::memcpy(&sm[kBRes + nres * kWidth], pb0, 64 * 4);
     std::memcpy(&sm[kBRes + nres * kWidth + 64], pw1, 64 * 4);
     sm[kBRes + nres * kWidth + 128] = pb1[0];
 
     MlpModel* m = new MlpModel();
-    m->width = width; m->nres = nres; m->dtype = dtype;
+    m->width = width; m->nres = nres; m->dtype = dtype; m->head = head;
     cudaError_t e;
     SmallParams small;
     std::memset(&small, 0, sizeof(SmallParams));
@@ -605,7 +611,7 @@ void mlp_destroy(MlpModel* m) {
 
 MlpGroupEntry mlp_group_entry(const MlpModel* m) {
     MlpGroupEntry e{};
-    if (m) { e.wstages = m->d_stages; e.small = m->d_small; e.nres = m->nres; }
+    if (m) { e.wstages = m->d_stages; e.small = m->d_small; e.nres = m->nres; e.head = m->head; }
     return e;
 }
 

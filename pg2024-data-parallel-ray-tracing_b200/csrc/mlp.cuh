@@ -9,7 +9,7 @@
 namespace dprt {
 
 // one row of the grouped launch's table: the proxy network of one scene object (wstages == nullptr: no model, rows keep 0)
-struct MlpGroupEntry { const uint8_t* wstages; const float* small; int32_t nres; int32_t pad_; };
+struct MlpGroupEntry { const uint8_t* wstages; const float* small; int32_t nres; int32_t head; };     // head: 0 = LeakyReLU output, 1 = Sigmoid
 
 struct MlpModel;   // device-resident, pre-tiled weights of one NeuralVisNetworkWith{4,6}Res256SingleOutput
 

@@ -11,7 +11,11 @@ parameter names* as the reference classes, so a reference ``state_dict`` loads u
 
 PyTorch is used on this (training / export) side only; inference inside the renderer is mlp.cu.
 
-Blob layout ("proxy weight blob", little-endian): u32 magic 'LMRP' (0x50524D4C), u32 width, u32 nres, u32 0,
+* ``ResidualProxy(128, 4)`` == ``NeuralVisNetworkWith4Res128SingleOutput`` (module.py:839-878); ``sigmoid=True`` gives the
+  ``...SingleOutputSigmoid`` heads (module.py:880-958). The 512-wide trunk (module.py:701-753) can be trained and packed,
+  but libdprt only runs 256- and 128-wide trunks.
+
+Blob layout ("proxy weight blob", little-endian): u32 magic 'LMRP' (0x50524D4C), u32 width, u32 nres, u32 flags (bit 0: Sigmoid head),
 then fp32 row-major tensors in this order: enc3.L0 W[32,3] b[32], enc3.L1 W[width/2,32] b[width/2],
 enc2.L0 W[32,2] b[32], enc2.L1 W[width/2,32] b[width/2], nres x (W[width,width] b[width]),
 post.L0 W[64,width] b[64], post.L1 W[1,64] b[1].
@@ -28,8 +32,9 @@ def _torch():
     return torch
 
 
-def make_proxy(width=256, nres=4):
-    """Build the torch module (deferred import so that the renderer side never needs torch)."""
+def make_proxy(width=256, nres=4, sigmoid=False):
+    """Build the torch module (deferred import so that the renderer side never needs torch). sigmoid: the
+    ``...SingleOutputSigmoid`` heads (module.py:880-958) end in nn.Sigmoid instead of nn.LeakyReLU."""
     torch = _torch()
     nn = torch.nn
     F = torch.nn.functional
@@ -43,22 +48,22 @@ def make_proxy(width=256, nres=4):
             return F.leaky_relu(x + self.block(x))
 
     class ResidualProxy(nn.Module):
-        def __init__(self, w, n):
+        def __init__(self, w, n, sig):
             super().__init__()
-            self.width, self.nres = w, n
+            self.width, self.nres, self.sigmoid = w, n, bool(sig)
             self.encoding3to64 = nn.Sequential(nn.Linear(3, 32), nn.LeakyReLU(), nn.Linear(32, w // 2), nn.LeakyReLU())
             self.encoding2to64 = nn.Sequential(nn.Linear(2, 32), nn.LeakyReLU(), nn.Linear(32, w // 2), nn.LeakyReLU())
             self.res_block = nn.Sequential(*[_Res(w) for _ in range(n)])
-            self.post_block = nn.Sequential(nn.Linear(w, 64), nn.LeakyReLU(), nn.Linear(64, 1), nn.LeakyReLU())
+            self.post_block = nn.Sequential(nn.Linear(w, 64), nn.LeakyReLU(), nn.Linear(64, 1), nn.Sigmoid() if sig else nn.LeakyReLU())
 
         def forward(self, x):
             out1 = torch.cat([self.encoding3to64(x[:, 0:3]), self.encoding2to64(x[:, 3:5])], dim=1)
             return self.post_block(out1 + self.res_block(out1))
 
-    return ResidualProxy(width, nres)
+    return ResidualProxy(width, nres, sigmoid)
 
 
-def pack_state_dict(sd, width=256, nres=4):
+def pack_state_dict(sd, width=256, nres=4, sigmoid=False):
     """state_dict (reference key names) -> blob bytes."""
     def t(name):
         v = sd[name]
@@ -74,16 +79,16 @@ def pack_state_dict(sd, width=256, nres=4):
     half = width // 2
     expect = (32 * 3 + 32 + half * 32 + half) + (32 * 2 + 32 + half * 32 + half) + nres * (width * width + width) + (64 * width + 64) + 65
     assert body.size == expect, (body.size, expect)
-    return struct.pack("<IIII", MAGIC, width, nres, 0) + body.tobytes()
+    return struct.pack("<IIII", MAGIC, width, nres, 1 if sigmoid else 0) + body.tobytes()
 
 
 def pack_module(module):
-    return pack_state_dict(module.state_dict(), module.width, module.nres)
+    return pack_state_dict(module.state_dict(), module.width, module.nres, getattr(module, "sigmoid", False))
 
 
 def unpack_blob(blob):
     """blob -> dict of numpy arrays (for numpy-side reference math)."""
-    magic, width, nres, _ = struct.unpack_from("<IIII", blob, 0)
+    magic, width, nres, flags = struct.unpack_from("<IIII", blob, 0)
     assert magic == MAGIC
     a = np.frombuffer(blob, np.float32, offset=16)
     half = width // 2
@@ -95,7 +100,7 @@ def unpack_blob(blob):
         o[0] += n
         return v
 
-    d = {"width": width, "nres": nres}
+    d = {"width": width, "nres": nres, "sigmoid": bool(flags & 1)}
     d["e3w0"], d["e3b0"], d["e3w1"], d["e3b1"] = take(32, 3), take(32), take(half, 32), take(half)
     d["e2w0"], d["e2b0"], d["e2w1"], d["e2b1"] = take(32, 2), take(32), take(half, 32), take(half)
     d["rw"], d["rb"] = [], []

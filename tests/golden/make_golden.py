@@ -50,11 +50,13 @@ def mlp_golden():
     g = torch.Generator().manual_seed(0)
     x = torch.rand(512, 5, generator=g).half().float()          # the renderer feeds fp16 features
     out = {"x_f16": x.half().numpy().view(np.uint16)}
-    for name, width, nres in (("NeuralVisNetworkWith4Res256SingleOutput", 256, 4), ("NeuralVisNetworkWith6Res256SingleOutput", 256, 6)):
+    for name, width, nres, sig in (("NeuralVisNetworkWith4Res256SingleOutput", 256, 4, False), ("NeuralVisNetworkWith6Res256SingleOutput", 256, 6, False),
+                                   ("NeuralVisNetworkWith4Res128SingleOutput", 128, 4, False), ("NeuralVisNetworkWith4Res128SingleOutputSigmoid", 128, 4, True),
+                                   ("NeuralVisNetworkWith4Res256SingleOutputSigmoid", 256, 4, True)):
         torch.manual_seed(19990201)
         m_ref = getattr(ref, name)().eval()
         torch.manual_seed(19990201)
-        m_own = dprt.proxy.make_proxy(width, nres).eval()
+        m_own = dprt.proxy.make_proxy(width, nres, sigmoid=sig).eval()
         sd_ref, sd_own = m_ref.state_dict(), m_own.state_dict()
         assert list(sd_ref.keys()) == list(sd_own.keys()), "parameter names differ from the reference"
         for k in sd_ref:
@@ -62,13 +64,17 @@ def mlp_golden():
         with torch.no_grad():
             y = m_ref(x)
             assert torch.equal(y, m_own(x))
-        out[f"y_{nres}res{width}"] = y.numpy().reshape(-1).astype(np.float32)
+        tag = f"{nres}res{width}" + ("_sigmoid" if sig else "")
+        out[f"y_{tag}"] = y.numpy().reshape(-1).astype(np.float32)
+        if sig:
+            print(name, "y range", float(y.min()), float(y.max()))
+            continue
         # decision-test variant: outputs spread around 0.5 (same transform applied to both)
         dprt.proxy.spread_output_(m_own, gain=3.0, seed=1)
         m_ref.load_state_dict(m_own.state_dict())
         with torch.no_grad():
             ys = m_ref(x)
-        out[f"y_{nres}res{width}_spread"] = ys.numpy().reshape(-1).astype(np.float32)
+        out[f"y_{tag}_spread"] = ys.numpy().reshape(-1).astype(np.float32)
         print(name, "y range", float(y.min()), float(y.max()), "spread range", float(ys.min()), float(ys.max()))
     np.savez_compressed(os.path.join(HERE, "mlp_golden.npz"), **out)
     print("mlp_golden.npz written")

@@ -49,6 +49,39 @@ def test_mlp_matches_reference_module_golden(gpu_required, oracle, golden_dir, n
     assert np.abs(y - yo).max() <= tol
 
 
+@pytest.mark.parametrize("width,nres,sig,spread", [(128, 4, False, False), (128, 4, False, True), (128, 4, True, False), (256, 4, True, False)])
+def test_mlp_other_reference_variants(gpu_required, oracle, golden_dir, width, nres, sig, spread):
+    """The 128-wide trunk (embedded in the 256-wide kernel with zero weights) and the Sigmoid heads against the reference's
+    own module.py outputs (tests/golden/mlp_golden.npz), fp16 operands, 1e-3 abs."""
+    import torch
+    g = np.load(os.path.join(golden_dir, "mlp_golden.npz"))
+    torch.manual_seed(19990201)
+    m = dprt.proxy.make_proxy(width, nres, sigmoid=sig).eval()
+    if spread:
+        dprt.proxy.spread_output_(m, gain=3.0, seed=1)
+    blob = dprt.proxy.pack_module(m)
+    R = _renderer_with_proxy(blob, 1)
+    x16 = g["x_f16"]
+    y = R.mlp_infer(1, 0, x16).view(np.float16).astype(np.float32)
+    ref = g[f"y_{nres}res{width}" + ("_sigmoid" if sig else "") + ("_spread" if spread else "")]
+    err = np.abs(y - ref).max()
+    print(f"width={width} nres={nres} sigmoid={sig} spread={spread} max|gpu-ref|={err:.3e}")
+    assert err <= 1e-3
+    R.close()
+
+
+def test_mlp_rejects_the_512_wide_trunk(gpu_required):
+    import torch
+    torch.manual_seed(1)
+    blob = dprt.proxy.pack_module(dprt.proxy.make_proxy(512, 4).eval())
+    cfg = dprt.make_config(16, 16, scene_size=2, proxy_mode=1)
+    R = dprt.Renderer(cfg, rank=0, world=2)
+    with pytest.raises(dprt.DprtError) as e:
+        R.upload_proxy(1, dprt.make_object_desc(1, [0, 0, 0], [1, 1, 1], is_proxy=1), blob, blob)
+    assert "512" in str(e.value)
+    R.close()
+
+
 @pytest.mark.parametrize("n", [1, 127, 128, 129, 300, 20000, 148 * 128 * 3 + 77])
 def test_mlp_ragged_batch_sizes(gpu_required, oracle, n):
     m = _model(4)

@@ -166,6 +166,25 @@ def test_mlp_oracle_matches_reference_module(oracle, golden_dir, nres):
     assert ((ref2 > 0.5).mean() > 0.2) and ((ref2 > 0.5).mean() < 0.8)      # decisions straddle the threshold
 
 
+@pytest.mark.parametrize("width,nres,sig", [(128, 4, False), (128, 4, True), (256, 4, True)])
+def test_mlp_oracle_matches_reference_module_other_variants(oracle, golden_dir, width, nres, sig):
+    """NeuralVisNetworkWith4Res128SingleOutput (module.py:839-878) and the ...SingleOutputSigmoid heads (:880-958): our torch
+    definition re-creates the reference classes bit for bit from the same seed, and the oracle's fp32 chain follows them."""
+    import torch
+    g = np.load(os.path.join(golden_dir, "mlp_golden.npz"))
+    torch.manual_seed(19990201)
+    m = dprt.proxy.make_proxy(width, nres, sigmoid=sig).eval()
+    x16 = g["x_f16"]
+    key = f"y_{nres}res{width}" + ("_sigmoid" if sig else "")
+    with torch.no_grad():
+        y_torch = m(torch.from_numpy(x16.view(np.float16).astype(np.float32))).numpy().reshape(-1)
+    assert np.array_equal(y_torch, g[key])
+    blob = dprt.proxy.pack_module(m)
+    assert dprt.proxy.unpack_blob(blob)["sigmoid"] == sig and dprt.proxy.unpack_blob(blob)["width"] == width
+    yf, _ = oracle.mlp_forward(blob, x16)
+    assert np.abs(yf - g[key]).max() < 2e-6
+
+
 def test_weight_blob_roundtrip():
     import torch
     torch.manual_seed(1)
