@@ -10,6 +10,7 @@
 //     secondary), so records are scattered straight to their final, contiguous, bucket-major position.
 // Output order is the reference's: bucket-major, original index order inside a bucket, dead entries dropped.
 #include <algorithm>
+#include <cstdlib>
 #include "dprt_internal.cuh"
 #include "p2p_exchange.cuh"
 
@@ -45,6 +46,14 @@ struct PathOps {
         const float4 a = s[0], b = s[1], c = s[2], e = s[3];
         d[0] = a; d[1] = b; d[2] = c; d[3] = e;
     }
+    // staged variant (partition_staged_kernel): key of record i from the last 8 bytes of its staged copy; where bucket b goes
+    __device__ __forceinline__ int key_staged(uint2 w, int i) const {
+        const int target = (int)w.x;
+        const bool valid = (w.y >> 16) & 0xffu;
+        if (!(valid && target >= 0 && target < W)) return -1;
+        return (target == me && i >= splitL) ? W : target;
+    }
+    __device__ __forceinline__ dprt_path_record* dst_base(int /*bucket*/) const { return out; }
 };
 
 // Peer-memory exchange (p2p_exchange.cuh): same keys as PathOps in settled-deque mode, but every bucket has its own
@@ -67,6 +76,13 @@ struct PeerPathOps {
         const float4 a = s[0], b = s[1], c = s[2], e = s[3];
         d[0] = a; d[1] = b; d[2] = c; d[3] = e;
     }
+    __device__ __forceinline__ int key_staged(uint2 w, int i) const {
+        const int target = (int)w.x;
+        const bool valid = (w.y >> 16) & 0xffu;
+        if (!(valid && target >= 0 && target < W)) return -1;
+        return (target == me && i >= splitL) ? W : target;
+    }
+    __device__ __forceinline__ dprt_path_record* dst_base(int bucket) const { return plan->dst[bucket]; }
 };
 
 struct QueryOps {
@@ -182,6 +198,140 @@ __global__ void __launch_bounds__(kThreads) partition_kernel(Ops ops, int n, con
     }
 }
 
+
+// ---- TMA-staged variant for the 64-byte path records -------------------------------------------------------------------
+// Same single-pass algorithm (launch-order tile ids, warp match ranks, 32-bucket decoupled look-back), different data
+// movement: the tile's 1024 records = 64 KiB arrive in shared memory as ONE bulk copy (cp.async.bulk + mbarrier: every byte
+// of the input crosses DRAM once, in full lines, and no thread spends instructions on it); keys are read from the staged
+// copy; the scatter runs in 64-byte record units -- four lanes per record, eight records per warp store instruction -- so a
+// run of records that stay together (the usual case in a stable partition) leaves the SM as contiguous 512-byte stores,
+// to local HBM or to a peer's receive buffer behind NVLink. The per-thread LDG/STG.128 version above stays for the NN queries.
+constexpr int kStageTile = 1024;
+constexpr int kStageSteps = kStageTile / 32;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <class Ops>
+__global__ void __launch_bounds__(kThreads) partition_staged_kernel(Ops ops, int n, const int32_t* __restrict__ hist, int32_t* __restrict__ offsets,
+                                                                     unsigned long long* tileState, uint32_t* tileCounter, uint32_t ticketBase,
+                                                                     uint32_t gen) {
+    extern __shared__ __align__(128) uint8_t s_stage[];            // kStageTile x 64 B
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ int s_tile;
+    __shared__ int s_cnt[kStageSteps][32];
+    __shared__ int s_base[32];
+    __shared__ uint32_t s_dst[kStageTile];                         // bucket << 27 | index inside the bucket, ~0 = dropped
+    __shared__ dprt_path_record* s_ptr[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int B = ops.B;
+    constexpr int kItems = kStageTile / kThreads;                  // 4
+
+    if (threadIdx.x == 0) s_tile = (int)(atomicAdd(tileCounter, 1u) - ticketBase);
+    if (ops.skip()) return;
+    for (int k = threadIdx.x; k < kStageSteps * 32; k += kThreads) (&s_cnt[0][0])[k] = 0;
+    if (threadIdx.x < 32) s_ptr[threadIdx.x] = threadIdx.x < B ? ops.dst_base(threadIdx.x) : nullptr;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int tile = s_tile;
+    const int first = tile * kStageTile;
+    const int valid = min(kStageTile, n - first);
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)valid * (uint32_t)sizeof(dprt_path_record);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&s_bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(s_stage)),
+                     "l"(ops.in + first), "r"(bytes), "r"(smem_addr(&s_bar))
+                     : "memory");
+    }
+    {   // everybody waits for the tile
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(smem_addr(&s_bar)) : "memory");
+        }
+    }
+
+    int key[kItems], rank[kItems];
+    const int wbase = warp * (32 * kItems);
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+        const int r = wbase + j * 32 + lane;
+        key[j] = r < valid ? ops.key_staged(*reinterpret_cast<const uint2*>(s_stage + (size_t)r * 64 + 56), first + r) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+        const bool v = key[j] >= 0;
+        const unsigned m = __ballot_sync(0xffffffffu, v);
+        rank[j] = 0;
+        if (v) {
+            const unsigned peers = __match_any_sync(m, key[j]);
+            rank[j] = __popc(peers & ((1u << lane) - 1u));
+            if (rank[j] == 0) s_cnt[warp * kItems + j][key[j]] = __popc(peers);
+        }
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        int run = 0;
+#pragma unroll 8
+        for (int st = 0; st < kStageSteps; st++) { const int c = s_cnt[st][lane]; s_cnt[st][lane] = run; run += c; }
+        int bucketBase = 0;
+        if (!Ops::kDirect) {
+            const int h = lane < B ? hist[lane] : 0;
+            int incl = h;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            bucketBase = incl - h;
+            if (tile == 0) {
+                if (lane < B) offsets[lane] = bucketBase;
+                if (lane == B - 1) offsets[B] = incl;
+            }
+        }
+        int excl = 0;
+        if (lane < B) {
+            volatile unsigned long long* st = tileState;
+            const unsigned long long g = (unsigned long long)gen << 32;
+            if (tile == 0) {
+                st[lane] = g | ST_INC | (uint32_t)run;
+            } else {
+                st[(size_t)tile * 32 + lane] = g | ST_AGG | (uint32_t)run;
+                int t = tile - 1;
+                for (;;) {
+                    unsigned long long wv;
+                    do { wv = st[(size_t)t * 32 + lane]; } while ((wv >> 32) != gen);
+                    const uint32_t v = (uint32_t)wv;
+                    excl += (int)(v & VAL_MASK);
+                    if ((v & ST_MASK) == ST_INC) break;
+                    t--;
+                }
+                st[(size_t)tile * 32 + lane] = g | ST_INC | (uint32_t)(excl + run);
+            }
+        }
+        s_base[lane] = bucketBase + excl;
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+        const int r = wbase + j * 32 + lane;
+        s_dst[r] = key[j] >= 0 ? (((uint32_t)key[j] << 27) | (uint32_t)(s_base[key[j]] + s_cnt[warp * kItems + j][key[j]] + rank[j])) : 0xffffffffu;
+    }
+    __syncwarp();                                                  // a warp scatters the records it ranked
+    // scatter: four lanes per record, eight records per instruction
+    const int sub = lane >> 2, part = lane & 3;
+#pragma unroll 4
+    for (int it = 0; it < (32 * kItems) / 8; it++) {
+        const int r = wbase + it * 8 + sub;
+        const uint32_t d = s_dst[r];
+        if (d != 0xffffffffu) {
+            const uint4 v = *reinterpret_cast<const uint4*>(s_stage + (size_t)r * 64 + part * 16);
+            reinterpret_cast<uint4*>(s_ptr[d >> 27] + (d & 0x7ffffffu))[part] = v;
+        }
+    }
+}
+
 __global__ void path_hist_kernel(const dprt_path_record* __restrict__ paths, int n, int W, int32_t* hist) {
     __shared__ int sh[32];
     if (threadIdx.x < 32) sh[threadIdx.x] = 0;
@@ -228,23 +378,47 @@ void launch_path_histogram(const dprt_path_record* paths, int n, int W, int32_t*
     if (n > 0) path_hist_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, stream>>>(paths, n, W, hist);
 }
 
+// DPRT_PARTITION_STAGED=0 selects the per-thread LDG/STG version for the path records too (A/B)
+bool partition_staged() { static bool v = [] { const char* e = getenv("DPRT_PARTITION_STAGED"); return !(e && e[0] == '0'); }(); return v; }
+
+template <class Ops>
+void run_partition_staged(Ops ops, int n, const int32_t* hist, int32_t* offsets, PartitionScratch& s, cudaStream_t stream) {
+    if (n <= 0) { if (!Ops::kDirect) empty_offsets_kernel<<<1, 64, 0, stream>>>(offsets, ops.B); return; }
+    static bool once = [] {
+        cudaFuncSetAttribute(partition_staged_kernel<PathOps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageTile * 64);
+        cudaFuncSetAttribute(partition_staged_kernel<PeerPathOps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageTile * 64);
+        return true;
+    }();
+    (void)once;
+    const int tiles = (n + kStageTile - 1) / kStageTile;
+    s.generation++;
+    partition_staged_kernel<Ops><<<tiles, kThreads, kStageTile * 64, stream>>>(ops, n, hist, offsets, s.tileState, s.tileCounter, s.tickets, s.generation);
+    s.tickets += (uint32_t)tiles;
+}
+
 void launch_partition_paths(const dprt_path_record* paths, int n, int W, int B, int me, int splitL, const int32_t* hist,
                             dprt_path_record* out, int32_t* offsets, PartitionScratch& s, cudaStream_t stream) {
     PathOps ops{paths, out, B, W, B > W ? me : -1, splitL};
-    run_partition<PathOps, 4>(ops, n, hist, offsets, s, stream);
+    if (partition_staged()) run_partition_staged<PathOps>(ops, n, hist, offsets, s, stream);
+    else run_partition<PathOps, 4>(ops, n, hist, offsets, s, stream);
 }
 
 void launch_partition_paths_peer(const dprt_path_record* paths, int n, int W, int me, int splitL, const P2PPlan* plan,
                                  PartitionScratch& s, cudaStream_t stream) {
     PeerPathOps ops{paths, plan, W + 1, W, me, splitL};
-    run_partition<PeerPathOps, 4>(ops, n, nullptr, nullptr, s, stream);
+    if (partition_staged()) run_partition_staged<PeerPathOps>(ops, n, nullptr, nullptr, s, stream);
+    else run_partition<PeerPathOps, 4>(ops, n, nullptr, nullptr, s, stream);
 }
 
 cudaError_t partition_preload_kernels() {
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, partition_kernel<PeerPathOps, 4>);
-    if (e != cudaSuccess) return e;
-    return cudaFuncGetAttributes(&fa, partition_kernel<PathOps, 4>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, partition_kernel<PathOps, 4>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, partition_staged_kernel<PeerPathOps>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, partition_staged_kernel<PathOps>);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(partition_staged_kernel<PathOps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageTile * 64);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(partition_staged_kernel<PeerPathOps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageTile * 64);
+    return e;
 }
 
 void launch_query_histogram(const dprt_nn_query* q, int n, int S, int insideOnly, int32_t* hist, cudaStream_t stream) {
