@@ -637,16 +637,32 @@ def run_dprt(args):
         X.reset_frame()
         X.run_sample(s)
 
-    def e2e_batch(first, count):
+    def e2e_run(first, count):
+        """Steps first .. first + count - 1, dealt round-robin to the contexts in flight (one host thread each). A frame's
+        average + ncclReduce + copy to host is issued by its own thread, in step order on every rank (a turn counter): one
+        communicator, one order of collectives -- and it overlaps the other contexts' rendering."""
         import threading
-        errs = []
+        errs, turn, cv = [], [first], threading.Condition()
 
         def work(j):
             try:
-                e2e_front(F.ctxs[j], first + j)
+                X = F.ctxs[j]
+                for s in range(first + j, first + count, K_inflight):
+                    e2e_front(X, s)
+                    with cv:
+                        while turn[0] != s and not errs:
+                            cv.wait(0.5)
+                    if errs:
+                        return
+                    X._ck(X.lib.dprt_reduce_image(X.h, 0, himgs[j][1].ctypes.data if rank == 0 else None), "dprt_reduce_image")   # device -> host, pinned
+                    with cv:
+                        turn[0] = s + 1
+                        cv.notify_all()
             except Exception as e:      # noqa: BLE001
                 errs.append(e)
-        th = [threading.Thread(target=work, args=(j,)) for j in range(1, count)]
+                with cv:
+                    cv.notify_all()
+        th = [threading.Thread(target=work, args=(j,)) for j in range(1, K_inflight)]
         for t in th:
             t.start()
         work(0)
@@ -654,18 +670,11 @@ def run_dprt(args):
             t.join()
         if errs:
             raise errs[0]
-        for j in range(count):                                               # device -> host, pinned
-            X = F.ctxs[j]
-            X._ck(X.lib.dprt_reduce_image(X.h, 0, himgs[j][1].ctypes.data if rank == 0 else None), "dprt_reduce_image")
-    e2e_batch(0, K_inflight)
+    e2e_run(0, K_inflight)
     barrier()
     st0 = F.stats()
     t0 = time.perf_counter()
-    done_steps = 0
-    while done_steps < args.steps:
-        c = min(K_inflight, args.steps - done_steps)
-        e2e_batch(args.warmup + done_steps, c)
-        done_steps += c
+    e2e_run(args.warmup, args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     st1 = F.stats()

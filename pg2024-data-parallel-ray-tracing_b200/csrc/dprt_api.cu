@@ -370,7 +370,7 @@ static int create_impl(const dprt_config* cfg, int rank, int world, int device, 
         CK(cudaMemsetAsync(ctx->d_mlpTable, 0, 2 * 32 * sizeof(MlpGroupEntry), ctx->stream));
         CK(cudaMalloc(&ctx->d_hist, 128 * sizeof(int32_t)));
         CK(cudaMemsetAsync(ctx->d_hist, 0, 128 * sizeof(int32_t), ctx->stream));
-        ctx->scratch.maxTiles = (int)((std::max(Q, N) + 1023) / 1024) + 1;
+        ctx->scratch.maxTiles = (int)((std::max(Q, N) + 255) / 256) + 1;       // the smallest tile any partition variant uses
         CK(cudaMalloc(&ctx->scratch.tileState, (size_t)ctx->scratch.maxTiles * 32 * sizeof(unsigned long long)));
         CK(cudaMemsetAsync(ctx->scratch.tileState, 0, (size_t)ctx->scratch.maxTiles * 32 * sizeof(unsigned long long), ctx->stream));
         CK(cudaMalloc(&ctx->scratch.tileCounter, sizeof(uint32_t)));

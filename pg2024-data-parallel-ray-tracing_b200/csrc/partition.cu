@@ -206,15 +206,16 @@ __global__ void __launch_bounds__(kThreads) partition_kernel(Ops ops, int n, con
 // copy; the scatter runs in 64-byte record units -- four lanes per record, eight records per warp store instruction -- so a
 // run of records that stay together (the usual case in a stable partition) leaves the SM as contiguous 512-byte stores,
 // to local HBM or to a peer's receive buffer behind NVLink. The per-thread LDG/STG.128 version above stays for the NN queries.
-constexpr int kStageTile = 1024;
-constexpr int kStageSteps = kStageTile / 32;
+
+constexpr int kStageTileDefault = 1024;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <class Ops>
+template <class Ops, int kStageTile>
 __global__ void __launch_bounds__(kThreads) partition_staged_kernel(Ops ops, int n, const int32_t* __restrict__ hist, int32_t* __restrict__ offsets,
                                                                      unsigned long long* tileState, uint32_t* tileCounter, uint32_t ticketBase,
                                                                      uint32_t gen) {
+    constexpr int kStageSteps = kStageTile / 32;
     extern __shared__ __align__(128) uint8_t s_stage[];            // kStageTile x 64 B
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ int s_tile;
@@ -381,19 +382,26 @@ void launch_path_histogram(const dprt_path_record* paths, int n, int W, int32_t*
 // DPRT_PARTITION_STAGED=0 selects the per-thread LDG/STG version for the path records too (A/B)
 bool partition_staged() { static bool v = [] { const char* e = getenv("DPRT_PARTITION_STAGED"); return !(e && e[0] == '0'); }(); return v; }
 
+int partition_tile() { static int v = [] { const char* e = getenv("DPRT_PARTITION_TILE"); const int t = e ? atoi(e) : kStageTileDefault; return (t == 256 || t == 512 || t == 1024) ? t : kStageTileDefault; }(); return v; }
+
+template <class Ops, int TILE>
+void launch_partition_staged(Ops ops, int n, const int32_t* hist, int32_t* offsets, PartitionScratch& s, cudaStream_t stream) {
+    static bool once = [] { cudaFuncSetAttribute(partition_staged_kernel<Ops, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 64); return true; }();
+    (void)once;
+    const int tiles = (n + TILE - 1) / TILE;
+    s.generation++;
+    partition_staged_kernel<Ops, TILE><<<tiles, kThreads, TILE * 64, stream>>>(ops, n, hist, offsets, s.tileState, s.tileCounter, s.tickets, s.generation);
+    s.tickets += (uint32_t)tiles;
+}
+
 template <class Ops>
 void run_partition_staged(Ops ops, int n, const int32_t* hist, int32_t* offsets, PartitionScratch& s, cudaStream_t stream) {
     if (n <= 0) { if (!Ops::kDirect) empty_offsets_kernel<<<1, 64, 0, stream>>>(offsets, ops.B); return; }
-    static bool once = [] {
-        cudaFuncSetAttribute(partition_staged_kernel<PathOps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageTile * 64);
-        cudaFuncSetAttribute(partition_staged_kernel<PeerPathOps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageTile * 64);
-        return true;
-    }();
-    (void)once;
-    const int tiles = (n + kStageTile - 1) / kStageTile;
-    s.generation++;
-    partition_staged_kernel<Ops><<<tiles, kThreads, kStageTile * 64, stream>>>(ops, n, hist, offsets, s.tileState, s.tileCounter, s.tickets, s.generation);
-    s.tickets += (uint32_t)tiles;
+    switch (partition_tile()) {
+        case 256: launch_partition_staged<Ops, 256>(ops, n, hist, offsets, s, stream); break;
+        case 512: launch_partition_staged<Ops, 512>(ops, n, hist, offsets, s, stream); break;
+        default: launch_partition_staged<Ops, 1024>(ops, n, hist, offsets, s, stream); break;
+    }
 }
 
 void launch_partition_paths(const dprt_path_record* paths, int n, int W, int B, int me, int splitL, const int32_t* hist,
@@ -414,10 +422,12 @@ cudaError_t partition_preload_kernels() {
     cudaFuncAttributes fa;
     cudaError_t e = cudaFuncGetAttributes(&fa, partition_kernel<PeerPathOps, 4>);
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, partition_kernel<PathOps, 4>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, partition_staged_kernel<PeerPathOps>);
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, partition_staged_kernel<PathOps>);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(partition_staged_kernel<PathOps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageTile * 64);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(partition_staged_kernel<PeerPathOps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStageTile * 64);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, partition_staged_kernel<PeerPathOps, 256>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, partition_staged_kernel<PeerPathOps, 512>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, partition_staged_kernel<PeerPathOps, 1024>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, partition_staged_kernel<PathOps, 256>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, partition_staged_kernel<PathOps, 512>);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, partition_staged_kernel<PathOps, 1024>);
     return e;
 }
 

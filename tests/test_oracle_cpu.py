@@ -250,10 +250,19 @@ def test_product_never_touches_the_oracle():
     for binary in (dprt.host.LIB_PATH, os.path.join(pkg, "dprt_render")):
         needed = subprocess.run(["readelf", "-d", binary], capture_output=True, text=True).stdout
         assert "oracle" not in needed and "libdprt" in (needed if binary.endswith("dprt_render") else "libdprt"), binary
-    for root_file in ("bench.py",):
-        src = open(os.path.join(os.path.dirname(pkg), root_file)).read()
-        uses = [m.start() for m in re.finditer(r"from oracle import", src)]
-        assert len(uses) == 2          # run_reference (the --impl reference arm) and cpu_baseline: the two allowed places
+    # bench.py may execute the oracle only as the checker / the CPU arm, never inside a timed GPU region: the --impl reference
+    # arm, the cpu_baseline leg, its counting pass (the roofline's algorithmic node / triangle counts, SURVEY.md 8d: after the
+    # timed region) and the N > 1 parity gate (before anything is timed). Every import sits inside one of those functions.
+    src = open(os.path.join(os.path.dirname(pkg), "bench.py")).read()
+    allowed = {"run_reference", "cpu_baseline", "oracle_bvh8_counts", "parity_gate"}
+    seen = set()
+    for m in re.finditer(r"from oracle import", src):
+        fn = re.findall(r"^def (\w+)\(", src[:m.start()], re.M)[-1]
+        assert fn in allowed, f"bench.py imports the oracle inside {fn}()"
+        seen.add(fn)
+    assert seen == allowed
+    body = src[src.index("def run_dprt("):src.index("def main(")]
+    assert "from oracle" not in body and "O." not in body.replace("dist.ReduceOp.", "")
 
 
 def test_no_cpu_fallback_without_gpu():
