@@ -379,8 +379,11 @@ void launch_path_histogram(const dprt_path_record* paths, int n, int W, int32_t*
     if (n > 0) path_hist_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, stream>>>(paths, n, W, hist);
 }
 
-// DPRT_PARTITION_STAGED=0 selects the per-thread LDG/STG version for the path records too (A/B)
-bool partition_staged() { static bool v = [] { const char* e = getenv("DPRT_PARTITION_STAGED"); return !(e && e[0] == '0'); }(); return v; }
+// DPRT_PARTITION_STAGED=1 selects the TMA-staged kernel for the path records. Off by default on the numbers
+// (profiles/ab_r2_partition_staged.txt): the kernel itself is 11 % faster (reorder 0.27 -> 0.31 of the HBM roofline), but
+// its 64 KiB of shared memory per CTA displace the trace kernels of the other samples in flight (different shared-memory
+// carve-out: the SMs have to drain), and the step gets 5 % slower.
+bool partition_staged() { static bool v = [] { const char* e = getenv("DPRT_PARTITION_STAGED"); return e && e[0] == '1'; }(); return v; }
 
 int partition_tile() { static int v = [] { const char* e = getenv("DPRT_PARTITION_TILE"); const int t = e ? atoi(e) : kStageTileDefault; return (t == 256 || t == 512 || t == 1024) ? t : kStageTileDefault; }(); return v; }
 
