@@ -788,14 +788,27 @@ __global__ void __launch_bounds__(kBlock) shadow_post_kernel(DevParams p, int nS
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) { p.traceQueue[0] = 0; p.traceQueue[1] = 0; p.traceQueue[2] = 0; }
-    if (i < nShadow) {
+    if (i < nShadow && p.proxyMode == 0) {
+        // proxies off: remote chunks are transparent to shadow rays, so a path the any-hit trace left valid adds its
+        // contribution (shadow_ray_kernel.cu:344-349). Only the last 36 bytes of the record are needed, and dead slots
+        // (occluded, delta BSDF, dead path) are recognised from the flag word alone.
+        const float4* q = reinterpret_cast<const float4*>(p.paths + (size_t)p.pathSize + i);
+        const float4 q3 = q[3];
+        if (__float_as_uint(q3.w) & F_VALID) {
+            const float4 q2 = q[2];
+            const float tx = q[1].w;
+            const size_t px = ((size_t)p.frameBufferSize * __float_as_int(q2.w) + __float_as_int(q2.z)) * 3;
+            const float inv = (float)p.spc;
+            p.direct[px + 0] += tx / inv;
+            p.direct[px + 1] += q2.x / inv;
+            p.direct[px + 2] += q2.y / inv;
+        }
+    } else if (i < nShadow) {
         const PathRegs path = load_path(p.paths + (size_t)p.pathSize + i);
         if (!(path.flags & F_VALID)) {
             clear_query_slots(p, i, 0);
         } else {
-            int r;
-            if (p.proxyMode == 0) { r = -1; clear_query_slots(p, i, 0); }   // proxies off: remote chunks are transparent to shadow rays
-            else r = proxy_march<false>(p, path, i, path.tMax, shHist);
+            const int r = proxy_march<false>(p, path, i, path.tMax, shHist);
             if (r < 0) {
                 const size_t px = ((size_t)p.frameBufferSize * path.shadowPathID + path.pixelIndex) * 3;
                 const float inv = (float)p.spc;
