@@ -733,7 +733,7 @@ def main():
     ap.add_argument("--layout", choices=("slabs", "cells"), default="slabs", help="N>1: how the unit cube is cut into chunks")
     ap.add_argument("--serial", type=int, default=0, help="1 = no shadow/traverse stream overlap inside dprt_render_sample, for A/B")
     ap.add_argument("--mlp-dtype", type=int, default=1, help="proxy MLP operands: 1 = fp16 (reference's NN_Float, meets 1e-3), 0 = bf16 (out of tolerance)")
-    ap.add_argument("--inflight", type=int, default=3, help="samples in flight per GPU in the timed region (contexts sharing one scene; 1 = strictly one sample at a time)")
+    ap.add_argument("--inflight", type=int, default=6, help="samples in flight per GPU in the timed region (contexts sharing one scene; 1 = strictly one sample at a time)")
     ap.add_argument("--count-scale", type=int, default=8, help="oracle BVH8 counting pass: frame reduced by this factor per side")
     ap.add_argument("--skip-oracle-counts", action="store_true", help="roofline bytes from the kernel's own counters (A/B runs only)")
     ap.add_argument("--skip-parity", action="store_true", help="N>1: skip the parity gate (A/B runs only)")

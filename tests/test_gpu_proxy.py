@@ -65,10 +65,12 @@ def _infer_and_sync(R, world, r, kind, off, total, tol, what):
     return pg
 
 
-@pytest.mark.parametrize("spread,tol", [(False, 1e-3), (True, 2e-2)])
-def test_proxy_branch_stagewise(gpu_required, oracle, spread, tol):
-    W, w, h, bounces = 2, 96, 54, 2
-    rs, world, _ = build_pair(oracle, W, 4000, w, h, bounces=bounces, proxy_mode=1, models=_models(W, spread), mlp_dtype=1)
+@pytest.mark.parametrize("spread,tol,W,w,h,tris", [(False, 1e-3, 2, 96, 54, 4000), (True, 2e-2, 2, 96, 54, 4000),
+                                                   (False, 1e-3, 4, 320, 180, 40000)])      # 4 owners, 3 proxies each, ~10^5 queries per stage
+def test_proxy_branch_stagewise(gpu_required, oracle, spread, tol, W, w, h, tris):
+    oracle.use_all_host_threads()
+    bounces = 2
+    rs, world, _ = build_pair(oracle, W, tris, w, h, bounces=bounces, proxy_mode=1, models=_models(W, spread), mlp_dtype=1)
     G = dprt.RankGroup(rs)
     N, spc, mc, S = w * h, rs[0].cfg.shadowPathCount, rs[0].cfg.maxCount, W
     for R in rs:
