@@ -34,6 +34,10 @@ import time
 
 import numpy as np
 
+# before CUDA initialises: one hardware queue per stream. Six samples in flight are twelve streams per GPU, and the peer-memory
+# exchange parks waiting kernels in them (libdprt refuses to wire more streams than queues)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

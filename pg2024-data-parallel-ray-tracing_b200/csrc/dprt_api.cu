@@ -34,6 +34,17 @@ namespace {
 
 std::string g_create_error;
 
+// Streams this library has created per device. The peer-memory exchange parks a waiting kernel in a context's stream;
+// when two streams share a hardware queue (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default) whatever is queued behind that kernel
+// waits with it, and with several contexts per rank (samples in flight) that can close a cycle across ranks. The waits are
+// bounded, so it would end in DPRT_ERR_STATE rather than a hang -- but it is refused up front instead (create_impl).
+std::atomic<int> g_streams[64];
+int max_connections() {
+    const char* e = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
+    const int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : (v > 32 ? 32 : v);
+}
+
 // NCCL is resolved with dlopen("libnccl.so.2") on first use instead of a link-time dependency: when the
 // process already holds a copy (torch bundles its own, newer one) glibc hands back that very library, and a
 // single-rank user of libdprt never needs NCCL at all.
@@ -118,6 +129,7 @@ struct dprt_ctx {
     bool p2pGroup = false;              // connected as an in-process group (dprt_*_group only)
     bool p2pGroupActive = false;        // the group driver is running the peer-memory exchange right now
     bool ownsComm = true;               // false: communicator borrowed from the parent context (dprt_create_shared)
+    int countedStreams = 0;             // this context's share of g_streams[device]
     P2PMailbox* d_mailbox = nullptr;
     dprt_path_record* d_active[2] = {nullptr, nullptr};    // arrivals land here (never in `paths`)
     P2PPeers* d_peers = nullptr;
@@ -342,6 +354,7 @@ static int create_impl(const dprt_config* cfg, int rank, int world, int device, 
     auto body = [&]() -> int {
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        if (device < 64) { g_streams[device]++; ctx->countedStreams++; }
         CK(cudaEventCreate(&ctx->ev0)); CK(cudaEventCreate(&ctx->ev1));
         const size_t N = ctx->N, spc = cfg->shadowPathCount, mc = cfg->maxCount;
         ctx->objects.resize(cfg->sceneSize);
@@ -391,6 +404,7 @@ static int create_impl(const dprt_config* cfg, int rank, int world, int device, 
             int lo = 0, hi = 0;
             CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));          // the main stream carries the critical path: aux gets the lowest priority
             CK(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, lo));
+            if (device < 64) { g_streams[device]++; ctx->countedStreams++; }
             CK(cudaEventCreateWithFlags(&ctx->evShade, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ctx->evAux, cudaEventDisableTiming));
             CK(cudaMalloc(&ctx->d_queue_aux, trace_scratch_bytes()));
@@ -434,6 +448,12 @@ static int create_impl(const dprt_config* cfg, int rank, int world, int device, 
         }
         // peer-memory exchange: a collective decision over the communicator (all ranks or none, p2p_connect_nccl)
         if (ctx->comm) { int pr = p2p_connect_nccl(ctx); if (pr) return pr; }
+        if (ctx->p2p && device < 64 && g_streams[device] > max_connections()) {
+            ctx->err = "the contexts of this process hold " + std::to_string((int)g_streams[device]) + " CUDA streams on this device but only " +
+                       std::to_string(max_connections()) + " hardware queues (CUDA_DEVICE_MAX_CONNECTIONS): the peer-memory exchange needs a queue per stream. "
+                       "Set CUDA_DEVICE_MAX_CONNECTIONS=32 before the first CUDA call, or keep fewer samples in flight";
+            return DPRT_ERR_STATE;
+        }
         CK(cudaStreamSynchronize(ctx->stream));
         return 0;
     };
@@ -455,6 +475,7 @@ int dprt_create_shared(const dprt_config* cfg, dprt_ctx* parent, dprt_ctx** out)
 void dprt_destroy(dprt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->device >= 0 && ctx->device < 64) g_streams[ctx->device] -= ctx->countedStreams;
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && ctx->ownsComm) g_nccl.CommDestroy(ctx->comm);
     for (auto& o : ctx->objects) {
@@ -1468,7 +1489,13 @@ int dprt_p2p_connect(dprt_ctx* ctx, const void* all_handles, int* enabled) {
 int dprt_p2p_enable(dprt_ctx* ctx, int enable) {
     if (!ctx) return DPRT_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    if (enable && ctx->d_mailbox) ctx->p2p = true; else p2p_free(ctx);
+    if (enable && ctx->d_mailbox) {
+        if (ctx->device < 64 && g_streams[ctx->device] > max_connections()) {
+            p2p_free(ctx);
+            return fail(ctx, DPRT_ERR_STATE, "more CUDA streams on this device than hardware queues (CUDA_DEVICE_MAX_CONNECTIONS): set it to 32 before the first CUDA call");
+        }
+        ctx->p2p = true;
+    } else p2p_free(ctx);
     return 0;
 }
 int dprt_p2p_enabled(const dprt_ctx* ctx) { return ctx && ctx->p2p ? 1 : 0; }

@@ -133,6 +133,7 @@ const char* arg(int argc, char** argv, const char* name, const char* dflt) {
 }  // namespace
 
 int main(int argc, char** argv) {
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);       // before the first CUDA call: one hardware queue per stream (--inflight)
     const std::string scenePath = arg(argc, argv, "--scene", ""), outPath = arg(argc, argv, "--out", "");
     if (scenePath.empty()) {
         fprintf(stderr, "usage: dprt_render --scene S.dprt [--out image.pfm] [--spp n] [--bounces n] [--proxy 0|1] [--path-gen 0|1] "

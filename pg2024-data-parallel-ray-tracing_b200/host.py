@@ -548,7 +548,9 @@ class Renderer:
 
 class SamplesInFlight:
     """K samples of a frame in flight on one rank (dprt.h "samples in flight"): K contexts sharing one uploaded scene and
-    the NCCL communicator, one host thread each; context j renders samples j, j + K, ... The frame is the primary's."""
+    the NCCL communicator, one host thread each; context j renders samples j, j + K, ... The frame is the primary's.
+    With W > 1 every context brings up to two streams that may hold a waiting kernel: the process needs
+    CUDA_DEVICE_MAX_CONNECTIONS >= 2 K in its environment before CUDA initialises (libdprt refuses otherwise)."""
 
     def __init__(self, primary, k=2):
         self.primary = primary

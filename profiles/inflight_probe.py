@@ -3,6 +3,7 @@
 usage: python profiles/inflight_probe.py [steps]"""
 import importlib, os, sys, threading, time
 import numpy as np
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")     # one hardware queue per stream (samples in flight)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 dprt = importlib.import_module("pg2024-data-parallel-ray-tracing_b200")

@@ -13,6 +13,7 @@ profiled sample, all-to-all bytes and GB/s, image-reduce ms, MLP queries/s, and 
 counters: the oracle cannot walk 100 M triangles here) -- device-timed, max over ranks."""
 import argparse, importlib, json, os, sys, time
 import numpy as np
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")     # one hardware queue per stream (samples in flight)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
