@@ -14,6 +14,8 @@ import sys
 
 import numpy as np
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")      # one hardware queue per stream (samples in flight)
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -73,10 +75,18 @@ def main():
     sent = torch.tensor([sg["paths_sent_offrank"]], dtype=torch.int64, device="cuda")
     dist.all_reduce(sent)
     assert int(sent.item()) > 0, "no path migrated: the scene does not exercise ncclSend/ncclRecv"
+    # the same frame with two samples in flight per rank: a second context per rank on the same communicator, its own
+    # mailboxes and receive buffers wired over the same peers (dprt_create_shared + dprt_adopt_scene)
+    F = dprt.SamplesInFlight(R, 2)
+    assert len(F.ctxs) == (2 if R.p2p_enabled else 1)
+    img_f = F.launch()
+    F.close()
     if rank == 0:
         assert np.isfinite(img).all() and img.max() > 0
         err = np.abs(img - img_o).max() / max(1e-30, float(np.abs(img_o).max()))
         assert err <= 1e-6, f"reduced image differs: {err}"
+        err_f = np.abs(img_f - img_o).max() / max(1e-30, float(np.abs(img_o).max()))
+        assert err_f <= 1e-6, f"image with two samples in flight differs: {err_f}"
         if W == 2:
             assert_bits_equal(img, img_o, "2-rank reduced image (a two-term fp32 sum is order-independent)")
         print(f"MGPU_CHECK_OK world={W} migrated_paths={int(sent.item())} image_rel_err={err:.2e} peer_memory_exchange={R.p2p_enabled}", flush=True)
