@@ -391,3 +391,26 @@ def test_bvh8_counting_walker_per_stage(oracle):
             assert rays == st[key], (r, stage, rays, st[key])
             assert nodes >= rays                                          # every walk fetches the root
         assert st["walked_traverse"] + st["walked_shade"] + st["walked_shadow"] + st["walked_secondary"] == st["rays_walked"]
+
+
+def test_per_rank_scene_generation_and_calibrated_cuts():
+    """make_scene(only=[k]) -- what every process of an N-GPU job calls -- gives rank k the same chunk as the full build, and all
+    ranks the same (analytic) box for every chunk; the calibrated slab cuts are well-formed and are what the default camera gets."""
+    cam = dprt.scene.default_camera(1920, 1080)
+    for W in (2, 4, 8):
+        cuts = dprt.scene.CALIBRATED_SLAB_CUTS[W]
+        assert len(cuts) == W + 1 and cuts[0] == 0.0 and cuts[-1] == 1.0 and all(b > a for a, b in zip(cuts, cuts[1:]))
+    full, _, _ = dprt.scene.make_scene(4, 8000, layout="slabs", camera=cam, only=range(4))
+    assert [float(c.aabb_min[0]) for c in full[1:]] == pytest.approx(dprt.scene.CALIBRATED_SLAB_CUTS[4][1:-1], abs=2e-4)
+    for k in (0, 3):
+        part, _, _ = dprt.scene.make_scene(4, 8000, layout="slabs", camera=cam, only=[k])
+        assert all((c.verts is None) == (c.index != k) for c in part)
+        assert np.array_equal(part[k].verts, full[k].verts) and np.array_equal(part[k].mats, full[k].mats)
+        for a, b in zip(full, part):
+            assert np.array_equal(a.aabb_min, b.aabb_min) and np.array_equal(a.aabb_max, b.aabb_max)
+    v = full[2].verts.reshape(-1, 3)
+    assert (v.min(0) >= full[2].aabb_min).all() and (v.max(0) <= full[2].aabb_max).all()       # the analytic box encloses the mesh
+    # another camera: no table entry applies, the primary-ray quantiles are used
+    other = dprt.make_camera((0.5, -1.5, 0.8), (0.5, 0.5, 0.3), (0.0, 0.0, 1.0), 40.0, 640, 360)
+    oc, _, _ = dprt.scene.make_scene(2, 2000, layout="slabs", camera=other)
+    assert abs(float(oc[1].aabb_min[0]) - dprt.scene.CALIBRATED_SLAB_CUTS[2][1]) > 1e-3
