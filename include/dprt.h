@@ -27,9 +27,10 @@ typedef struct dprt_bvh8 dprt_bvh8;
  * context that is only driven single-rank or through dprt_*_group(). */
 int  dprt_get_unique_id(void* out128);
 int  dprt_create(const dprt_config* cfg, int rank, int world, int device, const void* nccl_unique_id, dprt_ctx** out);
-/* A second context of the same rank (other frame size / scene) that BORROWS the parent's NCCL communicator instead of
- * creating one (several frames in one MPI job share MPI_COMM_WORLD the same way). Collective like dprt_create; the parent
- * must outlive it, and the two contexts' collectives must not interleave across ranks. */
+/* A second context of the same rank (other frame size / scene) that SHARES the parent's NCCL communicator instead of
+ * creating one (several frames in one MPI job share MPI_COMM_WORLD the same way). Collective like dprt_create; the
+ * communicator lives until the last context on it is destroyed (any order); the contexts' collectives must not interleave
+ * across ranks. */
 int  dprt_create_shared(const dprt_config* cfg, dprt_ctx* parent, dprt_ctx** out);
 void dprt_destroy(dprt_ctx* ctx);
 const char* dprt_last_error(const dprt_ctx* ctx);   /* ctx may be NULL: last create-time error */
@@ -113,8 +114,8 @@ int  dprt_reduce_image(dprt_ctx* ctx, int root, float* out_host);
  * migrate iterations of a sample carry 10^4..10^5 rays -- launches that last as long as their longest ray and leave most of
  * the GPU idle -- so a host may keep K samples in flight: K contexts of the same rank (dprt_create_shared), one host thread
  * each, context j rendering samples j, j + K, ... with dprt_render_sample. dprt_adopt_scene makes a context use another
- * one's uploaded scene (chunk geometry, proxies and their networks, materials, lights, camera) without owning it -- the owner
- * must outlive it and must not re-upload meanwhile. dprt_accumulate_from adds another context's directLighting (plane 0) and
+ * one's uploaded scene (chunk geometry, proxies and their networks: shared device memory, freed with the last context that
+ * uses it; materials, lights, camera: copied) -- a later re-upload on either side no longer reaches the other. dprt_accumulate_from adds another context's directLighting (plane 0) and
  * envLighting sums into this one's, after which dprt_reduce_image averages and reduces the whole frame. Each sample's
  * arithmetic is unchanged; only the order of the per-pixel sum over samples differs (image within 1e-6 relative). */
 int  dprt_adopt_scene(dprt_ctx* ctx, dprt_ctx* from);

@@ -14,6 +14,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -82,13 +83,31 @@ struct NcclApi {
 };
 NcclApi g_nccl;
 
+// Device memory of one scene object (chunk geometry or the two proxy networks). Shared, not copied, between the contexts of a
+// rank that render samples of the same scene (dprt_adopt_scene): freed when the last of them lets go, in whatever order
+// the contexts are destroyed.
+struct ObjMem {
+    int device = 0;
+    void* d_nodes = nullptr; void* d_tris = nullptr; void* d_normals = nullptr;
+    MlpModel* vis = nullptr; MlpModel* depth = nullptr;
+    ~ObjMem() {
+        cudaSetDevice(device);
+        if (d_nodes) cudaFree(d_nodes);
+        if (d_tris) cudaFree(d_tris);
+        if (d_normals) cudaFree(d_normals);
+        if (vis) mlp_destroy(vis);
+        if (depth) mlp_destroy(depth);
+    }
+};
+
 struct ObjectHost {
     bool present = false;
-    bool owned = true;               // false: device geometry and proxy networks belong to another context (dprt_adopt_scene)
     dprt_object_desc desc{};
+    std::shared_ptr<ObjMem> mem;     // owner of everything below
     void* d_nodes = nullptr; void* d_tris = nullptr; void* d_normals = nullptr;
     int64_t nnodes = 0, ntris = 0;
     MlpModel* vis = nullptr; MlpModel* depth = nullptr;
+    void release() { mem.reset(); d_nodes = d_tris = d_normals = nullptr; vis = depth = nullptr; nnodes = ntris = 0; }
 };
 
 }  // namespace
@@ -128,7 +147,7 @@ struct dprt_ctx {
     bool p2p = false;                   // tables connected: the deque exchange runs over peer memory
     bool p2pGroup = false;              // connected as an in-process group (dprt_*_group only)
     bool p2pGroupActive = false;        // the group driver is running the peer-memory exchange right now
-    bool ownsComm = true;               // false: communicator borrowed from the parent context (dprt_create_shared)
+    std::shared_ptr<void> commKeep;     // the communicator's owner handle, shared with the contexts created from this one (dprt_create_shared)
     int countedStreams = 0;             // this context's share of g_streams[device]
     P2PMailbox* d_mailbox = nullptr;
     dprt_path_record* d_active[2] = {nullptr, nullptr};    // arrivals land here (never in `paths`)
@@ -440,11 +459,12 @@ static int create_impl(const dprt_config* cfg, int rank, int world, int device, 
         for (int i = 0; i < cfg->sceneSize; i++) { ctx->objects[i].desc.nodeID = 0; ctx->objects[i].desc.isProxy = 1; }
         if ((r = upload_objects(ctx))) return r;
         if (parent && parent->comm && world > 1) {
-            ctx->comm = parent->comm; ctx->ownsComm = false;              // collectives of the two contexts must not interleave
+            ctx->comm = parent->comm; ctx->commKeep = parent->commKeep;   // collectives of the two contexts must not interleave
         } else if (nccl_unique_id && world > 1) {
             ncclUniqueId id; std::memcpy(&id, nccl_unique_id, 128);
             if (!g_nccl.load()) { ctx->err = g_nccl.error; return DPRT_ERR_NCCL; }
             NK(g_nccl.CommInitRank(&ctx->comm, world, id, rank));
+            ctx->commKeep = std::shared_ptr<void>((void*)ctx->comm, [](void* c) { if (c) g_nccl.CommDestroy((ncclComm_t)c); });
         }
         // peer-memory exchange: a collective decision over the communicator (all ranks or none, p2p_connect_nccl)
         if (ctx->comm) { int pr = p2p_connect_nccl(ctx); if (pr) return pr; }
@@ -477,15 +497,8 @@ void dprt_destroy(dprt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->device >= 0 && ctx->device < 64) g_streams[ctx->device] -= ctx->countedStreams;
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    if (ctx->comm && ctx->ownsComm) g_nccl.CommDestroy(ctx->comm);
-    for (auto& o : ctx->objects) {
-        if (!o.owned) continue;
-        if (o.d_nodes) cudaFree(o.d_nodes);
-        if (o.d_tris) cudaFree(o.d_tris);
-        if (o.d_normals) cudaFree(o.d_normals);
-        if (o.vis) mlp_destroy(o.vis);
-        if (o.depth) mlp_destroy(o.depth);
-    }
+    ctx->comm = nullptr; ctx->commKeep.reset();          // ncclCommDestroy when the last context on this communicator goes
+    for (auto& o : ctx->objects) o.release();
     for (int i = 0; i < DPRT_BUF_COUNT; i++) if (ctx->buf_ptr[i]) cudaFree(ctx->buf_ptr[i]);
     for (void* p : ctx->user_allocs) cudaFree(p);
     if (ctx->d_objects) cudaFree(ctx->d_objects);
@@ -622,23 +635,21 @@ int dprt_upload_chunk(dprt_ctx* ctx, int si, const dprt_object_desc* desc, const
     if (bvh8_build(verts9, mat_ids, ntris, -1.f, b)) return fail(ctx, DPRT_ERR_INVALID, "bvh8_build failed");
     if (b.max_depth > 36) return fail(ctx, DPRT_ERR_CAPACITY, "BVH8 deeper than the traversal stack");
     ObjectHost& o = ctx->objects[si];
-    if (o.owned) {
-        if (o.d_nodes) cudaFree(o.d_nodes);
-        if (o.d_tris) cudaFree(o.d_tris);
-        if (o.d_normals) cudaFree(o.d_normals);
-    } else { o.vis = o.depth = nullptr; }
-    o.owned = true;
-    o.d_nodes = o.d_tris = o.d_normals = nullptr;
+    CK(cudaStreamSynchronize(ctx->stream));            // nothing in flight reads the old geometry
+    o.release();
+    auto mem = std::make_shared<ObjMem>();
+    mem->device = ctx->device;
     o.desc = *desc; o.desc.isProxy = 0; o.present = true;
-    o.nnodes = (int64_t)b.nodes.size(); o.ntris = (int64_t)b.tris.size();
-    CK(cudaMalloc(&o.d_nodes, b.nodes.size() * sizeof(dprt_bvh8_node)));
-    CK(cudaMalloc(&o.d_tris, b.tris.size() * sizeof(dprt_bvh8_tri)));
-    CK(cudaMemcpy(o.d_nodes, b.nodes.data(), b.nodes.size() * sizeof(dprt_bvh8_node), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(o.d_tris, b.tris.data(), b.tris.size() * sizeof(dprt_bvh8_tri), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&mem->d_nodes, b.nodes.size() * sizeof(dprt_bvh8_node)));
+    CK(cudaMalloc(&mem->d_tris, b.tris.size() * sizeof(dprt_bvh8_tri)));
+    CK(cudaMemcpy(mem->d_nodes, b.nodes.data(), b.nodes.size() * sizeof(dprt_bvh8_node), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(mem->d_tris, b.tris.data(), b.tris.size() * sizeof(dprt_bvh8_tri), cudaMemcpyHostToDevice));
     if (normals9) {
-        CK(cudaMalloc(&o.d_normals, (size_t)ntris * 9 * sizeof(float)));
-        CK(cudaMemcpy(o.d_normals, normals9, (size_t)ntris * 9 * sizeof(float), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&mem->d_normals, (size_t)ntris * 9 * sizeof(float)));
+        CK(cudaMemcpy(mem->d_normals, normals9, (size_t)ntris * 9 * sizeof(float), cudaMemcpyHostToDevice));
     }
+    o.mem = mem; o.d_nodes = mem->d_nodes; o.d_tris = mem->d_tris; o.d_normals = mem->d_normals;
+    o.nnodes = (int64_t)b.nodes.size(); o.ntris = (int64_t)b.tris.size();
     return upload_objects(ctx);
 }
 
@@ -648,13 +659,14 @@ int dprt_upload_proxy(dprt_ctx* ctx, int si, const dprt_object_desc* desc, const
     if (desc->nodeID < 0 || desc->nodeID >= ctx->world) return fail(ctx, DPRT_ERR_INVALID, "nodeID out of range");
     CK(cudaSetDevice(ctx->device));
     ObjectHost& o = ctx->objects[si];
-    if (!o.owned) { o.vis = o.depth = nullptr; o.d_nodes = o.d_tris = o.d_normals = nullptr; o.owned = true; }
+    CK(cudaStreamSynchronize(ctx->stream));            // a launch in flight may still read the old networks / table rows
+    o.release();
+    auto mem = std::make_shared<ObjMem>();
+    mem->device = ctx->device;
     o.desc = *desc; o.desc.isProxy = 1; o.present = true;
-    if (o.vis) { mlp_destroy(o.vis); o.vis = nullptr; }
-    if (o.depth) { mlp_destroy(o.depth); o.depth = nullptr; }
-    if (vis_blob && mlp_create(vis_blob, vis_bytes, ctx->cfg.mlpDtype, &o.vis, ctx->err)) return DPRT_ERR_INVALID;
-    if (depth_blob && mlp_create(depth_blob, depth_bytes, ctx->cfg.mlpDtype, &o.depth, ctx->err)) return DPRT_ERR_INVALID;
-    CK(cudaStreamSynchronize(ctx->stream));            // a launch in flight may still read the old table rows
+    if (vis_blob && mlp_create(vis_blob, vis_bytes, ctx->cfg.mlpDtype, &mem->vis, ctx->err)) return DPRT_ERR_INVALID;
+    if (depth_blob && mlp_create(depth_blob, depth_bytes, ctx->cfg.mlpDtype, &mem->depth, ctx->err)) return DPRT_ERR_INVALID;
+    o.mem = mem; o.vis = mem->vis; o.depth = mem->depth;
     const MlpGroupEntry ev = mlp_group_entry(o.vis), ed = mlp_group_entry(o.depth);
     CK(cudaMemcpy(ctx->d_mlpTable + si, &ev, sizeof(ev), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_mlpTable + 32 + si, &ed, sizeof(ed), cudaMemcpyHostToDevice));
@@ -668,18 +680,7 @@ int dprt_adopt_scene(dprt_ctx* ctx, dprt_ctx* from) {
         return fail(ctx, DPRT_ERR_INVALID, "dprt_adopt_scene: the two contexts must be the same rank, device, scene size and proxy operand type");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream)); CK(cudaStreamSynchronize(from->stream));
-    for (int i = 0; i < ctx->cfg.sceneSize; i++) {
-        ObjectHost& o = ctx->objects[i];
-        if (o.owned) {
-            if (o.d_nodes) cudaFree(o.d_nodes);
-            if (o.d_tris) cudaFree(o.d_tris);
-            if (o.d_normals) cudaFree(o.d_normals);
-            if (o.vis) mlp_destroy(o.vis);
-            if (o.depth) mlp_destroy(o.depth);
-        }
-        o = from->objects[i];
-        o.owned = false;
-    }
+    for (int i = 0; i < ctx->cfg.sceneSize; i++) ctx->objects[i] = from->objects[i];      // shares the device memory (ObjMem)
     CK(cudaMemcpy(ctx->d_materials, from->d_materials, sizeof(dprt_material) * DPRT_MAX_MATERIALS, cudaMemcpyDeviceToDevice));
     CK(cudaMemcpy(ctx->d_lights, from->d_lights, sizeof(dprt_light_tri) * DPRT_MAX_LIGHTS, cudaMemcpyDeviceToDevice));
     CK(cudaMemcpy(ctx->d_mlpTable, from->d_mlpTable, 2 * 32 * sizeof(MlpGroupEntry), cudaMemcpyDeviceToDevice));
