@@ -188,9 +188,9 @@ def run_reference(args):
     cores = O.num_threads()
     sample = (f"{args.steps} x runSample over the full {w}x{h} frame of the same 1-chunk scene" if scale == 1 else
               f"{args.steps} x runSample over a {w}x{h} frame (1/{scale} per side of {fw}x{fh}) of the same {W}-chunk scene")
-    cfg_out = workload_config(args, W, fw, fh)
-    cfg_out["reference_arm_frame"] = f"{w}x{h}"
+    cfg_out = workload_config(args, W, fw, fh)          # N = 1: the very same workload, so the very same config
     if scale != 1:
+        cfg_out["reference_arm_frame"] = f"{w}x{h}"
         cfg_out["workload"] += f" -- the CPU arm renders a {w}x{h} sub-sampled frame of it (rate metric, same scene and camera)"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": W, "steps": args.steps, "warmup": args.warmup,
