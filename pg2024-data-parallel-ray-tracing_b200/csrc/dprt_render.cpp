@@ -12,8 +12,18 @@
 //   "DPRTSCN1" | int32 nObjects nMaterials nLights | dprt_camera | dprt_material[nMaterials] | dprt_light_tri[nLights]
 //   per object: dprt_object_desc (isProxy ignored) | int64 ntris | float verts[9 ntris] | float normals[9 ntris]
 //               | int32 mats[ntris] | int64 visBytes | vis blob | int64 depthBytes | depth blob   (proxy MLP weights, may be 0)
-// Output: PFM (RGB float32, bottom-up as the format demands) on the root rank, one JSON line of statistics on stdout.
+//               [--frames F] [--camera-move dx,dy,dz] [--camera-target x,y,z] [--light-move dx,dy,dz] [--light-start dx,dy,dz]
+//                                      the frame loop of launch() (renderer.cpp:1938-2059): per frame the first two lights move by
+//                                      -light-move (after a one-off +light-start, LIGHT_MOVE :1941-1966) and the camera origin by
+//                                      +camera-move (CAMERA_MOVE :1968-1983; re-aimed at --camera-target when given, else translated);
+//                                      frame f is written as <f><name> like std::to_string(cframe) + exrFilename (:2055-2058)
+//   dprt_render --convert in.pfm out.exr     no GPU: re-encode an image (the reference's Image::save writes EXR)
+//
+// Output on the root rank: OpenEXR (uncompressed scanlines, float32 B/G/R) when the name ends in .exr, else PFM (RGB float32,
+// bottom-up as the format demands); one JSON line of statistics per frame on stdout.
+#include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -78,6 +88,85 @@ bool write_pfm(const std::string& path, const float* rgb, int w, int h) {
     return true;
 }
 
+// Minimal OpenEXR 2 writer: single-part scanline file, NO_COMPRESSION, three FLOAT channels (stored alphabetically: B, G, R),
+// increasing-Y line order. What Image::save(width, height, pixels, exrFilename) produces in the reference (renderer.cpp:2055-2058).
+bool write_exr(const std::string& path, const float* rgb, int w, int h) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    std::vector<char> hd;
+    auto put = [&](const void* p, size_t n) { hd.insert(hd.end(), (const char*)p, (const char*)p + n); };
+    auto puts0 = [&](const char* s) { put(s, std::strlen(s) + 1); };
+    auto i32 = [&](int32_t v) { put(&v, 4); };
+    auto f32 = [&](float v) { put(&v, 4); };
+    const uint32_t magic = 20000630u, version = 2u;
+    put(&magic, 4); put(&version, 4);
+    puts0("channels"); puts0("chlist"); i32(3 * (2 + 16) + 1);
+    for (const char* c : {"B", "G", "R"}) { puts0(c); i32(2 /* FLOAT */); const char z[4] = {0, 0, 0, 0}; put(z, 4); i32(1); i32(1); }
+    { const char z = 0; put(&z, 1); }
+    puts0("compression"); puts0("compression"); i32(1); { const char c = 0; put(&c, 1); }
+    puts0("dataWindow"); puts0("box2i"); i32(16); i32(0); i32(0); i32(w - 1); i32(h - 1);
+    puts0("displayWindow"); puts0("box2i"); i32(16); i32(0); i32(0); i32(w - 1); i32(h - 1);
+    puts0("lineOrder"); puts0("lineOrder"); i32(1); { const char c = 0; put(&c, 1); }
+    puts0("pixelAspectRatio"); puts0("float"); i32(4); f32(1.0f);
+    puts0("screenWindowCenter"); puts0("v2f"); i32(8); f32(0.0f); f32(0.0f);
+    puts0("screenWindowWidth"); puts0("float"); i32(4); f32(1.0f);
+    { const char z = 0; put(&z, 1); }
+    const uint64_t rowBytes = 8 + (uint64_t)w * 12;
+    uint64_t off = hd.size() + (uint64_t)h * 8;
+    for (int y = 0; y < h; y++) { put(&off, 8); off += rowBytes; }
+    bool ok = fwrite(hd.data(), 1, hd.size(), f) == hd.size();
+    std::vector<float> row((size_t)w * 3);
+    for (int y = 0; y < h && ok; y++) {
+        const float* src = rgb + (size_t)y * w * 3;
+        for (int x = 0; x < w; x++) { row[x] = src[3 * x + 2]; row[(size_t)w + x] = src[3 * x + 1]; row[2 * (size_t)w + x] = src[3 * x]; }
+        const int32_t yy = y, bytes = (int32_t)(w * 12);
+        ok = fwrite(&yy, 4, 1, f) == 1 && fwrite(&bytes, 4, 1, f) == 1 && fwrite(row.data(), 4, row.size(), f) == row.size();
+    }
+    fclose(f);
+    return ok;
+}
+
+bool read_pfm(const std::string& path, std::vector<float>& rgb, int& w, int& h) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    char tag[3] = {0}; float scale = 0.f;
+    bool ok = fscanf(f, "%2s %d %d %f", tag, &w, &h, &scale) == 4 && std::strcmp(tag, "PF") == 0 && w > 0 && h > 0 && scale < 0.f;
+    if (ok) { fgetc(f); rgb.resize((size_t)w * h * 3); }
+    for (int row = h - 1; ok && row >= 0; row--) ok = fread(rgb.data() + (size_t)row * w * 3, sizeof(float), (size_t)w * 3, f) == (size_t)w * 3;
+    fclose(f);
+    return ok;
+}
+
+bool ends_with(const std::string& s, const char* suf) { const size_t n = std::strlen(suf); return s.size() >= n && s.compare(s.size() - n, n, suf) == 0; }
+bool write_image(const std::string& path, const float* rgb, int w, int h) { return ends_with(path, ".exr") ? write_exr(path, rgb, w, h) : write_pfm(path, rgb, w, h); }
+
+// "<dir>/<frame><name>" like std::to_string(cframe) + exrFilename (renderer.cpp:2058)
+std::string frame_name(const std::string& path, int frame, int frames) {
+    if (frames <= 1) return path;
+    const size_t slash = path.find_last_of('/');
+    const std::string dir = slash == std::string::npos ? "" : path.substr(0, slash + 1);
+    return dir + std::to_string(frame) + (slash == std::string::npos ? path : path.substr(slash + 1));
+}
+
+bool parse3(const char* s, float v[3]) { return s && std::sscanf(s, "%f,%f,%f", v, v + 1, v + 2) == 3; }
+
+// camera.m_origin += move; camera.updateTransformMatrix() (renderer.cpp:1968-1983). With a target the basis is re-aimed (the
+// lengths of U and V carry the field of view and the aspect ratio); without one the camera is translated.
+void move_camera(dprt_camera& c, const float move[3], const float* target) {
+    for (int a = 0; a < 3; a++) c.origin[a] = c.origin[a] + move[a];
+    if (!target) return;
+    auto len = [](const double* v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+    const double U0[3] = {c.U[0], c.U[1], c.U[2]}, V0[3] = {c.V[0], c.V[1], c.V[2]};
+    const double lu = len(U0), lv = len(V0);
+    double w[3] = {(double)target[0] - c.origin[0], (double)target[1] - c.origin[1], (double)target[2] - c.origin[2]};
+    const double lw = len(w); for (double& x : w) x /= lw;
+    const double up[3] = {c.V[0] / lv, c.V[1] / lv, c.V[2] / lv};
+    double u[3] = {w[1] * up[2] - w[2] * up[1], w[2] * up[0] - w[0] * up[2], w[0] * up[1] - w[1] * up[0]};
+    const double lu2 = len(u); for (double& x : u) x /= lu2;
+    const double v[3] = {u[1] * w[2] - u[2] * w[1], u[2] * w[0] - u[0] * w[2], u[0] * w[1] - u[1] * w[0]};
+    for (int a = 0; a < 3; a++) { c.U[a] = (float)(u[a] * lu); c.V[a] = (float)(v[a] * lv); c.W[a] = (float)w[a]; }
+}
+
 // the AccelerationStructure table of one rank (renderer.cpp:1812-1842): own objects as geometry, the others as proxies
 int upload_scene(dprt_ctx* ctx, const Scene& sc, int rank) {
     int r;
@@ -134,10 +223,17 @@ const char* arg(int argc, char** argv, const char* name, const char* dflt) {
 
 int main(int argc, char** argv) {
     setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);       // before the first CUDA call: one hardware queue per stream (--inflight)
+    if (argc == 4 && !std::strcmp(argv[1], "--convert")) {            // no GPU involved
+        std::vector<float> rgb; int w = 0, h = 0;
+        if (!read_pfm(argv[2], rgb, w, h)) { fprintf(stderr, "dprt_render: cannot read PFM %s\n", argv[2]); return 1; }
+        if (!write_image(argv[3], rgb.data(), w, h)) { fprintf(stderr, "dprt_render: cannot write %s\n", argv[3]); return 1; }
+        return 0;
+    }
     const std::string scenePath = arg(argc, argv, "--scene", ""), outPath = arg(argc, argv, "--out", "");
     if (scenePath.empty()) {
         fprintf(stderr, "usage: dprt_render --scene S.dprt [--out image.pfm] [--spp n] [--bounces n] [--proxy 0|1] [--path-gen 0|1] "
-                        "[--inflight K] [--world W | --nccl-id-file F]\n");
+                        "[--inflight K] [--world W | --nccl-id-file F] [--frames F] [--camera-move x,y,z] [--camera-target x,y,z] "
+                        "[--light-move x,y,z] [--light-start x,y,z]\n       dprt_render --convert in.pfm out.exr\n");
         return 2;
     }
     Scene sc; std::string err;
@@ -172,6 +268,40 @@ int main(int argc, char** argv) {
     if (inflight < 1) inflight = 1;
     if (inflight > cfg.spp) inflight = cfg.spp;
     int r;
+    // frame loop of launch() (renderer.cpp:1938-2059)
+    const int frames = std::max(1, std::atoi(arg(argc, argv, "--frames", "1")));
+    float camMove[3] = {0, 0, 0}, camTarget[3], lightMove[3] = {0, 0, 0}, lightStart[3] = {0, 0, 0};
+    const bool haveCamMove = parse3(arg(argc, argv, "--camera-move", nullptr), camMove);
+    const bool haveTarget = parse3(arg(argc, argv, "--camera-target", nullptr), camTarget);
+    const bool haveLightMove = parse3(arg(argc, argv, "--light-move", nullptr), lightMove);
+    parse3(arg(argc, argv, "--light-start", nullptr), lightStart);
+    // per frame: LIGHT_MOVE (:1941-1966) then CAMERA_MOVE (:1968-1983), uploaded to every context of this process
+    auto advance_frame = [&](int frame, const std::vector<dprt_ctx*>& all) -> int {
+        if (haveLightMove) {
+            const size_t nl = std::min<size_t>(2, sc.lights.size());
+            for (size_t i = 0; i < nl; i++) {
+                dprt_light_tri& L = sc.lights[i];
+                for (int a = 0; a < 3; a++) {
+                    if (frame == 0) { L.p0[a] = L.p0[a] + lightStart[a]; L.p1[a] = L.p1[a] + lightStart[a]; L.p2[a] = L.p2[a] + lightStart[a]; }
+                    L.p0[a] = L.p0[a] - lightMove[a]; L.p1[a] = L.p1[a] - lightMove[a]; L.p2[a] = L.p2[a] - lightMove[a];
+                }
+            }
+        }
+        if (haveCamMove) move_camera(sc.cam, camMove, haveTarget ? camTarget : nullptr);
+        for (dprt_ctx* c : all) {
+            int rr;
+            if (haveLightMove && (rr = dprt_set_lights(c, sc.lights.data(), (int)sc.lights.size()))) return rr;
+            if (haveCamMove && (rr = dprt_set_camera(c, &sc.cam))) return rr;
+        }
+        return 0;
+    };
+    auto save_frame = [&](int frame) -> bool {
+        if (rank != 0 || outPath.empty()) return true;
+        const std::string name = frame_name(outPath, frame, frames);
+        if (write_image(name, image.data(), cfg.width, cfg.height)) return true;
+        fprintf(stderr, "dprt_render: cannot write %s\n", name.c_str());
+        return false;
+    };
     // K - 1 more contexts of this rank on the same communicator, sharing the uploaded scene (collective across ranks)
     auto make_inflight = [&](dprt_ctx* ctx) -> int {
         if (world > 1 && !dprt_p2p_enabled(ctx)) return 0;          // the NCCL fallback exchange needs the communicator to itself
@@ -210,14 +340,20 @@ int main(int argc, char** argv) {
         ctxs.push_back(ctx);
         if ((r = upload_scene(ctx, sc, rank))) return die("scene upload", ctx, r);
         if ((r = make_inflight(ctx))) return die("samples in flight", nullptr, r);
-        const auto t0 = std::chrono::steady_clock::now();
-        if ((r = dprt_reset_frame(ctx))) return die("dprt_reset_frame", ctx, r);
-        { const char* what = ""; dprt_ctx* bad = ctx; if ((r = render_samples(ctx, extra, cfg.spp, &what, &bad))) return die(what, bad, r); }
-        if ((r = dprt_reduce_image(ctx, 0, rank == 0 ? image.data() : nullptr))) return die("dprt_reduce_image", ctx, r);
-        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        dprt_stats st; dprt_get_stats(ctx, &st);
-        printf("{\"rank\": %d, \"world\": %d, \"seconds\": %.6f, \"rays_walked\": %lld, \"paths_sent_offrank\": %lld, \"exchange_iters\": %lld}\n",
-               rank, world, sec, (long long)st.rays_walked, (long long)st.paths_sent_offrank, (long long)st.exchange_iters);
+        std::vector<dprt_ctx*> all{ctx};
+        all.insert(all.end(), extra.begin(), extra.end());
+        for (int frame = 0; frame < frames; frame++) {
+            if ((r = advance_frame(frame, all))) return die("frame setup", ctx, r);
+            const auto t0 = std::chrono::steady_clock::now();
+            for (dprt_ctx* c : all) if ((r = dprt_reset_frame(c))) return die("dprt_reset_frame", c, r);
+            { const char* what = ""; dprt_ctx* bad = ctx; if ((r = render_samples(ctx, extra, cfg.spp, &what, &bad))) return die(what, bad, r); }
+            if ((r = dprt_reduce_image(ctx, 0, rank == 0 ? image.data() : nullptr))) return die("dprt_reduce_image", ctx, r);
+            const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            dprt_stats st; dprt_get_stats(ctx, &st);
+            printf("{\"frame\": %d, \"rank\": %d, \"world\": %d, \"seconds\": %.6f, \"rays_walked\": %lld, \"paths_sent_offrank\": %lld, \"exchange_iters\": %lld}\n",
+                   frame, rank, world, sec, (long long)st.rays_walked, (long long)st.paths_sent_offrank, (long long)st.exchange_iters);
+            if (!save_frame(frame)) return 1;
+        }
     } else {
         // ---- in-process rank group (or a single rank) ----
         int ndev = std::atoi(arg(argc, argv, "--devices", "1"));      // chunk owner k runs on GPU k % ndev
@@ -228,25 +364,27 @@ int main(int argc, char** argv) {
             if ((r = upload_scene(ctxs[k], sc, k))) return die("scene upload", ctxs[k], r);
         }
         if (world == 1 && (r = make_inflight(ctxs[0]))) return die("samples in flight", nullptr, r);
-        const auto t0 = std::chrono::steady_clock::now();
-        for (int k = 0; k < world; k++) if ((r = dprt_reset_frame(ctxs[k]))) return die("dprt_reset_frame", ctxs[k], r);
-        if (world == 1) {
-            const char* what = ""; dprt_ctx* bad = ctxs[0];
-            if ((r = render_samples(ctxs[0], extra, cfg.spp, &what, &bad))) return die(what, bad, r);
-        } else {
-            for (int s = 0; s < cfg.spp; s++)
-                if ((r = dprt_render_sample_group(ctxs.data(), world, s))) return die("dprt_render_sample_group", ctxs[0], r);
+        std::vector<dprt_ctx*> all(ctxs);
+        all.insert(all.end(), extra.begin(), extra.end());
+        for (int frame = 0; frame < frames; frame++) {
+            if ((r = advance_frame(frame, all))) return die("frame setup", ctxs[0], r);
+            const auto t0 = std::chrono::steady_clock::now();
+            for (dprt_ctx* c : all) if ((r = dprt_reset_frame(c))) return die("dprt_reset_frame", c, r);
+            if (world == 1) {
+                const char* what = ""; dprt_ctx* bad = ctxs[0];
+                if ((r = render_samples(ctxs[0], extra, cfg.spp, &what, &bad))) return die(what, bad, r);
+            } else {
+                for (int s = 0; s < cfg.spp; s++)
+                    if ((r = dprt_render_sample_group(ctxs.data(), world, s))) return die("dprt_render_sample_group", ctxs[0], r);
+            }
+            r = world == 1 ? dprt_reduce_image(ctxs[0], 0, image.data()) : dprt_reduce_image_group(ctxs.data(), world, 0, image.data());
+            if (r) return die("dprt_reduce_image", ctxs[0], r);
+            const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            long long walked = 0, sent = 0;
+            for (int k = 0; k < world; k++) { dprt_stats st; dprt_get_stats(ctxs[k], &st); walked += st.rays_walked; sent += st.paths_sent_offrank; }
+            printf("{\"frame\": %d, \"rank\": 0, \"world\": %d, \"seconds\": %.6f, \"rays_walked\": %lld, \"paths_sent_offrank\": %lld}\n", frame, world, sec, walked, sent);
+            if (!save_frame(frame)) return 1;
         }
-        r = world == 1 ? dprt_reduce_image(ctxs[0], 0, image.data()) : dprt_reduce_image_group(ctxs.data(), world, 0, image.data());
-        if (r) return die("dprt_reduce_image", ctxs[0], r);
-        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        long long walked = 0, sent = 0;
-        for (int k = 0; k < world; k++) { dprt_stats st; dprt_get_stats(ctxs[k], &st); walked += st.rays_walked; sent += st.paths_sent_offrank; }
-        printf("{\"rank\": 0, \"world\": %d, \"seconds\": %.6f, \"rays_walked\": %lld, \"paths_sent_offrank\": %lld}\n", world, sec, walked, sent);
-    }
-    if (rank == 0 && !outPath.empty() && !write_pfm(outPath, image.data(), cfg.width, cfg.height)) {
-        fprintf(stderr, "dprt_render: cannot write %s\n", outPath.c_str());
-        return 1;
     }
     for (dprt_ctx* c : extra) dprt_destroy(c);         // borrowers before the owner of the scene and the communicator
     for (dprt_ctx* c : ctxs) dprt_destroy(c);

@@ -268,6 +268,49 @@ def save_scene(path, chunks, materials, lights, cam, models=None):
                 f.write(b)
 
 
+def load_exr(path):
+    """The OpenEXR subset dprt_render writes (single part, uncompressed scanlines, FLOAT channels B/G/R, increasing Y)
+    -> [h, w, 3] RGB float32. Enough of a reader to check the writer without an EXR library."""
+    import struct
+    b = open(path, "rb").read()
+    magic, version = struct.unpack_from("<II", b, 0)
+    assert magic == 20000630 and (version & 0xff) == 2 and not (version & 0x1e00), "not a single-part scanline OpenEXR 2 file"
+    o, attrs = 8, {}
+    while b[o] != 0:
+        e = b.index(b"\0", o); name = b[o:e].decode(); o = e + 1
+        e = b.index(b"\0", o); typ = b[o:e].decode(); o = e + 1
+        (size,) = struct.unpack_from("<i", b, o); o += 4
+        attrs[name] = (typ, b[o:o + size]); o += size
+    o += 1
+    assert attrs["compression"][1] == b"\0" and attrs["lineOrder"][1] == b"\0"
+    x0, y0, x1, y1 = struct.unpack("<4i", attrs["dataWindow"][1])
+    w, h = x1 - x0 + 1, y1 - y0 + 1
+    chans, c = [], attrs["channels"][1]
+    p = 0
+    while c[p] != 0:
+        e = c.index(b"\0", p); nm = c[p:e].decode(); p = e + 1
+        (ptype,) = struct.unpack_from("<i", c, p); p += 16
+        assert ptype == 2, "FLOAT channels only"
+        chans.append(nm)
+    assert chans == sorted(chans) and set(chans) == {"R", "G", "B"}
+    offs = struct.unpack_from(f"<{h}Q", b, o)
+    img = np.zeros((h, w, 3), np.float32)
+    for k, off in enumerate(offs):
+        y, size = struct.unpack_from("<ii", b, off)
+        assert size == w * 4 * len(chans)
+        row = np.frombuffer(b, "<f4", w * len(chans), off + 8).reshape(len(chans), w)
+        for ci, nm in enumerate(chans):
+            img[y - y0, :, "RGB".index(nm)] = row[ci]
+    return img
+
+
+def save_pfm(path, img):
+    a = np.ascontiguousarray(img, np.float32)
+    with open(path, "wb") as f:
+        f.write(f"PF\n{a.shape[1]} {a.shape[0]}\n-1.0\n".encode())
+        f.write(a[::-1].tobytes())
+
+
 def load_pfm(path):
     """RGB float32 PFM as written by dprt_render (little endian, bottom-up) -> [h, w, 3] top-down."""
     with open(path, "rb") as f:

@@ -414,3 +414,28 @@ def test_per_rank_scene_generation_and_calibrated_cuts():
     other = dprt.make_camera((0.5, -1.5, 0.8), (0.5, 0.5, 0.3), (0.0, 0.0, 1.0), 40.0, 640, 360)
     oc, _, _ = dprt.scene.make_scene(2, 2000, layout="slabs", camera=other)
     assert abs(float(oc[1].aabb_min[0]) - dprt.scene.CALIBRATED_SLAB_CUTS[2][1]) > 1e-3
+
+
+def test_exr_writer_round_trip(tmp_path):
+    """the reference saves its frames as EXR (renderer.cpp:2055-2058). dprt_render's writer, exercised
+    without a GPU through `--convert`, against this repository's own minimal reader and, when OpenCV was built with
+    OpenEXR, against that independent one -- bit for bit."""
+    import subprocess
+    binary = os.path.join(os.path.dirname(dprt.host.LIB_PATH), "dprt_render")
+    img = (np.random.default_rng(3).random((37, 53, 3)) * 40.0 - 2.0).astype(np.float32)
+    img[0, 0] = [0.0, np.float32(1e-30), np.float32(6.5e4)]
+    pfm, exr = str(tmp_path / "a.pfm"), str(tmp_path / "a.exr")
+    dprt.scene.save_pfm(pfm, img)
+    assert np.array_equal(dprt.scene.load_pfm(pfm), img)
+    p = subprocess.run([binary, "--convert", pfm, exr], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert np.array_equal(dprt.scene.load_exr(exr).view(np.uint32), img.view(np.uint32))
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    try:
+        import cv2
+        x = cv2.imread(exr, cv2.IMREAD_UNCHANGED)
+    except Exception:
+        x = None
+    if x is not None:
+        assert np.array_equal(x[..., ::-1], img)
+    assert subprocess.run([binary, "--convert", str(tmp_path / "missing.pfm"), exr], capture_output=True).returncode == 1
