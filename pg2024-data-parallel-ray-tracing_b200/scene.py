@@ -146,6 +146,40 @@ def make_lights(scale=1.0):
     return L
 
 
+def reference_lights(scene="default"):
+    """The per-scene area-light tables of the reference's launch() (renderer.cpp:1725-1796: one #if branch per scene), as
+    dprt_light_tri records: "default" (the #else branch: Moana island), "san_miguel", "air_drome", "bistro". The coordinates
+    are scene data in the reference's world units; the triangle vertex order is the reference's (it fixes the light normal)."""
+    base = np.array([891.443777, 505.928150, 154.625939], np.float32)
+    grey = np.float32(505.928150)
+    tables = {
+        "default": ([(101346.539, 202660.438, 189948.188), (106779.617, 187339.562, 201599.453), (83220.3828, 202660.438, 198400.547),
+                     (101346.539, 202660.438, 189948.188), (88653.4609, 187339.562, 210051.812), (83220.3828, 202660.438, 198400.547)],
+                    [((0, 1, 2), base), ((3, 4, 5), base)]),
+        "san_miguel": ([(14779.412109375, 153398.8125, -4307.61865234375), (-2001.59326171875, 146156.09375, -12428.0302734375),
+                        (4770.7685546875, 157817.109375, 12434.7119140625), (-2001.59326171875, 146156.09375, -12428.0302734375)],
+                       [((0, 2, 3), base), ((3, 1, 0), base)]),
+        "air_drome": ([(-2114.32861328125, 81.61964416503906, 140.63539123535156), (-2114.179443359375, 81.80250549316406, -59.34486389160156),
+                       (-1942.9859619140625, 442.6954345703125, 140.6354217529297), (-1942.8370361328125, 442.87811279296875, -59.34484100341797)],
+                      [((0, 3, 2), base), ((0, 1, 3), base)]),
+        "bistro": ([(0.12184541672468185, 8.149029731750488, 0.31903180480003357), (0.13482901453971863, 8.29036808013916, 0.45987018942832947),
+                    (0.2922881841659546, 8.166015625, 0.3377407491207123), (0.3052719831466675, 8.307354927062988, 0.4785784184932709),
+                    (-4.677332878112793, 9.999991416931152, -6.165306091308594), (3.3226675987243652, 9.999991416931152, -6.165306091308594),
+                    (-4.677332878112793, 9.999991416931152, 13.834686279296875), (3.3226675987243652, 9.999991416931152, 13.834686279296875),
+                    (6.292665004730225, 4.862171173095703, 1.3878426551818848), (6.260426998138428, 4.918705940246582, 1.4343327283859253),
+                    (6.340075969696045, 4.868965148925781, 1.4374041557312012), (6.307837963104248, 4.925500869750977, 1.4838939905166626)],
+                   [((0, 2, 3), 10.0 * grey), ((3, 1, 0), 10.0 * grey), ((7, 6, 4), 0.001 * grey), ((4, 5, 7), 0.001 * grey),
+                    ((8, 10, 11), 30.0 * grey), ((11, 9, 8), 30.0 * grey)]),
+    }
+    pts, tris = tables[scene]
+    P = np.asarray(pts, np.float32)
+    L = np.zeros(len(tris), D.LIGHT_DTYPE)
+    for k, ((a, b, c), le) in enumerate(tris):
+        L["p0"][k], L["p1"][k], L["p2"][k] = P[a], P[b], P[c]
+        L["Le"][k] = np.broadcast_to(np.float32(le), 3)
+    return L
+
+
 # x-cuts of the benchmark landscape (seed 0, default_camera) that equalise the rays each chunk owner walks over ALL bounces
 # of the per-sample loop, measured with the oracle on a coarse mesh: profiles/calibrate_slabs.py (which prints this table).
 # Empty entry: fall back to the primary-ray quantiles of balanced_slab_layout.

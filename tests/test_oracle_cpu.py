@@ -439,3 +439,16 @@ def test_exr_writer_round_trip(tmp_path):
     if x is not None:
         assert np.array_equal(x[..., ::-1], img)
     assert subprocess.run([binary, "--convert", str(tmp_path / "missing.pfm"), exr], capture_output=True).returncode == 1
+
+
+def test_reference_light_tables():
+    """The per-scene light tables of renderer.cpp:1725-1796 as dprt_light_tri records: counts, radiance, non-degenerate area."""
+    n = {"default": 2, "san_miguel": 2, "air_drome": 2, "bistro": 6}
+    for name, count in n.items():
+        L = dprt.scene.reference_lights(name)
+        assert L.dtype == D.LIGHT_DTYPE and L.size == count and count <= 16
+        area = 0.5 * np.linalg.norm(np.cross(L["p1"] - L["p0"], L["p2"] - L["p0"]), axis=1)
+        deg = {"san_miguel": 1}.get(name, 0)         # the reference lists one San Miguel corner twice: its second triangle has no area
+        assert (area > 0).sum() == count - deg and (L["Le"] > 0).all()
+    assert np.allclose(dprt.scene.reference_lights("default")["Le"][0], [891.443777, 505.928150, 154.625939])
+    assert np.allclose(dprt.scene.reference_lights("bistro")["Le"][4], 30.0 * 505.928150)
