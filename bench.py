@@ -9,18 +9,22 @@ One STEP = one pass of the hot path = one `runSample` (renderer.cpp:1457-1574: p
 Workload (config.workload): BASELINE.json configs[1]'s scene per GPU -- a synthetic 1 M-triangle chunk and
 1920x1080 pixels PER GPU (W = N chunks, frame scaled by sqrt(N) per side so pixels/GPU and triangles/GPU stay
 fixed: weak scaling), 1 sample per step, bounces=4, spc=4 shadow paths per hit. For N > 1 the chunks are x-slabs of one
-continuous terrain, cut where the primary rays' load is equal (scene.balanced_slab_layout). The literal configs[1] case
+continuous terrain, cut where every owner walks the same number of rays over all bounces (scene.CALIBRATED_SLAB_CUTS,
+profiles/calibrate_slabs.py), and before anything is timed a small frame goes through the same data plane and is compared
+with the oracle bit for bit ("parity" in the JSON line; a mismatch aborts the run). The literal configs[1] case
 (closest-hit primary rays only, through host buffers) and the proxy MLP of configs[0] are measured beside it at
 N=1 and reported in the same JSON line ("primary_closest_hit", "proxy_mlp").
 
 A ray = one (origin, direction, tmin, tmax) query that actually WALKED one rank's chunk BVH in TraRay / MainRay /
 ShadowRay / SecondaryRay (dprt_stats.rays_walked, counted on the device; records that only ride along in a launch and
 MainRay queries answered from the hit cache are not rays; the CPU arm counts the same events, and it does re-trace
-MainRay). value = rays of all ranks / max-over-ranks device time, inputs resident in HBM, no per-stage events inside
-the timed region (the stages overlap). Per-stage times, `roofline` and `stages` come from a second, strictly serial
-pass over the same samples with CUDA-event pairs around every stage launch. e2e = the same metric through the
-host-facing call sequence of Renderer::launch with host buffers (camera, lights and materials uploaded, image reduced
-and copied to pinned host memory) inside the timed region.
+MainRay). value = rays of all ranks / max-over-ranks device time of the K steps, inputs resident in HBM, --inflight samples
+in flight per GPU (one context and host thread each, dprt.h "samples in flight"), no per-stage events inside the timed
+region (the stages overlap). Per-stage times, `roofline` (algorithmic node / triangle counts from the ORACLE's walk over
+the uploaded BVH8), `reorder`, `image_reduce` and `stages` come from a second, strictly serial single-context pass over
+the same samples with CUDA-event pairs around every stage launch. e2e = the same metric through the host-facing call
+sequence of Renderer::launch with host buffers (camera, lights and materials uploaded, frame reset, one sample, image
+reduced and copied to pinned host memory) per step, inside the timed region.
 """
 import argparse
 import importlib
