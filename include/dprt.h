@@ -55,6 +55,42 @@ int  dprt_upload_chunk(dprt_ctx* ctx, int scene_index, const dprt_object_desc* d
  * documented in DESIGN.md ("proxy weight blob"); either may be NULL ("padding" entries of the reference). */
 int  dprt_upload_proxy(dprt_ctx* ctx, int scene_index, const dprt_object_desc* desc, const void* vis_blob,
                        size_t vis_bytes, const void* depth_blob, size_t depth_bytes);
+/* ---- real-scene front end (pipeline_helper.cpp:145-220, kernel.cu:190-292,311-359,
+ * distributed_traversal_kernel.cu:82-158, renderer.cpp:1621-1721) -------------------------------------------------------
+ * Geometry arrives the way the reference's SBT records hold it -- meshes with INDEXED normals and texture coordinates, placed
+ * by (nested, host-composed) instance transforms -- and is flattened at upload: world-space corners, per-corner normals
+ * (inverse-transpose of the instance matrix) and per-corner texture coordinates, primitive id = running index over
+ * (instance, triangle). The closest-hit program then reads 36 + 24 contiguous bytes per hit instead of chasing two index
+ * arrays (180 GB of HBM buy that; a two-level BVH for Moana-scale instancing is what comes next). The flatten is
+ * host code and callable without a device: count first, then fill caller-owned arrays. uv6 may be NULL; has_uv (may be
+ * NULL) tells whether any mesh carries texture coordinates. */
+int64_t dprt_flatten_count(const dprt_mesh_desc* meshes, int n_meshes, const dprt_instance_desc* instances, int64_t n_instances);
+int  dprt_flatten_instances(const dprt_mesh_desc* meshes, int n_meshes, const dprt_instance_desc* instances, int64_t n_instances,
+                            float* verts9, float* normals9, float* uv6, int32_t* mat_ids, int* has_uv);
+/* dprt_upload_chunk with per-corner texture coordinates (uv6 = ntris*6 floats: u0 v0 u1 v1 u2 v2; NULL = none). */
+int  dprt_upload_chunk_uv(dprt_ctx* ctx, int scene_index, const dprt_object_desc* desc, const float* verts9, const float* normals9,
+                          const float* uv6, const int32_t* mat_ids, int64_t ntris);
+/* flatten + dprt_upload_chunk_uv: one scene object from its meshes and instances (GAS build + SBT records of the reference) */
+int  dprt_upload_instanced_chunk(dprt_ctx* ctx, int scene_index, const dprt_object_desc* desc, const dprt_mesh_desc* meshes,
+                                 int n_meshes, const dprt_instance_desc* instances, int64_t n_instances);
+/* params.albedoTextures[texture_index] (renderer.cpp:1621-1721): width*height RGBA float texels, row 0 first (v = 0), filtered
+ * bilinearly with wrap addressing on normalised coordinates like the reference's texture descriptor -- in software, in exact
+ * binary32, not by the texture unit's 9-bit fixed-point weights. rgba = NULL removes the texture. */
+int  dprt_set_texture(dprt_ctx* ctx, int texture_index, const float* rgba, int width, int height);
+/* HitGroupData.textureIndex per material (pipeline_helper.cpp:185): -1 = untextured. A textured material takes its base
+ * colour from the texture (kernel.cu:251-281) and drops intersections whose opacity (alpha) is below 0.05 in EVERY trace --
+ * the __anyhit__ah program of all five pipelines (kernel.cu:311-359, distributed_traversal_kernel.cu:110-158, ...). */
+int  dprt_set_material_textures(dprt_ctx* ctx, const int32_t* texture_index, int n);
+/* params.envLightTexture (renderer.cpp:1851; calculateEnvironmentLighting kernel.cu:28-48): lat-long RGBA float map looked up
+ * at (phi / 2pi, theta / pi) after phi += rotation_offset; wraps in u, clamps in v. rgba = NULL restores the analytic sky
+ * of cfg.envColor. */
+int  dprt_set_env_map(dprt_ctx* ctx, const float* rgba, int width, int height, float rotation_offset);
+/* The two texture look-ups above on host arrays, compiled from the very source the kernels use (dprt_math.cuh): lets a
+ * machine without a GPU compare the arithmetic with the oracle. out4 = n RGBA results. */
+int  dprt_spec_texture_sample(const float* rgba, int width, int height, const float* u, const float* v, int64_t n, int clamp_v,
+                              float* out4);
+int  dprt_spec_env_lookup(const float* rgba, int width, int height, float rotation_offset, const float* dirs3, int64_t n, float* out3);
+
 int  dprt_set_materials(dprt_ctx* ctx, const dprt_material* mats, int n);
 int  dprt_set_lights(dprt_ctx* ctx, const dprt_light_tri* lights, int n);   /* renderer.cpp:1798-1808 */
 int  dprt_set_camera(dprt_ctx* ctx, const dprt_camera* cam);                /* params.camera, :1990 */

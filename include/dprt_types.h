@@ -82,6 +82,36 @@ typedef struct dprt_material {
     int32_t bsdfType;         /* 0 = Diffuse (Lambertian), 1 = Water */
 } dprt_material;
 
+/* ---- real-scene front end ------------------------------------------------------------------------
+ * One triangle mesh of a scene object with its shading attributes in the reference's INDEXED form: a GAS plus the
+ * HitGroupData of its SBT record (pipeline_helper.cpp:182-193: normals / normalIndices / texCoords / texCoordsIndices /
+ * materialID; kernel.cu:205-262 reads them per hit). All pointers are caller-owned host memory. */
+typedef struct dprt_mesh_desc {
+    const float*   positions;        /* nPositions * 3, object space */
+    int64_t        nPositions;
+    const int32_t* indices;          /* ntris * 3 vertex indices */
+    int64_t        ntris;
+    const float*   normals;          /* nNormals * 3 */
+    int64_t        nNormals;
+    const int32_t* normalIndices;    /* ntris * 3 */
+    const float*   texCoords;        /* nTexCoords * 2; NULL = the mesh has no texture coordinates */
+    int64_t        nTexCoords;
+    const int32_t* texCoordIndices;  /* ntris * 3; NULL with texCoords */
+    int32_t        materialID;       /* HitGroupData.materialID: one material (base colour, BSDF, texture) per mesh record */
+    int32_t        pad_;
+} dprt_mesh_desc;
+
+/* One instance of a mesh inside a scene object: the reference nests up to three traversable levels ("obj for small
+ * details / instanced details yields element / instanced element yields scene object", pipeline_helper.cpp:268-272);
+ * the host composes the levels into one object-to-world matrix per leaf instance (row-major 3x4). */
+typedef struct dprt_instance_desc {
+    int32_t mesh;                    /* index into the mesh array */
+    int32_t pad_;
+    float   objectToWorld[12];
+} dprt_instance_desc;
+
+#define DPRT_MAX_TEXTURES 64         /* albedoTextures[] slots (renderer.cpp:1621-1721) */
+
 /* moana Triangle light + radiance (renderer.cpp:1725-1808, kernel.cu:95-99). */
 typedef struct dprt_light_tri {
     float p0[3], p1[3], p2[3];
@@ -149,7 +179,10 @@ typedef struct dprt_bvh8_node {
     uint8_t  qhix[8], qhiy[8], qhiz[8];
 } dprt_bvh8_node;
 
-/* Leaf-ordered triangle, 48 bytes. */
+/* Leaf-ordered triangle, 48 bytes. pad_ is 0 for a chunk without texture coordinates; for a chunk uploaded with them it
+ * holds the chunk's triangle count in every record: the per-corner texture coordinates (32 bytes per triangle, leaf order:
+ * u0 v0 u1 v1 | u2 v2 0 0) follow the triangle array in the same allocation, so a kernel that holds a triangle pointer finds
+ * them without another table (bvh_traverse.cuh: alpha cut-out any-hit). */
 typedef struct dprt_bvh8_tri {
     float    v0[3]; int32_t primID;
     float    v1[3]; int32_t matID;
@@ -240,4 +273,5 @@ static_assert(sizeof(dprt_bvh8_node) == 80, "dprt_bvh8_node must be 80 bytes");
 static_assert(sizeof(dprt_bvh8_tri) == 48, "dprt_bvh8_tri must be 48 bytes");
 static_assert(sizeof(dprt_ray) == 32 && sizeof(dprt_hit) == 8, "ray/hit layout");
 static_assert(sizeof(dprt_config) == 64 && sizeof(dprt_object_desc) == 84 && sizeof(dprt_camera) == 56, "config layout");
+static_assert(sizeof(dprt_mesh_desc) == 88 && sizeof(dprt_instance_desc) == 56, "mesh / instance layout");
 #endif

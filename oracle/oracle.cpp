@@ -18,6 +18,9 @@
 //   trainingcode/module.py:36-45,755-837        4Res256/6Res256 proxy MLP      -> mlp_forward_row (fp32)
 //   optix/vis_ray_kernel.cu:98-161              Vis pipeline (training samples) -> orc_gen_train_data
 //   optix/precom_ray_kernel.cu:193-299          Precom pipeline (training samples) -> orc_gen_precom_data
+//   optix/kernel.cu:190-292,311-359 (+ the __anyhit__ah of every pipeline), pipeline_helper.cpp:182-193,
+//   renderer.cpp:1621-1721, kernel.cu:28-48      indexed / instanced meshes, albedo + opacity maps, alpha cut-out,
+//                                                environment map                 -> flatten_object, Texture, alpha_ignored, env_radiance
 //
 // PARITY PINNING. The reference ships no tests or golden vectors and cannot be built (README.md:5). What is
 // pinned against reference code executed in the build container: tea<4>/lcg/rnd against optix/random.hpp
@@ -216,11 +219,19 @@ bool aabb_hit(V3 ol, V3 dl, const float* mn, const float* mx, float tmin, float 
 // ---- the oracle's own accelerator: median-split binary BVH, double-precision padded slab test ----
 struct Hit { float t; int prim; float alpha, beta; };
 
+struct World;
+struct Mesh;
+// the __anyhit__ah program (kernel.cu:311-359 and its copies in the other pipelines): true = optixIgnoreIntersection()
+bool alpha_ignored(const World& w, const Mesh& m, int prim, float alpha, float beta);
+
 struct Mesh {
     std::vector<float> verts;     // 9 per tri
     std::vector<float> normals;   // 9 per tri
+    std::vector<float> uvs;       // 6 per tri (u0 v0 u1 v1 u2 v2), empty = the object has no texture coordinates
     std::vector<int32_t> mats;
     int ntris = 0;
+    const World* world = nullptr; // textures + material table for the alpha cut-out test (set when the object is added)
+    bool cut(int prim, float al, float be) const { return world && !uvs.empty() && alpha_ignored(*world, *this, prim, al, be); }
     struct Node { double lo[3], hi[3]; int left, right, first, count; };
     std::vector<Node> nodes;
     std::vector<int> order;
@@ -298,6 +309,7 @@ struct Mesh {
             for (int i = n.first; i < n.first + n.count; i++) {
                 int p = order[i]; float t, al, be;
                 if (tri_hit(rs, o, &verts[9 * (size_t)p], tmin, tmax, &t, &al, &be)) {
+                    if (cut(p, al, be)) continue;
                     if (any) { hit.t = t; hit.prim = p; hit.alpha = al; hit.beta = be; return true; }
                     if (t < tbest || (t == tbest && p < bestPrim)) { tbest = t; bestPrim = p; ba = al; bb = be; found = true; }
                 }
@@ -311,7 +323,7 @@ struct Mesh {
         float tbest = tmax; int bestPrim = 0x7fffffff; bool found = false; float ba = 0, bb = 0;
         for (int p = 0; p < ntris; p++) {
             float t, al, be;
-            if (tri_hit(rs, o, &verts[9 * (size_t)p], tmin, tmax, &t, &al, &be))
+            if (tri_hit(rs, o, &verts[9 * (size_t)p], tmin, tmax, &t, &al, &be) && !cut(p, al, be))
                 if (t < tbest || (t == tbest && p < bestPrim)) { tbest = t; bestPrim = p; ba = al; bb = be; found = true; }
         }
         hit.t = tbest; hit.prim = found ? bestPrim : -1; hit.alpha = ba; hit.beta = bb;
@@ -366,6 +378,36 @@ struct Mlp {
     }
 };
 
+// ---- textures: tex2D<float4> on a linear-filtered, normalised-coordinate texture object (renderer.cpp:1700-1710), restated in
+// binary32 (the texture unit's fixed-point weights are not reproducible on a CPU; DESIGN.md "Arithmetic specification"):
+// sample position x = u W - 0.5 between texel centres floor(x) and floor(x) + 1, weight frac(x); lerp(a, b, f) = fma(f, b - a, a)
+// along u in both rows, then along v. u always wraps; v wraps (albedo maps) or clamps (lat-long environment map).
+struct Texture {
+    int w = 0, h = 0;
+    std::vector<float> texels;    // RGBA, row-major, row 0 = v 0
+    static int wrap_index(int i, int n) { if (i < 0) i += n; if (i >= n) i -= n; return i; }
+    void sample(float u, float v, bool clampV, float* out4) const {
+        if (!(fabsf(u) < 1e30f)) u = 0.0f;
+        if (!(fabsf(v) < 1e30f)) v = 0.0f;
+        u -= floorf(u);
+        if (clampV) v = fminf(fmaxf(v, 0.0f), 1.0f); else v -= floorf(v);
+        const float x = fmaf(u, (float)w, -0.5f), y = fmaf(v, (float)h, -0.5f);
+        const float xf = floorf(x), yf = floorf(y);
+        const float fx = x - xf, fy = y - yf;
+        const int xi = (int)xf, yi = (int)yf;
+        const int xa = wrap_index(xi, w), xb = wrap_index(xi + 1, w);
+        const int ya = clampV ? std::min(std::max(yi, 0), h - 1) : wrap_index(yi, h);
+        const int yb = clampV ? std::min(std::max(yi + 1, 0), h - 1) : wrap_index(yi + 1, h);
+        const float* r0 = &texels[4 * ((size_t)ya * w)];
+        const float* r1 = &texels[4 * ((size_t)yb * w)];
+        for (int c = 0; c < 4; c++) {
+            const float top = fmaf(fx, r0[4 * xb + c] - r0[4 * xa + c], r0[4 * xa + c]);
+            const float bot = fmaf(fx, r1[4 * xb + c] - r1[4 * xa + c], r1[4 * xa + c]);
+            out4[c] = fmaf(fy, bot - top, top);
+        }
+    }
+};
+
 struct World;
 struct Rank;
 // ---- world: all scene objects + W simulated ranks ----
@@ -403,13 +445,54 @@ struct World {
     dprt_camera cam{};
     std::vector<Rank> ranks;
     bool countBvh8 = false;          // orc_count_bvh8: walk the product's BVH8 beside every trace, for the counters only
+    // real-scene front end: params.albedoTextures (renderer.cpp:1621-1721), HitGroupData.textureIndex per material
+    // (pipeline_helper.cpp:185), params.envLightTexture (renderer.cpp:1851)
+    std::vector<Texture> textures;
+    std::vector<int32_t> matTex;
+    Texture envMap; float envRotation = 0.0f;
 
     bool is_proxy(int rank, int i) const { return objects[i].desc.nodeID != rank; }
+    // texture of a material, or null
+    const Texture* texture_of(int matID) const {
+        if (matID < 0 || matID >= (int)matTex.size()) return nullptr;
+        const int t = matTex[matID];
+        if (t < 0 || t >= (int)textures.size() || textures[t].texels.empty()) return nullptr;
+        return &textures[t];
+    }
     V3 env_radiance(V3 d) const {
+        if (!envMap.texels.empty()) {
+            // calculateEnvironmentLighting (kernel.cu:28-48): lat-long map at (phi / 2pi, theta / pi), phi rotated
+            float phi, theta;
+            cartesian_to_spherical(d, &phi, &theta);
+            phi += envRotation;
+            if (phi > 6.28318530717958647692f) phi -= 6.28318530717958647692f;
+            float c[4];
+            envMap.sample(phi / 6.28318530717958647692f, theta / 3.14159265358979323846f, true, c);
+            return v3(c[0], c[1], c[2]);
+        }
         float wv = fmaf(0.5f, d.z, 0.5f);
         return v3(cfg.envColor[0] * wv, cfg.envColor[1] * wv, cfg.envColor[2] * wv);
     }
 };
+
+// texture coordinate at the hit: gamma t0 + alpha t1 + beta t2 (kernel.cu:264-265), gamma = 1 - alpha - beta
+inline float interp3(float t0, float t1, float t2, float alpha, float beta) {
+    const float gamma = 1.0f - alpha - beta;
+    return fmaf(beta, t2, fmaf(alpha, t1, gamma * t0));
+}
+inline void hit_uv(const Mesh& m, int prim, float alpha, float beta, float* u, float* v) {
+    const float* t = &m.uvs[6 * (size_t)prim];
+    *u = interp3(t[0], t[2], t[4], alpha, beta);
+    *v = interp3(t[1], t[3], t[5], alpha, beta);
+}
+bool alpha_ignored(const World& w, const Mesh& m, int prim, float alpha, float beta) {
+    const Texture* T = w.texture_of(m.mats[prim]);
+    if (!T) return false;
+    float u, v, c[4];
+    hit_uv(m, prim, alpha, beta, &u, &v);
+    T->sample(u, v, false, c);
+    return c[3] < 0.05f;          // opacity below the cut-out threshold: kernel.cu:349-355
+}
 
 void add_env(World& w, Rank& r, dprt_path_record& p) {
     V3 e = w.env_radiance(v3(p.direction[0], p.direction[1], p.direction[2]));
@@ -421,7 +504,8 @@ void add_env(World& w, Rank& r, dprt_path_record& p) {
 // ---- scalar walker over the PRODUCT's BVH8 blob: per-ray node/triangle counters for the roofline ----
 struct Bvh8Count { int64_t nodes, tris; };
 // any = true: any-hit semantics, the walk stops at the first accepted triangle (near-first depth-first order)
-bool bvh8_walk(const dprt_bvh8_node* nodes, const dprt_bvh8_tri* tris, V3 o, V3 d, float tmin, float tmax, Hit& hit, Bvh8Count& cnt, bool any = false) {
+bool bvh8_walk(const dprt_bvh8_node* nodes, const dprt_bvh8_tri* tris, V3 o, V3 d, float tmin, float tmax, Hit& hit, Bvh8Count& cnt, bool any = false,
+               const Mesh* cutouts = nullptr) {
     Shear rs = make_shear(d);
     const float dxs = fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x);
     const float dys = fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y);
@@ -475,6 +559,7 @@ bool bvh8_walk(const dprt_bvh8_node* nodes, const dprt_bvh8_tri* tris, V3 o, V3 
             float tv[9] = {t.v0[0], t.v0[1], t.v0[2], t.v1[0], t.v1[1], t.v1[2], t.v2[0], t.v2[1], t.v2[2]};
             float tt, al, be;
             if (tri_hit(rs, o, tv, tmin, tmax, &tt, &al, &be)) {
+                if (cutouts && cutouts->cut(t.primID, al, be)) continue;
                 if (any) { hit.t = tt; hit.prim = t.primID; hit.alpha = al; hit.beta = be; return true; }
                 if (tt < tbest || (tt == tbest && t.primID < bestPrim)) { tbest = tt; bestPrim = t.primID; ba = al; bb = be; found = true; }
             }
@@ -523,7 +608,7 @@ void count_local(const World& w, Rank& r, int stage, V3 o, V3 d, float tmin, flo
         if (skipVisited && ((visited >> ob.desc.nodeID) & 1u)) continue;
         walkedAny = true;
         Hit h;
-        const bool hit = bvh8_walk(ob.nodes8.data(), ob.tris8.data(), o, d, tmin, tMax, h, c, any);
+        const bool hit = bvh8_walk(ob.nodes8.data(), ob.tris8.data(), o, d, tmin, tMax, h, c, any, &ob.mesh);
         if (hit) { if (any) break; tMax = h.t; }
     }
     if (!walkedAny) return;
@@ -693,7 +778,15 @@ void shade(World& w, Rank& r) {
         }
         const Object& ob = w.objects[hobj];
         const dprt_material mat = w.materials[ob.mesh.mats[h.prim]];
-        const V3 albedo = v3(mat.baseColor[0], mat.baseColor[1], mat.baseColor[2]);
+        V3 albedo = v3(mat.baseColor[0], mat.baseColor[1], mat.baseColor[2]);
+        if (!ob.mesh.uvs.empty()) {      // kernel.cu:251-281: textured material -> base colour from the albedo map
+            if (const Texture* T = w.texture_of(ob.mesh.mats[h.prim])) {
+                float u, v, c[4];
+                hit_uv(ob.mesh, h.prim, h.alpha, h.beta, &u, &v);
+                T->sample(u, v, false, c);
+                albedo = v3(c[0], c[1], c[2]);
+            }
+        }
         const V3 point = at(o, d, h.t);
         const V3 woWorld = neg(d);
         const float* nn = &ob.mesh.normals[9 * (size_t)h.prim];
@@ -1077,9 +1170,146 @@ int orc_world_add_object(void* wp, int si, const dprt_object_desc* desc, const f
     ob.mesh.verts.assign(verts9, verts9 + 9 * ntris);
     if (normals9) ob.mesh.normals.assign(normals9, normals9 + 9 * ntris); else ob.mesh.normals.assign(9 * ntris, 0.f);
     if (mat_ids) ob.mesh.mats.assign(mat_ids, mat_ids + ntris); else ob.mesh.mats.assign(ntris, 0);
+    ob.mesh.uvs.clear(); ob.mesh.world = w;
     ob.mesh.build();
     return 0;
 }
+// dprt_upload_chunk_uv: per-corner texture coordinates beside the geometry (uv6 may be NULL)
+int orc_world_add_object_uv(void* wp, int si, const dprt_object_desc* desc, const float* verts9, const float* normals9, const float* uv6,
+                            const int32_t* mat_ids, int64_t ntris) {
+    if (orc_world_add_object(wp, si, desc, verts9, normals9, mat_ids, ntris)) return -1;
+    Mesh& m = ((World*)wp)->objects[si].mesh;
+    if (uv6) m.uvs.assign(uv6, uv6 + 6 * ntris); else m.uvs.clear();
+    return 0;
+}
+
+// Indexed, instanced meshes -> flat per-corner streams: the oracle's own restatement of what the reference does per hit
+// (kernel.cu:205-240: corners through optixTransformPointFromObjectToWorldSpace, normals through
+// optixTransformNormalFromObjectToWorldSpace = inverse transpose, attributes through normalIndices / texCoordsIndices),
+// applied once per (instance, triangle). Primitive id = running index over instances, then triangles.
+// Arithmetic: corner row = fma(m2, z, fma(m1, y, fma(m0, x, m3))); normal matrix = cofactors(A) / det(A) in binary64
+// (products and differences in the order written), rounded to binary32; normal row = fma(g2, nz, fma(g1, ny, g0 nx)).
+static int64_t flat_count(const dprt_mesh_desc* meshes, int nm, const dprt_instance_desc* inst, int64_t ni) {
+    if (!meshes || !inst || nm < 1 || ni < 1) return -1;
+    int64_t total = 0;
+    for (int64_t i = 0; i < ni; i++) {
+        if (inst[i].mesh < 0 || inst[i].mesh >= nm) return -1;
+        const dprt_mesh_desc& m = meshes[inst[i].mesh];
+        if (m.ntris < 0) return -1;
+        total += m.ntris;
+    }
+    return total;
+}
+static int flat_fill(const dprt_mesh_desc* meshes, int nm, const dprt_instance_desc* inst, int64_t ni, std::vector<float>& verts,
+                     std::vector<float>& normals, std::vector<float>& uvs, std::vector<int32_t>& mats, bool& anyUv) {
+    const int64_t total = flat_count(meshes, nm, inst, ni);
+    if (total <= 0) return -1;
+    verts.resize(9 * (size_t)total); normals.resize(9 * (size_t)total); uvs.assign(6 * (size_t)total, 0.0f); mats.resize((size_t)total);
+    anyUv = false;
+    size_t p = 0;
+    for (int64_t i = 0; i < ni; i++) {
+        const dprt_mesh_desc& m = meshes[inst[i].mesh];
+        const float* X = inst[i].objectToWorld;
+        double A[3][3], C[3][3];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) A[r][c] = (double)X[4 * r + c];
+        C[0][0] = A[1][1] * A[2][2] - A[1][2] * A[2][1];
+        C[0][1] = -(A[1][0] * A[2][2] - A[1][2] * A[2][0]);
+        C[0][2] = A[1][0] * A[2][1] - A[1][1] * A[2][0];
+        C[1][0] = -(A[0][1] * A[2][2] - A[0][2] * A[2][1]);
+        C[1][1] = A[0][0] * A[2][2] - A[0][2] * A[2][0];
+        C[1][2] = -(A[0][0] * A[2][1] - A[0][1] * A[2][0]);
+        C[2][0] = A[0][1] * A[1][2] - A[0][2] * A[1][1];
+        C[2][1] = -(A[0][0] * A[1][2] - A[0][2] * A[1][0]);
+        C[2][2] = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+        const double det = A[0][0] * C[0][0] + A[0][1] * C[0][1] + A[0][2] * C[0][2];
+        if (det == 0.0 || det != det || std::isinf(det)) return -1;
+        const double rdet = 1.0 / det;
+        float G[3][3];
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) G[r][c] = (float)(C[r][c] * rdet);
+        if (m.ntris > 0 && m.texCoords) anyUv = true;
+        for (int64_t t = 0; t < m.ntris; t++, p++) {
+            for (int k = 0; k < 3; k++) {
+                const int vi = m.indices[3 * t + k], nidx = m.normalIndices[3 * t + k];
+                if (vi < 0 || vi >= m.nPositions || nidx < 0 || nidx >= m.nNormals) return -1;
+                const V3 q = xform_point(X, v3(m.positions[3 * (size_t)vi], m.positions[3 * (size_t)vi + 1], m.positions[3 * (size_t)vi + 2]));
+                verts[9 * p + 3 * k] = q.x; verts[9 * p + 3 * k + 1] = q.y; verts[9 * p + 3 * k + 2] = q.z;
+                const float nx = m.normals[3 * (size_t)nidx], ny = m.normals[3 * (size_t)nidx + 1], nz = m.normals[3 * (size_t)nidx + 2];
+                for (int r = 0; r < 3; r++) normals[9 * p + 3 * k + r] = fmaf(G[r][2], nz, fmaf(G[r][1], ny, G[r][0] * nx));
+                if (m.texCoords) {
+                    const int ti = m.texCoordIndices[3 * t + k];
+                    if (ti < 0 || ti >= m.nTexCoords) return -1;
+                    uvs[6 * p + 2 * k] = m.texCoords[2 * (size_t)ti]; uvs[6 * p + 2 * k + 1] = m.texCoords[2 * (size_t)ti + 1];
+                }
+            }
+            mats[p] = m.materialID;
+        }
+    }
+    return 0;
+}
+// the flat streams themselves (tests compare them with dprt_flatten_instances bit for bit); buffers sized by orc_flatten_count
+int64_t orc_flatten_count(const dprt_mesh_desc* meshes, int nm, const dprt_instance_desc* inst, int64_t ni) { return flat_count(meshes, nm, inst, ni); }
+int orc_flatten(const dprt_mesh_desc* meshes, int nm, const dprt_instance_desc* inst, int64_t ni, float* verts9, float* normals9, float* uv6,
+                int32_t* mats, int* hasUv) {
+    std::vector<float> v, n, u; std::vector<int32_t> m; bool any = false;
+    if (flat_fill(meshes, nm, inst, ni, v, n, u, m, any)) return -1;
+    std::memcpy(verts9, v.data(), v.size() * 4); std::memcpy(normals9, n.data(), n.size() * 4);
+    if (uv6) std::memcpy(uv6, u.data(), u.size() * 4);
+    if (mats) std::memcpy(mats, m.data(), m.size() * 4);
+    if (hasUv) *hasUv = any ? 1 : 0;
+    return 0;
+}
+// dprt_upload_instanced_chunk
+int orc_world_add_instanced_object(void* wp, int si, const dprt_object_desc* desc, const dprt_mesh_desc* meshes, int nm,
+                                   const dprt_instance_desc* inst, int64_t ni) {
+    std::vector<float> v, n, u; std::vector<int32_t> m; bool any = false;
+    if (flat_fill(meshes, nm, inst, ni, v, n, u, m, any)) return -1;
+    return orc_world_add_object_uv(wp, si, desc, v.data(), n.data(), any ? u.data() : nullptr, m.data(), (int64_t)m.size());
+}
+// dprt_set_texture / dprt_set_material_textures / dprt_set_env_map
+int orc_world_set_texture(void* wp, int ti, const float* rgba, int width, int height) {
+    World* w = (World*)wp;
+    if (!w || ti < 0 || ti >= DPRT_MAX_TEXTURES) return -1;
+    if ((int)w->textures.size() <= ti) w->textures.resize(ti + 1);
+    Texture& T = w->textures[ti];
+    if (!rgba) { T = Texture(); return 0; }
+    if (width < 1 || height < 1) return -1;
+    T.w = width; T.h = height; T.texels.assign(rgba, rgba + 4 * (size_t)width * height);
+    return 0;
+}
+int orc_world_set_material_textures(void* wp, const int32_t* tex, int n) {
+    World* w = (World*)wp;
+    if (!w || !tex || n < 1) return -1;
+    w->matTex.assign(tex, tex + n);
+    return 0;
+}
+int orc_world_set_env_map(void* wp, const float* rgba, int width, int height, float rotation) {
+    World* w = (World*)wp;
+    if (!w) return -1;
+    w->envMap = Texture(); w->envRotation = rotation;
+    if (rgba) {
+        if (width < 1 || height < 1) return -1;
+        w->envMap.w = width; w->envMap.h = height; w->envMap.texels.assign(rgba, rgba + 4 * (size_t)width * height);
+    }
+    return 0;
+}
+// the two look-ups on their own (tests: against dprt_spec_texture_sample / dprt_spec_env_lookup and a numpy model)
+int orc_texture_sample(const float* rgba, int width, int height, const float* u, const float* v, int64_t n, int clampV, float* out4) {
+    if (!rgba || width < 1 || height < 1) return -1;
+    Texture T; T.w = width; T.h = height; T.texels.assign(rgba, rgba + 4 * (size_t)width * height);
+    for (int64_t i = 0; i < n; i++) T.sample(u[i], v[i], clampV != 0, out4 + 4 * i);
+    return 0;
+}
+int orc_env_lookup(const float* rgba, int width, int height, float rotation, const float* dirs3, int64_t n, float* out3) {
+    if (!rgba || width < 1 || height < 1) return -1;
+    World w; w.envRotation = rotation;
+    w.envMap.w = width; w.envMap.h = height; w.envMap.texels.assign(rgba, rgba + 4 * (size_t)width * height);
+    for (int64_t i = 0; i < n; i++) {
+        const V3 e = w.env_radiance(v3(dirs3[3 * i], dirs3[3 * i + 1], dirs3[3 * i + 2]));
+        out3[3 * i] = e.x; out3[3 * i + 1] = e.y; out3[3 * i + 2] = e.z;
+    }
+    return 0;
+}
+
 int orc_world_set_model(void* wp, int si, int kind, const void* blob, size_t bytes) {
     World* w = (World*)wp;
     if (!w || si < 0 || si >= (int)w->objects.size()) return -1;

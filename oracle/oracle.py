@@ -27,6 +27,16 @@ def lib():
         L.orc_world_create.argtypes = [C.POINTER(D.Config), C.c_int]
         L.orc_world_destroy.argtypes = [C.c_void_p]
         L.orc_world_add_object.argtypes = [C.c_void_p, C.c_int, C.POINTER(D.ObjectDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.orc_world_add_object_uv.argtypes = [C.c_void_p, C.c_int, C.POINTER(D.ObjectDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.orc_world_add_instanced_object.argtypes = [C.c_void_p, C.c_int, C.POINTER(D.ObjectDesc), C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
+        L.orc_flatten_count.restype = C.c_int64
+        L.orc_flatten_count.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
+        L.orc_flatten.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.orc_world_set_texture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.orc_world_set_material_textures.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_world_set_env_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float]
+        L.orc_texture_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+        L.orc_env_lookup.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_world_set_model.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         L.orc_world_set_materials.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_world_set_lights.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -116,6 +126,36 @@ def bvh8_trace(nodes, tris, rays):
     return hits, int(nv.value), int(tt.value)
 
 
+def flatten_instances(meshes, instances):
+    """The oracle's own flatten of indexed, instanced meshes: (verts9, normals9, uv6 or None, mat_ids)."""
+    md, nm, ins, ni, keep = D.pack_meshes(meshes, instances)
+    n = lib().orc_flatten_count(md, nm, ins, ni)
+    if n <= 0:
+        raise RuntimeError("orc_flatten_count: invalid description")
+    v, nr, uv, mats = np.zeros((n, 9), np.float32), np.zeros((n, 9), np.float32), np.zeros((n, 6), np.float32), np.zeros(n, np.int32)
+    has = C.c_int(0)
+    if lib().orc_flatten(md, nm, ins, ni, _p(v), _p(nr), _p(uv), _p(mats), C.byref(has)):
+        raise RuntimeError("orc_flatten failed")
+    del keep
+    return v, nr, (uv if has.value else None), mats
+
+
+def texture_sample(rgba, u, v, clamp_v=False):
+    t = np.ascontiguousarray(rgba, np.float32)
+    uu, vv = np.ascontiguousarray(u, np.float32), np.ascontiguousarray(v, np.float32)
+    out = np.zeros((uu.size, 4), np.float32)
+    assert lib().orc_texture_sample(_p(t), t.shape[1], t.shape[0], _p(uu), _p(vv), uu.size, int(clamp_v), _p(out)) == 0
+    return out
+
+
+def env_lookup(rgba, rotation, dirs):
+    t = np.ascontiguousarray(rgba, np.float32)
+    d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+    out = np.zeros((d.shape[0], 3), np.float32)
+    assert lib().orc_env_lookup(_p(t), t.shape[1], t.shape[0], float(rotation), _p(d), d.shape[0], _p(out)) == 0
+    return out
+
+
 class World:
     """All scene objects + W simulated ranks (the in-process stand-in for the MPI job)."""
 
@@ -141,6 +181,36 @@ class World:
         n = None if normals9 is None else np.ascontiguousarray(normals9, np.float32)
         m = None if mat_ids is None else np.ascontiguousarray(mat_ids, np.int32)
         assert self.L.orc_world_add_object(self.h, scene_index, C.byref(desc), _p(v), _p(n), _p(m), v.shape[0]) == 0
+
+    def add_object_uv(self, scene_index, desc, verts9, normals9, uv6, mat_ids):
+        v = np.ascontiguousarray(verts9, np.float32).reshape(-1, 9)
+        n = None if normals9 is None else np.ascontiguousarray(normals9, np.float32)
+        u = None if uv6 is None else np.ascontiguousarray(uv6, np.float32)
+        m = None if mat_ids is None else np.ascontiguousarray(mat_ids, np.int32)
+        assert self.L.orc_world_add_object_uv(self.h, scene_index, C.byref(desc), _p(v), _p(n), _p(u), _p(m), v.shape[0]) == 0
+
+    def add_instanced_object(self, scene_index, desc, meshes, instances):
+        md, nm, ins, ni, keep = D.pack_meshes(meshes, instances)
+        assert self.L.orc_world_add_instanced_object(self.h, scene_index, C.byref(desc), md, nm, ins, ni) == 0
+        del keep
+
+    def set_texture(self, texture_index, rgba):
+        if rgba is None:
+            assert self.L.orc_world_set_texture(self.h, texture_index, None, 0, 0) == 0
+            return
+        t = np.ascontiguousarray(rgba, np.float32)
+        assert self.L.orc_world_set_texture(self.h, texture_index, _p(t), t.shape[1], t.shape[0]) == 0
+
+    def set_material_textures(self, texture_index):
+        t = np.ascontiguousarray(texture_index, np.int32)
+        assert self.L.orc_world_set_material_textures(self.h, _p(t), t.size) == 0
+
+    def set_env_map(self, rgba, rotation_offset=0.0):
+        if rgba is None:
+            assert self.L.orc_world_set_env_map(self.h, None, 0, 0, 0.0) == 0
+            return
+        t = np.ascontiguousarray(rgba, np.float32)
+        assert self.L.orc_world_set_env_map(self.h, _p(t), t.shape[1], t.shape[0], float(rotation_offset)) == 0
 
     def set_model(self, scene_index, kind, blob):
         b = np.frombuffer(blob, np.uint8)

@@ -171,6 +171,26 @@ DPRT_D uint32_t trav_node(Trav& s, uint2* stack, TraceCount& cnt, const uint32_t
     return tmask;
 }
 
+// ---- alpha cut-out (the __anyhit__ah program of every pipeline: kernel.cu:311-359, distributed_traversal_kernel.cu:110-158,
+// shadow_ray_kernel.cu:42-90, secondary_ray_kernel.cu:66-114, vis / precom :33-81) ------------------------------------------
+// A candidate intersection with a triangle whose material has a texture is dropped when the texture's opacity at the hit's
+// texture coordinate is below 0.05 (optixIgnoreIntersection). Chunks uploaded with texture coordinates carry their triangle
+// count in the w word of every triangle's third vector (0 otherwise: the test below is one compare on a register the
+// intersection already loaded) and their per-corner coordinates behind the triangle array, 32 bytes per triangle.
+struct TexCtx { const DevTexture* textures; const int32_t* matTex; };
+
+__device__ __noinline__ bool alpha_cutout_ignored(const DevTexture* __restrict__ textures, const int32_t* __restrict__ matTex,
+                                                   const float4* __restrict__ tris, int ntris, uint32_t ti, int matID, float al, float be) {
+    const int tex = __ldg(matTex + matID);
+    if (tex < 0) return false;
+    const DevTexture T = textures[tex];
+    if (T.texels == nullptr) return false;
+    const float4* uv = tris + 3 * (size_t)ntris + 2 * (size_t)ti;
+    const float4 a = __ldg(uv), b = __ldg(uv + 1);
+    const float u = tex_interp(a.x, a.z, b.x, al, be), v = tex_interp(a.y, a.w, b.y, al, be);
+    return tex_bilinear_alpha(T, u, v) < 0.05f;
+}
+
 // ---- warp-wide triangle queue -----------------------------------------------------------------------
 #define DPRT_QCAP 128                      // queue capacity per warp (pairs)
 #define DPRT_TRI_BITS 27                   // queue entry = owner lane << 27 | triangle index
@@ -226,7 +246,7 @@ DPRT_D void wq_append(WarpQueue& w, int& qlen, int lane, bool busy, Trav& s, int
 // Tests the last min(32, qlen) pairs of the queue with all lanes and hands the closest accepted hit of each owner
 // back to it. ANY: the owner keeps the first accepted hit. Warp-synchronous; every lane of the warp must call it.
 template <bool ANY, bool COUNT>
-DPRT_D void tri_round(WarpQueue& w, int& qlen, int lane, Trav& s, int obj, int& pend, TraceCount& cnt) {
+DPRT_D void tri_round(WarpQueue& w, int& qlen, int lane, Trav& s, int obj, int& pend, TraceCount& cnt, const TexCtx& tc) {
     __syncwarp();
     const int n = min(32, qlen);
     const bool valid = lane < n;
@@ -244,8 +264,11 @@ DPRT_D void tri_round(WarpQueue& w, int& qlen, int lane, Trav& s, int obj, int& 
         if (COUNT) cnt.tris++;
         float t;
         if (tri_intersect(rs, v3(ra.x, ra.y, ra.z), v3(a.x, a.y, a.z), v3(b.x, b.y, b.z), v3(c.x, c.y, c.z), ra.w, w.tlimit[owner], &t, &al, &be)) {
-            key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(uint32_t)__float_as_int(a.w);
-            atomicMin(&w.key[owner], key);
+            const int nuv = __float_as_int(c.w);       // != 0: the chunk has texture coordinates (alpha cut-outs possible)
+            if (nuv == 0 || !alpha_cutout_ignored(tc.textures, tc.matTex, w.tris[owner], nuv, ti, __float_as_int(b.w), al, be)) {
+                key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(uint32_t)__float_as_int(a.w);
+                atomicMin(&w.key[owner], key);
+            }
         }
         atomicAdd(&w.cnt[owner], 1);
     }
@@ -302,9 +325,9 @@ DPRT_D int coop_append(WarpQueue& w, int& qlen, int lane, int owner, uint2& tg, 
 
 template <bool ANY, bool COUNT>
 DPRT_D void coop_run(WarpQueue& w, uint32_t* __restrict__ pool, int& qlen, int lane, int L, Trav& s, uint2* stack, int obj, int& pend,
-                     bool& exh, TraceCount& cnt, const uint32_t magic) {
+                     bool& exh, TraceCount& cnt, const uint32_t magic, const TexCtx& tc) {
     const unsigned FULL = 0xffffffffu;
-    while (qlen > 0) tri_round<ANY, COUNT>(w, qlen, lane, s, obj, pend, cnt);     // every owner's queued pairs first
+    while (qlen > 0) tri_round<ANY, COUNT>(w, qlen, lane, s, obj, pend, cnt, tc);     // every owner's queued pairs first
     // the owner's ray, in every lane's registers
     const float ox = __shfl_sync(FULL, s.o.x, L), oy = __shfl_sync(FULL, s.o.y, L), oz = __shfl_sync(FULL, s.o.z, L);
     const float idx = __shfl_sync(FULL, s.idx, L), idy = __shfl_sync(FULL, s.idy, L), idz = __shfl_sync(FULL, s.idz, L);
@@ -332,7 +355,7 @@ DPRT_D void coop_run(WarpQueue& w, uint32_t* __restrict__ pool, int& qlen, int l
         if (lane == L) pend += added;
         const bool more = __ballot_sync(FULL, ctg.y != 0u) != 0u;
         if (qlen > 0 && (qlen >= 32 || more || plen == 0)) {
-            tri_round<ANY, COUNT>(w, qlen, lane, s, obj, pend, cnt);
+            tri_round<ANY, COUNT>(w, qlen, lane, s, obj, pend, cnt, tc);
             ct = __shfl_sync(FULL, s.tbest, L);
             if (ANY && __shfl_sync(FULL, (int)(s.hitTri >= 0), L)) {          // accepted: drop what is left of this ray
                 qlen = 0; plen = 0; ctg.y = 0u;

@@ -22,6 +22,7 @@
 #include "dprt.h"
 #include "dprt_internal.cuh"
 #include "bvh_build.h"
+#include "scene_flatten.h"
 #include "mlp.cuh"
 #include "p2p_exchange.cuh"
 
@@ -100,6 +101,12 @@ struct ObjMem {
     }
 };
 
+// Texels of one albedo / opacity map or of the environment map; shared between the contexts of a rank like ObjMem.
+struct TexMem {
+    int device = 0; void* d = nullptr; int w = 0, h = 0;
+    ~TexMem() { cudaSetDevice(device); if (d) cudaFree(d); }
+};
+
 struct ObjectHost {
     bool present = false;
     dprt_object_desc desc{};
@@ -124,6 +131,11 @@ struct dprt_ctx {
     DevObject* d_objects = nullptr;
     dprt_material* d_materials = nullptr;
     dprt_light_tri* d_lights = nullptr;
+    // real-scene front end: texture table (DPRT_MAX_TEXTURES slots), texture index per material (-1 = none), environment map
+    DevTexture* d_textures = nullptr;
+    int32_t* d_matTex = nullptr;
+    std::shared_ptr<TexMem> tex[DPRT_MAX_TEXTURES];
+    std::shared_ptr<TexMem> envTex;
     size_t buf_bytes[DPRT_BUF_COUNT] = {0};
     void* buf_ptr[DPRT_BUF_COUNT] = {nullptr};
     MlpGroupEntry* d_mlpTable = nullptr; // [2][32]: per kind (vis, depth) the proxy network of every scene object (grouped MLP launch)
@@ -381,6 +393,10 @@ static int create_impl(const dprt_config* cfg, int rank, int world, int device, 
         CK(cudaMalloc(&ctx->d_materials, sizeof(dprt_material) * DPRT_MAX_MATERIALS));
         CK(cudaMemsetAsync(ctx->d_materials, 0, sizeof(dprt_material) * DPRT_MAX_MATERIALS, ctx->stream));
         CK(cudaMalloc(&ctx->d_lights, sizeof(dprt_light_tri) * DPRT_MAX_LIGHTS));
+        CK(cudaMalloc(&ctx->d_textures, sizeof(DevTexture) * DPRT_MAX_TEXTURES));
+        CK(cudaMemsetAsync(ctx->d_textures, 0, sizeof(DevTexture) * DPRT_MAX_TEXTURES, ctx->stream));      // texels == null: empty slot
+        CK(cudaMalloc(&ctx->d_matTex, sizeof(int32_t) * DPRT_MAX_MATERIALS));
+        CK(cudaMemsetAsync(ctx->d_matTex, 0xff, sizeof(int32_t) * DPRT_MAX_MATERIALS, ctx->stream));        // -1: untextured
         int r;
         if ((r = alloc_buf(ctx, DPRT_BUF_PATHS, (1 + spc) * N * sizeof(dprt_path_record)))) return r;
         if ((r = alloc_buf(ctx, DPRT_BUF_TRANSFER, N * sizeof(dprt_path_record)))) return r;
@@ -437,6 +453,7 @@ static int create_impl(const dprt_config* cfg, int rank, int world, int device, 
 
         DevParams& p = ctx->hp;
         p.objects = ctx->d_objects; p.materials = ctx->d_materials; p.lights = ctx->d_lights;
+        p.textures = ctx->d_textures; p.matTex = ctx->d_matTex; p.envMap = DevTexture{nullptr, 0, 0}; p.envRotation = 0.0f;
         p.paths = (dprt_path_record*)ctx->buf_ptr[DPRT_BUF_PATHS];
         p.transfer = (dprt_path_record*)ctx->buf_ptr[DPRT_BUF_TRANSFER];
         p.transferOffset = (int32_t*)ctx->buf_ptr[DPRT_BUF_TRANSFER_OFFSET];
@@ -504,6 +521,10 @@ void dprt_destroy(dprt_ctx* ctx) {
     if (ctx->d_objects) cudaFree(ctx->d_objects);
     if (ctx->d_materials) cudaFree(ctx->d_materials);
     if (ctx->d_lights) cudaFree(ctx->d_lights);
+    if (ctx->d_textures) cudaFree(ctx->d_textures);
+    if (ctx->d_matTex) cudaFree(ctx->d_matTex);
+    for (auto& t : ctx->tex) t.reset();
+    ctx->envTex.reset();
     if (ctx->d_hist) cudaFree(ctx->d_hist);
     if (ctx->d_mlpTable) cudaFree(ctx->d_mlpTable);
     if (ctx->scratch.tileState) cudaFree(ctx->scratch.tileState);
@@ -626,10 +647,14 @@ int dprt_bvh8_copy(const dprt_bvh8* b, dprt_bvh8_node* nodes_out, dprt_bvh8_tri*
 }
 void dprt_bvh8_free(dprt_bvh8* b) { delete b; }
 
-int dprt_upload_chunk(dprt_ctx* ctx, int si, const dprt_object_desc* desc, const float* verts9, const float* normals9,
-                      const int32_t* mat_ids, int64_t ntris) {
+int dprt_upload_chunk_uv(dprt_ctx* ctx, int si, const dprt_object_desc* desc, const float* verts9, const float* normals9,
+                         const float* uv6, const int32_t* mat_ids, int64_t ntris) {
     if (!ctx || !desc || !verts9 || si < 0 || si >= ctx->cfg.sceneSize || ntris <= 0) return DPRT_ERR_INVALID;
     if (desc->nodeID < 0 || desc->nodeID >= ctx->world) return fail(ctx, DPRT_ERR_INVALID, "nodeID out of range");
+    if (ntris >= ((int64_t)1 << 27)) return fail(ctx, DPRT_ERR_CAPACITY, "more than 2^27 triangles in one chunk (bvh_traverse.cuh: DPRT_TRI_BITS)");
+    if (mat_ids)
+        for (int64_t i = 0; i < ntris; i++)
+            if (mat_ids[i] < 0 || mat_ids[i] >= DPRT_MAX_MATERIALS) return fail(ctx, DPRT_ERR_INVALID, "material id out of range");
     CK(cudaSetDevice(ctx->device));
     Bvh8 b;
     if (bvh8_build(verts9, mat_ids, ntris, -1.f, b)) return fail(ctx, DPRT_ERR_INVALID, "bvh8_build failed");
@@ -640,17 +665,120 @@ int dprt_upload_chunk(dprt_ctx* ctx, int si, const dprt_object_desc* desc, const
     auto mem = std::make_shared<ObjMem>();
     mem->device = ctx->device;
     o.desc = *desc; o.desc.isProxy = 0; o.present = true;
+    const size_t nt = b.tris.size();
+    // texture coordinates: 32 bytes per triangle in leaf order behind the triangle array (dprt_bvh8_tri.pad_ = triangle count)
+    std::vector<float> uvLeaf;
+    if (uv6) {
+        uvLeaf.assign(nt * 8, 0.0f);
+        for (size_t t = 0; t < nt; t++) {
+            b.tris[t].pad_ = (int32_t)nt;
+            const float* u = uv6 + 6 * (size_t)b.tris[t].primID;
+            for (int k = 0; k < 6; k++) uvLeaf[8 * t + k] = u[k];
+        }
+    }
     CK(cudaMalloc(&mem->d_nodes, b.nodes.size() * sizeof(dprt_bvh8_node)));
-    CK(cudaMalloc(&mem->d_tris, b.tris.size() * sizeof(dprt_bvh8_tri)));
+    CK(cudaMalloc(&mem->d_tris, nt * sizeof(dprt_bvh8_tri) + uvLeaf.size() * sizeof(float)));
     CK(cudaMemcpy(mem->d_nodes, b.nodes.data(), b.nodes.size() * sizeof(dprt_bvh8_node), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(mem->d_tris, b.tris.data(), b.tris.size() * sizeof(dprt_bvh8_tri), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(mem->d_tris, b.tris.data(), nt * sizeof(dprt_bvh8_tri), cudaMemcpyHostToDevice));
+    if (uv6) CK(cudaMemcpy((char*)mem->d_tris + nt * sizeof(dprt_bvh8_tri), uvLeaf.data(), uvLeaf.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (normals9) {
         CK(cudaMalloc(&mem->d_normals, (size_t)ntris * 9 * sizeof(float)));
         CK(cudaMemcpy(mem->d_normals, normals9, (size_t)ntris * 9 * sizeof(float), cudaMemcpyHostToDevice));
     }
     o.mem = mem; o.d_nodes = mem->d_nodes; o.d_tris = mem->d_tris; o.d_normals = mem->d_normals;
-    o.nnodes = (int64_t)b.nodes.size(); o.ntris = (int64_t)b.tris.size();
+    o.nnodes = (int64_t)b.nodes.size(); o.ntris = (int64_t)nt;
     return upload_objects(ctx);
+}
+
+int dprt_upload_chunk(dprt_ctx* ctx, int si, const dprt_object_desc* desc, const float* verts9, const float* normals9,
+                      const int32_t* mat_ids, int64_t ntris) {
+    return dprt_upload_chunk_uv(ctx, si, desc, verts9, normals9, nullptr, mat_ids, ntris);
+}
+
+int64_t dprt_flatten_count(const dprt_mesh_desc* meshes, int n_meshes, const dprt_instance_desc* instances, int64_t n_instances) {
+    return flatten_count(meshes, n_meshes, instances, n_instances);
+}
+int dprt_flatten_instances(const dprt_mesh_desc* meshes, int n_meshes, const dprt_instance_desc* instances, int64_t n_instances,
+                           float* verts9, float* normals9, float* uv6, int32_t* mat_ids, int* has_uv) {
+    return flatten_instances(meshes, n_meshes, instances, n_instances, verts9, normals9, uv6, mat_ids, has_uv) ? DPRT_ERR_INVALID : 0;
+}
+
+int dprt_upload_instanced_chunk(dprt_ctx* ctx, int si, const dprt_object_desc* desc, const dprt_mesh_desc* meshes, int n_meshes,
+                                const dprt_instance_desc* instances, int64_t n_instances) {
+    if (!ctx || !desc) return DPRT_ERR_INVALID;
+    const int64_t nt = flatten_count(meshes, n_meshes, instances, n_instances);
+    if (nt <= 0) return fail(ctx, DPRT_ERR_INVALID, "dprt_upload_instanced_chunk: invalid mesh / instance description");
+    std::vector<float> verts((size_t)nt * 9), normals((size_t)nt * 9), uv((size_t)nt * 6);
+    std::vector<int32_t> mats((size_t)nt);
+    int hasUv = 0;
+    if (flatten_instances(meshes, n_meshes, instances, n_instances, verts.data(), normals.data(), uv.data(), mats.data(), &hasUv))
+        return fail(ctx, DPRT_ERR_INVALID, "dprt_upload_instanced_chunk: index out of range or singular instance transform");
+    return dprt_upload_chunk_uv(ctx, si, desc, verts.data(), normals.data(), hasUv ? uv.data() : nullptr, mats.data(), nt);
+}
+
+// ---- textures, environment map (renderer.cpp:1621-1721, :1851) ------------------------------------
+namespace {
+int upload_texels(dprt_ctx* ctx, const float* rgba, int width, int height, std::shared_ptr<TexMem>& out) {
+    auto m = std::make_shared<TexMem>();
+    m->device = ctx->device; m->w = width; m->h = height;
+    const size_t bytes = (size_t)width * height * 4 * sizeof(float);
+    CK(cudaMalloc(&m->d, bytes));
+    CK(cudaMemcpy(m->d, rgba, bytes, cudaMemcpyHostToDevice));
+    out = m;
+    return 0;
+}
+int upload_texture_table(dprt_ctx* ctx) {
+    DevTexture h[DPRT_MAX_TEXTURES];
+    for (int i = 0; i < DPRT_MAX_TEXTURES; i++)
+        h[i] = ctx->tex[i] ? DevTexture{(const float4*)ctx->tex[i]->d, ctx->tex[i]->w, ctx->tex[i]->h} : DevTexture{nullptr, 0, 0};
+    CK(cudaMemcpy(ctx->d_textures, h, sizeof(h), cudaMemcpyHostToDevice));
+    return 0;
+}
+}  // namespace
+
+int dprt_set_texture(dprt_ctx* ctx, int ti, const float* rgba, int width, int height) {
+    if (!ctx || ti < 0 || ti >= DPRT_MAX_TEXTURES) return DPRT_ERR_INVALID;
+    if (rgba && (width < 1 || height < 1 || (int64_t)width * height > ((int64_t)1 << 28))) return fail(ctx, DPRT_ERR_INVALID, "texture size");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));            // nothing in flight samples the old texels
+    if (ctx->aux) CK(cudaStreamSynchronize(ctx->aux));
+    std::shared_ptr<TexMem> m;
+    if (rgba) { int r = upload_texels(ctx, rgba, width, height, m); if (r) return r; }
+    ctx->tex[ti] = m;
+    return upload_texture_table(ctx);
+}
+
+int dprt_set_material_textures(dprt_ctx* ctx, const int32_t* texture_index, int n) {
+    if (!ctx || !texture_index || n < 1 || n > DPRT_MAX_MATERIALS) return DPRT_ERR_INVALID;
+    for (int i = 0; i < n; i++)
+        if (texture_index[i] < -1 || texture_index[i] >= DPRT_MAX_TEXTURES) return fail(ctx, DPRT_ERR_INVALID, "texture index out of range");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->aux) CK(cudaStreamSynchronize(ctx->aux));
+    CK(cudaMemcpy(ctx->d_matTex, texture_index, sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int dprt_set_env_map(dprt_ctx* ctx, const float* rgba, int width, int height, float rotation_offset) {
+    if (!ctx) return DPRT_ERR_INVALID;
+    if (rgba && (width < 1 || height < 1 || (int64_t)width * height > ((int64_t)1 << 28))) return fail(ctx, DPRT_ERR_INVALID, "environment map size");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->aux) CK(cudaStreamSynchronize(ctx->aux));
+    std::shared_ptr<TexMem> m;
+    if (rgba) { int r = upload_texels(ctx, rgba, width, height, m); if (r) return r; }
+    ctx->envTex = m;
+    ctx->hp.envMap = m ? DevTexture{(const float4*)m->d, m->w, m->h} : DevTexture{nullptr, 0, 0};
+    ctx->hp.envRotation = rotation_offset;
+    return 0;
+}
+
+// the same two look-ups on host arrays, from the source the kernels compile (dprt_math.cuh); no device involved
+int dprt_spec_texture_sample(const float* rgba, int width, int height, const float* u, const float* v, int64_t n, int clamp_v, float* out4) {
+    return spec_texture_sample(rgba, width, height, u, v, n, clamp_v, out4);
+}
+int dprt_spec_env_lookup(const float* rgba, int width, int height, float rotation_offset, const float* dirs3, int64_t n, float* out3) {
+    return spec_env_lookup(rgba, width, height, rotation_offset, dirs3, n, out3);
 }
 
 int dprt_upload_proxy(dprt_ctx* ctx, int si, const dprt_object_desc* desc, const void* vis_blob, size_t vis_bytes,
@@ -684,6 +812,10 @@ int dprt_adopt_scene(dprt_ctx* ctx, dprt_ctx* from) {
     CK(cudaMemcpy(ctx->d_materials, from->d_materials, sizeof(dprt_material) * DPRT_MAX_MATERIALS, cudaMemcpyDeviceToDevice));
     CK(cudaMemcpy(ctx->d_lights, from->d_lights, sizeof(dprt_light_tri) * DPRT_MAX_LIGHTS, cudaMemcpyDeviceToDevice));
     CK(cudaMemcpy(ctx->d_mlpTable, from->d_mlpTable, 2 * 32 * sizeof(MlpGroupEntry), cudaMemcpyDeviceToDevice));
+    for (int i = 0; i < DPRT_MAX_TEXTURES; i++) ctx->tex[i] = from->tex[i];                 // shares the texels (TexMem)
+    CK(cudaMemcpy(ctx->d_textures, from->d_textures, sizeof(DevTexture) * DPRT_MAX_TEXTURES, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(ctx->d_matTex, from->d_matTex, sizeof(int32_t) * DPRT_MAX_MATERIALS, cudaMemcpyDeviceToDevice));
+    ctx->envTex = from->envTex; ctx->hp.envMap = from->hp.envMap; ctx->hp.envRotation = from->hp.envRotation;
     ctx->hp.lightCount = from->hp.lightCount;
     if (from->hp.camera.width == ctx->cfg.width && from->hp.camera.height == ctx->cfg.height) ctx->hp.camera = from->hp.camera;
     return upload_objects(ctx);
@@ -1738,7 +1870,7 @@ int dprt_trace_closest_device(dprt_ctx* ctx, const void* rays_dev, int64_t n, vo
     CK(cudaSetDevice(ctx->device));
     { int r = ensure_ray_park(ctx, (size_t)n); if (r) return r; }
     StageScope sc_(ctx, DPRT_STAGE_TRACE_CLOSEST, n > 0);
-    launch_trace_closest(ctx->d_objects, ctx->cfg.sceneSize, (const dprt_ray*)rays_dev, (dprt_hit*)hits_dev, n, ctx->d_queue,
+    launch_trace_closest(ctx->d_objects, ctx->cfg.sceneSize, ctx->d_textures, ctx->d_matTex, (const dprt_ray*)rays_dev, (dprt_hit*)hits_dev, n, ctx->d_queue,
                          ctx->hp.counters, ctx->d_rayPark, ctx->stream);
     ctx->stats.kernel_launches += n > 0;
     ctx->stats.rays_traverse += n;
@@ -1774,7 +1906,7 @@ int dprt_gen_train_data(dprt_ctx* ctx, int si, const dprt_ray* rays_host, int64_
     CK(cudaMemcpyAsync(d, rays_host, rb, cudaMemcpyHostToDevice, ctx->stream));
     {
         StageScope sc_(ctx, DPRT_STAGE_TRACE_CLOSEST);
-        launch_trace_closest(ctx->d_objects + si, 1, (const dprt_ray*)d, (dprt_hit*)(d + rb), n, ctx->d_queue, ctx->hp.counters, nullptr, ctx->stream);   // startObj only
+        launch_trace_closest(ctx->d_objects + si, 1, ctx->d_textures, ctx->d_matTex, (const dprt_ray*)d, (dprt_hit*)(d + rb), n, ctx->d_queue, ctx->hp.counters, nullptr, ctx->stream);   // startObj only
         launch_train_features(ctx->d_objects + si, (const dprt_ray*)d, (const dprt_hit*)(d + rb), n, (float*)(d + rb + hb), (float*)(d + rb + hb + fb), ctx->stream);
     }
     ctx->stats.kernel_launches += 2;
@@ -1803,7 +1935,7 @@ int dprt_gen_precom_data(dprt_ctx* ctx, int si, const dprt_ray* rays_host, int64
     {
         StageScope sc_(ctx, DPRT_STAGE_TRACE_CLOSEST);
         launch_precom_features(ctx->d_objects + si, d_rays, n, d_feat, d_ta, ctx->stream);                 // proxy AABB (aabbHandle)
-        launch_trace_closest(ctx->d_objects + si, 1, d_rays, d_hits, n, ctx->d_queue, ctx->hp.counters, nullptr, ctx->stream);   // originHandle, tMax = inf
+        launch_trace_closest(ctx->d_objects + si, 1, ctx->d_textures, ctx->d_matTex, d_rays, d_hits, n, ctx->d_queue, ctx->hp.counters, nullptr, ctx->stream);   // originHandle, tMax = inf
         launch_precom_labels(ctx->d_objects + si, d_hits, d_ta, n, d_label, d_valid, ctx->stream);
     }
     ctx->stats.kernel_launches += 3;

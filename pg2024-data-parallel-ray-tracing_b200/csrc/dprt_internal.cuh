@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "dprt_types.h"
+#include "dprt_math.cuh"
 
 namespace dprt {
 
@@ -77,6 +78,11 @@ struct DevParams {
                                    // rank are counted in bucket worldSize instead of bucket worldID (INT_MAX: reference)
     int32_t* secLive;              // per path slot of the last Target_Node_Update: pixel whose tMax scratch it used, or -1
     int32_t* livePixel;            // per path slot of the last MainRay launch: pixel that got shadow paths, or -1
+    // real-scene front end (dprt.h): albedo / opacity maps, texture index per material (-1 = none), environment map
+    const DevTexture* textures;    // DPRT_MAX_TEXTURES slots, texels == null: slot empty
+    const int32_t*    matTex;      // DPRT_MAX_MATERIALS entries
+    DevTexture        envMap;      // texels == null: analytic sky of envColor
+    float             envRotation;
 };
 
 // stage launches (all asynchronous on `stream`)
@@ -88,8 +94,8 @@ void launch_secondary_trace(const DevParams& p, int n, cudaStream_t stream);
 int trace_kernels_per_stage();  // kernels one traversal stage launches (trace, the parked tail's finish kernel, post)
 size_t trace_scratch_bytes();   // per-context scratch of the persistent trace kernel (queue head + cooperative-mode pools)
 // park: n HitRec of scratch for the tail of the launch (kernels.cu "tail parking"), or null
-void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ray* rays, dprt_hit* hits, int64_t n,
-                          int32_t* queue, unsigned long long* counters, HitRec* park, cudaStream_t stream);
+void launch_trace_closest(const DevObject* objects, int sceneSize, const DevTexture* textures, const int32_t* matTex, const dprt_ray* rays,
+                          dprt_hit* hits, int64_t n, int32_t* queue, unsigned long long* counters, HitRec* park, cudaStream_t stream);
 
 // Vis pipeline epilogue (vis_ray_kernel.cu:145-160): features and label of every traced training ray of object `obj`
 void launch_train_features(const DevObject* obj, const dprt_ray* rays, const dprt_hit* hits, int64_t n, float* features,
@@ -100,6 +106,10 @@ void launch_train_features(const DevObject* obj, const dprt_ray* rays, const dpr
 void launch_precom_features(const DevObject* obj, dprt_ray* rays, int64_t n, float* features, float* t_aabb, cudaStream_t stream);
 void launch_precom_labels(const DevObject* obj, const dprt_hit* hits, const float* t_aabb, int64_t n, float* labels, uint8_t* valid,
                           cudaStream_t stream);
+
+// dprt_spec_*: the texture / environment look-ups of dprt_math.cuh on host arrays (kernels.cu: same source, host compile)
+int spec_texture_sample(const float* rgba, int width, int height, const float* u, const float* v, int64_t n, int clampV, float* out4);
+int spec_env_lookup(const float* rgba, int width, int height, float rotationOffset, const float* dirs3, int64_t n, float* out3);
 
 // partition / bucketing (partition.cu)
 struct PartitionScratch {

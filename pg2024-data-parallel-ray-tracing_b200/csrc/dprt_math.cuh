@@ -15,10 +15,13 @@
 #include <float.h>
 
 #define DPRT_D __device__ __forceinline__
+// also compiled for the host: the texture / environment look-ups are exported as dprt_spec_* so that a machine without a GPU
+// can compare this very source with the oracle
+#define DPRT_HD __host__ __device__ __forceinline__
 
 struct V3 { float x, y, z; };
 
-DPRT_D V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+DPRT_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
 DPRT_D V3 v3sub(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
 DPRT_D V3 v3add(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
 DPRT_D V3 v3mul(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
@@ -69,19 +72,19 @@ DPRT_D void det_sincos2pi(float x, float* s, float* c) {
     if (q == 2 || q == 3) ss = -ss;
     *s = ss; *c = cc;
 }
-DPRT_D float det_asin_poly(float x) {      // |x| <= 0.5
+DPRT_HD float det_asin_poly(float x) {      // |x| <= 0.5
     float z = x * x;
     float p = fmaf(fmaf(fmaf(fmaf(4.2163199048e-2f, z, 2.4181311049e-2f), z, 4.5470025998e-2f), z, 7.4953002686e-2f), z,
                    1.6666752422e-1f);
     return fmaf(p * z, x, x);
 }
-DPRT_D float det_acos(float x) {           // x clamped to [-1,1] by the caller
+DPRT_HD float det_acos(float x) {           // x clamped to [-1,1] by the caller
     const float PI = 3.14159265358979323846f, PIO2 = 1.57079632679489661923f;
     if (x > 0.5f) { float s = sqrtf(0.5f * (1.0f - x)); return 2.0f * det_asin_poly(s); }
     if (x < -0.5f) { float s = sqrtf(0.5f * (1.0f + x)); return PI - 2.0f * det_asin_poly(s); }
     return PIO2 - det_asin_poly(x);
 }
-DPRT_D float det_atan_pos(float t) {       // t >= 0
+DPRT_HD float det_atan_pos(float t) {       // t >= 0
     const float PIO2 = 1.57079632679489661923f, PIO4 = 0.78539816339744830962f;
     float y0, x;
     if (t > 2.414213562373095f) { y0 = PIO2; x = -(1.0f / t); }
@@ -91,7 +94,7 @@ DPRT_D float det_atan_pos(float t) {       // t >= 0
     float p = fmaf(fmaf(fmaf(8.05374449538e-2f, z, -1.38776856032e-1f), z, 1.99777106478e-1f), z, -3.33329491539e-1f);
     return y0 + fmaf(p * z, x, x);
 }
-DPRT_D float det_atan2(float y, float x) {
+DPRT_HD float det_atan2(float y, float x) {
     const float PI = 3.14159265358979323846f, PIO2 = 1.57079632679489661923f;
     if (x == 0.0f) { if (y > 0.0f) return PIO2; if (y < 0.0f) return -PIO2; return 0.0f; }
     float a = det_atan_pos(fabsf(y) / fabsf(x));
@@ -100,7 +103,7 @@ DPRT_D float det_atan2(float y, float x) {
 }
 // Coordinates::cartesianToSpherical (+ForTrain, same convention: src/cuda/bvh_intersection.cu:18-26):
 // phi = atan2(y,x) wrapped to [0,2pi), theta = acos(clamp(z,-1,1)).
-DPRT_D void det_cartesian_to_spherical(V3 d, float* phi, float* theta) {
+DPRT_HD void det_cartesian_to_spherical(V3 d, float* phi, float* theta) {
     float p = det_atan2(d.y, d.x);
     if (p < 0.0f) p += 6.28318530717958647692f;
     *phi = p;
@@ -211,3 +214,69 @@ DPRT_D bool aabb_intersect(V3 ol, V3 dl, const float* mn, const float* mx, float
 // float -> IEEE binary16, round to nearest even (the reference's __float2half).
 DPRT_D uint16_t f32_to_f16_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
 DPRT_D float f16_bits_to_f32(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+
+// ---- textures: albedo / opacity maps and the environment map (real-scene front end) ----
+// tex2D<float4>() of kernel.cu:274-279 / :40-44 on a cudaFilterModeLinear, normalised-coordinate texture object
+// (renderer.cpp:1700-1710), as binary32 arithmetic instead of the texture unit's 9-bit fixed-point weights, so that the
+// oracle reproduces it bit for bit: sample point x = u W - 0.5, texels floor(x) and floor(x) + 1, weights frac(x);
+// lerp(a, b, f) = fma(f, b - a, a), first along u in both rows, then along v. u wraps; v wraps (albedo maps: both address
+// modes are Wrap in the reference) or clamps (lat-long environment map: theta / pi in [0, 1]).
+struct DevTexture { const float4* texels; int32_t width, height; };     // RGBA float texels, row-major, row 0 = v 0
+
+#ifdef __CUDA_ARCH__
+#define DPRT_LDG4(p) __ldg(p)
+#else
+#define DPRT_LDG4(p) (*(p))
+#endif
+
+struct TexTap { int i00, i10, i01, i11; float fx, fy; };
+
+DPRT_HD TexTap tex_taps(int W, int H, float u, float v, bool clampV) {
+    if (!(fabsf(u) < 1e30f)) u = 0.0f;          // NaN / inf / absurd coordinates: texel (0, 0) side of the map, never UB
+    if (!(fabsf(v) < 1e30f)) v = 0.0f;
+    u = u - floorf(u);
+    v = clampV ? fminf(fmaxf(v, 0.0f), 1.0f) : v - floorf(v);
+    const float x = fmaf(u, (float)W, -0.5f), y = fmaf(v, (float)H, -0.5f);
+    const float x0f = floorf(x), y0f = floorf(y);
+    TexTap t;
+    t.fx = x - x0f; t.fy = y - y0f;
+    int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
+    if (x0 < 0) x0 += W;
+    if (x1 >= W) x1 -= W;
+    if (clampV) { if (y0 < 0) y0 = 0; if (y1 > H - 1) y1 = H - 1; }
+    else { if (y0 < 0) y0 += H; if (y1 >= H) y1 -= H; }
+    t.i00 = y0 * W + x0; t.i10 = y0 * W + x1; t.i01 = y1 * W + x0; t.i11 = y1 * W + x1;
+    return t;
+}
+DPRT_HD float tex_lerp2(float c00, float c10, float c01, float c11, float fx, float fy) {
+    const float a = fmaf(fx, c10 - c00, c00), b = fmaf(fx, c11 - c01, c01);
+    return fmaf(fy, b - a, a);
+}
+DPRT_HD float4 tex_bilinear(const DevTexture& T, float u, float v, bool clampV) {
+    const TexTap t = tex_taps(T.width, T.height, u, v, clampV);
+    const float4 c00 = DPRT_LDG4(T.texels + t.i00), c10 = DPRT_LDG4(T.texels + t.i10), c01 = DPRT_LDG4(T.texels + t.i01), c11 = DPRT_LDG4(T.texels + t.i11);
+    float4 r;
+    r.x = tex_lerp2(c00.x, c10.x, c01.x, c11.x, t.fx, t.fy);
+    r.y = tex_lerp2(c00.y, c10.y, c01.y, c11.y, t.fx, t.fy);
+    r.z = tex_lerp2(c00.z, c10.z, c01.z, c11.z, t.fx, t.fy);
+    r.w = tex_lerp2(c00.w, c10.w, c01.w, c11.w, t.fx, t.fy);
+    return r;
+}
+// opacity only (the any-hit program reads albedo.w, kernel.cu:349)
+DPRT_HD float tex_bilinear_alpha(const DevTexture& T, float u, float v) {
+    const TexTap t = tex_taps(T.width, T.height, u, v, false);
+    return tex_lerp2(DPRT_LDG4(T.texels + t.i00).w, DPRT_LDG4(T.texels + t.i10).w, DPRT_LDG4(T.texels + t.i01).w, DPRT_LDG4(T.texels + t.i11).w, t.fx, t.fy);
+}
+// texture coordinate at barycentrics (alpha, beta) = weights of corners 1, 2 (kernel.cu:264-265): gamma t0 + alpha t1 + beta t2
+DPRT_HD float tex_interp(float t0, float t1, float t2, float alpha, float beta) {
+    const float gamma = 1.0f - alpha - beta;
+    return fmaf(beta, t2, fmaf(alpha, t1, gamma * t0));
+}
+// calculateEnvironmentLighting (kernel.cu:28-48, distributed_traversal_kernel.cu:82-103): lat-long look-up of a direction
+DPRT_HD float4 env_map_lookup(const DevTexture& T, float rotationOffset, V3 d) {
+    float phi, theta;
+    det_cartesian_to_spherical(d, &phi, &theta);
+    phi += rotationOffset;
+    if (phi > 6.28318530717958647692f) phi -= 6.28318530717958647692f;
+    return tex_bilinear(T, phi / 6.28318530717958647692f, theta / 3.14159265358979323846f, true);
+}

@@ -58,6 +58,10 @@ DPRT_D void store_zero_path(dprt_path_record* p) {
 // calculateEnvironmentLighting (distributed_traversal_kernel.cu:82-103): the reference looks a lat-long
 // texture up at (phi/2pi, theta/pi); the synthetic scenes use the analytic sky Le = envColor*(0.5+0.5*d.z).
 DPRT_D V3 env_radiance(const DevParams& p, V3 d) {
+    if (p.envMap.texels) {           // dprt_set_env_map: params.envLightTexture
+        const float4 e = env_map_lookup(p.envMap, p.envRotation, d);
+        return v3(e.x, e.y, e.z);
+    }
     float w = fmaf(0.5f, d.z, 0.5f);
     return v3(p.envColor[0] * w, p.envColor[1] * w, p.envColor[2] * w);
 }
@@ -149,6 +153,7 @@ struct TraceArgs {
     int tailBudget;
     int32_t* parkList;               // capacity: one entry per lane of the trace grid (a lane holds one ray when it parks)
     HitRec* park;                    // closest-hit modes: resume state per ray index (the stage's hits[] array, or scratch for TM_RAYS)
+    const DevTexture* textures; const int32_t* matTex;      // alpha cut-outs (bvh_traverse.cuh: alpha_cutout_ignored)
 };
 
 constexpr int kParkCapacity = 148 * 8 * 128 + 4096;       // >= lanes of the largest trace grid
@@ -228,6 +233,7 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
     __shared__ WarpQueue s_wq[kTraceBlock / 32];
     WarpQueue& w = s_wq[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
+    const TexCtx tc = {a.textures, a.matTex};
     Trav s;
     uint2 stack[DPRT_STACK];
     int idx = -1, obj = 0, pend = 0;
@@ -313,7 +319,7 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
             // tested first (pend == 0 in every lane), step (2) then completes whatever is complete, the rest is parked.
 #if DPRT_TAIL_PARK
             const bool parkNow = exhausted && a.tailBudget > 0 && ++tail > a.tailBudget;
-            if (parkNow) { while (qlen > 0) tri_round<ANY, COUNT>(w, qlen, lane, s, obj, pend, cnt); }
+            if (parkNow) { while (qlen > 0) tri_round<ANY, COUNT>(w, qlen, lane, s, obj, pend, cnt, tc); }
 #else
             constexpr bool parkNow = false;
 #endif
@@ -381,7 +387,7 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
                 const unsigned workM = __ballot_sync(FULL, idx >= 0 && obj < a.sceneSize && !exh);
                 if (workM != 0u && __popc(__ballot_sync(FULL, idx >= 0)) <= a.coop) {
                     coop_run<ANY, COUNT>(w, a.coopPool + (size_t)(blockIdx.x * (kTraceBlock / 32) + (threadIdx.x >> 5)) * DPRT_POOLCAP, qlen, lane,
-                                         __ffs(workM) - 1, s, stack, obj, pend, exh, cnt, a.prmtMagic);
+                                         __ffs(workM) - 1, s, stack, obj, pend, exh, cnt, a.prmtMagic, tc);
                     continue;
                 }
             }
@@ -390,7 +396,7 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_k
             const bool canNode = busy && obj < a.sceneSize && !exh && s.tg.y == 0u;
             const unsigned nodeM = __ballot_sync(FULL, canNode);
             const unsigned waitM = __ballot_sync(FULL, busy && !canNode);
-            if (qlen > 0 && (qlen >= 32 || nodeM == 0u || __popc(waitM) >= a.triVote)) tri_round<ANY, COUNT>(w, qlen, lane, s, obj, pend, cnt);
+            if (qlen > 0 && (qlen >= 32 || nodeM == 0u || __popc(waitM) >= a.triVote)) tri_round<ANY, COUNT>(w, qlen, lane, s, obj, pend, cnt, tc);
             else if (canNode) {
                 // Up to nodesPerStep nodes per warp step: most nodes yield no leaf triangles, and the warp-level bookkeeping
                 // around a step costs as much as the slab tests of a node. A lane stops early when it has triangles to queue.
@@ -435,6 +441,7 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_f
     const int lane = threadIdx.x & 31;
     const int count = a.queue[1];
     if (count <= 0) return;
+    const TexCtx tc = {a.textures, a.matTex};
     w.key[lane] = ~0ull; w.cnt[lane] = 0;
     __syncwarp();
     uint32_t* pool = a.coopPool + (size_t)(blockIdx.x * (kTraceBlock / 32) + (threadIdx.x >> 5)) * DPRT_POOLCAP;
@@ -472,7 +479,7 @@ __global__ void __launch_bounds__(kTraceBlock, trace_min_blocks<MODE>()) trace_f
                 }
                 resume = false;
                 __syncwarp();
-                coop_run<ANY, COUNT>(w, pool, qlen, lane, 0, s, stack, obj, pend, exh, cnt, a.prmtMagic);
+                coop_run<ANY, COUNT>(w, pool, qlen, lane, 0, s, stack, obj, pend, exh, cnt, a.prmtMagic, tc);
                 if (ANY && __shfl_sync(FULL, (int)(s.hitTri >= 0), 0)) break;
                 obj = next_object(a, obj + 1, skipMask);
             }
@@ -624,7 +631,17 @@ __global__ void __launch_bounds__(kBlock) shade_post_kernel(DevParams p, int n) 
     const float4 tb = __ldg(ob.tris + 3 * (size_t)htri + 1);
     const int matID = __float_as_int(tb.w);
     const dprt_material mat = p.materials[matID];
-    const V3 albedo = v3(mat.baseColor[0], mat.baseColor[1], mat.baseColor[2]);
+    V3 albedo = v3(mat.baseColor[0], mat.baseColor[1], mat.baseColor[2]);
+    {   // kernel.cu:251-281: a textured material takes its base colour from the albedo map at the interpolated coordinate
+        const int nuv = __float_as_int(__ldg(ob.tris + 3 * (size_t)htri + 2).w);
+        const int tex = nuv != 0 ? p.matTex[matID] : -1;
+        if (tex >= 0 && p.textures[tex].texels) {
+            const float4* uv = ob.tris + 3 * (size_t)nuv + 2 * (size_t)htri;
+            const float4 ua = __ldg(uv), ub = __ldg(uv + 1);
+            const float4 c = tex_bilinear(p.textures[tex], tex_interp(ua.x, ua.z, ub.x, h1.x, h1.y), tex_interp(ua.y, ua.w, ub.y, h1.x, h1.y), false);
+            albedo = v3(c.x, c.y, c.z);
+        }
+    }
     const V3 point = v3at(o, d, ht);
     const V3 woWorld = v3neg(d);
     V3 normal;
@@ -972,10 +989,31 @@ TraceArgs trace_args(const DevParams& p, dprt_path_record* recs) {
     a.refill = tune_refill(); a.triVote = tune_trivote(); a.prmtMagic = 0x47000000u; a.coop = tune_coop(); a.nodesPerStep = tune_nodes();
     a.hitCache = p.hitCache; a.epoch = p.hitEpoch; a.cacheHits = p.cacheHits;
     a.tailBudget = tune_tail(); a.parkList = nullptr; a.park = p.hits;
+    a.textures = p.textures; a.matTex = p.matTex;
     return a;
 }
 
 }  // namespace
+
+// dprt_spec_texture_sample / dprt_spec_env_lookup: host loops over the DPRT_HD functions of dprt_math.cuh
+int spec_texture_sample(const float* rgba, int width, int height, const float* u, const float* v, int64_t n, int clampV, float* out4) {
+    if (!rgba || !u || !v || !out4 || width < 1 || height < 1 || n < 0) return DPRT_ERR_INVALID;
+    const DevTexture T = {reinterpret_cast<const float4*>(rgba), width, height};
+    for (int64_t i = 0; i < n; i++) {
+        const float4 c = tex_bilinear(T, u[i], v[i], clampV != 0);
+        out4[4 * i + 0] = c.x; out4[4 * i + 1] = c.y; out4[4 * i + 2] = c.z; out4[4 * i + 3] = c.w;
+    }
+    return 0;
+}
+int spec_env_lookup(const float* rgba, int width, int height, float rotationOffset, const float* dirs3, int64_t n, float* out3) {
+    if (!rgba || !dirs3 || !out3 || width < 1 || height < 1 || n < 0) return DPRT_ERR_INVALID;
+    const DevTexture T = {reinterpret_cast<const float4*>(rgba), width, height};
+    for (int64_t i = 0; i < n; i++) {
+        const float4 c = env_map_lookup(T, rotationOffset, v3(dirs3[3 * i], dirs3[3 * i + 1], dirs3[3 * i + 2]));
+        out3[3 * i + 0] = c.x; out3[3 * i + 1] = c.y; out3[3 * i + 2] = c.z;
+    }
+    return 0;
+}
 
 int trace_kernels_per_stage() { return 2 + (tune_tail() > 0 ? 1 : 0); }     // trace [+ finish] + post
 
@@ -1030,8 +1068,8 @@ void launch_precom_features(const DevObject* obj, dprt_ray* rays, int64_t n, flo
 void launch_precom_labels(const DevObject* obj, const dprt_hit* hits, const float* t_aabb, int64_t n, float* labels, uint8_t* valid, cudaStream_t s) {
     if (n > 0) precom_label_kernel<<<blocks_for(n), kBlock, 0, s>>>(obj, hits, t_aabb, n, labels, valid);
 }
-void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ray* rays, dprt_hit* hits, int64_t n,
-                          int32_t* queue, unsigned long long* counters, HitRec* park, cudaStream_t s) {
+void launch_trace_closest(const DevObject* objects, int sceneSize, const DevTexture* textures, const int32_t* matTex, const dprt_ray* rays,
+                          dprt_hit* hits, int64_t n, int32_t* queue, unsigned long long* counters, HitRec* park, cudaStream_t s) {
     if (n <= 0) return;
     TraceArgs a;
     a.objects = objects; a.sceneSize = sceneSize; a.worldID = 0; a.recs = nullptr; a.hits = nullptr;
@@ -1039,6 +1077,7 @@ void launch_trace_closest(const DevObject* objects, int sceneSize, const dprt_ra
     a.refill = tune_refill(); a.triVote = tune_trivote(); a.prmtMagic = 0x47000000u; a.coop = tune_coop(); a.nodesPerStep = tune_nodes();
     a.hitCache = nullptr; a.epoch = 0u; a.cacheHits = nullptr;
     a.tailBudget = tune_tail(); a.parkList = nullptr; a.park = park;       // park: n records of scratch, or null (no tail parking)
+    a.textures = textures; a.matTex = matTex;
     launch_trace<TM_RAYS>(a, n, s);
 }
 

@@ -28,6 +28,57 @@ class Camera(C.Structure):
                 ("width", C.c_int32), ("height", C.c_int32)]
 
 
+class MeshDesc(C.Structure):
+    """dprt_mesh_desc: one GAS + its HitGroupData in indexed form (pipeline_helper.cpp:182-193)."""
+    _fields_ = [("positions", C.c_void_p), ("nPositions", C.c_int64), ("indices", C.c_void_p), ("ntris", C.c_int64),
+                ("normals", C.c_void_p), ("nNormals", C.c_int64), ("normalIndices", C.c_void_p),
+                ("texCoords", C.c_void_p), ("nTexCoords", C.c_int64), ("texCoordIndices", C.c_void_p),
+                ("materialID", C.c_int32), ("pad_", C.c_int32)]
+
+
+class InstanceDesc(C.Structure):
+    """dprt_instance_desc: mesh index + row-major 3x4 object-to-world matrix."""
+    _fields_ = [("mesh", C.c_int32), ("pad_", C.c_int32), ("objectToWorld", C.c_float * 12)]
+
+
+MAX_TEXTURES = 64
+MAX_MATERIALS = 256
+
+
+def pack_meshes(meshes, instances):
+    """meshes: list of dicts {positions [nP,3], indices [nT,3], normals [nN,3], normal_indices [nT,3], texcoords [nU,2] | None,
+    texcoord_indices [nT,3] | None, material int}; instances: list of (mesh index, 3x4 float matrix).
+    Returns (MeshDesc array, n_meshes, InstanceDesc array, n_instances, keepalive list of the numpy arrays behind the pointers)."""
+    keep = []
+
+    def arr(a, dt, cols):
+        a = np.ascontiguousarray(a, dt).reshape(-1, cols)
+        keep.append(a)
+        return a
+
+    md = (MeshDesc * len(meshes))()
+    for k, m in enumerate(meshes):
+        pos, idx = arr(m["positions"], np.float32, 3), arr(m["indices"], np.int32, 3)
+        nrm, nidx = arr(m["normals"], np.float32, 3), arr(m["normal_indices"], np.int32, 3)
+        assert nidx.shape == idx.shape
+        md[k].positions, md[k].nPositions = pos.ctypes.data, pos.shape[0]
+        md[k].indices, md[k].ntris = idx.ctypes.data, idx.shape[0]
+        md[k].normals, md[k].nNormals = nrm.ctypes.data, nrm.shape[0]
+        md[k].normalIndices = nidx.ctypes.data
+        if m.get("texcoords") is not None:
+            tc, tidx = arr(m["texcoords"], np.float32, 2), arr(m["texcoord_indices"], np.int32, 3)
+            assert tidx.shape == idx.shape
+            md[k].texCoords, md[k].nTexCoords, md[k].texCoordIndices = tc.ctypes.data, tc.shape[0], tidx.ctypes.data
+        else:
+            md[k].texCoords, md[k].nTexCoords, md[k].texCoordIndices = None, 0, None
+        md[k].materialID = int(m["material"])
+    ins = (InstanceDesc * len(instances))()
+    for k, (mi, M) in enumerate(instances):
+        ins[k].mesh = int(mi)
+        ins[k].objectToWorld[:] = np.asarray(M, np.float32).reshape(12).tolist()
+    return md, len(meshes), ins, len(instances), keep
+
+
 class Stats(C.Structure):
     _fields_ = [("rays_traverse", C.c_int64), ("rays_shade", C.c_int64), ("rays_shadow", C.c_int64),
                 ("rays_secondary", C.c_int64), ("nn_queries", C.c_int64), ("paths_sent_offrank", C.c_int64),
@@ -57,6 +108,7 @@ TRI_DTYPE = np.dtype([("v0", "<f4", 3), ("primID", "<i4"), ("v1", "<f4", 3), ("m
 assert PATH_DTYPE.itemsize == 64 and QUERY_DTYPE.itemsize == 48 and RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 8
 assert NODE_DTYPE.itemsize == 80 and TRI_DTYPE.itemsize == 48 and MATERIAL_DTYPE.itemsize == 16 and LIGHT_DTYPE.itemsize == 48
 assert C.sizeof(Config) == 64 and C.sizeof(ObjectDesc) == 84 and C.sizeof(Camera) == 56 and C.sizeof(Stats) == 128
+assert C.sizeof(MeshDesc) == 88 and C.sizeof(InstanceDesc) == 56
 
 P2P_HANDLE_BYTES = 208     # DPRT_P2P_HANDLE_BYTES
 

@@ -33,6 +33,16 @@ _PROTOTYPES = {
     "dprt_bvh8_free": (None, [C.c_void_p]),
     "dprt_upload_chunk": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(D.ObjectDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "dprt_upload_proxy": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(D.ObjectDesc), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "dprt_flatten_count": (C.c_int64, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+    "dprt_flatten_instances": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_int)]),
+    "dprt_upload_chunk_uv": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(D.ObjectDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "dprt_upload_instanced_chunk": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(D.ObjectDesc), C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
+    "dprt_set_texture": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "dprt_set_material_textures": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "dprt_set_env_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float]),
+    "dprt_spec_texture_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "dprt_spec_env_lookup": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
     "dprt_set_materials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "dprt_set_lights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "dprt_set_camera": (C.c_int, [C.c_void_p, C.POINTER(D.Camera)]),
@@ -151,6 +161,45 @@ def build_bvh8(verts9, mat_ids=None, pad=-1.0):
     finally:
         lib.dprt_bvh8_free(h)
     return nodes, tris, int(md.value)
+
+
+def flatten_instances(meshes, instances):
+    """dprt_flatten_instances (host only, no GPU): indexed meshes + instance transforms -> (verts9 [n,9], normals9 [n,9],
+    uv6 [n,6] or None, mat_ids [n]); primitive id = running index over (instance, triangle). See ctypes_defs.pack_meshes."""
+    lib = load_library()
+    md, nm, ins, ni, keep = D.pack_meshes(meshes, instances)
+    n = lib.dprt_flatten_count(md, nm, ins, ni)
+    if n <= 0:
+        raise DprtError(f"dprt_flatten_count: invalid mesh / instance description ({n})")
+    v, nr, uv, mats = np.zeros((n, 9), np.float32), np.zeros((n, 9), np.float32), np.zeros((n, 6), np.float32), np.zeros(n, np.int32)
+    has = C.c_int(0)
+    rc = lib.dprt_flatten_instances(md, nm, ins, ni, _ptr(v), _ptr(nr), _ptr(uv), _ptr(mats), C.byref(has))
+    del keep
+    if rc:
+        raise DprtError(f"dprt_flatten_instances failed ({rc})")
+    return v, nr, (uv if has.value else None), mats
+
+
+def spec_texture_sample(rgba, u, v, clamp_v=False):
+    """dprt_spec_texture_sample (host only): bilinear look-up of an [h, w, 4] float texture at (u, v) from the kernels' source."""
+    t = np.ascontiguousarray(rgba, np.float32)
+    uu, vv = np.ascontiguousarray(u, np.float32), np.ascontiguousarray(v, np.float32)
+    out = np.zeros((uu.size, 4), np.float32)
+    rc = load_library().dprt_spec_texture_sample(_ptr(t), t.shape[1], t.shape[0], _ptr(uu), _ptr(vv), uu.size, int(clamp_v), _ptr(out))
+    if rc:
+        raise DprtError(f"dprt_spec_texture_sample failed ({rc})")
+    return out
+
+
+def spec_env_lookup(rgba, rotation, dirs):
+    """dprt_spec_env_lookup (host only): environment-map radiance of unit directions [n, 3]."""
+    t = np.ascontiguousarray(rgba, np.float32)
+    d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+    out = np.zeros((d.shape[0], 3), np.float32)
+    rc = load_library().dprt_spec_env_lookup(_ptr(t), t.shape[1], t.shape[0], float(rotation), _ptr(d), d.shape[0], _ptr(out))
+    if rc:
+        raise DprtError(f"dprt_spec_env_lookup failed ({rc})")
+    return out
 
 
 def plan_exchange(gathered_offsets, rank):
@@ -338,6 +387,43 @@ class Renderer:
         m = None if mat_ids is None else np.ascontiguousarray(mat_ids, np.int32)
         self._ck(self.lib.dprt_upload_chunk(self.h, scene_index, C.byref(desc), _ptr(v), _ptr(n), _ptr(m), v.shape[0]),
                  "dprt_upload_chunk")
+
+    def upload_chunk_uv(self, scene_index, desc, verts9, normals9, uv6, mat_ids):
+        """dprt_upload_chunk_uv: flat triangles with per-corner texture coordinates (uv6 [n,6] or None)."""
+        v = np.ascontiguousarray(verts9, np.float32).reshape(-1, 9)
+        n = None if normals9 is None else np.ascontiguousarray(normals9, np.float32).reshape(-1, 9)
+        u = None if uv6 is None else np.ascontiguousarray(uv6, np.float32).reshape(-1, 6)
+        m = None if mat_ids is None else np.ascontiguousarray(mat_ids, np.int32)
+        self._ck(self.lib.dprt_upload_chunk_uv(self.h, scene_index, C.byref(desc), _ptr(v), _ptr(n), _ptr(u), _ptr(m), v.shape[0]),
+                 "dprt_upload_chunk_uv")
+
+    def upload_instanced_chunk(self, scene_index, desc, meshes, instances):
+        """dprt_upload_instanced_chunk: indexed meshes (ctypes_defs.pack_meshes dicts) placed by (mesh, 3x4 matrix) instances."""
+        md, nm, ins, ni, keep = D.pack_meshes(meshes, instances)
+        self._ck(self.lib.dprt_upload_instanced_chunk(self.h, scene_index, C.byref(desc), md, nm, ins, ni), "dprt_upload_instanced_chunk")
+        del keep
+
+    def set_texture(self, texture_index, rgba):
+        """params.albedoTextures[texture_index]: [h, w, 4] float RGBA (alpha = opacity), or None to remove it."""
+        if rgba is None:
+            self._ck(self.lib.dprt_set_texture(self.h, texture_index, None, 0, 0), "dprt_set_texture")
+            return
+        t = np.ascontiguousarray(rgba, np.float32)
+        assert t.ndim == 3 and t.shape[2] == 4
+        self._ck(self.lib.dprt_set_texture(self.h, texture_index, _ptr(t), t.shape[1], t.shape[0]), "dprt_set_texture")
+
+    def set_material_textures(self, texture_index):
+        t = np.ascontiguousarray(texture_index, np.int32)
+        self._ck(self.lib.dprt_set_material_textures(self.h, _ptr(t), t.size), "dprt_set_material_textures")
+
+    def set_env_map(self, rgba, rotation_offset=0.0):
+        """params.envLightTexture: [h, w, 4] float lat-long map, or None for the analytic sky."""
+        if rgba is None:
+            self._ck(self.lib.dprt_set_env_map(self.h, None, 0, 0, 0.0), "dprt_set_env_map")
+            return
+        t = np.ascontiguousarray(rgba, np.float32)
+        assert t.ndim == 3 and t.shape[2] == 4
+        self._ck(self.lib.dprt_set_env_map(self.h, _ptr(t), t.shape[1], t.shape[0], float(rotation_offset)), "dprt_set_env_map")
 
     def upload_proxy(self, scene_index, desc, vis_blob=None, depth_blob=None):
         vb = None if vis_blob is None else np.frombuffer(vis_blob, np.uint8)

@@ -75,3 +75,41 @@ def random_rays(n, seed, lo=-0.2, hi=1.2):
     rays["tMin"] = D.DPRT_EPSILON
     rays["tMax"] = np.finfo(np.float32).max
     return rays
+
+
+def build_garden_pair(O, W, width, height, *, spp=1, bounces=2, gpu=True, device=0, textures=True, env_map=True, clusters=18,
+                      ground=(40, 40), main_ray_retrace=0, serial_stages=0, reference_migrate=0):
+    """The real-scene front end on both sides: W instanced, textured scene objects (real_scene.make_garden)
+    go through dprt_upload_instanced_chunk / dprt_set_texture / dprt_set_material_textures / dprt_set_env_map and through the
+    oracle's own flatten and texture code. gpu=False builds the oracle world only. Returns (renderers, world, garden)."""
+    g = dprt.real_scene.make_garden(W, clusters=clusters, ground=ground)
+    cfg = dprt.make_config(width, height, spp=spp, bounces=bounces, scene_size=W, proxy_mode=0, main_ray_retrace=main_ray_retrace,
+                           serial_stages=serial_stages, reference_migrate=reference_migrate)
+    cam = dprt.scene.default_camera(width, height)
+    world = O.World(cfg, W)
+    for ob in g["objects"]:
+        world.add_instanced_object(ob.index, ob.desc(False), ob.meshes, ob.instances)
+    world.set_materials(g["materials"]); world.set_lights(g["lights"]); world.set_camera(cam)
+    if textures:
+        for slot, t in g["textures"].items():
+            world.set_texture(slot, t)
+        world.set_material_textures(g["material_textures"])
+    if env_map:
+        world.set_env_map(g["env_map"], g["env_rotation"])
+    rs = []
+    for r in range(W if gpu else 0):
+        R = dprt.Renderer(cfg, rank=r, world=W, device=device)
+        for ob in g["objects"]:
+            if ob.node_id == r:
+                R.upload_instanced_chunk(ob.index, ob.desc(False), ob.meshes, ob.instances)
+            else:
+                R.upload_proxy(ob.index, ob.desc(True), None, None)
+        R.set_materials(g["materials"]); R.set_lights(g["lights"]); R.set_camera(cam)
+        if textures:
+            for slot, t in g["textures"].items():
+                R.set_texture(slot, t)
+            R.set_material_textures(g["material_textures"])
+        if env_map:
+            R.set_env_map(g["env_map"], g["env_rotation"])
+        rs.append(R)
+    return rs, world, g
