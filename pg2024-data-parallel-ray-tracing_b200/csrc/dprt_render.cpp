@@ -12,6 +12,12 @@
 //   "DPRTSCN1" | int32 nObjects nMaterials nLights | dprt_camera | dprt_material[nMaterials] | dprt_light_tri[nLights]
 //   per object: dprt_object_desc (isProxy ignored) | int64 ntris | float verts[9 ntris] | float normals[9 ntris]
 //               | int32 mats[ntris] | int64 visBytes | vis blob | int64 depthBytes | depth blob   (proxy MLP weights, may be 0)
+// Real-scene variant (real_scene.py:save_scene_v2; the front end of SURVEY.md 8f row 3 -- textures, cut-outs, environment map):
+//   "DPRTSCN2" | int32 nObjects nMaterials nLights nTextures | dprt_camera | dprt_material[nMaterials] | int32 matTex[nMaterials]
+//   | dprt_light_tri[nLights] | per texture: int32 slot width height | float rgba[4 w h]   (params.albedoTextures, renderer.cpp:1621-1721)
+//   | int32 envWidth envHeight (0 0 = analytic sky) | float rotationOffset | float rgba[4 w h]   (params.envLightTexture, :1851)
+//   per object: dprt_object_desc | int64 ntris | int32 hasUv | verts | normals | float uv[6 ntris] if hasUv | mats | vis blob | depth blob
+//   (instanced / indexed meshes arrive flattened: the file is written after dprt_flatten_instances)
 //               [--frames F] [--camera-move dx,dy,dz] [--camera-target x,y,z] [--light-move dx,dy,dz] [--light-start dx,dy,dz]
 //                                      the frame loop of launch() (renderer.cpp:1938-2059): per frame the first two lights move by
 //                                      -light-move (after a one-off +light-start, LIGHT_MOVE :1941-1966) and the camera origin by
@@ -39,37 +45,68 @@ namespace {
 struct Object {
     dprt_object_desc desc;
     int64_t ntris = 0;
-    std::vector<float> verts, normals;
+    std::vector<float> verts, normals, uvs;          // uvs: 6 per triangle, empty = no texture coordinates
     std::vector<int32_t> mats;
     std::vector<char> vis, depth;
 };
+struct Texture { int32_t slot = 0, w = 0, h = 0; std::vector<float> rgba; };
 struct Scene {
     dprt_camera cam;
     std::vector<dprt_material> materials;
+    std::vector<int32_t> matTex;                     // texture slot per material (-1 = none); empty for DPRTSCN1 files
     std::vector<dprt_light_tri> lights;
+    std::vector<Texture> textures;
+    Texture env; float envRotation = 0.f;            // env.w == 0: analytic sky
     std::vector<Object> objects;
 };
 
 bool read_exact(FILE* f, void* p, size_t n) { return n == 0 || fread(p, 1, n, f) == n; }
 
+bool read_texels(FILE* f, Texture& t) {
+    if (t.w < 1 || t.h < 1 || (int64_t)t.w * t.h > (int64_t(1) << 28)) return false;
+    t.rgba.resize(4 * (size_t)t.w * t.h);
+    return read_exact(f, t.rgba.data(), t.rgba.size() * 4);
+}
+
 bool load_scene(const std::string& path, Scene& sc, std::string& err) {
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) { err = "cannot open " + path; return false; }
-    char magic[8]; int32_t hdr[3];
-    bool ok = read_exact(f, magic, 8) && std::memcmp(magic, "DPRTSCN1", 8) == 0 && read_exact(f, hdr, sizeof(hdr));
-    if (ok) ok = hdr[0] >= 1 && hdr[0] <= 32 && hdr[1] >= 1 && hdr[1] <= DPRT_MAX_MATERIALS && hdr[2] >= 1 && hdr[2] <= DPRT_MAX_LIGHTS;
+    char magic[8]; int32_t hdr[4] = {0, 0, 0, 0};
+    bool ok = read_exact(f, magic, 8);
+    const bool v2 = ok && std::memcmp(magic, "DPRTSCN2", 8) == 0;
+    ok = ok && (v2 || std::memcmp(magic, "DPRTSCN1", 8) == 0) && read_exact(f, hdr, v2 ? 16 : 12);
+    if (ok) ok = hdr[0] >= 1 && hdr[0] <= 32 && hdr[1] >= 1 && hdr[1] <= DPRT_MAX_MATERIALS && hdr[2] >= 1 && hdr[2] <= DPRT_MAX_LIGHTS &&
+                 hdr[3] >= 0 && hdr[3] <= DPRT_MAX_TEXTURES;
     if (ok) {
         sc.materials.resize(hdr[1]); sc.lights.resize(hdr[2]); sc.objects.resize(hdr[0]);
-        ok = read_exact(f, &sc.cam, sizeof(sc.cam)) && read_exact(f, sc.materials.data(), sizeof(dprt_material) * hdr[1]) &&
-             read_exact(f, sc.lights.data(), sizeof(dprt_light_tri) * hdr[2]);
+        ok = read_exact(f, &sc.cam, sizeof(sc.cam)) && read_exact(f, sc.materials.data(), sizeof(dprt_material) * hdr[1]);
+        if (ok && v2) { sc.matTex.resize(hdr[1]); ok = read_exact(f, sc.matTex.data(), 4 * (size_t)hdr[1]); }
+        ok = ok && read_exact(f, sc.lights.data(), sizeof(dprt_light_tri) * hdr[2]);
+    }
+    if (ok && v2) {
+        sc.textures.resize(hdr[3]);
+        for (Texture& t : sc.textures) {
+            int32_t th[3];
+            ok = ok && read_exact(f, th, 12);
+            if (!ok) break;
+            t.slot = th[0]; t.w = th[1]; t.h = th[2];
+            ok = t.slot >= 0 && t.slot < DPRT_MAX_TEXTURES && read_texels(f, t);
+        }
+        int32_t eh[2] = {0, 0};
+        ok = ok && read_exact(f, eh, 8) && read_exact(f, &sc.envRotation, 4);
+        if (ok && (eh[0] != 0 || eh[1] != 0)) { sc.env.w = eh[0]; sc.env.h = eh[1]; ok = read_texels(f, sc.env); }
     }
     for (size_t k = 0; ok && k < sc.objects.size(); k++) {
         Object& o = sc.objects[k];
+        int32_t hasUv = 0;
         ok = read_exact(f, &o.desc, sizeof(o.desc)) && read_exact(f, &o.ntris, 8) && o.ntris >= 0 && o.ntris < (int64_t(1) << 27);
+        if (ok && v2) ok = read_exact(f, &hasUv, 4);
         if (!ok) break;
         o.verts.resize(9 * (size_t)o.ntris); o.normals.resize(9 * (size_t)o.ntris); o.mats.resize((size_t)o.ntris);
+        if (hasUv) o.uvs.resize(6 * (size_t)o.ntris);
         int64_t vb = 0, db = 0;
         ok = read_exact(f, o.verts.data(), o.verts.size() * 4) && read_exact(f, o.normals.data(), o.normals.size() * 4) &&
+             read_exact(f, o.uvs.data(), o.uvs.size() * 4) &&
              read_exact(f, o.mats.data(), o.mats.size() * 4) && read_exact(f, &vb, 8) && vb >= 0 && vb < (int64_t(1) << 30);
         if (ok) { o.vis.resize((size_t)vb); ok = read_exact(f, o.vis.data(), (size_t)vb) && read_exact(f, &db, 8) && db >= 0 && db < (int64_t(1) << 30); }
         if (ok) { o.depth.resize((size_t)db); ok = read_exact(f, o.depth.data(), (size_t)db); }
@@ -175,7 +212,7 @@ int upload_scene(dprt_ctx* ctx, const Scene& sc, int rank) {
         dprt_object_desc d = o.desc;
         if (o.desc.nodeID == rank) {
             d.isProxy = 0;
-            if ((r = dprt_upload_chunk(ctx, (int)k, &d, o.verts.data(), o.normals.data(), o.mats.data(), o.ntris))) return r;
+            if ((r = dprt_upload_chunk_uv(ctx, (int)k, &d, o.verts.data(), o.normals.data(), o.uvs.empty() ? nullptr : o.uvs.data(), o.mats.data(), o.ntris))) return r;
         } else {
             d.isProxy = 1;
             if ((r = dprt_upload_proxy(ctx, (int)k, &d, o.vis.empty() ? nullptr : o.vis.data(), o.vis.size(),
@@ -183,6 +220,10 @@ int upload_scene(dprt_ctx* ctx, const Scene& sc, int rank) {
         }
     }
     if ((r = dprt_set_materials(ctx, sc.materials.data(), (int)sc.materials.size()))) return r;
+    // albedo / opacity maps, texture slot per material, environment map (renderer.cpp:1621-1721, :1851)
+    for (const Texture& t : sc.textures) if ((r = dprt_set_texture(ctx, t.slot, t.rgba.data(), t.w, t.h))) return r;
+    if (!sc.matTex.empty() && (r = dprt_set_material_textures(ctx, sc.matTex.data(), (int)sc.matTex.size()))) return r;
+    if (sc.env.w > 0 && (r = dprt_set_env_map(ctx, sc.env.rgba.data(), sc.env.w, sc.env.h, sc.envRotation))) return r;
     if ((r = dprt_set_lights(ctx, sc.lights.data(), (int)sc.lights.size()))) return r;
     return dprt_set_camera(ctx, &sc.cam);
 }

@@ -351,3 +351,41 @@ def load_texture(path):
         a = raw[..., 3:4] if raw.shape[2] > 3 else np.ones(raw.shape[:2] + (1,), np.float32)
         img = np.concatenate([rgb, a], -1)
     return np.ascontiguousarray(img[::-1], np.float32)
+
+
+def save_scene_v2(path, garden, cam, flatten):
+    """Scene file of the C++ host in its real-scene variant (csrc/dprt_render.cpp documents the layout): the dict of make_garden
+    (or the same keys filled from load_obj / load_texture) with every object flattened by `flatten` = host.flatten_instances
+    (dprt_flatten_instances: what dprt_upload_instanced_chunk would do)."""
+    import ctypes as C
+    mats, mat_tex = np.ascontiguousarray(garden["materials"], D.MATERIAL_DTYPE), np.full(len(garden["materials"]), -1, np.int32)
+    mt = np.asarray(garden.get("material_textures", []), np.int32)
+    mat_tex[:mt.size] = mt
+    textures = garden.get("textures") or {}
+    with open(path, "wb") as f:
+        f.write(b"DPRTSCN2")
+        f.write(np.array([len(garden["objects"]), len(mats), len(garden["lights"]), len(textures)], np.int32).tobytes())
+        f.write(bytes(C.string_at(C.addressof(cam), C.sizeof(cam))))
+        f.write(mats.tobytes()); f.write(mat_tex.tobytes())
+        f.write(np.ascontiguousarray(garden["lights"], D.LIGHT_DTYPE).tobytes())
+        for slot in sorted(textures):
+            t = np.ascontiguousarray(textures[slot], np.float32)
+            f.write(np.array([slot, t.shape[1], t.shape[0]], np.int32).tobytes()); f.write(t.tobytes())
+        env = garden.get("env_map")
+        if env is None:
+            f.write(np.array([0, 0], np.int32).tobytes()); f.write(np.float32(0.0).tobytes())
+        else:
+            e = np.ascontiguousarray(env, np.float32)
+            f.write(np.array([e.shape[1], e.shape[0]], np.int32).tobytes()); f.write(np.float32(garden.get("env_rotation", 0.0)).tobytes())
+            f.write(e.tobytes())
+        for ob in garden["objects"]:
+            v, n, uv, m = flatten(ob.meshes, ob.instances)
+            d = ob.desc(False)
+            f.write(bytes(C.string_at(C.addressof(d), C.sizeof(d))))
+            f.write(np.array([v.shape[0]], np.int64).tobytes())
+            f.write(np.array([0 if uv is None else 1], np.int32).tobytes())
+            f.write(np.ascontiguousarray(v, np.float32).tobytes()); f.write(np.ascontiguousarray(n, np.float32).tobytes())
+            if uv is not None:
+                f.write(np.ascontiguousarray(uv, np.float32).tobytes())
+            f.write(np.ascontiguousarray(m, np.int32).tobytes())
+            f.write(np.array([0], np.int64).tobytes()); f.write(np.array([0], np.int64).tobytes())      # no proxy networks

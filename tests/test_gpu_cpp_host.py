@@ -97,3 +97,34 @@ def test_dprt_render_frame_loop_animation_and_exr(gpu_required, oracle, tmp_path
         err = np.abs(img - img_o).max() / max(1e-30, float(np.abs(img_o).max()))
         assert err <= 1e-6, (f, err)                       # two samples in flight: the per-pixel sum over samples in another order
     assert not np.array_equal(dprt.scene.load_exr(str(tmp_path / "0anim.exr")), dprt.scene.load_exr(str(tmp_path / "2anim.exr")))
+
+
+@pytest.mark.parametrize("W", [1, 2])
+def test_dprt_render_real_scene_file_matches_oracle(gpu_required, oracle, tmp_path, W):
+    """The real-scene variant of the scene file (DPRTSCN2: flattened instanced geometry with texture coordinates, albedo /
+    opacity maps, texture slot per material, environment map) through the C++ host: the oracle's bits."""
+    from helpers import build_garden_pair
+    w, h, spp, bounces = 160, 90, 2, 3
+    _, world, g = build_garden_pair(oracle, W, w, h, spp=spp, bounces=bounces, gpu=False)
+    if W > 1:      # dprt_render stripes path generation over the ranks of a group
+        cfg = dprt.make_config(w, h, spp=spp, bounces=bounces, scene_size=W, path_gen_mode=1)
+        world2 = oracle.World(cfg, W)
+        for ob in g["objects"]:
+            world2.add_instanced_object(ob.index, ob.desc(False), ob.meshes, ob.instances)
+        world2.set_materials(g["materials"]); world2.set_lights(g["lights"]); world2.set_camera(dprt.scene.default_camera(w, h))
+        for slot, t in g["textures"].items():
+            world2.set_texture(slot, t)
+        world2.set_material_textures(g["material_textures"]); world2.set_env_map(g["env_map"], g["env_rotation"])
+        world = world2
+    img_o = world.launch()
+    scene, out = str(tmp_path / "garden.dprt"), str(tmp_path / "garden.pfm")
+    dprt.real_scene.save_scene_v2(scene, g, dprt.scene.default_camera(w, h), dprt.flatten_instances)
+    p = subprocess.run([BIN, "--scene", scene, "--out", out, "--spp", str(spp), "--bounces", str(bounces), "--world", str(W)],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    img = dprt.scene.load_pfm(out)
+    if W == 1:
+        assert_bits_equal(img.reshape(-1), np.asarray(img_o, np.float32).reshape(-1), "dprt_render image of the garden")
+    else:
+        err = np.abs(img - img_o).max() / max(1e-30, float(np.abs(img_o).max()))
+        assert err <= 1e-6, err

@@ -289,9 +289,17 @@ def test_cpp_host_binary_builds_and_fails_loudly_without_gpu(tmp_path):
     open(bad, "wb").write(open(scene, "rb").read()[:1000])
     p = subprocess.run([binp, "--scene", bad], capture_output=True, text=True)
     assert p.returncode == 1 and "malformed" in p.stderr
+    # the real-scene variant of the file (textures, texture coordinates, environment map) parses as well
+    g = dprt.real_scene.make_garden(1, clusters=3, ground=(8, 8))
+    scene2 = str(tmp_path / "garden.dprt")
+    dprt.real_scene.save_scene_v2(scene2, g, dprt.scene.default_camera(32, 18), dprt.flatten_instances)
+    open(bad, "wb").write(open(scene2, "rb").read()[:-100])
+    p = subprocess.run([binp, "--scene", bad], capture_output=True, text=True)
+    assert p.returncode == 1 and "malformed" in p.stderr
     if not torch.cuda.is_available():
-        p = subprocess.run([binp, "--scene", scene, "--out", str(tmp_path / "o.pfm")], capture_output=True, text=True)
-        assert p.returncode == 1 and "no CUDA device" in p.stderr and not os.path.exists(str(tmp_path / "o.pfm"))
+        for sc in (scene, scene2):
+            p = subprocess.run([binp, "--scene", sc, "--out", str(tmp_path / "o.pfm")], capture_output=True, text=True)
+            assert p.returncode == 1 and "no CUDA device" in p.stderr and not os.path.exists(str(tmp_path / "o.pfm"))
 
 
 def test_bvh8_build_host_only_properties():
