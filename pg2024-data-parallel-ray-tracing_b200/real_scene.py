@@ -191,9 +191,10 @@ class InstancedObject:
         return int(sum(np.asarray(self.meshes[mi]["indices"]).reshape(-1, 3).shape[0] for mi, _ in self.instances))
 
 
-def make_garden(W=1, clusters=18, ground=(40, 40), seed=0):
+def make_garden(W=1, clusters=18, ground=(40, 40), seed=0, cluster_scale=0.05):
     """W scene objects (x-slabs of the unit square, one per rank). Returns a dict: objects [InstancedObject], materials,
-    material_textures [int32 per material], textures {slot: rgba}, env_map, env_rotation, lights."""
+    material_textures [int32 per material], textures {slot: rgba}, env_map, env_rotation, lights. cluster_scale: size of an
+    element instance (between cluster_scale and 2 cluster_scale): shrink it when asking for thousands of clusters."""
     mats = np.zeros(5, D.MATERIAL_DTYPE)
     mats["baseColor"][MAT_GROUND] = (0.9, 0.1, 0.9)     # never seen: the checker map replaces it
     mats["baseColor"][MAT_LEAF] = (0.9, 0.1, 0.9)
@@ -221,9 +222,9 @@ def make_garden(W=1, clusters=18, ground=(40, 40), seed=0):
         for j in range(n):
             cx = x0 + (0.08 + 0.84 * r[j, 0]) * (x1 - x0)
             cy = 0.06 + 0.88 * r[j, 1]
-            s = 0.05 + 0.05 * r[j, 2]
+            s = cluster_scale * (1.0 + r[j, 2])
             mirror = -1.0 if j % 5 == 3 else 1.0                    # a mirrored instance: det < 0
-            M = _affine((s * mirror, s * (0.8 + 0.4 * r[j, 3]), s), 2 * np.pi * r[j, 4], (cx, cy, float(ground_height(cx, cy)) - 0.01))
+            M = _affine((s * mirror, s * (0.8 + 0.4 * r[j, 3]), s), 2 * np.pi * r[j, 4], (cx, cy, float(ground_height(cx, cy)) - 0.2 * s))
             inst.append(("element", "cluster" if r[j, 5] < 0.7 else "thicket", M))
         objects.append(InstancedObject(k, k, meshes, flatten_hierarchy(inst, elements)))
     return {"objects": objects, "materials": mats, "material_textures": mat_tex,

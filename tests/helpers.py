@@ -78,11 +78,11 @@ def random_rays(n, seed, lo=-0.2, hi=1.2):
 
 
 def build_garden_pair(O, W, width, height, *, spp=1, bounces=2, gpu=True, device=0, textures=True, env_map=True, clusters=18,
-                      ground=(40, 40), main_ray_retrace=0, serial_stages=0, reference_migrate=0):
+                      ground=(40, 40), cluster_scale=0.05, main_ray_retrace=0, serial_stages=0, reference_migrate=0):
     """The real-scene front end on both sides: W instanced, textured scene objects (real_scene.make_garden)
     go through dprt_upload_instanced_chunk / dprt_set_texture / dprt_set_material_textures / dprt_set_env_map and through the
     oracle's own flatten and texture code. gpu=False builds the oracle world only. Returns (renderers, world, garden)."""
-    g = dprt.real_scene.make_garden(W, clusters=clusters, ground=ground)
+    g = dprt.real_scene.make_garden(W, clusters=clusters, ground=ground, cluster_scale=cluster_scale)
     cfg = dprt.make_config(width, height, spp=spp, bounces=bounces, scene_size=W, proxy_mode=0, main_ray_retrace=main_ray_retrace,
                            serial_stages=serial_stages, reference_migrate=reference_migrate)
     cam = dprt.scene.default_camera(width, height)

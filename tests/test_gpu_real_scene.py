@@ -115,3 +115,18 @@ def test_garden_samples_in_flight_share_textures(gpu_required, oracle):
         S.close()
     img_o = world.launch()
     assert np.allclose(img_g, img_o, rtol=1e-6, atol=1e-7)
+
+
+def test_garden_full_size_one_million_instanced_triangles_1080p(gpu_required, oracle):
+    """Benchmark-size case of the front end: ~1 M instanced triangles (30 K leaf instances, three levels), 1920x1080, textures,
+    cut-outs and environment map on -- the image and every path record bit-exact against the oracle."""
+    w, h = 1920, 1080
+    rs, world, g = build_garden_pair(oracle, 1, w, h, spp=1, bounces=2, clusters=9000, ground=(300, 300), cluster_scale=0.004)
+    assert g["objects"][0].ntris > 900000
+    R = rs[0]
+    img_g, img_o = R.launch(), world.launch()
+    assert_bits_equal(img_g, img_o, "garden image, 1 M instanced triangles at 1080p")
+    n = R.path_size
+    assert n == world.path_size(0) and n > 100000
+    tot = n * (1 + R.cfg.shadowPathCount)
+    assert_records_equal(R.download(D.BUF_PATHS, tot), world.download(0, D.BUF_PATHS, tot), "paths + shadow paths after the last bounce")
