@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 
 namespace dprt {
@@ -40,6 +41,7 @@ struct Node2 {
     Box box;
     int left = -1, right = -1;   // children (internal)
     int first = 0, count = 0;    // primitive range (leaf when count > 0)
+    int pfirst = 0, pcount = 0;  // primitive range of the whole subtree (every node)
 };
 
 struct Builder2 {
@@ -63,14 +65,15 @@ struct Builder2 {
             cb.grow(&pcen[3 * (size_t)p]);
         }
         node.box = bb;
+        node.pfirst = first; node.pcount = count;
         if (count <= 3) { node.first = first; node.count = count; return; }
 
-        constexpr int NB = 16;
+        constexpr int NB = 16, NBMAX = NB;
         int best_axis = -1, best_split = -1; float best_cost = std::numeric_limits<float>::max();
         for (int a = 0; a < 3; a++) {
             float ext = cb.hi[a] - cb.lo[a];
             if (!(ext > 0.f)) continue;
-            Box bins[NB]; int cnt[NB];
+            Box bins[NBMAX]; int cnt[NBMAX];
             for (int b = 0; b < NB; b++) { bins[b].reset(); cnt[b] = 0; }
             float scale = NB / ext;
             for (int i = first; i < first + count; i++) {
@@ -79,7 +82,7 @@ struct Builder2 {
                 b = std::min(NB - 1, std::max(0, b));
                 bins[b].grow(pbox[p]); cnt[b]++;
             }
-            float rarea[NB]; int rcnt[NB];
+            float rarea[NBMAX]; int rcnt[NBMAX];
             Box acc; acc.reset(); int c = 0;
             for (int b = NB - 1; b > 0; b--) { acc.grow(bins[b]); c += cnt[b]; rarea[b] = acc.half_area(); rcnt[b] = c; }
             acc.reset(); c = 0;
@@ -168,7 +171,58 @@ int bvh8_build(const float* verts, const int32_t* mat_ids, int64_t ntris64, floa
         b2.build(root, 0, ntris, 0);
     }
 
-    // ---- collapse to 8-wide, BFS so that the internal children of a node are contiguous ----
+    // ---- collapse to 8-wide: the SAH-optimal choice by dynamic programming (Ylitie, Karras, Laine 2017, section 3.1) ----
+    // C(n, i) = least SAH cost of representing the subtree of binary node n by at most i wide-BVH roots, a root being a wide
+    // internal node (cost cNode x area, its <= 8 children are roots of n's two subtrees) or a leaf slot with <= 3 triangles
+    // (cost cPrim x triangles x area):
+    //   C(n, 1) = min(leaf(n), cNode A_n + min_k C(left, k) + C(right, 8 - k))
+    //   C(n, i) = min(C(n, i - 1), min_k C(left, k) + C(right, i - k))
+    // A top-down greedy collapse ("open the largest child until there are eight") leaves ragged bottoms -- wide nodes with two or
+    // three leaf children, 42 % slot occupancy on the benchmark chunk -- and every such node costs a ray a full node step.
+    // cNode : cPrim = 4 : 1 is the trace kernel's issue-slot ratio of a node step to a triangle test (profiles/bvh_quality.py).
+    const int nn = b2.nnodes.load();
+    const float cNode = getenv("DPRT_BVH_CNODE") ? (float)atof(getenv("DPRT_BVH_CNODE")) : 4.0f;
+    const float cPrim = 1.0f;
+    // DPRT_BVH_COLLAPSE=greedy | optimal (A/B in profiles/ab_r2_bvh_collapse.txt)
+    const bool greedy = !(getenv("DPRT_BVH_COLLAPSE") && std::strcmp(getenv("DPRT_BVH_COLLAPSE"), "optimal") == 0);
+    const float INF = std::numeric_limits<float>::max();
+    std::vector<float> C((size_t)nn * 8);          // C[n * 8 + i - 1]
+    std::vector<uint8_t> K((size_t)nn * 8);        // i = 1: 1 = leaf, 2 = wide node; i >= 2: roots given to the left child, 0 = as for i - 1
+    std::vector<uint8_t> K8((size_t)nn);           // wide node rooted at n: roots given to its left child
+    for (int n = nn - 1; n >= 0; n--) {            // children are allocated after their parent: decreasing index = bottom-up
+        const Node2& nd = n2[n];
+        const float A = nd.box.half_area();
+        float* c = &C[(size_t)n * 8]; uint8_t* k = &K[(size_t)n * 8];
+        if (nd.count > 0) { for (int i = 0; i < 8; i++) { c[i] = A * (float)nd.count * cPrim; k[i] = 1; } continue; }
+        const float* cl = &C[(size_t)nd.left * 8]; const float* cr = &C[(size_t)nd.right * 8];
+        float dist[9]; uint8_t dk[9];
+        for (int j = 2; j <= 8; j++) {
+            float best = INF; int bk = 1;
+            for (int x = 1; x < j; x++) { const float v = cl[x - 1] + cr[j - x - 1]; if (v < best) { best = v; bk = x; } }
+            dist[j] = best; dk[j] = (uint8_t)bk;
+        }
+        K8[n] = dk[8];
+        const float cLeaf = nd.pcount <= 3 ? A * (float)nd.pcount * cPrim : INF;
+        const float cInt = dist[8] + A * cNode;
+        c[0] = std::min(cLeaf, cInt); k[0] = cLeaf <= cInt ? 1 : 2;
+        for (int i = 2; i <= 8; i++) {
+            if (dist[i] < c[i - 2]) { c[i - 1] = dist[i]; k[i - 1] = dk[i]; } else { c[i - 1] = c[i - 2]; k[i - 1] = 0; }
+        }
+    }
+    struct Child { int n; bool leaf; };
+    struct Collector {
+        const std::vector<Node2>& n2; const std::vector<uint8_t>& K;
+        void run(int n, int i, Child* out, int& cnt) const {
+            const Node2& nd = n2[n];
+            if (nd.count > 0) { out[cnt++] = Child{n, true}; return; }
+            if (i == 1) { out[cnt++] = Child{n, K[(size_t)n * 8] == 1}; return; }
+            const int k = K[(size_t)n * 8 + i - 1];
+            if (k == 0) { run(n, i - 1, out, cnt); return; }
+            run(nd.left, k, out, cnt); run(nd.right, i - k, out, cnt);
+        }
+    } collector{n2, K};
+
+    // BFS so that the internal children of a node are contiguous
     struct Item { int n2; int out; int depth; };
     std::vector<Item> queue;
     out.nodes.resize(1);
@@ -179,25 +233,27 @@ int bvh8_build(const float* verts, const int32_t* mat_ids, int64_t ntris64, floa
         Item it = queue[qh++];
         out.max_depth = std::max(out.max_depth, it.depth);
         const Node2& nd = n2[it.n2];
-        int ch[8]; int nch = 0;
-        if (nd.count > 0) { ch[nch++] = it.n2; }     // root that is itself a leaf
-        else { ch[nch++] = nd.left; ch[nch++] = nd.right; }
-        for (;;) {                                    // greedy: open the internal child with the largest area
-            if (nch >= 8) break;
-            int best = -1; float ba = -1.f;
-            for (int i = 0; i < nch; i++) {
-                const Node2& c = n2[ch[i]];
-                if (c.count > 0) continue;
-                float a = c.box.half_area();
-                if (a > ba) { ba = a; best = i; }
+        Child ch[8]; int nch = 0;
+        if (nd.count > 0 || (it.n2 == root && K[(size_t)root * 8] == 1)) ch[nch++] = Child{it.n2, true};     // a root that is itself a leaf
+        else if (!greedy) { collector.run(nd.left, K8[it.n2], ch, nch); collector.run(nd.right, 8 - K8[it.n2], ch, nch); }
+        else {
+            ch[nch++] = Child{nd.left, n2[nd.left].count > 0}; ch[nch++] = Child{nd.right, n2[nd.right].count > 0};
+            for (;;) {                                // greedy: open the internal child with the largest area
+                if (nch >= 8) break;
+                int best = -1; float ba = -1.f;
+                for (int i = 0; i < nch; i++) {
+                    if (ch[i].leaf) continue;
+                    float a = n2[ch[i].n].box.half_area();
+                    if (a > ba) { ba = a; best = i; }
+                }
+                if (best < 0) break;
+                int l = n2[ch[best].n].left, r = n2[ch[best].n].right;
+                ch[best] = Child{l, n2[l].count > 0}; ch[nch++] = Child{r, n2[r].count > 0};
             }
-            if (best < 0) break;
-            int l = n2[ch[best]].left, r = n2[ch[best]].right;
-            ch[best] = l; ch[nch++] = r;
         }
         // node frame
         Box nb; nb.reset();
-        for (int i = 0; i < nch; i++) nb.grow(n2[ch[i]].box);
+        for (int i = 0; i < nch; i++) nb.grow(n2[ch[i].n].box);
         // The frame is padded by a little more than any child will be (children get pad + 2^-7 of a quantisation step,
         // the slack the traversal kernel's folded dequantisation needs, bvh_traverse.cuh), so no child bound clamps.
         Box padded = nb;
@@ -211,7 +267,7 @@ int bvh8_build(const float* verts, const int32_t* mat_ids, int64_t ntris64, floa
         float ncx[3];
         for (int a = 0; a < 3; a++) ncx[a] = 0.5f * (nb.lo[a] + nb.hi[a]);
         for (int c = 0; c < nch; c++) {
-            const Box& cb = n2[ch[c]].box;
+            const Box& cb = n2[ch[c].n].box;
             float d[3];
             for (int a = 0; a < 3; a++) d[a] = 0.5f * (cb.lo[a] + cb.hi[a]) - ncx[a];
             for (int s = 0; s < 8; s++) {
@@ -230,9 +286,9 @@ int bvh8_build(const float* verts, const int32_t* mat_ids, int64_t ntris64, floa
             }
             child_done[bc] = true; slot_used[bs] = true; slot_of[bc] = bs;
         }
-        int child_in_slot[8];
-        for (int s = 0; s < 8; s++) child_in_slot[s] = -1;
-        for (int c = 0; c < nch; c++) child_in_slot[slot_of[c]] = ch[c];
+        int child_in_slot[8]; bool leaf_in_slot[8];
+        for (int s = 0; s < 8; s++) { child_in_slot[s] = -1; leaf_in_slot[s] = false; }
+        for (int c = 0; c < nch; c++) { child_in_slot[slot_of[c]] = ch[c].n; leaf_in_slot[slot_of[c]] = ch[c].leaf; }
 
         dprt_bvh8_node node;
         std::memset(&node, 0, sizeof(node));
@@ -243,7 +299,7 @@ int bvh8_build(const float* verts, const int32_t* mat_ids, int64_t ntris64, floa
         node.triBase = (uint32_t)out.tris.size();
         int ninternal = 0;
         for (int s = 0; s < 8; s++)
-            if (child_in_slot[s] >= 0 && n2[child_in_slot[s]].count == 0) ninternal++;
+            if (child_in_slot[s] >= 0 && !leaf_in_slot[s]) ninternal++;
         node.childBase = (uint32_t)out.nodes.size();
         if (ninternal) out.nodes.resize(out.nodes.size() + ninternal);
         int irank = 0, toff = 0;
@@ -255,22 +311,23 @@ int bvh8_build(const float* verts, const int32_t* mat_ids, int64_t ntris64, floa
                 continue;
             }
             const Node2& cn = n2[c];
-            if (cn.count == 0) {
+            if (!leaf_in_slot[s]) {
                 node.imask |= (uint8_t)(1u << s);
                 queue.push_back({c, (int)node.childBase + irank, it.depth + 1});
                 irank++;
             } else {
-                uint8_t unary = cn.count == 1 ? 1 : (cn.count == 2 ? 3 : 7);
+                const int lcount = cn.pcount;            // <= 3: a binary leaf, or a subtree the collapse turned into one leaf slot
+                uint8_t unary = lcount == 1 ? 1 : (lcount == 2 ? 3 : 7);
                 node.tmask |= (uint32_t)unary << (3 * s);
-                for (int k = 0; k < cn.count; k++) {
-                    int p = idx[cn.first + k];
+                for (int k = 0; k < lcount; k++) {
+                    int p = idx[cn.pfirst + k];
                     dprt_bvh8_tri t;
                     const float* v = verts + 9 * (size_t)p;
                     std::memcpy(t.v0, v, 12); std::memcpy(t.v1, v + 3, 12); std::memcpy(t.v2, v + 6, 12);
                     t.primID = p; t.matID = mat_ids ? mat_ids[p] : 0; t.pad_ = 0;
                     out.tris.push_back(t);
                 }
-                toff += cn.count;
+                toff += lcount;
             }
             // conservative quantisation of the padded child box, verified in double
             uint8_t* qlo[3] = {&node.qlox[s], &node.qloy[s], &node.qloz[s]};

@@ -321,6 +321,32 @@ def test_bvh8_build_host_only_properties():
     assert depth >= 2
 
 
+@pytest.mark.parametrize("collapse", ["greedy", "optimal"])
+def test_bvh8_collapse_modes_same_hits_fewer_nodes(oracle, monkeypatch, collapse):
+    """Both collapses of the builder (greedy top-down / SAH-optimal dynamic programme, DPRT_BVH_COLLAPSE) give a valid BVH8: a
+    scalar walk over the blob finds exactly the hits of the oracle's own binary BVH and of brute force; the optimal collapse
+    needs about half the nodes for the same triangles."""
+    from helpers import random_rays
+    monkeypatch.setenv("DPRT_BVH_COLLAPSE", collapse)
+    chunks, _, _ = dprt.scene.make_scene(1, 30000, water_frac=0.0)
+    c = chunks[0]
+    nodes, tris, depth = dprt.build_bvh8(c.verts, c.mats)
+    assert sorted(tris["primID"].tolist()) == list(range(c.verts.shape[0])) and depth <= 36
+    monkeypatch.setenv("DPRT_BVH_COLLAPSE", "greedy")
+    n_greedy = dprt.build_bvh8(c.verts, c.mats)[0].size
+    assert nodes.size == n_greedy if collapse == "greedy" else nodes.size < 0.65 * n_greedy
+    cfg = dprt.make_config(16, 16, scene_size=1)
+    world = oracle.World(cfg, 1)
+    world.add_object(0, c.desc(False), c.verts, c.normals, c.mats)
+    rays = np.concatenate([random_rays(20000, 5), dprt.scene.camera_rays(dprt.scene.default_camera(160, 90))])
+    hb, nv, tt = oracle.bvh8_trace(nodes, tris, rays)
+    ho = world.trace_closest(0, rays)
+    assert np.array_equal(hb["primID"], ho["primID"]) and np.array_equal(hb["t"].view(np.uint32), ho["t"].view(np.uint32))
+    hbrute = world.trace_closest(0, rays[:2000], brute=True)
+    assert np.array_equal(hb["primID"][:2000], hbrute["primID"])
+    assert (hb["primID"] >= 0).sum() > 5000 and nv > 0 and tt > 0
+
+
 def test_balanced_slab_layout_cuts_equal_primary_load():
     """bench.py's N > 1 workload: x-slabs cut at the k/W quantiles of where the primary rays land on the (continuous)
     landscape. The cuts are increasing, span [0, 1], and an independent ray-march at another resolution finds the same
