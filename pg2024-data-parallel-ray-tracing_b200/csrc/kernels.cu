@@ -55,8 +55,9 @@ DPRT_D void store_zero_path(dprt_path_record* p) {
     q[0] = z; q[1] = z; q[2] = z; q[3] = z;
 }
 
-// calculateEnvironmentLighting (distributed_traversal_kernel.cu:82-103): the reference looks a lat-long
-// texture up at (phi/2pi, theta/pi); the synthetic scenes use the analytic sky Le = envColor*(0.5+0.5*d.z).
+// calculateEnvironmentLighting (distributed_traversal_kernel.cu:82-103, kernel.cu:28-48): the reference looks a lat-long
+// texture up at (phi/2pi, theta/pi) -- env_map_lookup when dprt_set_env_map installed one; the synthetic benchmark scenes
+// have none and use the analytic sky Le = envColor*(0.5+0.5*d.z).
 DPRT_D V3 env_radiance(const DevParams& p, V3 d) {
     if (p.envMap.texels) {           // dprt_set_env_map: params.envLightTexture
         const float4 e = env_map_lookup(p.envMap, p.envRotation, d);
