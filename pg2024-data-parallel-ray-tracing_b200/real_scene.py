@@ -357,7 +357,8 @@ def load_texture(path):
 def save_scene_v2(path, garden, cam, flatten):
     """Scene file of the C++ host in its real-scene variant (csrc/dprt_render.cpp documents the layout): the dict of make_garden
     (or the same keys filled from load_obj / load_texture) with every object flattened by `flatten` = host.flatten_instances
-    (dprt_flatten_instances: what dprt_upload_instanced_chunk would do)."""
+    (dprt_flatten_instances: what dprt_upload_instanced_chunk would do); an object that already carries its flat streams
+    as `.flat = (verts9, normals9, uv6 or None, mat_ids)` is written as is (obj2scene.py cuts one flattened scene into chunks)."""
     import ctypes as C
     mats, mat_tex = np.ascontiguousarray(garden["materials"], D.MATERIAL_DTYPE), np.full(len(garden["materials"]), -1, np.int32)
     mt = np.asarray(garden.get("material_textures", []), np.int32)
@@ -380,7 +381,7 @@ def save_scene_v2(path, garden, cam, flatten):
             f.write(np.array([e.shape[1], e.shape[0]], np.int32).tobytes()); f.write(np.float32(garden.get("env_rotation", 0.0)).tobytes())
             f.write(e.tobytes())
         for ob in garden["objects"]:
-            v, n, uv, m = flatten(ob.meshes, ob.instances)
+            v, n, uv, m = ob.flat if getattr(ob, "flat", None) is not None else flatten(ob.meshes, ob.instances)
             d = ob.desc(False)
             f.write(bytes(C.string_at(C.addressof(d), C.sizeof(d))))
             f.write(np.array([v.shape[0]], np.int64).tobytes())

@@ -2,6 +2,8 @@
 texture / environment look-ups of the PRODUCT (libdprt.so, host-only entry points compiled from the kernels' own source)
 against the oracle bit for bit, both against a float64 numpy model, and the oracle's alpha cut-out / textured shading.
 No GPU needed; the GPU parity of the same scene is tests/test_gpu_real_scene.py."""
+import os
+
 import numpy as np
 import pytest
 
@@ -189,3 +191,81 @@ def test_texture_loader_flips_like_stbi(tmp_path):
     t = dprt.real_scene.load_texture(str(tmp_path / "t.pfm"))
     assert t.shape == (3, 2, 4) and (t[..., 3] == 1).all()
     assert (t[2, :, :3] == 1).all() and (t[0, :, :3] == 0).all()  # row 0 = v 0 = the image's bottom row
+
+
+def _read_scene_v2(path):
+    """Minimal reader of the DPRTSCN2 layout documented in csrc/dprt_render.cpp (the C++ host has the real one)."""
+    import ctypes as C
+    b = open(path, "rb").read()
+    assert b[:8] == b"DPRTSCN2"
+    nobj, nmat, nlight, ntex = np.frombuffer(b, "<i4", 4, 8)
+    o = 24 + C.sizeof(D.Camera)
+    mats = np.frombuffer(b, D.MATERIAL_DTYPE, nmat, o); o += mats.nbytes
+    mat_tex = np.frombuffer(b, "<i4", nmat, o); o += 4 * nmat
+    lights = np.frombuffer(b, D.LIGHT_DTYPE, nlight, o); o += lights.nbytes
+    textures = {}
+    for _ in range(ntex):
+        slot, w, h = np.frombuffer(b, "<i4", 3, o); o += 12
+        textures[int(slot)] = np.frombuffer(b, "<f4", 4 * w * h, o).reshape(h, w, 4); o += 16 * w * h
+    ew, eh = np.frombuffer(b, "<i4", 2, o); o += 8
+    rot = float(np.frombuffer(b, "<f4", 1, o)[0]); o += 4
+    env = None
+    if ew:
+        env = np.frombuffer(b, "<f4", 4 * ew * eh, o).reshape(eh, ew, 4); o += 16 * ew * eh
+    objs = []
+    for _ in range(nobj):
+        o += C.sizeof(D.ObjectDesc)
+        nt = int(np.frombuffer(b, "<i8", 1, o)[0]); o += 8
+        has_uv = int(np.frombuffer(b, "<i4", 1, o)[0]); o += 4
+        v = np.frombuffer(b, "<f4", 9 * nt, o).reshape(nt, 9); o += 36 * nt
+        o += 36 * nt
+        uv = None
+        if has_uv:
+            uv = np.frombuffer(b, "<f4", 6 * nt, o).reshape(nt, 6); o += 24 * nt
+        m = np.frombuffer(b, "<i4", nt, o); o += 4 * nt
+        for _ in range(2):
+            o += 8 + int(np.frombuffer(b, "<i8", 1, o)[0])
+        objs.append((v, uv, m))
+    assert o == len(b)
+    return mats, mat_tex, lights, textures, env, rot, objs
+
+
+def test_obj2scene_converter(tmp_path):
+    """OBJ + MTL + texture image -> DPRTSCN2 scene file (host only): materials, BSDF types, texture slots, chunks by x-slab; the
+    C++ host parses the result."""
+    import importlib.util
+    import subprocess
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("obj2scene", os.path.join(root, "pg2024-data-parallel-ray-tracing_b200", "obj2scene.py"))
+    o2s = importlib.util.module_from_spec(spec); spec.loader.exec_module(o2s)
+    g = dprt.real_scene.make_garden(W=1, clusters=3, ground=(12, 12))
+    names = ["ground", "leaf", "rock", "water", "leaf2"]
+    obj = tmp_path / "garden.obj"
+    dprt.real_scene.save_obj(str(obj), g["objects"][0].meshes, names)
+    obj.write_text("mtllib garden.mtl\n" + obj.read_text())
+    (tmp_path / "garden.mtl").write_text(
+        "newmtl ground\nKd 0.5 0.5 0.5\nmap_Kd checker.pfm\nnewmtl leaf\nKd 0.1 0.6 0.1\nmap_Kd checker.pfm\n"
+        "newmtl rock\nKd 0.55 0.5 0.45\nnewmtl water\nNi 1.33\nillum 7\nnewmtl leaf2\nKd 0.2 0.7 0.2\n")
+    dprt.scene.save_pfm(str(tmp_path / "checker.pfm"), dprt.real_scene.checker_texture(8)[..., :3])
+    dprt.scene.save_pfm(str(tmp_path / "sky.pfm"), dprt.real_scene.sky_env_map(16, 8)[..., :3])
+    out = str(tmp_path / "garden.dprt")
+    info = o2s.convert(str(obj), out, world=2, width=64, height=36, env=str(tmp_path / "sky.pfm"), env_rotation=0.5)
+    ntris = sum(np.asarray(m["indices"]).reshape(-1, 3).shape[0] for m in g["objects"][0].meshes)
+    order = ["ground", "leaf", "leaf2", "rock", "water"]           # material indices follow first use in the OBJ
+    assert info["triangles"] == ntris and info["materials"] == order and sum(info["chunks"]) == ntris and len(info["chunks"]) == 2
+    mats, mat_tex, lights, textures, env, rot, objs = _read_scene_v2(out)
+    assert mat_tex.tolist() == [0, 0, -1, -1, -1] and list(textures) == [0] and textures[0].shape == (8, 8, 4)
+    assert mats["bsdfType"].tolist() == [0, 0, 0, 0, 1] and np.allclose(mats["baseColor"][3], (0.55, 0.5, 0.45))
+    assert env.shape == (8, 16, 4) and abs(rot - 0.5) < 1e-7 and lights.size == 2
+    # row 0 of a loaded texture is the image's bottom row (stbi flip): save_pfm wrote the checker top-down
+    assert np.array_equal(textures[0][::-1, :, :3], dprt.real_scene.checker_texture(8)[..., :3])
+    assert sum(o[0].shape[0] for o in objs) == ntris and all(o[1] is not None for o in objs)
+    assert objs[0][0].reshape(-1, 3, 3)[:, :, 0].mean(1).max() <= objs[1][0].reshape(-1, 3, 3)[:, :, 0].mean(1).min() + 1e-6      # x-slabs
+    # light normals face the scene (down along `up`)
+    for L in lights:
+        assert np.cross(L["p1"] - L["p0"], L["p2"] - L["p0"])[2] < 0 and L["p0"][2] > objs[0][0].reshape(-1, 3)[:, 2].max()
+    binp = os.path.join(os.path.dirname(dprt.host.LIB_PATH), "dprt_render")
+    if not torch.cuda.is_available():
+        p = subprocess.run([binp, "--scene", out, "--world", "2"], capture_output=True, text=True)
+        assert p.returncode == 1 and "no CUDA device" in p.stderr and "malformed" not in p.stderr
